@@ -1,0 +1,67 @@
+"""Golden-vector case list shared by tests/golden/make_golden.py and the parity tests.
+
+Each case names a reference composition (oracle ``kind``), preset, raster and absolute frame index.
+Frames are small (24 rows) with an explicit line standard so the fixtures stay a few MB in total;
+``LineConfig((W, 24), standard)`` is a legal reference configuration (line.py:50-55).
+"""
+import collections
+
+Case = collections.namedtuple('Case', 'kind variant width height standard chroma_avg frame seed content')
+
+
+def _c(kind, variant, std, frame, width=720, height=24, avg=False, seed=None, content='smooth'):
+    return Case(kind, variant, width, height, std, avg, frame, frame * 7 + 1 if seed is None else seed, content)
+
+
+GOLDEN_CASES = [
+    # NTSC family (ntsc.py, comb.py)
+    _c('ntsc', 'NTSC', 'NTSC_525', 0),
+    _c('ntsc_comb', 'NTSC', 'NTSC_525', 1),
+    _c('ntsc_3d', 'NTSC', 'NTSC_525', 2),
+    _c('ntsc_3d', 'NTSC443', 'NTSC_525', 7),
+    _c('ntsc', 'NTSC361', 'NTSC_525', 3, content='noise'),
+    _c('ntsc_comb', 'NTSC_A', 'BAIRD_405', 4),
+    _c('ntsc', 'NTSC_I', 'GERBER_625', 5),
+    _c('ntsc_comb', 'NTSC_N', 'GERBER_625', 6),
+    # PAL family (pal.py)
+    _c('pal_s', 'PAL', 'GERBER_625', 0),
+    _c('pal_d', 'PAL', 'GERBER_625', 1),
+    _c('pal_d', 'PAL', 'GERBER_625', 2, content='noise'),
+    _c('pal_3d', 'PAL', 'GERBER_625', 3),
+    _c('pal_d', 'PAL_M', 'NTSC_525', 5),
+    _c('pal_s', 'PAL_M', 'NTSC_525', 2),
+    _c('pal_3d', 'PAL_N', 'GERBER_625', 6),
+    # SECAM (secam.py) incl. ColorAveragingModem encoder (comb.py:130-167)
+    _c('secam', 'SECAM', 'GERBER_625', 0),
+    _c('secam', 'SECAM', 'GERBER_625', 1, avg=True),
+    _c('secam', 'SECAM', 'GERBER_625', 4, content='noise'),
+    _c('secam', 'SECAM_I', 'GERBER_625', 2),
+    _c('secam', 'SECAM_II', 'GERBER_625', 3),
+    _c('secam', 'SECAM_III', 'GERBER_625', 5),
+    _c('secam', 'SECAM_A', 'BAIRD_405', 2),
+    _c('secam', 'SECAM_M', 'NTSC_525', 3),
+    _c('secam', 'SECAM_N', 'GERBER_625', 4),
+    # NIIR / SECAM-IV (niir.py)
+    _c('niir', 'PAL', 'GERBER_625', 1),
+    _c('niir_hue', 'PAL', 'GERBER_625', 2),
+    # 819-line AM proto-SECAM (protosecam.py)
+    _c('protosecam', 'SECAM_1957', 'FRENCH_819', 1),
+    _c('protosecam', 'SECAM_1957', 'FRENCH_819', 2, avg=True),
+    # D2-MAC (mac.py)
+    _c('mac', 'D2MAC_12MHZ', 'GERBER_625', 0),
+    _c('mac', 'D2MAC_12MHZ', 'GERBER_625', 1, avg=True),
+    _c('mac', 'D2MAC_7MHZ', 'GERBER_625', 3),
+    # 1920-wide (36 MHz / 47 MHz sampling)
+    _c('secam', 'SECAM_E', 'FRENCH_819', 1, width=1920),
+    _c('pal_d', 'PAL', 'GERBER_625', 2, width=1920),
+    _c('ntsc_3d', 'NTSC', 'NTSC_525', 1, width=1920),
+    _c('mac', 'D2MAC_7MHZ', 'GERBER_625', 1, width=1920),
+    _c('niir_hue', 'PAL', 'GERBER_625', 3, width=1920),
+]
+
+FLOAT_ROWS = (1, 10, 22)   # rows whose float64 composite / RGB lines are stored: field top, interior, field bottom
+
+
+def case_id(c):
+    return '%s-%s-%dx%d-%s%s-f%d-%s' % (c.kind, c.variant, c.width, c.height, c.standard,
+                                        '-avg' if c.chroma_avg else '', c.frame, c.content)
