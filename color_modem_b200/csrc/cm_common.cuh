@@ -1,0 +1,160 @@
+// Common device-side types of the colour-modem kernels (sm_100a).
+//
+// Execution model:
+//   * a CTA owns a small group of consecutive rows of ONE field of one frame; every intermediate signal of
+//     those rows lives in shared memory, HBM is touched once per input and once per output byte;
+//   * FIR / elementwise stages are parallel over samples (all threads of the CTA);
+//   * IIR stages (the reference's scipy.signal.lfilter calls, utils.py:28-36) are parallel over *chunks of a
+//     line*: one warp per (row, signal), lane t owns samples [t*L, (t+1)*L) in registers, runs the biquad
+//     cascade from zero state, and the true chunk-boundary states are recovered exactly with a warp-shuffle
+//     scan over the 2x2 state-transition powers (cm_iir.cuh).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define CM_LMAX 47          // max samples per lane per super-chunk in warp_iir (odd => conflict-free smem)
+#define CM_NWARPS 8
+#define CM_NTHREADS (CM_NWARPS * 32)
+#define CM_MAXSEC 6
+#define CM_NFILT 10
+#define CM_NRES 6
+#define CM_NSCAL 48
+#define CM_NPHASE 16
+
+struct FiltHdr {
+    int nsec, shift, n, L, nsuper, stride;   // n = input length of this use-site; L*32*nsuper >= n+shift
+    int off;                                 // offset (in elements) of the section tables in DevParams::tab
+    int _pad;
+};
+
+struct ResHdr {
+    int up, down, half, ntaps;
+    int off;                                 // offset (in elements) into DevParams::taps
+    int _pad[3];
+};
+
+template <typename T>
+struct DevParams {
+    int kind, flags;
+    int W, H, Wc, Wo;
+    int digital_shift, odd_first, even_first, ref_line, frame_cycle;
+    int _pad0;
+    unsigned long long frame_shift, line_shift;
+    unsigned long long phases[CM_NPHASE];
+    T scalars[CM_NSCAL];
+    T enc[9];
+    T dec[9];
+    FiltHdr filt[CM_NFILT];
+    ResHdr res[CM_NRES];
+    const T *tab;
+    const T *taps;
+};
+
+// Launch geometry / buffers of one call.
+template <typename T>
+struct IoArgs {
+    const uint8_t *in_u8;
+    const T *in_f;
+    uint8_t *out_u8;
+    T *out_f;
+    long long first_frame;
+    int nframes;
+    int nrows;        // rows per frame in the buffers (window)
+    int y0;           // line number of buffer row 0
+    int out_begin, out_count;
+    int rows_per_cta; // R
+    int groups_per_field;
+};
+
+// ------------------------------------------------------------------------------------------------------------
+// Real-number traits
+// ------------------------------------------------------------------------------------------------------------
+template <typename T> struct Real;
+
+template <> struct Real<float> {
+    static __device__ __forceinline__ void sincos_turns(unsigned long long ph, float &s, float &c) {
+        // ph: phase in turns, 0.64 fixed point.  Top 32 bits as signed => [-0.5, 0.5) turns => [-1, 1) half-turns.
+        float x = (float)(int)(unsigned)(ph >> 32) * 4.656612873077393e-10f;   // 2^-31
+        sincospif(x, &s, &c);
+    }
+    static __device__ __forceinline__ float from_u8(unsigned v) { return (float)v * (1.0f / 255.0f); }
+    static __device__ __forceinline__ float rsqrt_(float x) { return rsqrtf(x); }
+    static __device__ __forceinline__ float sqrt_(float x) { return sqrtf(x); }
+    static __device__ __forceinline__ float abs_(float x) { return fabsf(x); }
+    static __device__ __forceinline__ float atan2_(float y, float x) { return atan2f(y, x); }
+    static __device__ __forceinline__ float fma_(float a, float b, float c) { return fmaf(a, b, c); }
+};
+
+template <> struct Real<double> {
+    static __device__ __forceinline__ void sincos_turns(unsigned long long ph, double &s, double &c) {
+        double x = (double)(long long)ph * 1.084202172485504434e-19;           // 2^-63 => half-turns in [-1, 1)
+        sincospi(x, &s, &c);
+    }
+    static __device__ __forceinline__ double from_u8(unsigned v) { return (double)v / 255.0; }
+    static __device__ __forceinline__ double rsqrt_(double x) { return 1.0 / sqrt(x); }
+    static __device__ __forceinline__ double sqrt_(double x) { return sqrt(x); }
+    static __device__ __forceinline__ double abs_(double x) { return fabs(x); }
+    static __device__ __forceinline__ double atan2_(double y, double x) { return atan2(y, x); }
+    static __device__ __forceinline__ double fma_(double a, double b, double c) { return fma(a, b, c); }
+};
+
+// uint8(rint(255 * clip(v, 0, 1)))  — reference image.py:7-8 (numpy.rint = round-half-even = cvt.rni)
+template <typename T>
+__device__ __forceinline__ unsigned to_u8(T v) {
+    v = v < (T)0 ? (T)0 : (v > (T)1 ? (T)1 : v);
+    return (unsigned)__double2int_rn((double)(v * (T)255));
+}
+template <>
+__device__ __forceinline__ unsigned to_u8<float>(float v) {
+    v = fminf(fmaxf(v, 0.0f), 1.0f);
+    return (unsigned)__float2int_rn(v * 255.0f);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Raster / carrier phase — reference line.py:57-65, utils.py:82-88
+// ------------------------------------------------------------------------------------------------------------
+template <typename T>
+__device__ __forceinline__ int analog_line(const DevParams<T> &p, int line) {
+    int adj = line + p.digital_shift;
+    int half = adj >> 1;                       // floor division, also for negative adj (priming / field-top rows)
+    return ((adj & 1) == 0 ? p.even_first : p.odd_first) + half;
+}
+
+template <typename T>
+__device__ __forceinline__ bool is_alternate(const DevParams<T> &p, long long frame, int line) {
+    return ((analog_line(p, line) & 1) == (int)(frame & 1));
+}
+
+// Subcarrier phase at the first sample of `line`, in turns (0.64 fixed point; integer wrap == mod 2*pi).
+template <typename T>
+__device__ __forceinline__ unsigned long long start_phase(const DevParams<T> &p, long long frame, int line) {
+    unsigned long long fr = (unsigned long long)(frame % (long long)p.frame_cycle);
+    long long dl = (long long)(analog_line(p, line) - p.ref_line);
+    return fr * p.frame_shift + (unsigned long long)dl * p.line_shift;
+}
+
+// Row bookkeeping of a CTA: which buffer rows it outputs.
+struct RowGroup {
+    long long frame;      // absolute frame number
+    int fidx;             // frame index inside the batch
+    int r0;               // first output buffer row of the group
+    int count;            // rows in the group (same field: r0, r0+2, ...)
+};
+
+// Output rows [out_begin, out_begin+out_count) split by parity into two "fields"; each field into groups of R.
+template <typename T>
+__device__ __forceinline__ bool decode_group(const IoArgs<T> &io, RowGroup &g) {
+    int per_frame = 2 * io.groups_per_field;
+    int f = blockIdx.x / per_frame;
+    int rem = blockIdx.x - f * per_frame;
+    int field = rem / io.groups_per_field;
+    int gi = rem - field * io.groups_per_field;
+    int first = io.out_begin + field;                         // first row of this parity class
+    int rows_in_field = (io.out_count - field + 1) >> 1;      // rows out_begin+field, +2, ... < out_begin+out_count
+    int start = gi * io.rows_per_cta;
+    g.fidx = f;
+    g.frame = io.first_frame + f;
+    g.r0 = first + 2 * start;
+    g.count = min(io.rows_per_cta, rows_in_field - start);
+    return g.count > 0;
+}

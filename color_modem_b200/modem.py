@@ -1,0 +1,239 @@
+"""GPU-backed modem base: owns the native handles and implements both faces of the reference protocol.
+
+* frame batches (the fast path, what ImageModem and bench.py use): ``encode_frames`` / ``decode_frames`` on
+  CUDA ``torch.uint8`` tensors, or ``*_host`` on numpy arrays;
+* the reference's per-line protocol ``modulate(frame, line, r, g, b)`` / ``demodulate(frame, line, composite)``
+  (qam.py:68-72): float64 numpy rows in and out, with the same one-line memories and reset rule
+  (``frame != last_frame or line != last_line + 2``, e.g. comb.py:48) as the reference's stateful classes.
+  Each call gathers the neighbour rows it needs into a small row *window* and runs the same kernels on it.
+
+torch is used only for device memory and streams.
+"""
+import ctypes as C
+
+import numpy
+
+from . import _native as N
+
+
+def _torch():
+    import torch
+    if not torch.cuda.is_available():
+        raise N.NativeUnavailable('no CUDA device: color_modem_b200 has no CPU path')
+    return torch
+
+
+class GpuModem(object):
+    """Base of every modem composition.  Subclasses provide ``_fill_desc(desc)`` and the row-window policy."""
+    modulation_delay = 0
+    demodulation_delay = 0
+
+    def __init__(self, line_config, precision='fp32'):
+        if precision not in ('fp32', 'fp64'):
+            raise ValueError("precision must be 'fp32' or 'fp64'")
+        self.line_config = line_config
+        self.precision = precision
+        self._handles = {}
+        self._enc_mem = None      # per-line protocol memories
+        self._dec_mem = None
+
+    # ---- geometry ----------------------------------------------------------------------------------------
+    @property
+    def width(self):
+        return self.line_config.size[0]
+
+    @property
+    def height(self):
+        return self.line_config.size[1]
+
+    @property
+    def composite_width(self):
+        return self.width
+
+    @property
+    def output_width(self):
+        return self.width
+
+    # ---- native handle -----------------------------------------------------------------------------------
+    def _base_desc(self):
+        d = N.Desc()
+        std = self.line_config.line_standard
+        d.abi_version = N.ABI_VERSION
+        d.width, d.height = self.width, self.height
+        d.comp_width, d.out_width = self.composite_width, self.output_width
+        d.digital_shift = self.line_config._line_shift
+        d.odd_first = std.odd_field_first_active_line
+        d.even_first = std.even_field_first_active_line
+        d.ref_line = min(d.odd_first, d.even_first)
+        d.frame_cycle = 1
+        return d
+
+    def describe(self):
+        """The cm_desc handed to cm_create (pure host-side; usable without a GPU)."""
+        d = self._base_desc()
+        self._fill_desc(d)
+        return d
+
+    def _handle(self, precision=None):
+        precision = precision or self.precision
+        h = self._handles.get(precision)
+        if h is None:
+            lib = N.load()
+            _torch()
+            desc = self.describe()
+            ptr = C.c_void_p()
+            N.check(lib.cm_create(C.byref(desc), N.FP32 if precision == 'fp32' else N.FP64, C.byref(ptr)))
+            h = self._handles[precision] = ptr
+        return h
+
+    def close(self):
+        if self._handles:
+            lib = N.load()
+            for h in self._handles.values():
+                lib.cm_destroy(h)
+            self._handles = {}
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- frame batches on the device -----------------------------------------------------------------------
+    def encode_frames(self, rgb, first_frame=0, out=None, out_float=None):
+        """rgb: CUDA uint8 tensor [N, H, W, 3] -> composite uint8 [N, H, Wc] (ImageModem.modulate, image.py:27-56)."""
+        torch = _torch()
+        self._check(rgb, torch.uint8, (self.height, self.width, 3))
+        n = rgb.shape[0]
+        if out is None and out_float is None:
+            out = torch.empty((n, self.height, self.composite_width), dtype=torch.uint8, device=rgb.device)
+        with torch.cuda.device(rgb.device):
+            N.check(N.load().cm_encode_ex(self._handle(), None, rgb.data_ptr(), None,
+                                          out.data_ptr() if out is not None else None,
+                                          out_float.data_ptr() if out_float is not None else None,
+                                          int(first_frame), int(n), torch.cuda.current_stream().cuda_stream))
+        return out if out is not None else out_float
+
+    def decode_frames(self, comp, first_frame=0, out=None, out_float=None):
+        """comp: CUDA uint8 tensor [N, H, Wc] -> RGB uint8 [N, H, Wo, 3] (ImageModem.demodulate, image.py:58-84)."""
+        torch = _torch()
+        self._check(comp, torch.uint8, (self.height, self.composite_width))
+        n = comp.shape[0]
+        if out is None and out_float is None:
+            out = torch.empty((n, self.height, self.output_width, 3), dtype=torch.uint8, device=comp.device)
+        with torch.cuda.device(comp.device):
+            N.check(N.load().cm_decode_ex(self._handle(), None, comp.data_ptr(), None,
+                                          out.data_ptr() if out is not None else None,
+                                          out_float.data_ptr() if out_float is not None else None,
+                                          int(first_frame), int(n), torch.cuda.current_stream().cuda_stream))
+        return out if out is not None else out_float
+
+    @staticmethod
+    def _check(t, dtype, tail):
+        if not t.is_cuda or t.dtype != dtype or tuple(t.shape[1:]) != tuple(tail) or not t.is_contiguous():
+            raise ValueError('expected a contiguous CUDA %s tensor of shape [N, %s]' % (dtype, ', '.join(map(str, tail))))
+
+    # ---- frame batches with host buffers (H2D + kernels + D2H inside the native call) ------------------------
+    def encode_frames_host(self, rgb, first_frame=0):
+        rgb = numpy.ascontiguousarray(rgb, dtype=numpy.uint8)
+        if rgb.shape[1:] != (self.height, self.width, 3):
+            raise ValueError('expected uint8 [N, %d, %d, 3]' % (self.height, self.width))
+        out = numpy.empty((rgb.shape[0], self.height, self.composite_width), dtype=numpy.uint8)
+        N.check(N.load().cm_encode_frames_host(self._handle(), rgb.ctypes.data, out.ctypes.data, int(first_frame),
+                                               int(rgb.shape[0])))
+        return out
+
+    def decode_frames_host(self, comp, first_frame=0):
+        comp = numpy.ascontiguousarray(comp, dtype=numpy.uint8)
+        if comp.shape[1:] != (self.height, self.composite_width):
+            raise ValueError('expected uint8 [N, %d, %d]' % (self.height, self.composite_width))
+        out = numpy.empty((comp.shape[0], self.height, self.output_width, 3), dtype=numpy.uint8)
+        N.check(N.load().cm_decode_frames_host(self._handle(), comp.ctypes.data, out.ctypes.data, int(first_frame),
+                                               int(comp.shape[0])))
+        return out
+
+    # ---- float frames (parity tests: composite before the level map / RGB before clipping) -------------------
+    def _np_dtype(self):
+        return numpy.float32 if self.precision == 'fp32' else numpy.float64
+
+    def _run_window(self, encode, frame, y0, rows_in, out_row, mode=N.MODE_DEFAULT, rgb_in_u8=None):
+        """rows_in: float array [nrows, Win(, 3)] -> one output row as float64."""
+        torch = _torch()
+        dt = self._np_dtype()
+        tin = torch.from_numpy(numpy.ascontiguousarray(rows_in, dtype=dt)).cuda()
+        nrows = rows_in.shape[0]
+        wout = self.composite_width if encode else self.output_width
+        shape = (nrows, wout) if encode else (nrows, wout, 3)
+        tout = torch.zeros(shape, dtype=tin.dtype, device=tin.device)
+        win = N.Window(nrows, int(y0), int(out_row), 1, int(mode), 0)
+        fn = N.load().cm_encode_ex if encode else N.load().cm_decode_ex
+        N.check(fn(self._handle(), C.byref(win), None, tin.data_ptr(), None, tout.data_ptr(), int(frame), 1,
+                   torch.cuda.current_stream().cuda_stream))
+        return tout[out_row].double().cpu().numpy()
+
+    def encode_frame_float(self, rgb01, frame=0):
+        """[H, W, 3] float RGB -> [H, Wc] composite as returned line by line by modem.modulate."""
+        torch = _torch()
+        tin = torch.from_numpy(numpy.ascontiguousarray(rgb01, dtype=self._np_dtype())).cuda()
+        tout = torch.empty((self.height, self.composite_width), dtype=tin.dtype, device=tin.device)
+        N.check(N.load().cm_encode_ex(self._handle(), None, None, tin.data_ptr(), None, tout.data_ptr(), int(frame), 1,
+                                      torch.cuda.current_stream().cuda_stream))
+        return tout.double().cpu().numpy()
+
+    def decode_frame_float(self, comp, frame=0):
+        """[H, Wc] float composite (after un-levelling) -> [H, Wo, 3] RGB as returned by modem.demodulate."""
+        torch = _torch()
+        tin = torch.from_numpy(numpy.ascontiguousarray(comp, dtype=self._np_dtype())).cuda()
+        tout = torch.empty((self.height, self.output_width, 3), dtype=tin.dtype, device=tin.device)
+        N.check(N.load().cm_decode_ex(self._handle(), None, None, tin.data_ptr(), None, tout.data_ptr(), int(frame), 1,
+                                      torch.cuda.current_stream().cuda_stream))
+        return tout.double().cpu().numpy()
+
+    # ---- per-line protocol --------------------------------------------------------------------------------
+    encoder_lookahead = False     # True: encoder reads the next line of the field (ColorAveraging / HueCorrecting)
+    decoder_rows = 1              # 1: row itself; 2: + previous row; 3: previous, current and next (one-line delay)
+
+    def modulate(self, frame, line, r, g, b):
+        cur = numpy.stack([numpy.asarray(r, dtype=numpy.float64), numpy.asarray(g, dtype=numpy.float64),
+                           numpy.asarray(b, dtype=numpy.float64)], axis=-1)
+        if len(r) != self.width:
+            raise AssertionError('line length does not match the modem width')
+        if not self.encoder_lookahead:
+            return self._run_window(True, frame, line, cur[None], 0)
+        mem = self._enc_mem
+        cont = mem is not None and mem[0] == frame and line == mem[1] + 2
+        self._enc_mem = (frame, line, cur)
+        if not cont:      # comb.py:142-146 / niir.py:180-184: the line is paired with itself
+            return self._run_window(True, frame, line - 2, cur[None], 0)
+        rows = numpy.stack([mem[2], numpy.zeros_like(cur), cur])
+        return self._run_window(True, frame, line - 2, rows, 0)
+
+    def demodulate(self, frame, line, composite):
+        cur = numpy.asarray(composite, dtype=numpy.float64)
+        if len(cur) != self.composite_width:
+            raise AssertionError('line length does not match the modem width')
+        mem = self._dec_mem
+        cont = mem is not None and mem[0] == frame and line == mem[1] + 2
+        zero = numpy.zeros_like(cur)
+        if self.decoder_rows == 1:
+            rgb = self._run_window(False, frame, line, cur[None], 0)
+        elif self.decoder_rows == 2:
+            self._dec_mem = (frame, line, cur)
+            if cont:
+                rgb = self._run_window(False, frame, line - 2, numpy.stack([mem[2], zero, cur]), 2)
+            else:
+                rgb = self._run_window(False, frame, line, cur[None], 0)
+        else:
+            # one-line delay (Pal3DModem pal.py:180-234, Simple3DCombModem comb.py:96-113): the call for `line`
+            # returns row line-2, computed from rows line-4 (if any), line-2 and line.
+            if not cont:
+                self._dec_mem = (frame, line, cur, None)
+                rgb = self._run_window(False, frame, line, cur[None], 0, mode=N.MODE_BANDSPLIT_NOSTRIP)
+            else:
+                last, before = mem[2], mem[3]
+                self._dec_mem = (frame, line, cur, last)
+                if before is None:
+                    rgb = self._run_window(False, frame, line - 2, numpy.stack([last, zero, cur]), 0)
+                else:
+                    rgb = self._run_window(False, frame, line - 4, numpy.stack([before, zero, last, zero, cur]), 2)
+        return rgb[:, 0], rgb[:, 1], rgb[:, 2]

@@ -1,0 +1,103 @@
+"""QAM core design record: drop-in for ``color_modem.qam`` (qam.py:10-72) on the host side."""
+import collections
+
+import numpy
+
+from . import _native as N
+from . import _slots as S
+from . import utils
+from .modem import GpuModem
+
+QamConfig = collections.namedtuple('QamConfig', ['fsc', 'bandwidth3db', 'bandwidth20db'])
+
+
+class QamColorModem(object):
+    """Filter designs and carrier step of the quadrature modem (qam.py:14-18, 39-41).  Design record only."""
+
+    def __init__(self, wc, wp, ws, gpass, gstop):
+        self.wc = wc
+        self.carrier_phase_step = 0.5 * numpy.pi * wc
+        self._chroma_precorrect_lowpass = utils.iirdesign(wp, ws, gpass, gstop)
+        self._extract_chroma2x, self._remove_chroma2x = utils.iirsplitter(0.5 * wc, 0.5 * wp, 0.5 * ws, gpass, gstop)
+        self._demod_lowpass = utils.iirfilter(6, wc - 0.5 * ws, rs=48.0, btype='lowpass', ftype='cheby2')
+
+    @property
+    def extract_chroma_phase_shift(self):
+        return self._extract_chroma2x.phase_shift
+
+
+def put_filter(desc, slot, ff, n):
+    f = desc.filters[slot]
+    sos = ff.sos
+    if sos.shape[0] > N.MAX_SECTIONS:
+        raise ValueError('filter order %d exceeds the CUDA cascade limit' % (2 * sos.shape[0]))
+    f.nsec, f.shift, f.n = sos.shape[0], ff.shift, int(n)
+    for s in range(sos.shape[0]):
+        for k in range(5):
+            f.sos[s][k] = float(sos[s, k])
+    desc.nfilters = max(desc.nfilters, slot + 1)
+
+
+def put_resampler(desc, slot, up, down):
+    taps, half, up, down = utils.resampler_taps(up, down)
+    r = desc.resamplers[slot]
+    r.up, r.down, r.half, r.ntaps = up, down, half, len(taps)
+    if len(taps) > N.MAX_TAPS:
+        raise ValueError('resampler %d/%d needs %d taps (> %d)' % (up, down, len(taps), N.MAX_TAPS))
+    for i, t in enumerate(taps):
+        r.taps[i] = float(t)
+    desc.nresamplers = max(desc.nresamplers, slot + 1)
+
+
+class AbstractQamColorModem(GpuModem, utils.ConstantFrequencyCarrier):
+    """NTSC/PAL-style modem on the GPU (qam.py:61-72).  Subclasses set ENC / DEC matrices, kind and flags."""
+    ENC = None
+    DEC = None
+    kind = N.KIND_QAM_BANDSPLIT
+    flags = 0
+
+    def __init__(self, line_config, config, precision='fp32'):
+        GpuModem.__init__(self, line_config, precision)
+        self.config = config
+        fs = line_config.fs
+        self.qam = QamColorModem(2.0 * config.fsc / fs, 2.0 * config.bandwidth3db / fs,
+                                 2.0 * config.bandwidth20db / fs, 3.0, 20.0)
+
+    # host-side helpers of the reference protocol (tiny 3x3 matrix products; not on the hot path)
+    @classmethod
+    def encode_components(cls, r, g, b):
+        m = numpy.asarray(cls.ENC, dtype=numpy.float64).reshape(3, 3)
+        r, g, b = (numpy.asarray(x, dtype=numpy.float64) for x in (r, g, b))
+        return tuple(m[i, 0] * r + m[i, 1] * g + m[i, 2] * b for i in range(3))
+
+    @classmethod
+    def decode_components(cls, y, u, v):
+        m = numpy.asarray(cls.DEC, dtype=numpy.float64).reshape(3, 3)
+        y, u, v = (numpy.asarray(x, dtype=numpy.float64) for x in (y, u, v))
+        return tuple(m[i, 0] * y + m[i, 1] * u + m[i, 2] * v for i in range(3))
+
+    def _fill_desc(self, d):
+        W = self.width
+        std = self.line_config.line_standard
+        fsc = self.config.fsc
+        d.kind, d.flags = self.kind, self._flags()
+        d.frame_cycle = self.frame_cycle
+        d.frame_shift_turns = utils.turns_fixed((fsc / std.frame_rate) % 1.0)
+        d.line_shift_turns = utils.turns_fixed((fsc / (std.frame_rate * std.total_lines)) % 1.0)
+        for i in range(9):
+            d.enc_matrix[i] = self.ENC[i]
+            d.dec_matrix[i] = self.DEC[i]
+        q = self.qam
+        put_filter(d, S.QF_PRE_LP, q._chroma_precorrect_lowpass, W)
+        put_filter(d, S.QF_BP2X, q._extract_chroma2x, 2 * W)
+        put_filter(d, S.QF_BS2X, q._remove_chroma2x, 2 * W)
+        put_filter(d, S.QF_DEMOD_LP, q._demod_lowpass, 2 * W)
+        put_resampler(d, S.QR_UP2, 2, 1)
+        put_resampler(d, S.QR_DOWN2, 1, 2)
+        d.phases[S.QP_STEP1X] = utils.turns_fixed(q.wc / 2.0)
+        d.phases[S.QP_STEP2X] = utils.turns_fixed(q.wc / 4.0)
+        d.phases[S.QP_BP_SHIFT] = utils.radians_fixed(q.extract_chroma_phase_shift)
+        d.phases[S.QP_HALF_LS] = utils.radians_fixed(0.5 * self.line_shift)
+
+    def _flags(self):
+        return self.flags
