@@ -59,7 +59,9 @@ MODE_DEFAULT, MODE_BANDSPLIT_NOSTRIP = 0, 1
 
 EXPORTS = ['cm_abi_version', 'cm_last_error', 'cm_device_info', 'cm_create', 'cm_destroy', 'cm_encode_frames',
            'cm_decode_frames', 'cm_encode_ex', 'cm_decode_ex', 'cm_encode_frames_host', 'cm_decode_frames_host',
-           'cm_launch_count']
+           'cm_launch_count', 'cm_timing_enable', 'cm_timing_reset', 'cm_timing_read']
+
+K_ENCODE, K_BANDSPLIT, K_PALD, K_COMB, K_DECODE_OTHER = 0, 1, 2, 3, 4
 
 _lib = None
 
@@ -90,6 +92,9 @@ def load():
     lib.cm_encode_frames_host.argtypes = [vp, vp, vp, i64, i32]
     lib.cm_decode_frames_host.argtypes = [vp, vp, vp, i64, i32]
     lib.cm_launch_count.restype = C.c_int64
+    lib.cm_timing_enable.argtypes = [vp, C.c_int]
+    lib.cm_timing_reset.argtypes = [vp]
+    lib.cm_timing_read.argtypes = [vp, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int64)]
     if lib.cm_abi_version() != ABI_VERSION:
         raise NativeUnavailable('ABI version mismatch between %s and the Python binding' % LIB_NAME)
     _lib = lib

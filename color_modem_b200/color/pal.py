@@ -52,3 +52,36 @@ class PalDModem(PalSModem):
         qam.put_filter(d, S.QF_PALD_LP, self._filter, 2 * self.width)
         d.scalars[S.QS_PALD_SIN] = self._sin_factor
         d.scalars[S.QS_PALD_COS] = self._cos_factor
+
+
+class Pal3DModem(PalDModem):
+    """3-line PAL comb decoder with a one-line output delay (pal.py:130-234)."""
+    kind = N.KIND_PAL_3D
+
+    def __init__(self, line_config, variant=PalVariant.PAL, notch=0.0, use_sin=True, use_cos=True, avg=None,
+                 precision='fp32'):
+        if avg is not None:
+            raise NotImplementedError('avg= is a non-default knob that is not built (SURVEY.md §8f)')
+        super(Pal3DModem, self).__init__(line_config, variant, notch, precision)
+        lssin = numpy.sin(self.line_shift)
+        lscos = numpy.cos(self.line_shift)
+        if abs(lssin) < 0.1:
+            use_sin = False
+        if abs(lscos) > 0.9:
+            use_cos = False
+        self._use_sin, self._use_cos = bool(use_sin), bool(use_cos)
+        self.demodulation_delay = 1 if (use_sin or use_cos) else 0
+        self.decoder_rows = 3 if self.demodulation_delay else 2
+        self._sin_sum_factor = 0.5 / lssin if use_sin else 0.0
+        self._cos_u_factor = -0.5 / (1.0 - lscos) if use_cos else 0.0
+        self._cos_v_factor = -0.5 / (1.0 + lscos) if use_cos else 0.0
+
+    def _flags(self):
+        return self.flags | (N.FLAG_PAL3D_SIN if self._use_sin else 0) | (N.FLAG_PAL3D_COS if self._use_cos else 0)
+
+    def _fill_desc(self, d):
+        super(Pal3DModem, self)._fill_desc(d)
+        both = 0.5 if (self._use_sin and self._use_cos) else 1.0      # comb.avg of the two estimates, pal.py:210-218
+        d.scalars[S.QS_P3D_SINSUM] = both * self._sin_sum_factor
+        d.scalars[S.QS_P3D_COSU] = both * self._cos_u_factor
+        d.scalars[S.QS_P3D_COSV] = both * self._cos_v_factor

@@ -36,6 +36,9 @@ struct cm_modem {
     DevParams<double> pd;
     void *d_tab = nullptr;
     void *d_taps = nullptr;
+    bool timing = false;
+    struct Ev { cudaEvent_t a, b; int id; };
+    std::vector<Ev> events;
     // scratch for the *_host entry points
     void *d_in = nullptr, *d_out = nullptr;
     size_t in_cap = 0, out_cap = 0;
@@ -152,7 +155,10 @@ extern "C" int cm_create(const cm_desc *desc, int precision, cm_modem **out) {
     if (desc->frame_cycle <= 0) return fail(CM_ERR_INVALID, "frame_cycle must be positive%s");
     switch (desc->kind) {
         case CM_KIND_QAM_BANDSPLIT:
+        case CM_KIND_NTSC_COMB:
+        case CM_KIND_NTSC_3D:
         case CM_KIND_PAL_D:
+        case CM_KIND_PAL_3D:
             break;
         default:
             return fail(CM_ERR_UNSUPPORTED, "modem kind not built%s");
@@ -215,12 +221,64 @@ extern "C" void cm_destroy(cm_modem *m) {
     cudaFree(m->d_taps);
     cudaFree(m->d_in);
     cudaFree(m->d_out);
+    cm_timing_reset(m);
     delete m;
 }
 
 // ------------------------------------------------------------------------------------------------------------
 // launches
 // ------------------------------------------------------------------------------------------------------------
+struct LaunchTimer {
+    cm_modem *m;
+    cudaStream_t st;
+    cm_modem::Ev ev;
+    bool on;
+    LaunchTimer(cm_modem *m_, int id, cudaStream_t st_) : m(m_), st(st_), on(m_->timing) {
+        if (on) {
+            ev.id = id;
+            cudaEventCreate(&ev.a);
+            cudaEventCreate(&ev.b);
+            cudaEventRecord(ev.a, st);
+        }
+    }
+    ~LaunchTimer() {
+        if (on) {
+            cudaEventRecord(ev.b, st);
+            m->events.push_back(ev);
+        }
+    }
+};
+
+extern "C" int cm_timing_enable(cm_modem *m, int on) {
+    if (!m) return fail(CM_ERR_INVALID, "null handle%s");
+    m->timing = on != 0;
+    return CM_OK;
+}
+
+extern "C" int cm_timing_reset(cm_modem *m) {
+    if (!m) return fail(CM_ERR_INVALID, "null handle%s");
+    for (auto &e : m->events) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
+    m->events.clear();
+    return CM_OK;
+}
+
+extern "C" int cm_timing_read(cm_modem *m, int id, double *total_ms, int64_t *launches) {
+    if (!m) return fail(CM_ERR_INVALID, "null handle%s");
+    double tot = 0.0;
+    int64_t n = 0;
+    for (auto &e : m->events) {
+        if (e.id != id) continue;
+        CUDA_TRY(cudaEventSynchronize(e.b));
+        float ms = 0.f;
+        CUDA_TRY(cudaEventElapsedTime(&ms, e.a, e.b));
+        tot += ms;
+        ++n;
+    }
+    if (total_ms) *total_ms = tot;
+    if (launches) *launches = n;
+    return CM_OK;
+}
+
 template <typename T> static const DevParams<T> &params_of(const cm_modem *m);
 template <> const DevParams<float> &params_of<float>(const cm_modem *m) { return m->pf; }
 template <> const DevParams<double> &params_of<double>(const cm_modem *m) { return m->pd; }
@@ -263,6 +321,7 @@ static int launch_encode(cm_modem *m, IoArgs<T> io, cudaStream_t st) {
             int rc = set_smem(k_qam_encode<T>, bytes(R));
             if (rc) return rc;
             dim3 grid((unsigned)(io.nframes * 2 * io.groups_per_field));
+            LaunchTimer lt(m, CM_K_ENCODE, st);
             k_qam_encode<T><<<grid, 64 * R, bytes(R), st>>>(p, io);
             g_launches++;
             break;
@@ -286,6 +345,7 @@ static int launch_bandsplit(cm_modem *m, IoArgs<T> io, int luma_mode, cudaStream
     int rc = set_smem(k_qam_bandsplit<T>, bytes(R));
     if (rc) return rc;
     dim3 grid((unsigned)(io.nframes * 2 * io.groups_per_field));
+    LaunchTimer lt(m, CM_K_BANDSPLIT, st);
     k_qam_bandsplit<T><<<grid, 64 * R, bytes(R), st>>>(p, io, luma_mode);
     g_launches++;
     CUDA_TRY(cudaGetLastError());
@@ -304,7 +364,27 @@ static int launch_pald(cm_modem *m, IoArgs<T> io, cudaStream_t st) {
     int rc = set_smem(k_pald_combed<T>, bytes(R));
     if (rc) return rc;
     dim3 grid((unsigned)(io.nframes * 2 * io.groups_per_field));
+    LaunchTimer lt(m, CM_K_PALD, st);
     k_pald_combed<T><<<grid, 64 * R, bytes(R), st>>>(p, io);
+    g_launches++;
+    CUDA_TRY(cudaGetLastError());
+    return CM_OK;
+}
+
+template <typename T, int MODE>
+static int launch_comb(cm_modem *m, IoArgs<T> io, cudaStream_t st) {
+    const DevParams<T> &p = params_of<T>(m);
+    if (io.out_count <= 0) return CM_OK;
+    auto bytes = [&](int r) { return (128 + (size_t)(7 * r + 6) * p.W) * sizeof(T); };
+    int R = pick_rows(4, (size_t)m->smem_optin / 2, bytes);
+    if (!R) R = pick_rows(2, (size_t)m->smem_optin, bytes);
+    if (!R) return fail(CM_ERR_UNSUPPORTED, "line too wide for the comb kernel%s");
+    set_groups(io, R);
+    int rc = set_smem(k_qam_comb<T, MODE>, bytes(R));
+    if (rc) return rc;
+    dim3 grid((unsigned)(io.nframes * 2 * io.groups_per_field));
+    LaunchTimer lt(m, CM_K_COMB, st);
+    k_qam_comb<T, MODE><<<grid, 64 * R, bytes(R), st>>>(p, io);
     g_launches++;
     CUDA_TRY(cudaGetLastError());
     return CM_OK;
@@ -340,6 +420,32 @@ static int launch_decode(cm_modem *m, IoArgs<T> io, int mode, cudaStream_t st) {
             int rc = launch_bandsplit<T>(m, top, 0, st);
             if (rc) return rc;
             return launch_pald<T>(m, rest, st);
+        }
+        case CM_KIND_NTSC_COMB: {
+            IoArgs<T> top, rest;
+            split_top(io, top, rest);
+            int rc = launch_bandsplit<T>(m, top, 0, st);
+            if (rc) return rc;
+            if (p.flags & CM_FLAG_NTSC_NO_COMB)      // ntsc.py:71-72: chroma of the row itself, luma = c - remod
+                return launch_bandsplit<T>(m, rest, 1, st);
+            return launch_comb<T, COMB_NTSC2>(m, rest, st);
+        }
+        case CM_KIND_NTSC_3D:
+            if (p.flags & CM_FLAG_NTSC_NO_COMB) return launch_bandsplit<T>(m, io, 1, st);
+            return launch_comb<T, COMB_NTSC3>(m, io, st);
+        case CM_KIND_PAL_3D: {
+            if (!(p.flags & (CM_FLAG_PAL3D_SIN | CM_FLAG_PAL3D_COS))) {   // pal.py:181-182: plain PAL-D
+                IoArgs<T> top, rest;
+                split_top(io, top, rest);
+                int rc = launch_bandsplit<T>(m, top, 0, st);
+                if (rc) return rc;
+                return launch_pald<T>(m, rest, st);
+            }
+            IoArgs<T> top, rest;
+            split_top(io, top, rest);
+            int rc = launch_bandsplit<T>(m, top, 1, st);
+            if (rc) return rc;
+            return launch_comb<T, COMB_PAL3>(m, rest, st);
         }
         default:
             return fail(CM_ERR_UNSUPPORTED, "decode: modem kind not built%s");

@@ -1,0 +1,43 @@
+"""Frame-level driver — drop-in for ``color_modem.image.ImageModem`` (image.py:11-84).
+
+``ImageModem(modem).modulate(img, frame)`` / ``.demodulate(img, frame)`` take and return PIL images exactly like
+the reference.  The field-ordered line loop, delay priming and bottom-row wrap of image.py:47-55 / 75-83 are
+folded into the kernels' row-window rules, so a frame is one native call (host->device copy, kernels,
+device->host copy).  ``modulate_batch`` / ``demodulate_batch`` do the same for [N, H, W, C] uint8 arrays.
+"""
+import numpy
+
+
+class ImageModem(object):
+    def __init__(self, modem):
+        self._modem = modem
+
+    @staticmethod
+    def encode_composite_level(value):
+        return 0.6 * value + 0.2
+
+    @staticmethod
+    def decode_composite_level(value):
+        return (5.0 * value - 1.0) / 3.0
+
+    def modulate_batch(self, rgb_u8, first_frame=0):
+        return self._modem.encode_frames_host(rgb_u8, first_frame)
+
+    def demodulate_batch(self, comp_u8, first_frame=0):
+        return self._modem.decode_frames_host(comp_u8, first_frame)
+
+    def modulate(self, img, frame=0):
+        from PIL import Image
+        if img.mode != 'RGB':
+            img = img.convert('RGB')
+        rgb = numpy.asarray(img, dtype=numpy.uint8)
+        comp = self.modulate_batch(rgb[None], frame)[0]
+        return Image.fromarray(comp, 'L')
+
+    def demodulate(self, img, frame=0):
+        from PIL import Image
+        if img.mode != 'L':
+            img = img.convert('L')
+        comp = numpy.asarray(img, dtype=numpy.uint8)
+        rgb = self.demodulate_batch(comp[None], frame)[0]
+        return Image.fromarray(rgb, 'RGB')

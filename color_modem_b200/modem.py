@@ -86,6 +86,16 @@ class GpuModem(object):
             h = self._handles[precision] = ptr
         return h
 
+    # ---- per-kernel device timing (bench.py roofline) ------------------------------------------------------
+    def timing(self, on=True):
+        N.check(N.load().cm_timing_enable(self._handle(), 1 if on else 0))
+        N.check(N.load().cm_timing_reset(self._handle()))
+
+    def timing_read(self, kernel_id):
+        ms, n = C.c_double(0.0), C.c_int64(0)
+        N.check(N.load().cm_timing_read(self._handle(), int(kernel_id), C.byref(ms), C.byref(n)))
+        return ms.value, n.value
+
     def close(self):
         if self._handles:
             lib = N.load()

@@ -171,6 +171,21 @@ int cm_decode_ex(cm_modem *m, const cm_window *win, const uint8_t *comp_u8, cons
 int cm_encode_frames_host(cm_modem *m, const uint8_t *rgb, uint8_t *comp, int64_t first_frame, int32_t nframes);
 int cm_decode_frames_host(cm_modem *m, const uint8_t *comp, uint8_t *rgb, int64_t first_frame, int32_t nframes);
 
+/* Optional per-kernel device timing (CUDA events recorded on the launch stream around every kernel launch).
+ * bench.py uses it for the roofline line; it is off by default and costs nothing when off. */
+enum cm_kernel_id {
+    CM_K_ENCODE = 0,       /* fused encode kernel of the handle's family */
+    CM_K_BANDSPLIT = 1,    /* k_qam_bandsplit */
+    CM_K_PALD = 2,         /* k_pald_combed */
+    CM_K_COMB = 3,         /* k_qam_comb */
+    CM_K_DECODE_OTHER = 4, /* decode kernels of the non-QAM families */
+    CM_K_COUNT = 5
+};
+int cm_timing_enable(cm_modem *m, int on);
+int cm_timing_reset(cm_modem *m);
+/* Waits for the recorded events; returns summed milliseconds and number of launches of kernel `id`. */
+int cm_timing_read(cm_modem *m, int id, double *total_ms, int64_t *launches);
+
 /* Number of kernel launches issued by this library in the calling process (bench.py's gpu_launches). */
 int64_t cm_launch_count(void);
 

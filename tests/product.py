@@ -1,20 +1,29 @@
 """Build the product (color_modem_b200) modem composition for a test Case — mirrors tests/refload.make_modem."""
 from color_modem_b200.line import LineConfig, LineStandard
 
-BUILT_KINDS = {'ntsc', 'pal_s', 'pal_d'}
+BUILT_KINDS = {'ntsc', 'ntsc_comb', 'ntsc_3d', 'pal_s', 'pal_d', 'pal_3d'}
 
 
 def make_modem(c, precision='fp32'):
     from color_modem_b200.color import ntsc, pal
+    from color_modem_b200 import comb
     std = getattr(LineStandard, c.standard) if c.standard else None
     lc = LineConfig((c.width, c.height), std)
     k, v = c.kind, c.variant
     if k == 'ntsc':
         m = ntsc.NtscModem(lc, getattr(ntsc.NtscVariant, v), precision=precision)
+    elif k == 'ntsc_comb':
+        m = ntsc.NtscCombModem(lc, getattr(ntsc.NtscVariant, v), precision=precision)
+    elif k == 'ntsc_3d':
+        m = comb.Simple3DCombModem(ntsc.NtscCombModem(lc, getattr(ntsc.NtscVariant, v), precision=precision))
+    elif k == 'pal_3d':
+        m = pal.Pal3DModem(lc, getattr(pal.PalVariant, v), precision=precision)
     elif k == 'pal_s':
         m = pal.PalSModem(lc, getattr(pal.PalVariant, v), precision=precision)
     elif k == 'pal_d':
         m = pal.PalDModem(lc, getattr(pal.PalVariant, v), precision=precision)
     else:
         raise NotImplementedError(k)
+    if c.chroma_avg:
+        m = comb.ColorAveragingModem(m)
     return m
