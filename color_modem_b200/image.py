@@ -20,11 +20,11 @@ class ImageModem(object):
     def decode_composite_level(value):
         return (5.0 * value - 1.0) / 3.0
 
-    def modulate_batch(self, rgb_u8, first_frame=0):
-        return self._modem.encode_frames_host(rgb_u8, first_frame)
+    def modulate_batch(self, rgb_u8, first_frame=0, out=None):
+        return self._modem.encode_frames_host(rgb_u8, first_frame, out=out)
 
-    def demodulate_batch(self, comp_u8, first_frame=0):
-        return self._modem.decode_frames_host(comp_u8, first_frame)
+    def demodulate_batch(self, comp_u8, first_frame=0, out=None):
+        return self._modem.decode_frames_host(comp_u8, first_frame, out=out)
 
     def modulate(self, img, frame=0):
         from PIL import Image

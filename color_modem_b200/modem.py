@@ -144,20 +144,28 @@ class GpuModem(object):
             raise ValueError('expected a contiguous CUDA %s tensor of shape [N, %s]' % (dtype, ', '.join(map(str, tail))))
 
     # ---- frame batches with host buffers (H2D + kernels + D2H inside the native call) ------------------------
-    def encode_frames_host(self, rgb, first_frame=0):
+    @staticmethod
+    def _host_out(out, shape):
+        if out is None:
+            return numpy.empty(shape, dtype=numpy.uint8)
+        if out.dtype != numpy.uint8 or out.shape != shape or not out.flags['C_CONTIGUOUS']:
+            raise ValueError('out must be a C-contiguous uint8 array of shape %s' % (shape,))
+        return out
+
+    def encode_frames_host(self, rgb, first_frame=0, out=None):
         rgb = numpy.ascontiguousarray(rgb, dtype=numpy.uint8)
         if rgb.shape[1:] != (self.height, self.width, 3):
             raise ValueError('expected uint8 [N, %d, %d, 3]' % (self.height, self.width))
-        out = numpy.empty((rgb.shape[0], self.height, self.composite_width), dtype=numpy.uint8)
+        out = self._host_out(out, (rgb.shape[0], self.height, self.composite_width))
         N.check(N.load().cm_encode_frames_host(self._handle(), rgb.ctypes.data, out.ctypes.data, int(first_frame),
                                                int(rgb.shape[0])))
         return out
 
-    def decode_frames_host(self, comp, first_frame=0):
+    def decode_frames_host(self, comp, first_frame=0, out=None):
         comp = numpy.ascontiguousarray(comp, dtype=numpy.uint8)
         if comp.shape[1:] != (self.height, self.composite_width):
             raise ValueError('expected uint8 [N, %d, %d]' % (self.height, self.composite_width))
-        out = numpy.empty((comp.shape[0], self.height, self.output_width, 3), dtype=numpy.uint8)
+        out = self._host_out(out, (comp.shape[0], self.height, self.output_width, 3))
         N.check(N.load().cm_decode_frames_host(self._handle(), comp.ctypes.data, out.ctypes.data, int(first_frame),
                                                int(comp.shape[0])))
         return out
