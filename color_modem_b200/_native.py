@@ -27,7 +27,7 @@ class NativeUnavailable(RuntimeError):
 
 
 class Filter(C.Structure):
-    _fields_ = [('nsec', C.c_int32), ('shift', C.c_int32), ('n', C.c_int32), ('reserved', C.c_int32),
+    _fields_ = [('nsec', C.c_int32), ('shift', C.c_int32), ('n', C.c_int32), ('rate', C.c_int32),
                 ('sos', (C.c_double * 5) * MAX_SECTIONS)]
 
 

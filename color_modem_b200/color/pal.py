@@ -49,7 +49,7 @@ class PalDModem(PalSModem):
 
     def _fill_desc(self, d):
         super(PalDModem, self)._fill_desc(d)
-        qam.put_filter(d, S.QF_PALD_LP, self._filter, 2 * self.width)
+        qam.put_filter(d, S.QF_PALD_LP, self._filter, 2 * self.width, 2)
         d.scalars[S.QS_PALD_SIN] = self._sin_factor
         d.scalars[S.QS_PALD_COS] = self._cos_factor
 

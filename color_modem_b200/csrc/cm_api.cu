@@ -53,37 +53,44 @@ static void mat_mul(const double a[4], const double b[4], double out[4]) {
     memcpy(out, r, sizeof(r));
 }
 
+// Chunk length per lane: the kernels instantiate warp_iir for a few compile-time values per rate
+// (cm_iir.cuh: warp_iir); pick the one that wastes the least padding, preferring longer chunks on ties.
+static void pick_chunk(int rate, int total, int &L, int &nsuper) {
+    static const int c1[] = {47, 31, 23}, c2[] = {46, 30}, c3[] = {45, 39};
+    const int *cand = rate == 1 ? c1 : (rate == 2 ? c2 : c3);
+    const int ncand = rate == 1 ? 3 : 2;
+    long best = -1;
+    for (int i = 0; i < ncand; ++i) {
+        int ns = (total + 32 * cand[i] - 1) / (32 * cand[i]);
+        if (ns < 1) ns = 1;
+        long padded = (long)ns * 32 * cand[i];
+        if (best < 0 || padded < best) { best = padded; L = cand[i]; nsuper = ns; }
+    }
+}
+
 static void build_filter(const cm_filter &f, FiltHdr &h, std::vector<double> &tab) {
-    const int total = f.n + f.shift;
-    int nsuper = (total + 32 * CM_LMAX - 1) / (32 * CM_LMAX);
-    if (nsuper < 1) nsuper = 1;
-    int L = (total + 32 * nsuper - 1) / (32 * nsuper);
-    if (L < 1) L = 1;
-    if ((L & 1) == 0) L += 1;               // odd stride => conflict-free shared-memory access (CM_LMAX is odd)
+    int L = 0, nsuper = 0;
+    pick_chunk(f.rate, f.n + f.shift, L, nsuper);
     h.nsec = f.nsec;
     h.shift = f.shift;
     h.n = f.n;
     h.L = L;
     h.nsuper = nsuper;
-    h.stride = CM_SEC_H + 2 * L;
-    h.stride += (h.stride & 1);
+    h.rate = f.rate;
+    h.npad = 32 * L * nsuper;
     h.off = (int)tab.size();
     for (int s = 0; s < f.nsec; ++s) {
         const double *c = f.sos[s];
-        std::vector<double> sec(h.stride, 0.0);
+        std::vector<double> sec(CM_SEC_STRIDE, 0.0);
         for (int i = 0; i < 5; ++i) sec[i] = c[i];
         const double A[4] = {-c[3], 1.0, -c[4], 0.0};
-        double P[4] = {1.0, 0.0, 0.0, 1.0};               // A^i
-        for (int i = 0; i < L; ++i) {
-            sec[CM_SEC_H + 2 * i] = P[0];
-            sec[CM_SEC_H + 2 * i + 1] = P[1];
+        double M[4] = {1.0, 0.0, 0.0, 1.0};
+        for (int i = 0; i < L; ++i) {                     // M = A^L
             double Q[4];
-            mat_mul(A, P, Q);
-            memcpy(P, Q, sizeof(P));
+            mat_mul(A, M, Q);
+            memcpy(M, Q, sizeof(M));
         }
-        double M[4];
-        memcpy(M, P, sizeof(M));                          // A^L
-        for (int k = 0; k < 5; ++k) {
+        for (int k = 0; k < 5; ++k) {                     // M, M^2, M^4, M^8, M^16
             for (int i = 0; i < 4; ++i) sec[CM_SEC_MPOW + 4 * k + i] = M[i];
             double Q[4];
             mat_mul(M, M, Q);
@@ -114,6 +121,20 @@ static void fill_params(const cm_desc &d, DevParams<T> &p, const FiltHdr *fh, co
     for (int i = 0; i < CM_NSCAL; ++i) p.scalars[i] = (T)d.scalars[i];
     for (int i = 0; i < 9; ++i) { p.enc[i] = (T)d.enc_matrix[i]; p.dec[i] = (T)d.dec_matrix[i]; }
     for (int i = 0; i < CM_NFILT; ++i) p.filt[i] = fh[i];
+    // line-buffer geometry: every buffer that feeds an IIR is padded to the site's 32*L*nsuper
+    auto up4 = [](int v) { return (v + 3) & ~3; };
+    int n1p = up4(d.width > d.comp_width ? d.width : d.comp_width), n2p = 2 * up4(d.comp_width),
+        n3p = 3 * up4(d.comp_width);
+    for (int i = 0; i < CM_NFILT; ++i) {
+        if (!fh[i].nsec) continue;
+        if (fh[i].rate == 1 && fh[i].npad > n1p) n1p = fh[i].npad;
+        if (fh[i].rate == 2 && fh[i].npad > n2p) n2p = fh[i].npad;
+        if (fh[i].rate == 3 && fh[i].npad > n3p) n3p = fh[i].npad;
+    }
+    p.n1p = up4(n1p);
+    p.hb2 = up4((n2p + 1) / 2);
+    if (p.hb2 < p.n1p) p.hb2 = p.n1p;
+    p.hb3 = up4((n3p + 2) / 3);
     for (int i = 0; i < CM_NRES; ++i) p.res[i] = rh[i];
     p.tab = (const T *)tab;
     p.taps = (const T *)taps;
@@ -153,6 +174,8 @@ extern "C" int cm_create(const cm_desc *desc, int precision, cm_modem **out) {
         desc->nresamplers > CM_MAX_RESAMPLERS)
         return fail(CM_ERR_INVALID, "bad filter / resampler count%s");
     if (desc->frame_cycle <= 0) return fail(CM_ERR_INVALID, "frame_cycle must be positive%s");
+    if ((desc->width & 3) || (desc->comp_width & 3) || (desc->out_width & 3))
+        return fail(CM_ERR_UNSUPPORTED, "line widths must be multiples of 4 samples%s");
     switch (desc->kind) {
         case CM_KIND_QAM_BANDSPLIT:
         case CM_KIND_NTSC_COMB:
@@ -180,7 +203,7 @@ extern "C" int cm_create(const cm_desc *desc, int precision, cm_modem **out) {
     for (int i = 0; i < desc->nfilters; ++i) {
         const cm_filter &f = desc->filters[i];
         if (f.nsec == 0) continue;
-        if (f.nsec < 0 || f.nsec > CM_MAX_SECTIONS || f.shift < 0 || f.n <= 0) {
+        if (f.nsec < 0 || f.nsec > CM_MAX_SECTIONS || f.shift < 0 || f.n <= 0 || f.rate < 1 || f.rate > 3) {
             delete m;
             return fail(CM_ERR_INVALID, "bad cm_filter%s");
         }
@@ -314,7 +337,7 @@ static int launch_encode(cm_modem *m, IoArgs<T> io, cudaStream_t st) {
         case CM_KIND_NTSC_3D:
         case CM_KIND_PAL_D:
         case CM_KIND_PAL_3D: {
-            auto bytes = [&](int r) { return (size_t)r * 3 * p.W * sizeof(T); };
+            auto bytes = [&](int r) { return (size_t)r * 3 * p.n1p * sizeof(T); };
             int R = pick_rows(4, (size_t)m->smem_optin / 2, bytes);
             if (!R) return fail(CM_ERR_UNSUPPORTED, "line too wide for the encode kernel%s");
             set_groups(io, R);
@@ -337,7 +360,7 @@ template <typename T>
 static int launch_bandsplit(cm_modem *m, IoArgs<T> io, int luma_mode, cudaStream_t st) {
     const DevParams<T> &p = params_of<T>(m);
     if (io.out_count <= 0) return CM_OK;
-    auto bytes = [&](int r) { return (128 + (size_t)r * 9 * p.W) * sizeof(T); };
+    auto bytes = [&](int r) { return (128 + (size_t)r * (p.n1p + 8 * (size_t)p.hb2)) * sizeof(T); };
     int R = pick_rows(4, (size_t)m->smem_optin / 2, bytes);
     if (!R) R = pick_rows(1, (size_t)m->smem_optin, bytes);
     if (!R) return fail(CM_ERR_UNSUPPORTED, "line too wide for the band-split kernel%s");
@@ -356,7 +379,9 @@ template <typename T>
 static int launch_pald(cm_modem *m, IoArgs<T> io, cudaStream_t st) {
     const DevParams<T> &p = params_of<T>(m);
     if (io.out_count <= 0) return CM_OK;
-    auto bytes = [&](int r) { return (128 + (size_t)(7 * r + 3) * p.W) * sizeof(T); };
+    auto bytes = [&](int r) {
+        return (128 + (size_t)(r + 1) * (p.n1p + 2 * (size_t)p.hb2) + (size_t)r * 4 * p.hb2) * sizeof(T);
+    };
     int R = pick_rows(4, (size_t)m->smem_optin / 2, bytes);
     if (!R) R = pick_rows(2, (size_t)m->smem_optin, bytes);
     if (!R) return fail(CM_ERR_UNSUPPORTED, "line too wide for the PAL-D kernel%s");
@@ -375,7 +400,9 @@ template <typename T, int MODE>
 static int launch_comb(cm_modem *m, IoArgs<T> io, cudaStream_t st) {
     const DevParams<T> &p = params_of<T>(m);
     if (io.out_count <= 0) return CM_OK;
-    auto bytes = [&](int r) { return (128 + (size_t)(7 * r + 6) * p.W) * sizeof(T); };
+    auto bytes = [&](int r) {
+        return (128 + (size_t)(r + 2) * (p.n1p + 2 * (size_t)p.hb2) + (size_t)r * 4 * p.hb2) * sizeof(T);
+    };
     int R = pick_rows(4, (size_t)m->smem_optin / 2, bytes);
     if (!R) R = pick_rows(2, (size_t)m->smem_optin, bytes);
     if (!R) return fail(CM_ERR_UNSUPPORTED, "line too wide for the comb kernel%s");

@@ -12,7 +12,6 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
-#define CM_LMAX 47          // max samples per lane per super-chunk in warp_iir (odd => conflict-free smem)
 #define CM_NWARPS 8
 #define CM_NTHREADS (CM_NWARPS * 32)
 #define CM_MAXSEC 6
@@ -22,9 +21,9 @@
 #define CM_NPHASE 16
 
 struct FiltHdr {
-    int nsec, shift, n, L, nsuper, stride;   // n = input length of this use-site; L*32*nsuper >= n+shift
+    int nsec, shift, n, L, nsuper, rate;     // n = input length of this use-site; L*32*nsuper >= n+shift
     int off;                                 // offset (in elements) of the section tables in DevParams::tab
-    int _pad;
+    int npad;                                // 32 * L * nsuper
 };
 
 struct ResHdr {
@@ -38,7 +37,9 @@ struct DevParams {
     int kind, flags;
     int W, H, Wc, Wo;
     int digital_shift, odd_first, even_first, ref_line, frame_cycle;
-    int _pad0;
+    int n1p;          // padded length of 1x line buffers (multiple of 4, >= every 1x IIR site's npad)
+    int hb2;          // elements per phase of 2x polyphase buffers (multiple of 4, >= n1p)
+    int hb3;          // elements per phase of 3x polyphase buffers
     unsigned long long frame_shift, line_shift;
     unsigned long long phases[CM_NPHASE];
     T scalars[CM_NSCAL];

@@ -1,0 +1,95 @@
+// Global-memory I/O helpers: 4 pixels per thread, 32/128-bit accesses, u8 <-> real conversion.
+#pragma once
+#include "cm_common.cuh"
+#include "cm_fir.cuh"
+
+template <typename T>
+__device__ __forceinline__ void copy_taps(T *dst, const DevParams<T> &p, int nres) {
+    int total = 0;
+    for (int r = 0; r < nres; ++r) total = max(total, p.res[r].off + p.res[r].ntaps);
+    for (int i = threadIdx.x; i < total; i += blockDim.x) dst[i] = p.taps[i];
+}
+
+// 4 interleaved RGB pixels starting at pixel offset `px` (multiple of 4) of the input buffer
+template <typename T>
+__device__ __forceinline__ void load_rgb4(const IoArgs<T> &io, size_t px, T r[4], T g[4], T b[4]) {
+    if (io.in_f) {
+        T v[12];
+#pragma unroll
+        for (int q = 0; q < 3; ++q) ld4(io.in_f + px * 3 + 4 * q, v + 4 * q);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { r[i] = v[3 * i]; g[i] = v[3 * i + 1]; b[i] = v[3 * i + 2]; }
+    } else {
+        const uint32_t *w = reinterpret_cast<const uint32_t *>(io.in_u8 + px * 3);
+        const uint32_t w0 = __ldg(w), w1 = __ldg(w + 1), w2 = __ldg(w + 2);
+        unsigned char bytes[12];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            bytes[i] = (w0 >> (8 * i)) & 0xff;
+            bytes[4 + i] = (w1 >> (8 * i)) & 0xff;
+            bytes[8 + i] = (w2 >> (8 * i)) & 0xff;
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            r[i] = Real<T>::from_u8(bytes[3 * i]);
+            g[i] = Real<T>::from_u8(bytes[3 * i + 1]);
+            b[i] = Real<T>::from_u8(bytes[3 * i + 2]);
+        }
+    }
+}
+
+// composite row -> T (natural layout), from the u8 frame ((5*(v/255) - 1)/3, image.py:23-25,62) or the float buffer
+template <typename T>
+__device__ __forceinline__ void load_comp_row(T *dst, const IoArgs<T> &io, int fidx, int row, int Wc) {
+    const size_t base = ((size_t)fidx * io.nrows + row) * Wc;
+    for (int x = 4 * threadIdx.x; x < Wc; x += 4 * blockDim.x) {
+        T v[4];
+        if (io.in_f) {
+            ld4(io.in_f + base + x, v);
+        } else {
+            const uint32_t w = __ldg(reinterpret_cast<const uint32_t *>(io.in_u8 + base + x));
+#pragma unroll
+            for (int i = 0; i < 4; ++i) v[i] = ((T)5 * Real<T>::from_u8((w >> (8 * i)) & 0xff) - (T)1) / (T)3;
+        }
+        st4(dst + x, v);
+    }
+}
+
+// 4 composite samples out: float (before the level map) and/or u8 (0.6 v + 0.2, image.py:16-21)
+template <typename T>
+__device__ __forceinline__ void store_comp4(const IoArgs<T> &io, size_t off, const T v[4]) {
+    if (io.out_f) st4(io.out_f + off, v);
+    if (io.out_u8) {
+        uint32_t w = 0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) w |= to_u8((T)0.6 * v[i] + (T)0.2) << (8 * i);
+        *reinterpret_cast<uint32_t *>(io.out_u8 + off) = w;
+    }
+}
+
+// 4 decoded pixels out (inverse colour matrix, e.g. ntsc.py:36-41), float before clipping and/or u8
+template <typename T>
+__device__ __forceinline__ void store_rgb4(const DevParams<T> &p, const IoArgs<T> &io, int fidx, int row, int x0,
+                                           const T y[4], const T c1[4], const T c2[4]) {
+    T v[12];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        v[3 * i] = p.dec[0] * y[i] + p.dec[1] * c1[i] + p.dec[2] * c2[i];
+        v[3 * i + 1] = p.dec[3] * y[i] + p.dec[4] * c1[i] + p.dec[5] * c2[i];
+        v[3 * i + 2] = p.dec[6] * y[i] + p.dec[7] * c1[i] + p.dec[8] * c2[i];
+    }
+    const size_t o = (((size_t)fidx * io.nrows + row) * p.Wo + x0) * 3;
+    if (io.out_f) {
+#pragma unroll
+        for (int q = 0; q < 3; ++q) st4(io.out_f + o + 4 * q, v + 4 * q);
+    }
+    if (io.out_u8) {
+        uint32_t w[3] = {0, 0, 0};
+#pragma unroll
+        for (int i = 0; i < 12; ++i) w[i >> 2] |= to_u8(v[i]) << (8 * (i & 3));
+        uint32_t *dst = reinterpret_cast<uint32_t *>(io.out_u8 + o);
+        dst[0] = w[0];
+        dst[1] = w[1];
+        dst[2] = w[2];
+    }
+}

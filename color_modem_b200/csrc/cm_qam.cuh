@@ -1,52 +1,31 @@
 // QAM family kernels: NTSC / PAL encode, band-split decode, PAL-D delay-line decode, NTSC 2-line / 3-line comb,
 // PAL 3-line comb.  Reference: color_modem/qam.py, color/ntsc.py, color/pal.py, comb.py.
+//
+// Buffer conventions (cm_iir.cuh / cm_fir.cuh): 1x signals natural with pitch N1 = p.n1p; 2x signals polyphase
+// [E | O] with p.hb2 elements per phase, pitch N2 = 2 * p.hb2 (>= 2 * N1, so one 2x buffer can hold two 1x rows).
 #pragma once
 #include "cm_common.cuh"
 #include "cm_fir.cuh"
 #include "cm_iir.cuh"
+#include "cm_io.cuh"
 #include "cm_slots.h"
 
-// ------------------------------------------------------------------------------------------------------------
-// shared helpers
-// ------------------------------------------------------------------------------------------------------------
-template <typename T>
-__device__ __forceinline__ void copy_taps(T *dst, const DevParams<T> &p, int nres) {
-    int total = 0;
-    for (int r = 0; r < nres; ++r) total = max(total, p.res[r].off + p.res[r].ntaps);
-    for (int i = threadIdx.x; i < total; i += blockDim.x) dst[i] = p.taps[i];
-}
+#define CM_QUARTER_TURN 0x4000000000000000ull
 
-// composite row -> T, either from the u8 frame ((5*(v/255) - 1)/3, image.py:23-25,62) or from the float buffer
+// sin/cos of the subcarrier at 4 consecutive 1x samples starting at x0 (exact seed + 3 rotations)
 template <typename T>
-__device__ __forceinline__ void load_comp_row(T *dst, const IoArgs<T> &io, int fidx, int row, int Wc) {
-    const size_t base = ((size_t)fidx * io.nrows + row) * Wc;
-    if (io.in_f) {
-        for (int x = threadIdx.x; x < Wc; x += blockDim.x) dst[x] = io.in_f[base + x];
-    } else {
-        for (int x = threadIdx.x; x < Wc; x += blockDim.x)
-            dst[x] = ((T)5 * Real<T>::from_u8(io.in_u8[base + x]) - (T)1) / (T)3;
-    }
-}
-
-template <typename T>
-__device__ __forceinline__ void store_rgb(const DevParams<T> &p, const IoArgs<T> &io, int fidx, int row, int x,
-                                          T y, T c1, T c2) {
-    T r = p.dec[0] * y + p.dec[1] * c1 + p.dec[2] * c2;
-    T g = p.dec[3] * y + p.dec[4] * c1 + p.dec[5] * c2;
-    T b = p.dec[6] * y + p.dec[7] * c1 + p.dec[8] * c2;
-    const size_t o = (((size_t)fidx * io.nrows + row) * p.Wo + x) * 3;
-    if (io.out_f) { io.out_f[o] = r; io.out_f[o + 1] = g; io.out_f[o + 2] = b; }
-    if (io.out_u8) {
-        io.out_u8[o] = (uint8_t)to_u8(r);
-        io.out_u8[o + 1] = (uint8_t)to_u8(g);
-        io.out_u8[o + 2] = (uint8_t)to_u8(b);
+__device__ __forceinline__ void carrier4(unsigned long long ph_x0, T rs, T rc, T s[4], T c[4]) {
+    Real<T>::sincos_turns(ph_x0, s[0], c[0]);
+#pragma unroll
+    for (int i = 1; i < 4; ++i) {
+        s[i] = Real<T>::fma_(s[i - 1], rc, c[i - 1] * rs);
+        c[i] = Real<T>::fma_(c[i - 1], rc, -(s[i - 1] * rs));
     }
 }
 
 // ------------------------------------------------------------------------------------------------------------
 // Encode: RGB -> Y + sin(phi) LP(U) + cos(phi) LP(+-V)          qam.py:20-32, ntsc.py:27-45, pal.py:32-52
-// optional ColorAveragingModem front end (comb.py:141-152)
-// smem: R * 3 * W
+// optional ColorAveragingModem front end (comb.py:141-152).     smem: R * 3 * N1
 // ------------------------------------------------------------------------------------------------------------
 template <typename T>
 __global__ void __launch_bounds__(CM_NTHREADS)
@@ -55,56 +34,91 @@ k_qam_encode(const __grid_constant__ DevParams<T> p, const __grid_constant__ IoA
     T *sm = reinterpret_cast<T *>(smem_raw);
     RowGroup g;
     if (!decode_group(io, g)) return;
-    const int W = p.W;
+    const int W = p.W, N1 = p.n1p, W4 = W >> 2;
     const int warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     const bool avg = (p.flags & 2) != 0;
 
-    for (int idx = threadIdx.x; idx < g.count * W; idx += blockDim.x) {
-        const int k = idx / W, x = idx - k * W;
+    for (int k = 0; k < g.count; ++k) {
         const int row = g.r0 + 2 * k;
-        T rgb[3], nrgb[3];
-        const size_t o = (((size_t)g.fidx * io.nrows + row) * W + x) * 3;
         const int nrow = (row + 2 < io.nrows) ? row + 2 : row;
-        const size_t on = (((size_t)g.fidx * io.nrows + nrow) * W + x) * 3;
+        T *ys = sm + (size_t)k * 3 * N1, *us = ys + N1, *vs = us + N1;
+        for (int q = threadIdx.x; q < W4; q += blockDim.x) {
+            const int x = 4 * q;
+            T r[4], gg[4], b[4], y[4], u[4], v[4];
+            load_rgb4(io, ((size_t)g.fidx * io.nrows + row) * W + x, r, gg, b);
 #pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            rgb[c] = io.in_f ? io.in_f[o + c] : Real<T>::from_u8(io.in_u8[o + c]);
-            if (avg) nrgb[c] = io.in_f ? io.in_f[on + c] : Real<T>::from_u8(io.in_u8[on + c]);
+            for (int i = 0; i < 4; ++i) {
+                y[i] = p.enc[0] * r[i] + p.enc[1] * gg[i] + p.enc[2] * b[i];
+                u[i] = p.enc[3] * r[i] + p.enc[4] * gg[i] + p.enc[5] * b[i];
+                v[i] = p.enc[6] * r[i] + p.enc[7] * gg[i] + p.enc[8] * b[i];
+            }
+            if (avg) {
+                load_rgb4(io, ((size_t)g.fidx * io.nrows + nrow) * W + x, r, gg, b);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const T un = p.enc[3] * r[i] + p.enc[4] * gg[i] + p.enc[5] * b[i];
+                    const T vn = p.enc[6] * r[i] + p.enc[7] * gg[i] + p.enc[8] * b[i];
+                    u[i] = (T)0.5 * (un + u[i]);
+                    v[i] = (T)0.5 * (vn + v[i]);
+                }
+            }
+            st4(ys + x, y);
+            st4(us + x, u);
+            st4(vs + x, v);
         }
-        T *row_sm = sm + (size_t)k * 3 * W;
-        row_sm[x] = p.enc[0] * rgb[0] + p.enc[1] * rgb[1] + p.enc[2] * rgb[2];
-        T u = p.enc[3] * rgb[0] + p.enc[4] * rgb[1] + p.enc[5] * rgb[2];
-        T v = p.enc[6] * rgb[0] + p.enc[7] * rgb[1] + p.enc[8] * rgb[2];
-        if (avg) {
-            T un = p.enc[3] * nrgb[0] + p.enc[4] * nrgb[1] + p.enc[5] * nrgb[2];
-            T vn = p.enc[6] * nrgb[0] + p.enc[7] * nrgb[1] + p.enc[8] * nrgb[2];
-            u = (T)0.5 * (un + u);
-            v = (T)0.5 * (vn + v);
-        }
-        row_sm[W + x] = u;
-        row_sm[2 * W + x] = v;
     }
     __syncthreads();
+    for (int k = 0; k < g.count; ++k) cta_fill_tail<T, 1>(sm + (size_t)k * 3 * N1 + N1, (size_t)N1, 2, N1, W, N1);
+    __syncthreads();
+    const FiltHdr &fpre = p.filt[QF_PRE_LP];
     for (int t = warp; t < 2 * g.count; t += nwarps) {
-        T *buf = sm + (size_t)(t >> 1) * 3 * W + (1 + (t & 1)) * W;
-        warp_iir<T>(p.tab + p.filt[QF_PRE_LP].off, p.filt[QF_PRE_LP],
-                    [&](int j) { return buf[j]; }, [&](int j, T v) { buf[j] = v; });
+        T *buf = sm + (size_t)(t >> 1) * 3 * N1 + (1 + (t & 1)) * N1;
+        warp_iir<T, 1>(p.tab + fpre.off, fpre, [&](int q, int, int) { return buf[q]; },
+                       [&](int j, T v) { buf[j] = v; });
     }
     __syncthreads();
-    for (int idx = threadIdx.x; idx < g.count * W; idx += blockDim.x) {
-        const int k = idx / W, x = idx - k * W;
-        const int row = g.r0 + 2 * k;
-        const int line = io.y0 + row;
-        const T *row_sm = sm + (size_t)k * 3 * W;
-        unsigned long long ph = start_phase(p, g.frame, line) + (unsigned long long)x * p.phases[QP_STEP1X];
-        T s, c;
-        Real<T>::sincos_turns(ph, s, c);
-        T v = row_sm[2 * W + x];
-        if ((p.flags & 1) && is_alternate(p, g.frame, line)) v = -v;
-        T comp = row_sm[x] + (s * row_sm[W + x] + c * v);
-        const size_t o = ((size_t)g.fidx * io.nrows + row) * p.Wc + x;
-        if (io.out_f) io.out_f[o] = comp;
-        if (io.out_u8) io.out_u8[o] = (uint8_t)to_u8((T)0.6 * comp + (T)0.2);
+    T rs, rc;
+    Real<T>::sincos_turns(p.phases[QP_STEP1X], rs, rc);
+    for (int k = 0; k < g.count; ++k) {
+        const int row = g.r0 + 2 * k, line = io.y0 + row;
+        const T *ys = sm + (size_t)k * 3 * N1, *us = ys + N1, *vs = us + N1;
+        const unsigned long long ph0 = start_phase(p, g.frame, line);
+        const bool neg = (p.flags & 1) && is_alternate(p, g.frame, line);
+        for (int q = threadIdx.x; q < W4; q += blockDim.x) {
+            const int x = 4 * q;
+            T y[4], u[4], v[4], s[4], c[4], o[4];
+            ld4(ys + x, y);
+            ld4(us + x, u);
+            ld4(vs + x, v);
+            carrier4(ph0 + (unsigned long long)x * p.phases[QP_STEP1X], rs, rc, s, c);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) o[i] = y[i] + (s[i] * u[i] + c[i] * (neg ? -v[i] : v[i]));
+            store_comp4(io, ((size_t)g.fidx * io.nrows + row) * p.Wc + x, o);
+        }
+    }
+}
+
+// Re-modulation of (u, v) through the encoder and subtraction from the composite, then colour matrix + store:
+//   y = c - (sin(phi) u_lp + cos(phi) (+-v_lp))            comb.py:52-53, pal.py:225-226
+template <typename T>
+__device__ __forceinline__ void remod_store_row(const DevParams<T> &p, const IoArgs<T> &io, const RowGroup &g, int k,
+                                                const T *c, const T *ulp, const T *vlp, const T *u, const T *v,
+                                                T rs, T rc) {
+    const int row = g.r0 + 2 * k, line = io.y0 + row;
+    const unsigned long long ph0 = start_phase(p, g.frame, line);
+    const bool neg = (p.flags & 1) && is_alternate(p, g.frame, line);
+    for (int q = threadIdx.x; q < (p.W >> 2); q += blockDim.x) {
+        const int x = 4 * q;
+        T cc[4], a[4], b[4], uu[4], vv[4], s[4], co[4], y[4];
+        ld4(c + x, cc);
+        ld4(ulp + x, a);
+        ld4(vlp + x, b);
+        ld4(u + x, uu);
+        ld4(v + x, vv);
+        carrier4(ph0 + (unsigned long long)x * p.phases[QP_STEP1X], rs, rc, s, co);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) y[i] = cc[i] - (s[i] * a[i] + co[i] * (neg ? -b[i] : b[i]));
+        store_rgb4(p, io, g.fidx, row, x, y, uu, vv);
     }
 }
 
@@ -115,7 +129,7 @@ k_qam_encode(const __grid_constant__ DevParams<T> p, const __grid_constant__ IoA
 //   luma_mode 1: luma = c - remod(u, v)         (field-top rows of Pal3DModem, pal.py:191-202,225-226)
 //   luma_mode 2: luma = c                       (strip_chroma=False: the reset-branch return value of the comb
 //                                                decoders, CM_MODE_BANDSPLIT_NOSTRIP)
-// 2 warps per row.  smem per row: c[W] + 4 x [2W]
+// 2 warps per row.  smem: taps[128] + R * (c[N1] + 4 x [N2])
 // ------------------------------------------------------------------------------------------------------------
 template <typename T>
 __global__ void __launch_bounds__(CM_NTHREADS)
@@ -124,112 +138,128 @@ k_qam_bandsplit(const __grid_constant__ DevParams<T> p, const __grid_constant__ 
     T *sm = reinterpret_cast<T *>(smem_raw);
     RowGroup g;
     if (!decode_group(io, g)) return;
-    const int W = p.W, W2 = 2 * W;
+    const int W = p.W, W2 = 2 * W, N1 = p.n1p, hb = p.hb2, N2 = 2 * hb;
     const int warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-    T *taps = sm;                       // 128 elements reserved
+    T *taps = sm;
     T *rows = sm + 128;
-    const int per_row = 9 * W;
+    const size_t per_row = (size_t)N1 + 4 * (size_t)N2;     // c | a2 | b2 | l2 | v2
+    const T *hup = taps + p.res[QR_UP2].off, *hdn = taps + p.res[QR_DOWN2].off;
     copy_taps(taps, p, 2);
-    for (int k = 0; k < g.count; ++k) load_comp_row(rows + (size_t)k * per_row, io, g.fidx, g.r0 + 2 * k, W);
+    for (int k = 0; k < g.count; ++k) load_comp_row(rows + k * per_row, io, g.fidx, g.r0 + 2 * k, W);
     __syncthreads();
     for (int k = 0; k < g.count; ++k) {
-        T *c = rows + (size_t)k * per_row;
-        fir_up2(c + W, c, W, taps + p.res[QR_UP2].off, threadIdx.x, blockDim.x);
+        T *c = rows + k * per_row, *a2 = c + N1;
+        fir_up2(a2, a2 + hb, c, W, hup, threadIdx.x, blockDim.x);
     }
     __syncthreads();
-    // IIR phase 1: band-pass -> b2x, band-stop -> l2x
+    cta_fill_tail<T, 2>(rows + N1, per_row, g.count, hb, W2, N2);
+    __syncthreads();
+    // IIR phase 1: band-pass a2 -> b2, band-stop a2 -> l2
     for (int t = warp; t < 2 * g.count; t += nwarps) {
-        T *c = rows + (size_t)(t >> 1) * per_row;
-        const T *a2x = c + W;
+        T *c = rows + (t >> 1) * per_row;
+        const T *ae = c + N1, *ao = ae + hb;
         if ((t & 1) == 0) {
-            T *b2x = c + W + W2;
-            warp_iir<T>(p.tab + p.filt[QF_BP2X].off, p.filt[QF_BP2X],
-                        [&](int j) { return a2x[j]; }, [&](int j, T v) { b2x[j] = v; });
+            T *be = c + N1 + N2, *bo = be + hb;
+            const FiltHdr &f = p.filt[QF_BP2X];
+            warp_iir<T, 2>(p.tab + f.off, f, [&](int q, int ph, int) { return (ph ? ao : ae)[q]; },
+                           [&](int j, T v) { ((j & 1) ? bo : be)[j >> 1] = v; });
+            warp_fill_tail<T, 2>(be, hb, W2, N2);
         } else if (luma_mode == 0) {
-            T *l2x = c + W + 2 * W2;
-            warp_iir<T>(p.tab + p.filt[QF_BS2X].off, p.filt[QF_BS2X],
-                        [&](int j) { return a2x[j]; }, [&](int j, T v) { l2x[j] = v; });
+            T *le = c + N1 + 2 * N2, *lo = le + hb;
+            const FiltHdr &f = p.filt[QF_BS2X];
+            warp_iir<T, 2>(p.tab + f.off, f, [&](int q, int ph, int) { return (ph ? ao : ae)[q]; },
+                           [&](int j, T v) { ((j & 1) ? lo : le)[j >> 1] = v; });
         }
     }
     __syncthreads();
-    // IIR phase 2: product demodulation + low-pass.  u2x -> a2x (c2x is dead), v2x -> 4th buffer
+    // IIR phase 2: product demodulation + low-pass.  u2 -> a2 (dead), v2 -> 4th buffer
     for (int t = warp; t < 2 * g.count; t += nwarps) {
         const int k = t >> 1;
-        T *c = rows + (size_t)k * per_row;
-        const T *b2x = c + W + W2;
-        T *dst = (t & 1) ? (c + W + 3 * W2) : (c + W);
+        T *c = rows + k * per_row;
+        const T *be = c + N1 + N2, *bo = be + hb;
+        T *de = (t & 1) ? (c + N1 + 3 * N2) : (c + N1), *dod = de + hb;
         const int line = io.y0 + g.r0 + 2 * k;
         // sin for u, cos for v: cos(x) = sin(x + 1/4 turn)
-        const unsigned long long ph0 = start_phase(p, g.frame, line) + p.phases[QP_BP_SHIFT] +
-                                       ((t & 1) ? 0x4000000000000000ull : 0ull);
-        const unsigned long long step = p.phases[QP_STEP2X];
-        warp_iir<T>(p.tab + p.filt[QF_DEMOD_LP].off, p.filt[QF_DEMOD_LP],
-                    [&](int j) {
-                        T s, cc;
-                        Real<T>::sincos_turns(ph0 + (unsigned long long)j * step, s, cc);
-                        return (T)2 * s * b2x[j];
-                    },
-                    [&](int j, T v) { dst[j] = v; });
+        Carrier<T> car(start_phase(p, g.frame, line) + p.phases[QP_BP_SHIFT] + ((t & 1) ? CM_QUARTER_TURN : 0ull),
+                       p.phases[QP_STEP2X], W2);
+        const FiltHdr &f = p.filt[QF_DEMOD_LP];
+        warp_iir<T, 2>(p.tab + f.off, f,
+                       [&](int q, int ph, int i) {
+                           car.at(2 * q + ph, i == 0);
+                           return (T)2 * car.s * (ph ? bo : be)[q];
+                       },
+                       [&](int j, T v) { ((j & 1) ? dod : de)[j >> 1] = v; });
     }
     __syncthreads();
-    // down2 of u2x, v2x (and luma) -> u, v, y at 1x into the b2x region (dead now)
+    // down2 of u2, v2 -> u, v at 1x into the b2 region (dead now): u at [0, N1), v at [N1, 2 N1)
     for (int k = 0; k < g.count; ++k) {
-        T *c = rows + (size_t)k * per_row;
-        T *uo = c + W + W2, *vo = uo + W;
-        const T *h = taps + p.res[QR_DOWN2].off;
+        T *c = rows + k * per_row;
+        T *uo = c + N1 + N2, *vo = uo + N1;
         const bool alt = (p.flags & 1) && is_alternate(p, g.frame, io.y0 + g.r0 + 2 * k);
-        fir_down2(c + W, W2, h, threadIdx.x, blockDim.x, [&](int j, T v) { uo[j] = v; });
-        fir_down2(c + W + 3 * W2, W2, h, threadIdx.x, blockDim.x, [&](int j, T v) { vo[j] = alt ? -v : v; });
+        fir_down2(c + N1, c + N1 + hb, W, hdn, threadIdx.x, blockDim.x, [&](int j0, const T *y) { st4(uo + j0, y); });
+        fir_down2(c + N1 + 3 * N2, c + N1 + 3 * N2 + hb, W, hdn, threadIdx.x, blockDim.x, [&](int j0, const T *y) {
+            T v[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) v[i] = alt ? -y[i] : y[i];
+            st4(vo + j0, v);
+        });
     }
     __syncthreads();
     if (luma_mode == 0) {
         for (int k = 0; k < g.count; ++k) {
-            T *c = rows + (size_t)k * per_row;
-            const T *uo = c + W + W2, *vo = uo + W;
+            T *c = rows + k * per_row;
+            const T *uo = c + N1 + N2, *vo = uo + N1;
             const int row = g.r0 + 2 * k;
-            fir_down2(c + W + 2 * W2, W2, taps + p.res[QR_DOWN2].off, threadIdx.x, blockDim.x,
-                      [&](int j, T y) { store_rgb(p, io, g.fidx, row, j, y, uo[j], vo[j]); });
+            fir_down2(c + N1 + 2 * N2, c + N1 + 2 * N2 + hb, W, hdn, threadIdx.x, blockDim.x, [&](int j0, const T *y) {
+                T u[4], v[4];
+                ld4(uo + j0, u);
+                ld4(vo + j0, v);
+                store_rgb4(p, io, g.fidx, row, j0, y, u, v);
+            });
         }
         return;
     }
     if (luma_mode == 2) {
-        for (int idx = threadIdx.x; idx < g.count * W; idx += blockDim.x) {
-            const int k = idx / W, x = idx - k * W;
-            const T *c = rows + (size_t)k * per_row;
-            store_rgb(p, io, g.fidx, g.r0 + 2 * k, x, c[x], c[W + W2 + x], c[W + W2 + W + x]);
+        for (int k = 0; k < g.count; ++k) {
+            const T *c = rows + k * per_row;
+            for (int q = threadIdx.x; q < (W >> 2); q += blockDim.x) {
+                T y[4], u[4], v[4];
+                ld4(c + 4 * q, y);
+                ld4(c + N1 + N2 + 4 * q, u);
+                ld4(c + N1 + N2 + N1 + 4 * q, v);
+                store_rgb4(p, io, g.fidx, g.r0 + 2 * k, 4 * q, y, u, v);
+            }
         }
         return;
     }
-    // luma_mode 1: re-modulate (u, v) through the encoder's pre-lowpass and subtract from the composite
+    // luma_mode 1: encoder pre-lowpass of (u, v) into the a2 region, then re-modulate and subtract
+    for (int k = 0; k < g.count; ++k) cta_fill_tail<T, 1>(rows + k * per_row + N1 + N2, (size_t)N1, 2, N1, W, N1);
+    __syncthreads();
+    const FiltHdr &fpre = p.filt[QF_PRE_LP];
     for (int t = warp; t < 2 * g.count; t += nwarps) {
-        T *c = rows + (size_t)(t >> 1) * per_row;
-        const T *src = c + W + W2 + (t & 1) * W;
-        T *dst = c + W + (t & 1) * W;           // a2x region (u2x is dead after down2)
-        warp_iir<T>(p.tab + p.filt[QF_PRE_LP].off, p.filt[QF_PRE_LP],
-                    [&](int j) { return src[j]; }, [&](int j, T v) { dst[j] = v; });
+        T *c = rows + (t >> 1) * per_row;
+        const T *src = c + N1 + N2 + (t & 1) * N1;
+        T *dst = c + N1 + (t & 1) * N1;
+        warp_iir<T, 1>(p.tab + fpre.off, fpre, [&](int q, int, int) { return src[q]; },
+                       [&](int j, T v) { dst[j] = v; });
     }
     __syncthreads();
-    for (int idx = threadIdx.x; idx < g.count * W; idx += blockDim.x) {
-        const int k = idx / W, x = idx - k * W;
-        const T *c = rows + (size_t)k * per_row;
-        const int row = g.r0 + 2 * k, line = io.y0 + row;
-        T s, cc;
-        Real<T>::sincos_turns(start_phase(p, g.frame, line) + (unsigned long long)x * p.phases[QP_STEP1X], s, cc);
-        T vl = c[W + W + x];
-        if ((p.flags & 1) && is_alternate(p, g.frame, line)) vl = -vl;
-        T y = c[x] - (s * c[W + x] + cc * vl);
-        store_rgb(p, io, g.fidx, row, x, y, c[W + W2 + x], c[W + W2 + W + x]);
+    T rs, rc;
+    Real<T>::sincos_turns(p.phases[QP_STEP1X], rs, rc);
+    for (int k = 0; k < g.count; ++k) {
+        const T *c = rows + k * per_row;
+        remod_store_row(p, io, g, k, c, c + N1, c + N1 + N1, c + N1 + N2, c + N1 + N2 + N1, rs, rc);
     }
 }
 
 // ------------------------------------------------------------------------------------------------------------
 // PAL-D delay-line decode of rows that have a predecessor        pal.py:79-127 + comb.py:50-53
-// Per row k (k = -1 is the halo row y0-2):  G[k] = up2(down2(BP(up2 c[k])))       (extract_chroma, then the
-// up2 of _demodulate_am; all linear, so G of the sum/difference is the sum/difference of the G's)
+// Per row k (k = -1 is the halo row):  G[k] = up2(down2(BP(up2 c[k])))     (extract_chroma, then the up2 of
+// _demodulate_am; all linear, so G of the sum/difference of two rows is the sum/difference of their G's)
 //   S = down2(LP(sin(ph)       * (G[k] + G[k-1])))      D = down2(LP(sin(ph + pi/2) * (G[k] - G[k-1])))
 //   u = D sin(LS/2) + S cos(LS/2);  v = D cos(LS/2) - S sin(LS/2);  v = -v on alternate lines
 //   y = c - (sin(phi) LP_pre(u) + cos(phi) LP_pre(+-v))
-// smem: taps[128] + (R+1) * (c[W] + G[2W]) + R * 2 * [2W] work
+// smem: taps[128] + (R+1) * (c[N1] + G[N2]) + 2R * [N2] work
 // ------------------------------------------------------------------------------------------------------------
 template <typename T>
 __global__ void __launch_bounds__(CM_NTHREADS)
@@ -238,90 +268,99 @@ k_pald_combed(const __grid_constant__ DevParams<T> p, const __grid_constant__ Io
     T *sm = reinterpret_cast<T *>(smem_raw);
     RowGroup g;
     if (!decode_group(io, g)) return;
-    const int W = p.W, W2 = 2 * W;
+    const int W = p.W, W2 = 2 * W, N1 = p.n1p, hb = p.hb2, N2 = 2 * hb;
     const int warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     const int R = io.rows_per_cta;
     T *taps = sm;
-    T *cbuf = sm + 128;                         // (R+1) x W     composite rows, index k+1
-    T *gbuf = cbuf + (size_t)(R + 1) * W;       // (R+1) x 2W    G rows, index k+1
-    T *work = gbuf + (size_t)(R + 1) * W2;      // 2R x 2W
+    T *cbuf = sm + 128;                          // (R+1) x N1    composite rows, index k+1
+    T *gbuf = cbuf + (size_t)(R + 1) * N1;       // (R+1) x N2    G rows, index k+1
+    T *work = gbuf + (size_t)(R + 1) * N2;       // 2R x N2
     const int nin = g.count + 1;
+    const T *hup = taps + p.res[QR_UP2].off, *hdn = taps + p.res[QR_DOWN2].off;
     copy_taps(taps, p, 2);
-    for (int k = 0; k < nin; ++k) load_comp_row(cbuf + (size_t)k * W, io, g.fidx, g.r0 + 2 * (k - 1), W);
+    for (int k = 0; k < nin; ++k) load_comp_row(cbuf + (size_t)k * N1, io, g.fidx, g.r0 + 2 * (k - 1), W);
     __syncthreads();
-    for (int k = 0; k < nin; ++k)
-        fir_up2(gbuf + (size_t)k * W2, cbuf + (size_t)k * W, W, taps + p.res[QR_UP2].off, threadIdx.x, blockDim.x);
+    for (int k = 0; k < nin; ++k) {
+        T *b = gbuf + (size_t)k * N2;
+        fir_up2(b, b + hb, cbuf + (size_t)k * N1, W, hup, threadIdx.x, blockDim.x);
+    }
+    __syncthreads();
+    cta_fill_tail<T, 2>(gbuf, (size_t)N2, nin, hb, W2, N2);
     __syncthreads();
     for (int t = warp; t < nin; t += nwarps) {          // band-pass in place
-        T *b = gbuf + (size_t)t * W2;
-        warp_iir<T>(p.tab + p.filt[QF_BP2X].off, p.filt[QF_BP2X],
-                    [&](int j) { return b[j]; }, [&](int j, T v) { b[j] = v; });
+        T *be = gbuf + (size_t)t * N2, *bo = be + hb;
+        const FiltHdr &f = p.filt[QF_BP2X];
+        warp_iir<T, 2>(p.tab + f.off, f, [&](int q, int ph, int) { return (ph ? bo : be)[q]; },
+                       [&](int j, T v) { ((j & 1) ? bo : be)[j >> 1] = v; });
     }
     __syncthreads();
-    for (int k = 0; k < nin; ++k) {                     // E = down2(b2x) -> work[k][0..W)
-        T *e = work + (size_t)k * W;
-        fir_down2(gbuf + (size_t)k * W2, W2, taps + p.res[QR_DOWN2].off, threadIdx.x, blockDim.x,
-                  [&](int j, T v) { e[j] = v; });
+    for (int k = 0; k < nin; ++k) {                     // E = down2(b2) -> work[k][0..W)
+        T *e = work + (size_t)k * N1;
+        const T *b = gbuf + (size_t)k * N2;
+        fir_down2(b, b + hb, W, hdn, threadIdx.x, blockDim.x, [&](int j0, const T *y) { st4(e + j0, y); });
     }
     __syncthreads();
-    for (int k = 0; k < nin; ++k)                       // G = up2(E)
-        fir_up2(gbuf + (size_t)k * W2, work + (size_t)k * W, W, taps + p.res[QR_UP2].off, threadIdx.x, blockDim.x);
+    for (int k = 0; k < nin; ++k) {                     // G = up2(E)
+        T *b = gbuf + (size_t)k * N2;
+        fir_up2(b, b + hb, work + (size_t)k * N1, W, hup, threadIdx.x, blockDim.x);
+    }
+    __syncthreads();
+    cta_fill_tail<T, 2>(gbuf, (size_t)N2, nin, hb, W2, N2);
     __syncthreads();
     for (int t = warp; t < 2 * g.count; t += nwarps) {  // AM demodulation low-pass of sum / difference
         const int k = t >> 1;
-        const T *gc = gbuf + (size_t)(k + 1) * W2, *gl = gbuf + (size_t)k * W2;
-        T *dst = work + (size_t)t * W2;
+        const T *gce = gbuf + (size_t)(k + 1) * N2, *gco = gce + hb;
+        const T *gle = gbuf + (size_t)k * N2, *glo = gle + hb;
+        T *de = work + (size_t)t * N2, *dod = de + hb;
         const int line = io.y0 + g.r0 + 2 * k;
         const T sgn = (t & 1) ? (T)-1 : (T)1;
-        const unsigned long long ph0 = start_phase(p, g.frame, line) + p.phases[QP_BP_SHIFT] - p.phases[QP_HALF_LS] +
-                                       ((t & 1) ? 0x4000000000000000ull : 0ull);
-        const unsigned long long step = p.phases[QP_STEP2X];
-        warp_iir<T>(p.tab + p.filt[QF_PALD_LP].off, p.filt[QF_PALD_LP],
-                    [&](int j) {
-                        T s, cc;
-                        Real<T>::sincos_turns(ph0 + (unsigned long long)j * step, s, cc);
-                        return (gc[j] + sgn * gl[j]) * s;
-                    },
-                    [&](int j, T v) { dst[j] = v; });
+        Carrier<T> car(start_phase(p, g.frame, line) + p.phases[QP_BP_SHIFT] - p.phases[QP_HALF_LS] +
+                           ((t & 1) ? CM_QUARTER_TURN : 0ull),
+                       p.phases[QP_STEP2X], W2);
+        const FiltHdr &f = p.filt[QF_PALD_LP];
+        warp_iir<T, 2>(p.tab + f.off, f,
+                       [&](int q, int ph, int i) {
+                           car.at(2 * q + ph, i == 0);
+                           return Real<T>::fma_(sgn, (ph ? glo : gle)[q], (ph ? gco : gce)[q]) * car.s;
+                       },
+                       [&](int j, T v) { ((j & 1) ? dod : de)[j >> 1] = v; });
     }
     __syncthreads();
-    // S, D at 1x -> u, v (kept in gbuf rows: u at [k][0..W), v at [k][W..2W))
-    const T sf = p.scalars[QS_PALD_SIN], cf = p.scalars[QS_PALD_COS];
+    // S, D at 1x -> gbuf rows (G is dead): S at [k][0..N1), D at [k][N1..2 N1)
     for (int k = 0; k < g.count; ++k) {
-        T *so = gbuf + (size_t)k * W2, *dout = so + W;
-        const T *h = taps + p.res[QR_DOWN2].off;
-        fir_down2(work + (size_t)(2 * k) * W2, W2, h, threadIdx.x, blockDim.x, [&](int j, T v) { so[j] = v; });
-        fir_down2(work + (size_t)(2 * k + 1) * W2, W2, h, threadIdx.x, blockDim.x, [&](int j, T v) { dout[j] = v; });
+        T *so = gbuf + (size_t)k * N2, *dout = so + N1;
+        const T *ws = work + (size_t)(2 * k) * N2, *wd = work + (size_t)(2 * k + 1) * N2;
+        fir_down2(ws, ws + hb, W, hdn, threadIdx.x, blockDim.x, [&](int j0, const T *y) { st4(so + j0, y); });
+        fir_down2(wd, wd + hb, W, hdn, threadIdx.x, blockDim.x, [&](int j0, const T *y) { st4(dout + j0, y); });
     }
     __syncthreads();
-    for (int idx = threadIdx.x; idx < g.count * W; idx += blockDim.x) {
-        const int k = idx / W, x = idx - k * W;
-        T *so = gbuf + (size_t)k * W2;
-        const T s = so[x], d = so[W + x];
-        T u = d * sf + s * cf;
-        T v = d * cf - s * sf;
-        if (is_alternate(p, g.frame, io.y0 + g.r0 + 2 * k)) v = -v;
-        so[x] = u;
-        so[W + x] = v;
+    const T sf = p.scalars[QS_PALD_SIN], cf = p.scalars[QS_PALD_COS];
+    for (int k = 0; k < g.count; ++k) {                 // rotate (S, D) -> (u, v) in place, V switch
+        T *so = gbuf + (size_t)k * N2;
+        const bool alt = is_alternate(p, g.frame, io.y0 + g.r0 + 2 * k);
+        for (int x = threadIdx.x; x < W; x += blockDim.x) {
+            const T s = so[x], d = so[N1 + x];
+            const T v = d * cf - s * sf;
+            so[x] = d * sf + s * cf;
+            so[N1 + x] = alt ? -v : v;
+        }
     }
     __syncthreads();
+    for (int k = 0; k < g.count; ++k) cta_fill_tail<T, 1>(gbuf + (size_t)k * N2, (size_t)N1, 2, N1, W, N1);
+    __syncthreads();
+    const FiltHdr &fpre = p.filt[QF_PRE_LP];
     for (int t = warp; t < 2 * g.count; t += nwarps) {  // encoder pre-lowpass for the re-modulation
-        const T *src = gbuf + (size_t)(t >> 1) * W2 + (t & 1) * W;
-        T *dst = work + (size_t)t * W;
-        warp_iir<T>(p.tab + p.filt[QF_PRE_LP].off, p.filt[QF_PRE_LP],
-                    [&](int j) { return src[j]; }, [&](int j, T v) { dst[j] = v; });
+        const T *src = gbuf + (size_t)(t >> 1) * N2 + (t & 1) * N1;
+        T *dst = work + (size_t)t * N1;
+        warp_iir<T, 1>(p.tab + fpre.off, fpre, [&](int q, int, int) { return src[q]; },
+                       [&](int j, T v) { dst[j] = v; });
     }
     __syncthreads();
-    for (int idx = threadIdx.x; idx < g.count * W; idx += blockDim.x) {
-        const int k = idx / W, x = idx - k * W;
-        const int row = g.r0 + 2 * k, line = io.y0 + row;
-        T s, cc;
-        Real<T>::sincos_turns(start_phase(p, g.frame, line) + (unsigned long long)x * p.phases[QP_STEP1X], s, cc);
-        T vl = work[(size_t)(2 * k + 1) * W + x];
-        if (is_alternate(p, g.frame, line)) vl = -vl;
-        const T y = cbuf[(size_t)(k + 1) * W + x] - (s * work[(size_t)(2 * k) * W + x] + cc * vl);
-        store_rgb(p, io, g.fidx, row, x, y, gbuf[(size_t)k * W2 + x], gbuf[(size_t)k * W2 + W + x]);
-    }
+    T rs, rc;
+    Real<T>::sincos_turns(p.phases[QP_STEP1X], rs, rc);
+    for (int k = 0; k < g.count; ++k)
+        remod_store_row(p, io, g, k, cbuf + (size_t)(k + 1) * N1, work + (size_t)(2 * k) * N1,
+                        work + (size_t)(2 * k + 1) * N1, gbuf + (size_t)k * N2, gbuf + (size_t)k * N2 + N1, rs, rc);
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -339,7 +378,7 @@ k_pald_combed(const __grid_constant__ DevParams<T> p, const __grid_constant__ Io
 //         S = demod(c[k+1]-c[k-1]), D = demod(c[k+1]-2c[k]+c[k-1]) at the phase of row k,
 //         u = a_ss S.v + a_cu D.u,  v = a_ss S.u + a_cv D.v, V switch; c[k+1] := c[k] at the bottom
 //   then  y = c[k] - remod(u, v)  for all three.
-// smem: taps[128] + (R+2) * (c[W] + B[2W]) + 2R * [2W]
+// smem: taps[128] + (R+2) * (c[N1] + B[N2]) + 2R * [N2]
 // ------------------------------------------------------------------------------------------------------------
 enum { COMB_NTSC2 = 0, COMB_NTSC3 = 1, COMB_PAL3 = 2 };
 
@@ -350,117 +389,128 @@ k_qam_comb(const __grid_constant__ DevParams<T> p, const __grid_constant__ IoArg
     T *sm = reinterpret_cast<T *>(smem_raw);
     RowGroup g;
     if (!decode_group(io, g)) return;
-    const int W = p.W, W2 = 2 * W;
+    const int W = p.W, W2 = 2 * W, N1 = p.n1p, hb = p.hb2, N2 = 2 * hb;
     const int warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     const int R = io.rows_per_cta;
     T *taps = sm;
-    T *cbuf = sm + 128;                         // (R+2) x W    index k+1, k = -1 .. R
-    T *bbuf = cbuf + (size_t)(R + 2) * W;       // (R+2) x 2W
-    T *work = bbuf + (size_t)(R + 2) * W2;      // 2R x 2W
+    T *cbuf = sm + 128;                          // (R+2) x N1    index k+1, k = -1 .. R
+    T *bbuf = cbuf + (size_t)(R + 2) * N1;       // (R+2) x N2
+    T *work = bbuf + (size_t)(R + 2) * N2;       // 2R x N2
     const bool has_prev0 = g.r0 >= 2;                               // row k = -1 exists
     const bool has_next_last = g.r0 + 2 * g.count < io.nrows;       // row k = count exists
     const int k_lo = has_prev0 ? -1 : 0;
     const int k_hi = (MODE != COMB_NTSC2 && has_next_last) ? g.count : g.count - 1;
+    const int nin = k_hi - k_lo + 1;
+    const T *hup = taps + p.res[QR_UP2].off, *hdn = taps + p.res[QR_DOWN2].off;
     copy_taps(taps, p, 2);
-    for (int k = k_lo; k <= k_hi; ++k) load_comp_row(cbuf + (size_t)(k + 1) * W, io, g.fidx, g.r0 + 2 * k, W);
+    for (int k = k_lo; k <= k_hi; ++k) load_comp_row(cbuf + (size_t)(k + 1) * N1, io, g.fidx, g.r0 + 2 * k, W);
     __syncthreads();
-    for (int k = k_lo; k <= k_hi; ++k)
-        fir_up2(bbuf + (size_t)(k + 1) * W2, cbuf + (size_t)(k + 1) * W, W, taps + p.res[QR_UP2].off, threadIdx.x,
-                blockDim.x);
+    for (int k = k_lo; k <= k_hi; ++k) {
+        T *b = bbuf + (size_t)(k + 1) * N2;
+        fir_up2(b, b + hb, cbuf + (size_t)(k + 1) * N1, W, hup, threadIdx.x, blockDim.x);
+    }
     __syncthreads();
-    for (int t = warp; t < k_hi - k_lo + 1; t += nwarps) {
-        T *b = bbuf + (size_t)(k_lo + t + 1) * W2;
-        warp_iir<T>(p.tab + p.filt[QF_BP2X].off, p.filt[QF_BP2X],
-                    [&](int j) { return b[j]; }, [&](int j, T v) { b[j] = v; });
+    cta_fill_tail<T, 2>(bbuf + (size_t)(k_lo + 1) * N2, (size_t)N2, nin, hb, W2, N2);
+    __syncthreads();
+    for (int t = warp; t < nin; t += nwarps) {
+        T *be = bbuf + (size_t)(k_lo + t + 1) * N2, *bo = be + hb;
+        const FiltHdr &f = p.filt[QF_BP2X];
+        warp_iir<T, 2>(p.tab + f.off, f, [&](int q, int ph, int) { return (ph ? bo : be)[q]; },
+                       [&](int j, T v) { ((j & 1) ? bo : be)[j >> 1] = v; });
+        warp_fill_tail<T, 2>(be, hb, W2, N2);
     }
     __syncthreads();
     const unsigned long long step = p.phases[QP_STEP2X];
+    const FiltHdr &flp = p.filt[QF_DEMOD_LP];
     for (int t = warp; t < 2 * g.count; t += nwarps) {
         const int k = t >> 1;
         const bool is_v = (t & 1) != 0;
         const int line = io.y0 + g.r0 + 2 * k;
         const bool hp = (k > 0) || has_prev0;
         const bool hn = (k + 1 < g.count) || has_next_last;
-        const T *bc = bbuf + (size_t)(k + 1) * W2;
-        const T *bp = bbuf + (size_t)(hp ? k : k + 1) * W2;
-        const T *bn = bbuf + (size_t)(hn ? k + 2 : k + 1) * W2;
-        T *dst = work + (size_t)t * W2;
+        const T *bce = bbuf + (size_t)(k + 1) * N2, *bco = bce + hb;
+        const T *bpe = bbuf + (size_t)(hp ? k : k + 1) * N2, *bpo = bpe + hb;
+        const T *bne = bbuf + (size_t)(hn ? k + 2 : k + 1) * N2, *bno = bne + hb;
+        T *de = work + (size_t)t * N2, *dod = de + hb;
+        auto st = [&](int j, T v) { ((j & 1) ? dod : de)[j >> 1] = v; };
         const unsigned long long psi = start_phase(p, g.frame, line) + p.phases[QP_BP_SHIFT];
         if (MODE == COMB_NTSC2) {
             const T f2 = (T)2 * p.scalars[QS_NTSC_FACTOR];
-            const unsigned long long phi = psi - p.phases[QP_HALF_LS];
-            warp_iir<T>(p.tab + p.filt[QF_DEMOD_LP].off, p.filt[QF_DEMOD_LP],
-                        [&](int j) {
-                            T s, c;
-                            Real<T>::sincos_turns(phi + (unsigned long long)j * step, s, c);
-                            const T d = bc[j] - bp[j];
-                            return is_v ? -f2 * s * d : f2 * c * d;
-                        },
-                        [&](int j, T v) { dst[j] = v; });
+            // u: f 2 cos(phi) d = f2 sin(phi + 1/4) d;   v: -f 2 sin(phi) d
+            Carrier<T> car(psi - p.phases[QP_HALF_LS] + (is_v ? 0ull : CM_QUARTER_TURN), step, W2);
+            const T amp = is_v ? -f2 : f2;
+            warp_iir<T, 2>(p.tab + flp.off, flp,
+                           [&](int q, int ph, int i) {
+                               car.at(2 * q + ph, i == 0);
+                               return amp * car.s * ((ph ? bco : bce)[q] - (ph ? bpo : bpe)[q]);
+                           },
+                           st);
         } else if (MODE == COMB_NTSC3) {
             const T f = p.scalars[QS_NTSC_FACTOR];      // 0.5 * (2 f ...) = f ...
-            const unsigned long long phi = psi - p.phases[QP_HALF_LS];
-            const unsigned long long phin = start_phase(p, g.frame, line + 2) + p.phases[QP_BP_SHIFT] -
-                                            p.phases[QP_HALF_LS];
-            warp_iir<T>(p.tab + p.filt[QF_DEMOD_LP].off, p.filt[QF_DEMOD_LP],
-                        [&](int j) {
-                            T s, c, acc;
-                            const unsigned long long dj = (unsigned long long)j * step;
-                            if (hp) {
-                                Real<T>::sincos_turns(phi + dj, s, c);
-                                const T d = bc[j] - bp[j];
-                                acc = is_v ? -f * s * d : f * c * d;
-                            } else {
-                                Real<T>::sincos_turns(psi + dj, s, c);
-                                acc = is_v ? c * bc[j] : s * bc[j];
-                            }
-                            if (hn) {
-                                Real<T>::sincos_turns(phin + dj, s, c);
-                                const T d = bn[j] - bc[j];
-                                acc += is_v ? -f * s * d : f * c * d;
-                            }
-                            return acc;
-                        },
-                        [&](int j, T v) { dst[j] = v; });
+            const unsigned long long quarter = is_v ? 0ull : CM_QUARTER_TURN;
+            Carrier<T> car(hp ? (psi - p.phases[QP_HALF_LS] + quarter) : (psi + (is_v ? CM_QUARTER_TURN : 0ull)),
+                           step, W2);
+            Carrier<T> carn(start_phase(p, g.frame, line + 2) + p.phases[QP_BP_SHIFT] - p.phases[QP_HALF_LS] + quarter,
+                            step, W2);
+            const T amp = is_v ? -f : f;
+            warp_iir<T, 2>(p.tab + flp.off, flp,
+                           [&](int q, int ph, int i) {
+                               const int j = 2 * q + ph;
+                               car.at(j, i == 0);
+                               const T bc = (ph ? bco : bce)[q];
+                               T acc = hp ? amp * car.s * (bc - (ph ? bpo : bpe)[q]) : car.s * bc;
+                               if (hn) {
+                                   carn.at(j, i == 0);
+                                   acc = Real<T>::fma_(amp * carn.s, (ph ? bno : bne)[q] - bc, acc);
+                               }
+                               return acc;
+                           },
+                           st);
         } else {
             const T a_ss = (T)2 * p.scalars[QS_P3D_SINSUM];
             const T a_c = (T)2 * (is_v ? p.scalars[QS_P3D_COSV] : p.scalars[QS_P3D_COSU]);
-            warp_iir<T>(p.tab + p.filt[QF_DEMOD_LP].off, p.filt[QF_DEMOD_LP],
-                        [&](int j) {
-                            T s, c;
-                            Real<T>::sincos_turns(psi + (unsigned long long)j * step, s, c);
-                            const T curr_diff = bn[j] - bc[j], last_diff = bc[j] - bp[j];
-                            const T ssig = curr_diff + last_diff, dsig = curr_diff - last_diff;
-                            return is_v ? (a_ss * s * ssig + a_c * c * dsig) : (a_ss * c * ssig + a_c * s * dsig);
-                        },
-                        [&](int j, T v) { dst[j] = v; });
+            Carrier<T> car(psi, step, W2);
+            warp_iir<T, 2>(p.tab + flp.off, flp,
+                           [&](int q, int ph, int i) {
+                               car.at(2 * q + ph, i == 0);
+                               const T bc = (ph ? bco : bce)[q];
+                               const T curr_diff = (ph ? bno : bne)[q] - bc, last_diff = bc - (ph ? bpo : bpe)[q];
+                               const T ssig = curr_diff + last_diff, dsig = curr_diff - last_diff;
+                               return is_v ? (a_ss * car.s * ssig + a_c * car.c * dsig)
+                                           : (a_ss * car.c * ssig + a_c * car.s * dsig);
+                           },
+                           st);
         }
     }
     __syncthreads();
-    // u, v at 1x into bbuf rows: u at [k+1][0..W), v at [k+1][W..2W)   (the B's are dead now)
+    // u, v at 1x into bbuf rows (the B's are dead): u at [k+1][0..N1), v at [k+1][N1..2 N1)
     for (int t = 0; t < 2 * g.count; ++t) {
         const int k = t >> 1;
-        T *o = bbuf + (size_t)(k + 1) * W2 + (t & 1) * W;
+        T *o = bbuf + (size_t)(k + 1) * N2 + (t & 1) * N1;
+        const T *w = work + (size_t)t * N2;
         const bool neg = (MODE == COMB_PAL3) && (t & 1) && is_alternate(p, g.frame, io.y0 + g.r0 + 2 * k);
-        fir_down2(work + (size_t)t * W2, W2, taps + p.res[QR_DOWN2].off, threadIdx.x, blockDim.x,
-                  [&](int j, T v) { o[j] = neg ? -v : v; });
+        fir_down2(w, w + hb, W, hdn, threadIdx.x, blockDim.x, [&](int j0, const T *y) {
+            T v[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) v[i] = neg ? -y[i] : y[i];
+            st4(o + j0, v);
+        });
     }
     __syncthreads();
+    for (int k = 0; k < g.count; ++k) cta_fill_tail<T, 1>(bbuf + (size_t)(k + 1) * N2, (size_t)N1, 2, N1, W, N1);
+    __syncthreads();
+    const FiltHdr &fpre = p.filt[QF_PRE_LP];
     for (int t = warp; t < 2 * g.count; t += nwarps) {
-        const T *src = bbuf + (size_t)((t >> 1) + 1) * W2 + (t & 1) * W;
-        T *dst = work + (size_t)t * W;
-        warp_iir<T>(p.tab + p.filt[QF_PRE_LP].off, p.filt[QF_PRE_LP],
-                    [&](int j) { return src[j]; }, [&](int j, T v) { dst[j] = v; });
+        const T *src = bbuf + (size_t)((t >> 1) + 1) * N2 + (t & 1) * N1;
+        T *dst = work + (size_t)t * N1;
+        warp_iir<T, 1>(p.tab + fpre.off, fpre, [&](int q, int, int) { return src[q]; },
+                       [&](int j, T v) { dst[j] = v; });
     }
     __syncthreads();
-    for (int idx = threadIdx.x; idx < g.count * W; idx += blockDim.x) {
-        const int k = idx / W, x = idx - k * W;
-        const int row = g.r0 + 2 * k, line = io.y0 + row;
-        T s, cc;
-        Real<T>::sincos_turns(start_phase(p, g.frame, line) + (unsigned long long)x * p.phases[QP_STEP1X], s, cc);
-        T vl = work[(size_t)(2 * k + 1) * W + x];
-        if ((p.flags & 1) && is_alternate(p, g.frame, line)) vl = -vl;
-        const T y = cbuf[(size_t)(k + 1) * W + x] - (s * work[(size_t)(2 * k) * W + x] + cc * vl);
-        store_rgb(p, io, g.fidx, row, x, y, bbuf[(size_t)(k + 1) * W2 + x], bbuf[(size_t)(k + 1) * W2 + W + x]);
-    }
+    T rs, rc;
+    Real<T>::sincos_turns(p.phases[QP_STEP1X], rs, rc);
+    for (int k = 0; k < g.count; ++k)
+        remod_store_row(p, io, g, k, cbuf + (size_t)(k + 1) * N1, work + (size_t)(2 * k) * N1,
+                        work + (size_t)(2 * k + 1) * N1, bbuf + (size_t)(k + 1) * N2, bbuf + (size_t)(k + 1) * N2 + N1,
+                        rs, rc);
 }

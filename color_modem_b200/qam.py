@@ -26,12 +26,12 @@ class QamColorModem(object):
         return self._extract_chroma2x.phase_shift
 
 
-def put_filter(desc, slot, ff, n):
+def put_filter(desc, slot, ff, n, rate):
     f = desc.filters[slot]
     sos = ff.sos
     if sos.shape[0] > N.MAX_SECTIONS:
         raise ValueError('filter order %d exceeds the CUDA cascade limit' % (2 * sos.shape[0]))
-    f.nsec, f.shift, f.n = sos.shape[0], ff.shift, int(n)
+    f.nsec, f.shift, f.n, f.rate = sos.shape[0], ff.shift, int(n), int(rate)
     for s in range(sos.shape[0]):
         for k in range(5):
             f.sos[s][k] = float(sos[s, k])
@@ -88,10 +88,10 @@ class AbstractQamColorModem(GpuModem, utils.ConstantFrequencyCarrier):
             d.enc_matrix[i] = self.ENC[i]
             d.dec_matrix[i] = self.DEC[i]
         q = self.qam
-        put_filter(d, S.QF_PRE_LP, q._chroma_precorrect_lowpass, W)
-        put_filter(d, S.QF_BP2X, q._extract_chroma2x, 2 * W)
-        put_filter(d, S.QF_BS2X, q._remove_chroma2x, 2 * W)
-        put_filter(d, S.QF_DEMOD_LP, q._demod_lowpass, 2 * W)
+        put_filter(d, S.QF_PRE_LP, q._chroma_precorrect_lowpass, W, 1)
+        put_filter(d, S.QF_BP2X, q._extract_chroma2x, 2 * W, 2)
+        put_filter(d, S.QF_BS2X, q._remove_chroma2x, 2 * W, 2)
+        put_filter(d, S.QF_DEMOD_LP, q._demod_lowpass, 2 * W, 2)
         put_resampler(d, S.QR_UP2, 2, 1)
         put_resampler(d, S.QR_DOWN2, 1, 2)
         d.phases[S.QP_STEP1X] = utils.turns_fixed(q.wc / 2.0)

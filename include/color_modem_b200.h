@@ -79,7 +79,7 @@ typedef struct cm_filter {
     int32_t nsec;
     int32_t shift;
     int32_t n;        /* input length at this use-site (samples per line at the rate the filter runs at) */
-    int32_t reserved;
+    int32_t rate;     /* 1, 2 or 3: oversampling factor the filter runs at (selects the shared-memory layout) */
     double sos[CM_MAX_SECTIONS][5];
 } cm_filter;
 
