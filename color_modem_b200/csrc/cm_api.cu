@@ -1,48 +1,23 @@
-// C ABI of color_modem_b200 (include/color_modem_b200.h): handle management, filter-table construction,
-// kernel launches.  Host code only; the arithmetic lives in cm_*.cuh.
-#include <cuda_runtime.h>
+// C ABI of color_modem_b200 (include/color_modem_b200.h): handle management, filter-table construction and
+// dispatch to the per-family launchers (cm_qam.cu, cm_secam.cu, ...).  Host code only.
 #include <math.h>
 #include <stdio.h>
-#include <string.h>
 
 #include <atomic>
 #include <new>
-#include <vector>
 
-#include "../../include/color_modem_b200.h"
-#include "cm_common.cuh"
-#include "cm_qam.cuh"
+#include "cm_host.h"
+#include "cm_iir.cuh"
 
 static thread_local char g_err[512] = "";
 static std::atomic<long long> g_launches{0};
 
-static int fail(int code, const char *fmt, const char *detail = "") {
+int cm_fail(int code, const char *fmt, const char *detail) {
     snprintf(g_err, sizeof(g_err), fmt, detail);
     return code;
 }
-#define CUDA_TRY(expr)                                                              \
-    do {                                                                            \
-        cudaError_t _e = (expr);                                                    \
-        if (_e != cudaSuccess) return fail(CM_ERR_CUDA, #expr ": %s", cudaGetErrorString(_e)); \
-    } while (0)
-
-struct cm_modem {
-    cm_desc desc;
-    int precision;
-    int device;
-    int sm_count;
-    int smem_optin;
-    DevParams<float> pf;
-    DevParams<double> pd;
-    void *d_tab = nullptr;
-    void *d_taps = nullptr;
-    bool timing = false;
-    struct Ev { cudaEvent_t a, b; int id; };
-    std::vector<Ev> events;
-    // scratch for the *_host entry points
-    void *d_in = nullptr, *d_out = nullptr;
-    size_t in_cap = 0, out_cap = 0;
-};
+void cm_count_launch() { g_launches++; }
+static int fail(int code, const char *fmt, const char *detail = "") { return cm_fail(code, fmt, detail); }
 
 // ------------------------------------------------------------------------------------------------------------
 // filter tables (float64 on the host, cast to the handle's precision)
@@ -56,9 +31,9 @@ static void mat_mul(const double a[4], const double b[4], double out[4]) {
 // Chunk length per lane: the kernels instantiate warp_iir for a few compile-time values per rate
 // (cm_iir.cuh: warp_iir); pick the one that wastes the least padding, preferring longer chunks on ties.
 static void pick_chunk(int rate, int total, int &L, int &nsuper) {
-    static const int c1[] = {47, 31, 23}, c2[] = {46, 30}, c3[] = {45, 39};
+    static const int c1[] = {47, 31, 23}, c2[] = {50, 46, 30}, c3[] = {45, 39, 33};
     const int *cand = rate == 1 ? c1 : (rate == 2 ? c2 : c3);
-    const int ncand = rate == 1 ? 3 : 2;
+    const int ncand = 3;
     long best = -1;
     for (int i = 0; i < ncand; ++i) {
         int ns = (total + 32 * cand[i] - 1) / (32 * cand[i]);
@@ -133,7 +108,7 @@ static void fill_params(const cm_desc &d, DevParams<T> &p, const FiltHdr *fh, co
     }
     p.n1p = up4(n1p);
     p.hb2 = up4((n2p + 1) / 2);
-    if (p.hb2 < p.n1p) p.hb2 = p.n1p;
+    if (d.kind <= CM_KIND_PAL_3D && p.hb2 < p.n1p) p.hb2 = p.n1p;   // QAM kernels park two 1x rows in one 2x buffer
     p.hb3 = up4((n3p + 2) / 3);
     for (int i = 0; i < CM_NRES; ++i) p.res[i] = rh[i];
     p.tab = (const T *)tab;
@@ -182,6 +157,7 @@ extern "C" int cm_create(const cm_desc *desc, int precision, cm_modem **out) {
         case CM_KIND_NTSC_3D:
         case CM_KIND_PAL_D:
         case CM_KIND_PAL_3D:
+        case CM_KIND_SECAM:
             break;
         default:
             return fail(CM_ERR_UNSUPPORTED, "modem kind not built%s");
@@ -251,27 +227,6 @@ extern "C" void cm_destroy(cm_modem *m) {
 // ------------------------------------------------------------------------------------------------------------
 // launches
 // ------------------------------------------------------------------------------------------------------------
-struct LaunchTimer {
-    cm_modem *m;
-    cudaStream_t st;
-    cm_modem::Ev ev;
-    bool on;
-    LaunchTimer(cm_modem *m_, int id, cudaStream_t st_) : m(m_), st(st_), on(m_->timing) {
-        if (on) {
-            ev.id = id;
-            cudaEventCreate(&ev.a);
-            cudaEventCreate(&ev.b);
-            cudaEventRecord(ev.a, st);
-        }
-    }
-    ~LaunchTimer() {
-        if (on) {
-            cudaEventRecord(ev.b, st);
-            m->events.push_back(ev);
-        }
-    }
-};
-
 extern "C" int cm_timing_enable(cm_modem *m, int on) {
     if (!m) return fail(CM_ERR_INVALID, "null handle%s");
     m->timing = on != 0;
@@ -302,178 +257,36 @@ extern "C" int cm_timing_read(cm_modem *m, int id, double *total_ms, int64_t *la
     return CM_OK;
 }
 
-template <typename T> static const DevParams<T> &params_of(const cm_modem *m);
-template <> const DevParams<float> &params_of<float>(const cm_modem *m) { return m->pf; }
-template <> const DevParams<double> &params_of<double>(const cm_modem *m) { return m->pd; }
-
-template <typename K>
-static int set_smem(K kernel, size_t bytes) {
-    CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
-    return CM_OK;
-}
-
-// Largest R in [1, rmax] whose shared-memory footprint fits `budget`; 0 if even R = 1 does not fit.
-template <class F>
-static int pick_rows(int rmax, size_t budget, F bytes_for) {
-    for (int r = rmax; r >= 1; --r)
-        if (bytes_for(r) <= budget) return r;
-    return 0;
-}
-
 template <typename T>
-static void set_groups(IoArgs<T> &io, int R) {
-    io.rows_per_cta = R;
-    int rows_in_field = (io.out_count + 1) >> 1;
-    io.groups_per_field = (rows_in_field + R - 1) / R;
-}
-
-template <typename T>
-static int launch_encode(cm_modem *m, IoArgs<T> io, cudaStream_t st) {
-    const DevParams<T> &p = params_of<T>(m);
-    if (io.out_count <= 0) return CM_OK;
-    switch (p.kind) {
+static int dispatch_encode(cm_modem *m, IoArgs<T> io, cudaStream_t st) {
+    switch (m->desc.kind) {
         case CM_KIND_QAM_BANDSPLIT:
         case CM_KIND_NTSC_COMB:
         case CM_KIND_NTSC_3D:
         case CM_KIND_PAL_D:
-        case CM_KIND_PAL_3D: {
-            auto bytes = [&](int r) { return (size_t)r * 3 * p.n1p * sizeof(T); };
-            int R = pick_rows(4, (size_t)m->smem_optin / 2, bytes);
-            if (!R) return fail(CM_ERR_UNSUPPORTED, "line too wide for the encode kernel%s");
-            set_groups(io, R);
-            int rc = set_smem(k_qam_encode<T>, bytes(R));
-            if (rc) return rc;
-            dim3 grid((unsigned)(io.nframes * 2 * io.groups_per_field));
-            LaunchTimer lt(m, CM_K_ENCODE, st);
-            k_qam_encode<T><<<grid, 64 * R, bytes(R), st>>>(p, io);
-            g_launches++;
-            break;
-        }
+        case CM_KIND_PAL_3D:
+            return qam_encode<T>(m, io, st);
+        case CM_KIND_SECAM:
+            return secam_encode<T>(m, io, st);
         default:
             return fail(CM_ERR_UNSUPPORTED, "encode: modem kind not built%s");
     }
-    CUDA_TRY(cudaGetLastError());
-    return CM_OK;
 }
 
 template <typename T>
-static int launch_bandsplit(cm_modem *m, IoArgs<T> io, int luma_mode, cudaStream_t st) {
-    const DevParams<T> &p = params_of<T>(m);
-    if (io.out_count <= 0) return CM_OK;
-    auto bytes = [&](int r) { return (128 + (size_t)r * (p.n1p + 8 * (size_t)p.hb2)) * sizeof(T); };
-    int R = pick_rows(4, (size_t)m->smem_optin / 2, bytes);
-    if (!R) R = pick_rows(1, (size_t)m->smem_optin, bytes);
-    if (!R) return fail(CM_ERR_UNSUPPORTED, "line too wide for the band-split kernel%s");
-    set_groups(io, R);
-    int rc = set_smem(k_qam_bandsplit<T>, bytes(R));
-    if (rc) return rc;
-    dim3 grid((unsigned)(io.nframes * 2 * io.groups_per_field));
-    LaunchTimer lt(m, CM_K_BANDSPLIT, st);
-    k_qam_bandsplit<T><<<grid, 64 * R, bytes(R), st>>>(p, io, luma_mode);
-    g_launches++;
-    CUDA_TRY(cudaGetLastError());
-    return CM_OK;
-}
-
-template <typename T>
-static int launch_pald(cm_modem *m, IoArgs<T> io, cudaStream_t st) {
-    const DevParams<T> &p = params_of<T>(m);
-    if (io.out_count <= 0) return CM_OK;
-    auto bytes = [&](int r) {
-        return (128 + (size_t)(r + 1) * (p.n1p + 2 * (size_t)p.hb2) + (size_t)r * 4 * p.hb2) * sizeof(T);
-    };
-    int R = pick_rows(4, (size_t)m->smem_optin / 2, bytes);
-    if (!R) R = pick_rows(2, (size_t)m->smem_optin, bytes);
-    if (!R) return fail(CM_ERR_UNSUPPORTED, "line too wide for the PAL-D kernel%s");
-    set_groups(io, R);
-    int rc = set_smem(k_pald_combed<T>, bytes(R));
-    if (rc) return rc;
-    dim3 grid((unsigned)(io.nframes * 2 * io.groups_per_field));
-    LaunchTimer lt(m, CM_K_PALD, st);
-    k_pald_combed<T><<<grid, 64 * R, bytes(R), st>>>(p, io);
-    g_launches++;
-    CUDA_TRY(cudaGetLastError());
-    return CM_OK;
-}
-
-template <typename T, int MODE>
-static int launch_comb(cm_modem *m, IoArgs<T> io, cudaStream_t st) {
-    const DevParams<T> &p = params_of<T>(m);
-    if (io.out_count <= 0) return CM_OK;
-    auto bytes = [&](int r) {
-        return (128 + (size_t)(r + 2) * (p.n1p + 2 * (size_t)p.hb2) + (size_t)r * 4 * p.hb2) * sizeof(T);
-    };
-    int R = pick_rows(4, (size_t)m->smem_optin / 2, bytes);
-    if (!R) R = pick_rows(2, (size_t)m->smem_optin, bytes);
-    if (!R) return fail(CM_ERR_UNSUPPORTED, "line too wide for the comb kernel%s");
-    set_groups(io, R);
-    int rc = set_smem(k_qam_comb<T, MODE>, bytes(R));
-    if (rc) return rc;
-    dim3 grid((unsigned)(io.nframes * 2 * io.groups_per_field));
-    LaunchTimer lt(m, CM_K_COMB, st);
-    k_qam_comb<T, MODE><<<grid, 64 * R, bytes(R), st>>>(p, io);
-    g_launches++;
-    CUDA_TRY(cudaGetLastError());
-    return CM_OK;
-}
-
-// rows of [begin, begin+count) that have no predecessor in the window (r < 2) / that have one (r >= 2)
-template <typename T>
-static void split_top(const IoArgs<T> &io, IoArgs<T> &top, IoArgs<T> &rest) {
-    top = io;
-    rest = io;
-    int end = io.out_begin + io.out_count;
-    int top_end = end < 2 ? end : 2;
-    top.out_count = top_end > io.out_begin ? top_end - io.out_begin : 0;
-    int rest_begin = io.out_begin > 2 ? io.out_begin : 2;
-    rest.out_begin = rest_begin;
-    rest.out_count = end > rest_begin ? end - rest_begin : 0;
-}
-
-template <typename T>
-static int launch_decode(cm_modem *m, IoArgs<T> io, int mode, cudaStream_t st) {
-    const DevParams<T> &p = params_of<T>(m);
-    if (mode == CM_MODE_BANDSPLIT_NOSTRIP) {
-        if (p.kind < CM_KIND_QAM_BANDSPLIT || p.kind > CM_KIND_PAL_3D)
-            return fail(CM_ERR_INVALID, "CM_MODE_BANDSPLIT_NOSTRIP is only defined for the QAM family%s");
-        return launch_bandsplit<T>(m, io, 2, st);
-    }
-    switch (p.kind) {
+static int dispatch_decode(cm_modem *m, IoArgs<T> io, int mode, cudaStream_t st) {
+    const int kind = m->desc.kind;
+    if (mode == CM_MODE_BANDSPLIT_NOSTRIP && (kind < CM_KIND_QAM_BANDSPLIT || kind > CM_KIND_PAL_3D))
+        return fail(CM_ERR_INVALID, "CM_MODE_BANDSPLIT_NOSTRIP is only defined for the QAM family%s");
+    switch (kind) {
         case CM_KIND_QAM_BANDSPLIT:
-            return launch_bandsplit<T>(m, io, 0, st);
-        case CM_KIND_PAL_D: {
-            IoArgs<T> top, rest;
-            split_top(io, top, rest);
-            int rc = launch_bandsplit<T>(m, top, 0, st);
-            if (rc) return rc;
-            return launch_pald<T>(m, rest, st);
-        }
-        case CM_KIND_NTSC_COMB: {
-            IoArgs<T> top, rest;
-            split_top(io, top, rest);
-            int rc = launch_bandsplit<T>(m, top, 0, st);
-            if (rc) return rc;
-            if (p.flags & CM_FLAG_NTSC_NO_COMB)      // ntsc.py:71-72: chroma of the row itself, luma = c - remod
-                return launch_bandsplit<T>(m, rest, 1, st);
-            return launch_comb<T, COMB_NTSC2>(m, rest, st);
-        }
+        case CM_KIND_NTSC_COMB:
         case CM_KIND_NTSC_3D:
-            if (p.flags & CM_FLAG_NTSC_NO_COMB) return launch_bandsplit<T>(m, io, 1, st);
-            return launch_comb<T, COMB_NTSC3>(m, io, st);
-        case CM_KIND_PAL_3D: {
-            if (!(p.flags & (CM_FLAG_PAL3D_SIN | CM_FLAG_PAL3D_COS))) {   // pal.py:181-182: plain PAL-D
-                IoArgs<T> top, rest;
-                split_top(io, top, rest);
-                int rc = launch_bandsplit<T>(m, top, 0, st);
-                if (rc) return rc;
-                return launch_pald<T>(m, rest, st);
-            }
-            IoArgs<T> top, rest;
-            split_top(io, top, rest);
-            int rc = launch_bandsplit<T>(m, top, 1, st);
-            if (rc) return rc;
-            return launch_comb<T, COMB_PAL3>(m, rest, st);
-        }
+        case CM_KIND_PAL_D:
+        case CM_KIND_PAL_3D:
+            return qam_decode<T>(m, io, mode, st);
+        case CM_KIND_SECAM:
+            return secam_decode<T>(m, io, st);
         default:
             return fail(CM_ERR_UNSUPPORTED, "decode: modem kind not built%s");
     }
@@ -510,8 +323,8 @@ static int run_ex(cm_modem *m, bool encode, const cm_window *win, const uint8_t 
     }
     CUDA_TRY(cudaSetDevice(m->device));
     const int mode = win ? win->mode : CM_MODE_DEFAULT;
-    return encode ? launch_encode<T>(m, io, (cudaStream_t)stream)
-                  : launch_decode<T>(m, io, mode, (cudaStream_t)stream);
+    return encode ? dispatch_encode<T>(m, io, (cudaStream_t)stream)
+                  : dispatch_decode<T>(m, io, mode, (cudaStream_t)stream);
 }
 
 extern "C" int cm_encode_ex(cm_modem *m, const cm_window *win, const uint8_t *rgb_u8, const void *rgb_float,

@@ -19,6 +19,7 @@
 #define CM_NRES 6
 #define CM_NSCAL 48
 #define CM_NPHASE 16
+#define CM_QUARTER_TURN 0x4000000000000000ull
 
 struct FiltHdr {
     int nsec, shift, n, L, nsuper, rate;     // n = input length of this use-site; L*32*nsuper >= n+shift

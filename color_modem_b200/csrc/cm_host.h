@@ -1,0 +1,107 @@
+// Host-side internals shared by the translation units of libcolormodem_b200.so (not part of the C ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <string.h>
+
+#include <vector>
+
+#include "../../include/color_modem_b200.h"
+#include "cm_common.cuh"
+
+int cm_fail(int code, const char *fmt, const char *detail = "");
+void cm_count_launch();
+
+#define CUDA_TRY(expr)                                                                          \
+    do {                                                                                        \
+        cudaError_t _e = (expr);                                                                \
+        if (_e != cudaSuccess) return cm_fail(CM_ERR_CUDA, #expr ": %s", cudaGetErrorString(_e)); \
+    } while (0)
+
+struct cm_modem {
+    cm_desc desc;
+    int precision;
+    int device;
+    int sm_count;
+    int smem_optin;
+    DevParams<float> pf;
+    DevParams<double> pd;
+    void *d_tab = nullptr;
+    void *d_taps = nullptr;
+    bool timing = false;
+    struct Ev { cudaEvent_t a, b; int id; };
+    std::vector<Ev> events;
+    // scratch for the *_host entry points
+    void *d_in = nullptr, *d_out = nullptr;
+    size_t in_cap = 0, out_cap = 0;
+};
+
+struct LaunchTimer {
+    cm_modem *m;
+    cudaStream_t st;
+    cm_modem::Ev ev;
+    bool on;
+    LaunchTimer(cm_modem *m_, int id, cudaStream_t st_) : m(m_), st(st_), on(m_->timing) {
+        if (on) {
+            ev.id = id;
+            cudaEventCreate(&ev.a);
+            cudaEventCreate(&ev.b);
+            cudaEventRecord(ev.a, st);
+        }
+    }
+    ~LaunchTimer() {
+        if (on) {
+            cudaEventRecord(ev.b, st);
+            m->events.push_back(ev);
+        }
+    }
+};
+
+template <typename T> inline const DevParams<T> &params_of(const cm_modem *m);
+template <> inline const DevParams<float> &params_of<float>(const cm_modem *m) { return m->pf; }
+template <> inline const DevParams<double> &params_of<double>(const cm_modem *m) { return m->pd; }
+
+template <typename K>
+static int set_smem(K kernel, size_t bytes) {
+    CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    return CM_OK;
+}
+
+// Largest R in [1, rmax] whose shared-memory footprint fits `budget`; 0 if even R = 1 does not fit.
+template <class F>
+static int pick_rows(int rmax, size_t budget, F bytes_for) {
+    for (int r = rmax; r >= 1; --r)
+        if (bytes_for(r) <= budget) return r;
+    return 0;
+}
+
+template <typename T>
+static void set_groups(IoArgs<T> &io, int R) {
+    io.rows_per_cta = R;
+    int rows_in_field = (io.out_count + 1) >> 1;
+    io.groups_per_field = (rows_in_field + R - 1) / R;
+}
+
+// rows of [begin, begin+count) that have no predecessor in the window (r < 2) / that have one (r >= 2)
+template <typename T>
+static void split_top(const IoArgs<T> &io, IoArgs<T> &top, IoArgs<T> &rest) {
+    top = io;
+    rest = io;
+    int end = io.out_begin + io.out_count;
+    int top_end = end < 2 ? end : 2;
+    top.out_count = top_end > io.out_begin ? top_end - io.out_begin : 0;
+    int rest_begin = io.out_begin > 2 ? io.out_begin : 2;
+    rest.out_begin = rest_begin;
+    rest.out_count = end > rest_begin ? end - rest_begin : 0;
+}
+
+// per-family entry points (explicitly instantiated for float and double in cm_<family>.cu)
+template <typename T> int qam_encode(cm_modem *m, IoArgs<T> io, cudaStream_t st);
+template <typename T> int qam_decode(cm_modem *m, IoArgs<T> io, int mode, cudaStream_t st);
+template <typename T> int secam_encode(cm_modem *m, IoArgs<T> io, cudaStream_t st);
+template <typename T> int secam_decode(cm_modem *m, IoArgs<T> io, cudaStream_t st);
+template <typename T> int niir_encode(cm_modem *m, IoArgs<T> io, cudaStream_t st);
+template <typename T> int niir_decode(cm_modem *m, IoArgs<T> io, cudaStream_t st);
+template <typename T> int proto_encode(cm_modem *m, IoArgs<T> io, cudaStream_t st);
+template <typename T> int proto_decode(cm_modem *m, IoArgs<T> io, cudaStream_t st);
+template <typename T> int mac_encode(cm_modem *m, IoArgs<T> io, cudaStream_t st);
+template <typename T> int mac_decode(cm_modem *m, IoArgs<T> io, cudaStream_t st);

@@ -1,0 +1,129 @@
+// Launchers of the QAM family (NTSC / PAL): kernels in cm_qam.cuh.
+#include "cm_host.h"
+#include "cm_qam.cuh"
+
+template <typename T>
+int qam_encode(cm_modem *m, IoArgs<T> io, cudaStream_t st) {
+    const DevParams<T> &p = params_of<T>(m);
+    if (io.out_count <= 0) return CM_OK;
+    auto bytes = [&](int r) { return (size_t)r * 3 * p.n1p * sizeof(T); };
+    int R = pick_rows(4, (size_t)m->smem_optin / 2, bytes);
+    if (!R) return cm_fail(CM_ERR_UNSUPPORTED, "line too wide for the encode kernel%s");
+    set_groups(io, R);
+    int rc = set_smem(k_qam_encode<T>, bytes(R));
+    if (rc) return rc;
+    dim3 grid((unsigned)(io.nframes * 2 * io.groups_per_field));
+    {
+        LaunchTimer lt(m, CM_K_ENCODE, st);
+        k_qam_encode<T><<<grid, 64 * R, bytes(R), st>>>(p, io);
+    }
+    cm_count_launch();
+    CUDA_TRY(cudaGetLastError());
+    return CM_OK;
+}
+
+template <typename T>
+static int launch_bandsplit(cm_modem *m, IoArgs<T> io, int luma_mode, cudaStream_t st) {
+    const DevParams<T> &p = params_of<T>(m);
+    if (io.out_count <= 0) return CM_OK;
+    auto bytes = [&](int r) { return (128 + (size_t)r * (p.n1p + 8 * (size_t)p.hb2)) * sizeof(T); };
+    int R = pick_rows(4, (size_t)m->smem_optin / 2, bytes);
+    if (!R) R = pick_rows(1, (size_t)m->smem_optin, bytes);
+    if (!R) return cm_fail(CM_ERR_UNSUPPORTED, "line too wide for the band-split kernel%s");
+    set_groups(io, R);
+    int rc = set_smem(k_qam_bandsplit<T>, bytes(R));
+    if (rc) return rc;
+    dim3 grid((unsigned)(io.nframes * 2 * io.groups_per_field));
+    {
+        LaunchTimer lt(m, CM_K_BANDSPLIT, st);
+        k_qam_bandsplit<T><<<grid, 64 * R, bytes(R), st>>>(p, io, luma_mode);
+    }
+    cm_count_launch();
+    CUDA_TRY(cudaGetLastError());
+    return CM_OK;
+}
+
+template <typename T>
+static int launch_pald(cm_modem *m, IoArgs<T> io, cudaStream_t st) {
+    const DevParams<T> &p = params_of<T>(m);
+    if (io.out_count <= 0) return CM_OK;
+    auto bytes = [&](int r) {
+        return (128 + (size_t)(r + 1) * (p.n1p + 2 * (size_t)p.hb2) + (size_t)r * 4 * p.hb2) * sizeof(T);
+    };
+    int R = pick_rows(4, (size_t)m->smem_optin / 2, bytes);
+    if (!R) R = pick_rows(2, (size_t)m->smem_optin, bytes);
+    if (!R) return cm_fail(CM_ERR_UNSUPPORTED, "line too wide for the PAL-D kernel%s");
+    set_groups(io, R);
+    int rc = set_smem(k_pald_combed<T>, bytes(R));
+    if (rc) return rc;
+    dim3 grid((unsigned)(io.nframes * 2 * io.groups_per_field));
+    {
+        LaunchTimer lt(m, CM_K_PALD, st);
+        k_pald_combed<T><<<grid, 64 * R, bytes(R), st>>>(p, io);
+    }
+    cm_count_launch();
+    CUDA_TRY(cudaGetLastError());
+    return CM_OK;
+}
+
+template <typename T, int MODE>
+static int launch_comb(cm_modem *m, IoArgs<T> io, cudaStream_t st) {
+    const DevParams<T> &p = params_of<T>(m);
+    if (io.out_count <= 0) return CM_OK;
+    auto bytes = [&](int r) {
+        return (128 + (size_t)(r + 2) * (p.n1p + 2 * (size_t)p.hb2) + (size_t)r * 4 * p.hb2) * sizeof(T);
+    };
+    int R = pick_rows(4, (size_t)m->smem_optin / 2, bytes);
+    if (!R) R = pick_rows(2, (size_t)m->smem_optin, bytes);
+    if (!R) return cm_fail(CM_ERR_UNSUPPORTED, "line too wide for the comb kernel%s");
+    set_groups(io, R);
+    int rc = set_smem(k_qam_comb<T, MODE>, bytes(R));
+    if (rc) return rc;
+    dim3 grid((unsigned)(io.nframes * 2 * io.groups_per_field));
+    {
+        LaunchTimer lt(m, CM_K_COMB, st);
+        k_qam_comb<T, MODE><<<grid, 64 * R, bytes(R), st>>>(p, io);
+    }
+    cm_count_launch();
+    CUDA_TRY(cudaGetLastError());
+    return CM_OK;
+}
+
+template <typename T>
+int qam_decode(cm_modem *m, IoArgs<T> io, int mode, cudaStream_t st) {
+    const DevParams<T> &p = params_of<T>(m);
+    if (mode == CM_MODE_BANDSPLIT_NOSTRIP) return launch_bandsplit<T>(m, io, 2, st);
+    IoArgs<T> top, rest;
+    split_top(io, top, rest);
+    int rc;
+    switch (p.kind) {
+        case CM_KIND_QAM_BANDSPLIT:
+            return launch_bandsplit<T>(m, io, 0, st);
+        case CM_KIND_PAL_D:
+            rc = launch_bandsplit<T>(m, top, 0, st);
+            return rc ? rc : launch_pald<T>(m, rest, st);
+        case CM_KIND_NTSC_COMB:
+            rc = launch_bandsplit<T>(m, top, 0, st);
+            if (rc) return rc;
+            if (p.flags & CM_FLAG_NTSC_NO_COMB)      // ntsc.py:71-72: chroma of the row itself, luma = c - remod
+                return launch_bandsplit<T>(m, rest, 1, st);
+            return launch_comb<T, COMB_NTSC2>(m, rest, st);
+        case CM_KIND_NTSC_3D:
+            if (p.flags & CM_FLAG_NTSC_NO_COMB) return launch_bandsplit<T>(m, io, 1, st);
+            return launch_comb<T, COMB_NTSC3>(m, io, st);
+        case CM_KIND_PAL_3D:
+            if (!(p.flags & (CM_FLAG_PAL3D_SIN | CM_FLAG_PAL3D_COS))) {   // pal.py:181-182: plain PAL-D
+                rc = launch_bandsplit<T>(m, top, 0, st);
+                return rc ? rc : launch_pald<T>(m, rest, st);
+            }
+            rc = launch_bandsplit<T>(m, top, 1, st);
+            return rc ? rc : launch_comb<T, COMB_PAL3>(m, rest, st);
+        default:
+            return cm_fail(CM_ERR_UNSUPPORTED, "decode: not a QAM kind%s");
+    }
+}
+
+template int qam_encode<float>(cm_modem *, IoArgs<float>, cudaStream_t);
+template int qam_encode<double>(cm_modem *, IoArgs<double>, cudaStream_t);
+template int qam_decode<float>(cm_modem *, IoArgs<float>, int, cudaStream_t);
+template int qam_decode<double>(cm_modem *, IoArgs<double>, int, cudaStream_t);

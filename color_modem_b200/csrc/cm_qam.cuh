@@ -10,7 +10,6 @@
 #include "cm_io.cuh"
 #include "cm_slots.h"
 
-#define CM_QUARTER_TURN 0x4000000000000000ull
 
 // sin/cos of the subcarrier at 4 consecutive 1x samples starting at x0 (exact seed + 3 rotations)
 template <typename T>

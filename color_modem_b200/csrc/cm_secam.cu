@@ -1,0 +1,49 @@
+// Launchers of the SECAM family: kernels in cm_secam.cuh.
+#include "cm_host.h"
+#include "cm_secam.cuh"
+
+template <typename T>
+int secam_encode(cm_modem *m, IoArgs<T> io, cudaStream_t st) {
+    const DevParams<T> &p = params_of<T>(m);
+    if (io.out_count <= 0) return CM_OK;
+    auto bytes = [&](int r) { return (size_t)r * 2 * p.n1p * sizeof(T); };
+    int R = pick_rows(8, (size_t)m->smem_optin / 2, bytes);
+    if (!R) return cm_fail(CM_ERR_UNSUPPORTED, "line too wide for the SECAM encode kernel%s");
+    set_groups(io, R);
+    int rc = set_smem(k_secam_encode<T>, bytes(R));
+    if (rc) return rc;
+    dim3 grid((unsigned)(io.nframes * 2 * io.groups_per_field));
+    {
+        LaunchTimer lt(m, CM_K_ENCODE, st);
+        k_secam_encode<T><<<grid, 32 * R, bytes(R), st>>>(p, io);
+    }
+    cm_count_launch();
+    CUDA_TRY(cudaGetLastError());
+    return CM_OK;
+}
+
+template <typename T>
+int secam_decode(cm_modem *m, IoArgs<T> io, cudaStream_t st) {
+    const DevParams<T> &p = params_of<T>(m);
+    if (io.out_count <= 0) return CM_OK;
+    auto bytes = [&](int r) { return (128 + (size_t)(r + 1) * (2 * (size_t)p.n1p + 6 * (size_t)p.hb2)) * sizeof(T); };
+    int R = pick_rows(3, (size_t)m->smem_optin / 2, bytes);
+    if (!R) R = pick_rows(1, (size_t)m->smem_optin, bytes);
+    if (!R) return cm_fail(CM_ERR_UNSUPPORTED, "line too wide for the SECAM decode kernel%s");
+    set_groups(io, R);
+    int rc = set_smem(k_secam_decode<T>, bytes(R));
+    if (rc) return rc;
+    dim3 grid((unsigned)(io.nframes * 2 * io.groups_per_field));
+    {
+        LaunchTimer lt(m, CM_K_DECODE_OTHER, st);
+        k_secam_decode<T><<<grid, 64 * (R + 1), bytes(R), st>>>(p, io);
+    }
+    cm_count_launch();
+    CUDA_TRY(cudaGetLastError());
+    return CM_OK;
+}
+
+template int secam_encode<float>(cm_modem *, IoArgs<float>, cudaStream_t);
+template int secam_encode<double>(cm_modem *, IoArgs<double>, cudaStream_t);
+template int secam_decode<float>(cm_modem *, IoArgs<float>, cudaStream_t);
+template int secam_decode<double>(cm_modem *, IoArgs<double>, cudaStream_t);

@@ -1,0 +1,332 @@
+// SECAM kernels.  Reference: color_modem/color/secam.py.
+//
+// Encode (secam.py:261-276, 240-246): line-sequential D'R / D'B -> low-pass -> optional LF pre-emphasis ->
+// instantaneous frequency (clipped) -> FM synthesis with the complex "bell" gain G(f) evaluated per sample and a
+// running phase  start - angle(G[0]) + sum_{i=1..j} pi f[i].  The running phase is accumulated in 0.64
+// fixed-point turns with an integer prefix sum over the line (per-lane chunk sums + warp-shuffle scan), so it
+// cannot drift: the centre frequency enters as an exact integer constant and only the deviation goes through
+// floating point.
+//
+// Decode (secam.py:278-304, 127-149): Bessel band-stop -> luma; flipped warm-up prefix + Chebyshev band-pass
+// (+ anti-bell) -> quadrature FM discriminator at 2x (mix to baseband, low-pass I and Q, wrapped phase
+// difference of consecutive analytic samples == diff(unwrap(angle)), down2) -> clip -> scale -> optional
+// de-emphasis; each output row pairs its own colour-difference signal with the one of the previous row of the
+// field (zeros at the top).  The previous row's signal is recomputed by the CTA as a halo row.
+#pragma once
+#include "cm_common.cuh"
+#include "cm_fir.cuh"
+#include "cm_iir.cuh"
+#include "cm_io.cuh"
+#include "cm_slots.h"
+
+template <typename T> struct Fix64;
+template <> struct Fix64<float> {
+    static __device__ __forceinline__ long long half_turns(float f) { return __float2ll_rn(f * 9.2233720368547758e18f); }
+};
+template <> struct Fix64<double> {
+    static __device__ __forceinline__ long long half_turns(double f) { return __double2ll_rn(f * 9.2233720368547758e18); }
+};
+
+// secam.py:248-256 — 625-line numbers are hard-coded in the reference regardless of the line standard
+template <typename T>
+__device__ __forceinline__ bool secam_phase_inverted(const DevParams<T> &p, long long frame, int line) {
+    const int fr = (int)(frame % 6);
+    const int half = line >> 1;                                   // floor, also for negative lines
+    const int lif = ((line & 1) == 0 ? 23 : 336) + half;
+    int seq = (fr * 625 + lif) % 6;
+    if (seq < 0) seq += 6;
+    const bool inv = (p.phases[SP_INVERSIONS] >> seq) & 1ull;
+    return inv ^ ((fr & 1) == 1);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Encode.  One warp per row.   smem: R * 2 * N1   (luma | selected chroma -> composite)
+// ------------------------------------------------------------------------------------------------------------
+template <typename T>
+__device__ __forceinline__ void secam_bell(T f, T f0, T inv_f0, T m0, T kn, T kd, T &re, T &im) {
+    // G = m0 (1 + j kn F) / (1 + j kd F),  F = f/f0 - f0/f      (secam.py:241-243)
+    const T F = f * inv_f0 - f0 / f;
+    const T g = m0 / ((T)1 + kd * kd * F * F);
+    re = g * ((T)1 + kn * kd * F * F);
+    im = g * (kn - kd) * F;
+}
+
+template <typename T, int L>
+__device__ __forceinline__ void secam_fm_row(const DevParams<T> &p, const T *__restrict__ chroma, T *__restrict__ luma,
+                                             int W, bool alt, bool inverted) {
+    const int lane = threadIdx.x & 31;
+    const T fsc = alt ? p.scalars[SS_FSC_DB] : p.scalars[SS_FSC_DR];
+    const T fdev = alt ? p.scalars[SS_FDEV_DB] : p.scalars[SS_FDEV_DR];
+    const T dlo = p.scalars[SS_F_LO] - fsc, dhi = p.scalars[SS_F_HI] - fsc;
+    const T f0 = p.scalars[SS_BELL_F0], inv_f0 = (T)1 / f0;
+    const T m0 = p.scalars[SS_M0], kn = p.scalars[SS_KN], kd = p.scalars[SS_KD];
+    const unsigned long long centre = alt ? p.phases[SP_FSC_DB_HALF] : p.phases[SP_FSC_DR_HALF];
+    // phase[j] = start - angle(G[0]) + sum_{i=1..j} pi f[i]   (secam.py:244-245), in 0.64 fixed-point turns
+    unsigned long long run = inverted ? 0x8000000000000000ull : 0ull;     // start phase: pi or 0 (secam.py:273)
+    {
+        T d0 = fdev * chroma[0];
+        d0 = d0 < dlo ? dlo : (d0 > dhi ? dhi : d0);
+        T re, im;
+        secam_bell(fsc + d0, f0, inv_f0, m0, kn, kd, re, im);
+        run -= (unsigned long long)Fix64<T>::half_turns(Real<T>::atan2_(im, re) * (T)0.31830988618379067154);
+    }
+    const int nsuper = (W + 32 * L - 1) / (32 * L);
+    for (int c = 0; c < nsuper; ++c) {
+        const int base = (c * 32 + lane) * L;
+        T d[L];
+        unsigned long long acc[L];
+        unsigned long long sum = 0;
+#pragma unroll
+        for (int i = 0; i < L; ++i) {
+            const int j = base + i;
+            T dev = fdev * chroma[j < W ? j : W - 1];
+            dev = dev < dlo ? dlo : (dev > dhi ? dhi : dev);
+            d[i] = dev;
+            // advance of sample j: pi*f rad = f half-turns; sample 0 contributes nothing
+            if (j > 0 && j < W) sum += centre + (unsigned long long)Fix64<T>::half_turns(dev);
+            acc[i] = sum;
+        }
+        unsigned long long incl = sum;                                    // inclusive scan of the lane totals
+#pragma unroll
+        for (int k = 0; k < 5; ++k) {
+            const unsigned long long v = __shfl_up_sync(0xffffffffu, incl, 1 << k);
+            if (lane >= (1 << k)) incl += v;
+        }
+        const unsigned long long before = run + incl - sum;
+#pragma unroll
+        for (int i = 0; i < L; ++i) {
+            const int j = base + i;
+            if (j < W) {
+                T re, im, s, co;
+                secam_bell(fsc + d[i], f0, inv_f0, m0, kn, kd, re, im);
+                Real<T>::sincos_turns(before + acc[i], s, co);
+                luma[j] += re * co - im * s;
+            }
+        }
+        run += __shfl_sync(0xffffffffu, incl, 31);
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(CM_NTHREADS)
+k_secam_encode(const __grid_constant__ DevParams<T> p, const __grid_constant__ IoArgs<T> io) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T *sm = reinterpret_cast<T *>(smem_raw);
+    RowGroup g;
+    if (!decode_group(io, g)) return;
+    const int W = p.W, N1 = p.n1p, W4 = W >> 2;
+    const int warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const bool avg = (p.flags & 2) != 0;
+    for (int k = 0; k < g.count; ++k) {
+        const int row = g.r0 + 2 * k;
+        const int nrow = (row + 2 < io.nrows) ? row + 2 : row;
+        const bool alt = is_alternate(p, g.frame, io.y0 + row);
+        const int ci = alt ? 6 : 3;                         // D'B (row 2 of the matrix) on alternate lines, else D'R
+        T *ys = sm + (size_t)k * 2 * N1, *cs = ys + N1;
+        for (int q = threadIdx.x; q < W4; q += blockDim.x) {
+            const int x = 4 * q;
+            T r[4], gg[4], b[4], y[4], c[4];
+            load_rgb4(io, ((size_t)g.fidx * io.nrows + row) * W + x, r, gg, b);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                y[i] = p.enc[0] * r[i] + p.enc[1] * gg[i] + p.enc[2] * b[i];
+                c[i] = p.enc[ci] * r[i] + p.enc[ci + 1] * gg[i] + p.enc[ci + 2] * b[i];
+            }
+            if (avg) {
+                load_rgb4(io, ((size_t)g.fidx * io.nrows + nrow) * W + x, r, gg, b);
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    c[i] = (T)0.5 * ((p.enc[ci] * r[i] + p.enc[ci + 1] * gg[i] + p.enc[ci + 2] * b[i]) + c[i]);
+            }
+            st4(ys + x, y);
+            st4(cs + x, c);
+        }
+    }
+    __syncthreads();
+    for (int k = 0; k < g.count; ++k) cta_fill_tail<T, 1>(sm + (size_t)k * 2 * N1 + N1, (size_t)N1, 1, N1, W, N1);
+    __syncthreads();
+    for (int k = warp; k < g.count; k += nwarps) {
+        T *ys = sm + (size_t)k * 2 * N1, *cs = ys + N1;
+        const int line = io.y0 + g.r0 + 2 * k;
+        const FiltHdr &f = p.filt[SF_PRE_LP];
+        warp_iir<T, 1>(p.tab + f.off, f, [&](int q, int, int) { return cs[q]; }, [&](int j, T v) { cs[j] = v; });
+        if (p.flags & 128) {
+            warp_fill_tail<T, 1>(cs, N1, W, N1);
+            const FiltHdr &fe = p.filt[SF_PRE_EMPH];
+            warp_iir<T, 1>(p.tab + fe.off, fe, [&](int q, int, int) { return cs[q]; }, [&](int j, T v) { cs[j] = v; });
+        }
+        __syncwarp();
+        secam_fm_row<T, 23>(p, cs, ys, W, is_alternate(p, g.frame, line), secam_phase_inverted(p, g.frame, line));
+    }
+    __syncthreads();
+    for (int k = 0; k < g.count; ++k) {
+        const int row = g.r0 + 2 * k;
+        const T *ys = sm + (size_t)k * 2 * N1;
+        for (int q = threadIdx.x; q < W4; q += blockDim.x) {
+            T o[4];
+            ld4(ys + 4 * q, o);
+            store_comp4(io, ((size_t)g.fidx * io.nrows + row) * p.Wc + 4 * q, o);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Decode.  smem: taps[128] + (R+1) rows x ( c[N1] | cc[N1] | U2[N2] | I2[N2] | Q2[N2] )
+//   c  : composite, then luma (band-stop in place)
+//   cc : warm-up prefix + composite -> band-passed chroma -> later the colour-difference signal X
+//   U2 : up2(chroma), later the instantaneous frequency at 2x
+// ------------------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(CM_NTHREADS)
+k_secam_decode(const __grid_constant__ DevParams<T> p, const __grid_constant__ IoArgs<T> io) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T *sm = reinterpret_cast<T *>(smem_raw);
+    RowGroup g;
+    if (!decode_group(io, g)) return;
+    const int W = p.W, N1 = p.n1p, hb = p.hb2, N2 = 2 * hb;
+    const int warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const int pre = W / 40 - 1;                 // samples of flipped warm-up (secam.py:283)
+    const int ncc = W + pre, ncc4 = (ncc + 3) & ~3, n2 = 2 * ncc;
+    T *taps = sm;
+    T *rows = sm + 128;
+    const size_t per_row = 2 * (size_t)N1 + 3 * (size_t)N2;
+    const bool has_prev0 = g.r0 >= 2;
+    const int k_lo = has_prev0 ? -1 : 0;
+    const int nin = g.count - k_lo;
+    const T *hup = taps + p.res[SR_UP2].off, *hdn = taps + p.res[SR_DOWN2].off;
+    auto rowp = [&](int k) { return rows + (size_t)(k - k_lo) * per_row; };
+    copy_taps(taps, p, 2);
+    for (int k = k_lo; k < g.count; ++k) load_comp_row(rowp(k), io, g.fidx, g.r0 + 2 * k, W);
+    __syncthreads();
+    for (int k = k_lo; k < g.count; ++k) {
+        const T *c = rowp(k);
+        T *cc = rowp(k) + N1;
+        for (int i = threadIdx.x; i < N1; i += blockDim.x) {
+            T v;
+            if (i < pre) v = c[pre - i];                     // flip(composite[1 : W/40])
+            else if (i < ncc) v = c[i - pre];
+            else v = c[W - 1];                               // replicated tail for the IIR
+            cc[i] = v;
+        }
+        if (k >= 0) {
+            T *cm = rowp(k);
+            for (int i = W + threadIdx.x; i < N1; i += blockDim.x) cm[i] = c[W - 1];
+        }
+    }
+    __syncthreads();
+    // IIR phase 1: luma band-stop (rows k >= 0, in place) and chroma band-pass (+ anti-bell) on cc (all rows)
+    for (int t = warp; t < g.count + nin; t += nwarps) {
+        if (t < g.count) {
+            T *c = rowp(t);
+            const FiltHdr &f = p.filt[SF_LUMA_BS];
+            warp_iir<T, 1>(p.tab + f.off, f, [&](int q, int, int) { return c[q]; }, [&](int j, T v) { c[j] = v; });
+        } else {
+            T *cc = rowp(k_lo + (t - g.count)) + N1;
+            const FiltHdr &f = p.filt[SF_CHROMA_BP];
+            warp_iir<T, 1>(p.tab + f.off, f, [&](int q, int, int) { return cc[q]; }, [&](int j, T v) { cc[j] = v; });
+            if (p.flags & 64) {
+                warp_fill_tail<T, 1>(cc, N1, ncc, N1);
+                const FiltHdr &fb = p.filt[SF_ANTI_BELL];
+                warp_iir<T, 1>(p.tab + fb.off, fb, [&](int q, int, int) { return cc[q]; },
+                               [&](int j, T v) { cc[j] = v; });
+            }
+            __syncwarp();
+            for (int i = ncc + (threadIdx.x & 31); i < ncc4; i += 32) cc[i] = (T)0;   // zero pad for the resampler
+        }
+    }
+    __syncthreads();
+    for (int k = k_lo; k < g.count; ++k) {
+        T *u2 = rowp(k) + 2 * N1;
+        fir_up2(u2, u2 + hb, rowp(k) + N1, ncc4, hup, threadIdx.x, blockDim.x);
+    }
+    __syncthreads();
+    cta_fill_tail<T, 2>(rows + 2 * N1, per_row, nin, hb, n2, N2);
+    __syncthreads();
+    // IIR phase 2: mix to baseband and low-pass: I = LP(x cos), Q = LP(x sin)        secam.py:137-142
+    const FiltHdr &flp = p.filt[SF_FM_LP];
+    for (int t = warp; t < 2 * nin; t += nwarps) {
+        T *r = rows + (size_t)(t >> 1) * per_row;
+        const T *ue = r + 2 * N1, *uo = ue + hb;
+        T *de = r + 2 * N1 + ((t & 1) ? 2 : 1) * (size_t)N2, *dod = de + hb;
+        Carrier<T> car((t & 1) ? 0ull : CM_QUARTER_TURN, p.phases[SP_FM_STEP2X], n2);   // I: cos, Q: sin
+        warp_iir<T, 2>(p.tab + flp.off, flp,
+                       [&](int q, int ph, int i) {
+                           car.at(2 * q + ph, i == 0);
+                           return car.s * (ph ? uo : ue)[q];
+                       },
+                       [&](int j, T v) { ((j & 1) ? dod : de)[j >> 1] = v; });
+    }
+    __syncthreads();
+    // discriminator: wrapped phase step of z = I - jQ between consecutive 2x samples, first step 0 (secam.py:143-148)
+    const T fc = p.scalars[SS_FM_FC];
+    for (int k = k_lo; k < g.count; ++k) {
+        T *r = rowp(k);
+        const T *ie = r + 2 * N1 + N2, *io_ = ie + hb, *qe = r + 2 * N1 + 2 * (size_t)N2, *qo = qe + hb;
+        T *fe = r + 2 * N1, *fo = fe + hb;
+        for (int m = threadIdx.x; m < ncc4; m += blockDim.x) {
+            T f_even = (T)0, f_odd = (T)0;
+            if (m < ncc) {
+                const T i0 = ie[m], q0 = qe[m], i1 = io_[m], q1 = qo[m];
+                // sample 2m+1 vs 2m
+                f_odd = fc + (T)0.63661977236758134308 *
+                                 Real<T>::atan2_(i1 * q0 - q1 * i0, i1 * i0 + q1 * q0);
+                if (m > 0) {
+                    const T ip = io_[m - 1], qp = qo[m - 1];
+                    f_even = fc + (T)0.63661977236758134308 *
+                                      Real<T>::atan2_(i0 * qp - q0 * ip, i0 * ip + q0 * qp);
+                } else {
+                    f_even = fc;
+                }
+            }
+            fe[m] = f_even;
+            fo[m] = f_odd;
+        }
+    }
+    __syncthreads();
+    // down2, keep the last W samples, clip, scale to the colour-difference signal -> X in the cc buffer
+    for (int k = k_lo; k < g.count; ++k) {
+        T *r = rowp(k);
+        T *x = r + N1;
+        const bool alt = is_alternate(p, g.frame, io.y0 + g.r0 + 2 * k);
+        const T fsc = alt ? p.scalars[SS_FSC_DB] : p.scalars[SS_FSC_DR];
+        const T inv_dev = (T)1 / (alt ? p.scalars[SS_FDEV_DB] : p.scalars[SS_FDEV_DR]);
+        const T lo = p.scalars[SS_F_LO], hi = p.scalars[SS_F_HI];
+        fir_down2(r + 2 * N1, r + 2 * N1 + hb, ncc4, hdn, threadIdx.x, blockDim.x, [&](int j0, const T *y) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int j = j0 + i - pre;
+                if (j >= 0 && j < W) {
+                    T f = y[i];
+                    f = f < lo ? lo : (f > hi ? hi : f);
+                    x[j] = (f - fsc) * inv_dev;                // cc buffer is dead after the up2
+                }
+            }
+        });
+    }
+    __syncthreads();
+    cta_fill_tail<T, 1>(rows + N1, per_row, nin, N1, W, N1);
+    __syncthreads();
+    if (p.flags & 128) {
+        const FiltHdr &fd = p.filt[SF_DE_EMPH];
+        for (int t = warp; t < nin; t += nwarps) {
+            T *x = rows + (size_t)t * per_row + N1;
+            warp_iir<T, 1>(p.tab + fd.off, fd, [&](int q, int, int) { return x[q]; }, [&](int j, T v) { x[j] = v; });
+        }
+        __syncthreads();
+    }
+    for (int k = 0; k < g.count; ++k) {
+        const int row = g.r0 + 2 * k;
+        const bool alt = is_alternate(p, g.frame, io.y0 + row);
+        const bool hp = (k > 0) || has_prev0;
+        const T *luma = rowp(k), *xc = rowp(k) + N1, *xp = hp ? rowp(k - 1) + N1 : nullptr;
+        for (int q = threadIdx.x; q < (W >> 2); q += blockDim.x) {
+            T y[4], a[4], b[4] = {(T)0, (T)0, (T)0, (T)0};
+            ld4(luma + 4 * q, y);
+            ld4(xc + 4 * q, a);
+            if (hp) ld4(xp + 4 * q, b);
+            // secam.py:297-300: non-alternate rows carry D'R (dr = current, db = previous), alternate rows D'B
+            if (alt) store_rgb4(p, io, g.fidx, row, 4 * q, y, b, a);
+            else store_rgb4(p, io, g.fidx, row, 4 * q, y, a, b);
+        }
+    }
+}

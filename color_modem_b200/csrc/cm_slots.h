@@ -22,4 +22,31 @@
 #define QS_P3D_COSU 4    /* -0.5 / (1 - cos(LS))                              pal.py:171-173 */
 #define QS_P3D_COSV 5    /* -0.5 / (1 + cos(LS))                                             */
 
+
+/* ---- SECAM (secam.py) */
+#define SF_PRE_LP 0      /* _chroma_precorrect_lowpass   secam.py:171   rate 1, n = W            */
+#define SF_PRE_EMPH 1    /* _chroma_precorrect           secam.py:176   rate 1, n = W  (optional) */
+#define SF_LUMA_BS 2     /* _chroma_demod_luma_filter    secam.py:185   rate 1, n = W            */
+#define SF_CHROMA_BP 3   /* _chroma_demod_chroma_filter  secam.py:183   rate 1, n = W + W/40 - 1 */
+#define SF_ANTI_BELL 4   /* _chroma_demod_bell           secam.py:169   rate 1, same n (optional) */
+#define SF_FM_LP 5       /* FmDecoder._lowpass           secam.py:131   rate 2, n = 2 (W + W/40 - 1) */
+#define SF_DE_EMPH 6     /* _reverse_chroma_precorrect   secam.py:176   rate 1, n = W  (optional) */
+#define SR_UP2 0
+#define SR_DOWN2 1
+#define SP_FM_STEP2X 0   /* FmDecoder mixing phase per 2x sample: fc/4 turns (secam.py:137) */
+#define SP_FSC_DR_HALF 1 /* pi*fsc_dr per sample = fsc_dr/2 turns (secam.py:244) */
+#define SP_FSC_DB_HALF 2
+#define SP_INVERSIONS 3  /* bit i = _start_phase_inversions[i] (secam.py:163-166) -- raw integer */
+#define SS_FSC_DR 0      /* normalised (Nyquist = 1) frequencies, secam.py:156-162 */
+#define SS_FSC_DB 1
+#define SS_FDEV_DR 2
+#define SS_FDEV_DB 3
+#define SS_F_LO 4
+#define SS_F_HI 5
+#define SS_BELL_F0 6
+#define SS_M0 7
+#define SS_KN 8
+#define SS_KD 9
+#define SS_FM_FC 10      /* FmDecoder centre frequency (secam.py:179,187) */
+
 #endif

@@ -1,11 +1,11 @@
 """Build the product (color_modem_b200) modem composition for a test Case — mirrors tests/refload.make_modem."""
 from color_modem_b200.line import LineConfig, LineStandard
 
-BUILT_KINDS = {'ntsc', 'ntsc_comb', 'ntsc_3d', 'pal_s', 'pal_d', 'pal_3d'}
+BUILT_KINDS = {'ntsc', 'ntsc_comb', 'ntsc_3d', 'pal_s', 'pal_d', 'pal_3d', 'secam'}
 
 
 def make_modem(c, precision='fp32'):
-    from color_modem_b200.color import ntsc, pal
+    from color_modem_b200.color import ntsc, pal, secam
     from color_modem_b200 import comb
     std = getattr(LineStandard, c.standard) if c.standard else None
     lc = LineConfig((c.width, c.height), std)
@@ -18,6 +18,8 @@ def make_modem(c, precision='fp32'):
         m = comb.Simple3DCombModem(ntsc.NtscCombModem(lc, getattr(ntsc.NtscVariant, v), precision=precision))
     elif k == 'pal_3d':
         m = pal.Pal3DModem(lc, getattr(pal.PalVariant, v), precision=precision)
+    elif k == 'secam':
+        m = secam.SecamModem(lc, getattr(secam.SecamVariant, v), precision=precision)
     elif k == 'pal_s':
         m = pal.PalSModem(lc, getattr(pal.PalVariant, v), precision=precision)
     elif k == 'pal_d':
