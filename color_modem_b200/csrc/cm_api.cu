@@ -158,6 +158,9 @@ extern "C" int cm_create(const cm_desc *desc, int precision, cm_modem **out) {
         case CM_KIND_PAL_D:
         case CM_KIND_PAL_3D:
         case CM_KIND_SECAM:
+        case CM_KIND_NIIR:
+        case CM_KIND_PROTOSECAM:
+        case CM_KIND_MAC:
             break;
         default:
             return fail(CM_ERR_UNSUPPORTED, "modem kind not built%s");
@@ -268,6 +271,12 @@ static int dispatch_encode(cm_modem *m, IoArgs<T> io, cudaStream_t st) {
             return qam_encode<T>(m, io, st);
         case CM_KIND_SECAM:
             return secam_encode<T>(m, io, st);
+        case CM_KIND_NIIR:
+            return niir_encode<T>(m, io, st);
+        case CM_KIND_PROTOSECAM:
+            return proto_encode<T>(m, io, st);
+        case CM_KIND_MAC:
+            return mac_encode<T>(m, io, st);
         default:
             return fail(CM_ERR_UNSUPPORTED, "encode: modem kind not built%s");
     }
@@ -287,6 +296,12 @@ static int dispatch_decode(cm_modem *m, IoArgs<T> io, int mode, cudaStream_t st)
             return qam_decode<T>(m, io, mode, st);
         case CM_KIND_SECAM:
             return secam_decode<T>(m, io, st);
+        case CM_KIND_NIIR:
+            return niir_decode<T>(m, io, st);
+        case CM_KIND_PROTOSECAM:
+            return proto_decode<T>(m, io, st);
+        case CM_KIND_MAC:
+            return mac_decode<T>(m, io, st);
         default:
             return fail(CM_ERR_UNSUPPORTED, "decode: modem kind not built%s");
     }

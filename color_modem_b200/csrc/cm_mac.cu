@@ -1,0 +1,59 @@
+// Launchers of the D2-MAC family: kernels in cm_mac.cuh.
+#include "cm_host.h"
+#include "cm_mac.cuh"
+
+static int mac_taps_len(const cm_modem *m) {
+    int total = 0;
+    for (int r = 0; r < m->desc.nresamplers; ++r) total += m->desc.resamplers[r].ntaps;
+    return (total + 3) & ~3;
+}
+
+template <typename T>
+int mac_encode(cm_modem *m, IoArgs<T> io, cudaStream_t st) {
+    const DevParams<T> &p = params_of<T>(m);
+    if (io.out_count <= 0) return CM_OK;
+    if (p.Wc > 1080) return cm_fail(CM_ERR_UNSUPPORTED, "MAC widths above 1080 are not built%s");
+    const int tl = mac_taps_len(m);
+    auto bytes = [&](int r) { return ((size_t)tl + (size_t)r * (2 * (size_t)p.W + 720 + 360 + 1080)) * sizeof(T); };
+    int R = pick_rows(4, (size_t)m->smem_optin / 2, bytes);
+    if (!R) return cm_fail(CM_ERR_UNSUPPORTED, "line too wide for the MAC encode kernel%s");
+    set_groups(io, R);
+    int rc = set_smem(k_mac_encode<T>, bytes(R));
+    if (rc) return rc;
+    dim3 grid((unsigned)(io.nframes * 2 * io.groups_per_field));
+    {
+        LaunchTimer lt(m, CM_K_ENCODE, st);
+        k_mac_encode<T><<<grid, CM_NTHREADS, bytes(R), st>>>(p, io, tl);
+    }
+    cm_count_launch();
+    CUDA_TRY(cudaGetLastError());
+    return CM_OK;
+}
+
+template <typename T>
+int mac_decode(cm_modem *m, IoArgs<T> io, cudaStream_t st) {
+    const DevParams<T> &p = params_of<T>(m);
+    if (io.out_count <= 0) return CM_OK;
+    const int tl = mac_taps_len(m);
+    auto bytes = [&](int r) {
+        return ((size_t)tl + (size_t)(r + 1) * ((size_t)p.Wc + 1080 + 720 + 360 + 720)) * sizeof(T);
+    };
+    int R = pick_rows(4, (size_t)m->smem_optin / 2, bytes);
+    if (!R) return cm_fail(CM_ERR_UNSUPPORTED, "line too wide for the MAC decode kernel%s");
+    set_groups(io, R);
+    int rc = set_smem(k_mac_decode<T>, bytes(R));
+    if (rc) return rc;
+    dim3 grid((unsigned)(io.nframes * 2 * io.groups_per_field));
+    {
+        LaunchTimer lt(m, CM_K_DECODE_OTHER, st);
+        k_mac_decode<T><<<grid, CM_NTHREADS, bytes(R), st>>>(p, io, tl);
+    }
+    cm_count_launch();
+    CUDA_TRY(cudaGetLastError());
+    return CM_OK;
+}
+
+template int mac_encode<float>(cm_modem *, IoArgs<float>, cudaStream_t);
+template int mac_encode<double>(cm_modem *, IoArgs<double>, cudaStream_t);
+template int mac_decode<float>(cm_modem *, IoArgs<float>, cudaStream_t);
+template int mac_decode<double>(cm_modem *, IoArgs<double>, cudaStream_t);

@@ -1,0 +1,190 @@
+// D2-MAC kernels (time-compressed chroma + luma multiplex).  Reference: color_modem/color/mac.py.
+// Pure resampling and assembly: no IIR, no carrier.  Lines are resampled with the general polyphase FIR
+// (ratios 720/W, 360/W, width/1080, 1080/width; e.g. 3/8 -> 161 taps, 3/16 -> 321 taps, 2/3, 3/2).
+#pragma once
+#include "cm_common.cuh"
+#include "cm_fir.cuh"
+#include "cm_io.cuh"
+#include "cm_slots.h"
+
+// dst[0..n_out) = resample(src[0..n_in)) with resampler slot r (identity when the ratio is 1)
+template <typename T>
+__device__ __forceinline__ void mac_fit(const DevParams<T> &p, const T *taps, int r, const T *src, int n_in, T *dst,
+                                        int n_out, T add) {
+    const ResHdr rh = p.res[r];
+    if (rh.ntaps == 0) {
+        for (int j = threadIdx.x; j < n_out; j += blockDim.x) dst[j] = src[j] + add;
+    } else {
+        fir_general(src, n_in, n_out, rh, taps + rh.off, threadIdx.x, blockDim.x, [&](int j, T v) { dst[j] = v + add; });
+    }
+}
+
+// Encode.  smem: taps + R * ( luma[W] | chroma[W] | luma720 | ch360 | line1080 )
+template <typename T>
+__global__ void __launch_bounds__(CM_NTHREADS)
+k_mac_encode(const __grid_constant__ DevParams<T> p, const __grid_constant__ IoArgs<T> io, int taps_len) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T *sm = reinterpret_cast<T *>(smem_raw);
+    RowGroup g;
+    if (!decode_group(io, g)) return;
+    const int W = p.W, W4 = W >> 2, Wc = p.Wc;
+    const bool avg = (p.flags & 2) != 0;
+    T *taps = sm;
+    T *rows = sm + taps_len;
+    const size_t per_row = 2 * (size_t)W + 720 + 360 + 1080;
+    for (int i = threadIdx.x; i < taps_len; i += blockDim.x) taps[i] = p.taps[i];
+    for (int k = 0; k < g.count; ++k) {
+        const int row = g.r0 + 2 * k;
+        const int nrow = (row + 2 < io.nrows) ? row + 2 : row;
+        const int ci = is_alternate(p, g.frame, io.y0 + row) ? 6 : 3;      // D'B on alternate lines, else D'R
+        T *ys = rows + k * per_row, *cs = ys + W;
+        for (int q = threadIdx.x; q < W4; q += blockDim.x) {
+            const int x = 4 * q;
+            T r[4], gg[4], b[4], y[4], c[4];
+            load_rgb4(io, ((size_t)g.fidx * io.nrows + row) * W + x, r, gg, b);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                y[i] = p.enc[0] * r[i] + p.enc[1] * gg[i] + p.enc[2] * b[i];
+                c[i] = p.enc[ci] * r[i] + p.enc[ci + 1] * gg[i] + p.enc[ci + 2] * b[i];
+            }
+            if (avg) {
+                load_rgb4(io, ((size_t)g.fidx * io.nrows + nrow) * W + x, r, gg, b);
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    c[i] = (T)0.5 * ((p.enc[ci] * r[i] + p.enc[ci + 1] * gg[i] + p.enc[ci + 2] * b[i]) + c[i]);
+            }
+            st4(ys + x, y);
+            st4(cs + x, c);
+        }
+    }
+    __syncthreads();
+    for (int k = 0; k < g.count; ++k) {
+        T *ys = rows + k * per_row, *cs = ys + W, *l720 = cs + W, *c360 = l720 + 720;
+        mac_fit(p, taps, MR_LUMA_IN, ys, W, l720, 720, (T)0);
+        mac_fit(p, taps, MR_CHROMA_IN, cs, W, c360, 360, (T)0.5);          // mac.py:57 chroma += 0.5
+    }
+    __syncthreads();
+    for (int k = 0; k < g.count; ++k) {                                    // mac.py:58-69
+        const T *l = rows + k * per_row + 2 * W, *c = l + 720;
+        T *o = rows + k * per_row + 2 * W + 1080;
+        for (int i = threadIdx.x; i < 1080; i += blockDim.x) {
+            T v = (T)0.5;
+            if (i == 15) v = (T)0.4375 + (T)0.125 * c[2];
+            else if (i == 16) v = (T)0.25 + (T)0.5 * c[3];
+            else if (i == 17) v = (T)0.0625 + (T)0.875 * c[4];
+            else if (i >= 18 && i < 369) v = c[i - 13];
+            else if (i == 369) v = (T)0.875 * c[356] + (T)0.125 * l[8];
+            else if (i == 370) v = (T)0.5 * c[357] + (T)0.5 * l[9];
+            else if (i == 371) v = (T)0.125 * c[358] + (T)0.875 * l[10];
+            else if (i >= 372 && i < 1071) v = l[i - 361];
+            else if (i == 1071) v = (T)0.0625 + (T)0.875 * l[710];
+            else if (i == 1072) v = (T)0.25 + (T)0.5 * l[711];
+            else if (i == 1073) v = (T)0.4375 + (T)0.125 * l[712];
+            o[i] = v;
+        }
+    }
+    __syncthreads();
+    for (int k = 0; k < g.count; ++k) {
+        const T *o = rows + k * per_row + 2 * W + 1080;
+        T *dst = rows + k * per_row;                                      // luma / chroma rows are dead: Wc <= 2W? use luma720 area
+        (void)dst;
+        T *outrow = rows + k * per_row + 2 * W;                           // luma720|ch360 region (1080 elements) reused
+        mac_fit(p, taps, MR_OUT, o, 1080, outrow, Wc, (T)0);
+    }
+    __syncthreads();
+    for (int k = 0; k < g.count; ++k) {
+        const int row = g.r0 + 2 * k;
+        const T *outrow = rows + k * per_row + 2 * W;
+        for (int q = threadIdx.x; q < (Wc >> 2); q += blockDim.x) {
+            T o[4];
+            ld4(outrow + 4 * q, o);
+            store_comp4(io, ((size_t)g.fidx * io.nrows + row) * Wc + 4 * q, o);
+        }
+    }
+}
+
+// Decode.  smem: taps + (R+1) rows x ( comp[Wc4] | c1080 | luma720 | ch360 | XE[360] | XO[360] )
+template <typename T>
+__global__ void __launch_bounds__(CM_NTHREADS)
+k_mac_decode(const __grid_constant__ DevParams<T> p, const __grid_constant__ IoArgs<T> io, int taps_len) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T *sm = reinterpret_cast<T *>(smem_raw);
+    RowGroup g;
+    if (!decode_group(io, g)) return;
+    const int Wc = p.Wc;
+    T *taps = sm;
+    T *rows = sm + taps_len;
+    const size_t per_row = (size_t)Wc + 1080 + 720 + 360 + 720;
+    const bool has_prev0 = g.r0 >= 2;
+    const int k_lo = has_prev0 ? -1 : 0;
+    auto rowp = [&](int k) { return rows + (size_t)(k - k_lo) * per_row; };
+    for (int i = threadIdx.x; i < taps_len; i += blockDim.x) taps[i] = p.taps[i];
+    for (int k = k_lo; k < g.count; ++k) load_comp_row(rowp(k), io, g.fidx, g.r0 + 2 * k, Wc);
+    __syncthreads();
+    for (int k = k_lo; k < g.count; ++k) mac_fit(p, taps, MR_COMP_IN, rowp(k), Wc, rowp(k) + Wc, 1080, (T)0);
+    __syncthreads();
+    for (int k = k_lo; k < g.count; ++k) {                                 // mac.py:86-109
+        const T *c = rowp(k) + Wc;
+        T *l = rowp(k) + Wc + 1080, *ch = l + 720;
+        for (int i = threadIdx.x; i < 720 + 360; i += blockDim.x) {
+            if (i < 720) {
+                const T ch355 = c[368];                                     // chroma[355] = composite[368]
+                const T l8 = (T)8 * c[369] - (T)7 * ch355;
+                const T l712 = (T)8 * c[1073] - (T)3.5;
+                T v;
+                if (i < 8) v = l8;
+                else if (i == 8) v = l8;
+                else if (i == 9) v = (T)2 * c[370] - ch355;
+                else if (i == 10) v = (c[371] - (T)0.125 * ch355) / (T)0.875;
+                else if (i < 710) v = c[i + 361];
+                else if (i == 710) v = (c[1071] - (T)0.0625) / (T)0.875;
+                else if (i == 711) v = (T)2 * c[1072] - (T)0.5;
+                else v = l712;
+                l[i] = v;
+            } else {
+                const int m = i - 720;
+                const T l11 = c[372];                                       // luma[11] = composite[372]
+                const T c2 = (T)8 * c[15] - (T)3.5;
+                const T c358 = (T)8 * c[371] - (T)7 * l11;
+                T v;
+                if (m == 0) v = c2;
+                else if (m == 1) v = (T)0.5;                                // mac.py:105 writes element 0 only
+                else if (m == 2) v = c2;
+                else if (m == 3) v = (T)2 * c[16] - (T)0.5;
+                else if (m == 4) v = (c[17] - (T)0.0625) / (T)0.875;
+                else if (m < 356) v = c[m + 13];
+                else if (m == 356) v = (c[369] - (T)0.125 * l11) / (T)0.875;
+                else if (m == 357) v = (T)2 * c[370] - l11;
+                else v = c358;                                              // 358 and 359
+                ch[m] = v;
+            }
+        }
+    }
+    __syncthreads();
+    const T *hup = taps + p.res[MR_UP2].off;
+    for (int k = k_lo; k < g.count; ++k) {
+        T *ch = rowp(k) + Wc + 1080 + 720, *xe = ch + 360, *xo = xe + 360;
+        fir_up2(xe, xo, ch, 360, hup, threadIdx.x, blockDim.x);
+    }
+    __syncthreads();
+    for (int k = 0; k < g.count; ++k) {
+        const int row = g.r0 + 2 * k;
+        const bool alt = is_alternate(p, g.frame, io.y0 + row);
+        const bool hp = (k > 0) || has_prev0;
+        const T *l = rowp(k) + Wc + 1080, *xe = l + 720 + 360, *xo = xe + 360;
+        const T *pe = hp ? rowp(k - 1) + Wc + 1080 + 720 + 360 : nullptr, *po = hp ? pe + 360 : nullptr;
+        for (int q = threadIdx.x; q < 180; q += blockDim.x) {
+            T y[4], a[4], b[4];
+            ld4(l + 4 * q, y);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int x = 4 * q + i, m = x >> 1;
+                a[i] = ((x & 1) ? xo[m] : xe[m]) - (T)0.5;                   // mac.py:111
+                b[i] = hp ? ((x & 1) ? po[m] : pe[m]) - (T)0.5 : (T)0;
+            }
+            // mac.py:113-118: non-alternate rows carry D'R (dr = current, db = previous)
+            if (alt) store_rgb4(p, io, g.fidx, row, 4 * q, y, b, a);
+            else store_rgb4(p, io, g.fidx, row, 4 * q, y, a, b);
+        }
+    }
+}

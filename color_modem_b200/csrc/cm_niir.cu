@@ -1,0 +1,62 @@
+// Launchers of the 3x-oversampled AM families: NIIR / SECAM-IV (cm_niir.cuh) and 819-line proto-SECAM (cm_proto.cuh).
+#include "cm_host.h"
+#include "cm_niir.cuh"
+#include "cm_proto.cuh"
+
+template <typename T, class K, class F>
+static int launch_rows(cm_modem *m, IoArgs<T> io, cudaStream_t st, K kernel, F bytes, int rmax, int warps_per_row,
+                       int extra_rows, int timer_id, const char *what) {
+    if (io.out_count <= 0) return CM_OK;
+    int R = pick_rows(rmax, (size_t)m->smem_optin / 2, bytes);
+    if (!R) R = pick_rows(1, (size_t)m->smem_optin, bytes);
+    if (!R) return cm_fail(CM_ERR_UNSUPPORTED, "line too wide for the %s kernel", what);
+    set_groups(io, R);
+    int rc = set_smem(kernel, bytes(R));
+    if (rc) return rc;
+    dim3 grid((unsigned)(io.nframes * 2 * io.groups_per_field));
+    int threads = 32 * warps_per_row * (R + extra_rows);
+    if (threads > CM_NTHREADS) threads = CM_NTHREADS;
+    {
+        LaunchTimer lt(m, timer_id, st);
+        kernel<<<grid, threads, bytes(R), st>>>(params_of<T>(m), io);
+    }
+    cm_count_launch();
+    CUDA_TRY(cudaGetLastError());
+    return CM_OK;
+}
+
+template <typename T>
+int niir_encode(cm_modem *m, IoArgs<T> io, cudaStream_t st) {
+    const DevParams<T> &p = params_of<T>(m);
+    auto bytes = [&](int r) { return (size_t)r * 3 * p.n1p * sizeof(T); };
+    return launch_rows<T>(m, io, st, k_niir_encode<T>, bytes, 4, 2, 0, CM_K_ENCODE, "NIIR encode");
+}
+
+template <typename T>
+int niir_decode(cm_modem *m, IoArgs<T> io, cudaStream_t st) {
+    const DevParams<T> &p = params_of<T>(m);
+    auto bytes = [&](int r) { return (128 + (size_t)(r + 1) * (p.n1p + 9 * (size_t)p.hb3)) * sizeof(T); };
+    return launch_rows<T>(m, io, st, k_niir_decode<T>, bytes, 3, 2, 1, CM_K_DECODE_OTHER, "NIIR decode");
+}
+
+template <typename T>
+int proto_encode(cm_modem *m, IoArgs<T> io, cudaStream_t st) {
+    const DevParams<T> &p = params_of<T>(m);
+    auto bytes = [&](int r) { return (128 + (size_t)r * (2 * (size_t)p.n1p + 3 * (size_t)p.hb3)) * sizeof(T); };
+    return launch_rows<T>(m, io, st, k_proto_encode<T>, bytes, 4, 2, 0, CM_K_ENCODE, "proto-SECAM encode");
+}
+
+template <typename T>
+int proto_decode(cm_modem *m, IoArgs<T> io, cudaStream_t st) {
+    const DevParams<T> &p = params_of<T>(m);
+    auto bytes = [&](int r) { return (128 + (size_t)(r + 1) * (p.n1p + 9 * (size_t)p.hb3)) * sizeof(T); };
+    return launch_rows<T>(m, io, st, k_proto_decode<T>, bytes, 3, 2, 1, CM_K_DECODE_OTHER, "proto-SECAM decode");
+}
+
+#define CM_INST(fn)                                                      \
+    template int fn<float>(cm_modem *, IoArgs<float>, cudaStream_t);     \
+    template int fn<double>(cm_modem *, IoArgs<double>, cudaStream_t);
+CM_INST(niir_encode)
+CM_INST(niir_decode)
+CM_INST(proto_encode)
+CM_INST(proto_decode)

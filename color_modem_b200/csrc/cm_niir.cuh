@@ -1,0 +1,274 @@
+// NIIR / SECAM-IV kernels.  Reference: color_modem/color/niir.py.
+//
+// Encode (niir.py:40-48, 67-88, 166-202): chroma vector gets a +0.1 saturation offset in polar form (or, for the
+// hue-correcting encoder, the saturation-weighted hue of this row and the next row of the field with this row's
+// saturation), both components are low-passed, then normal rows carry db sin + dr cos (QAM) and alternate rows
+// the reference carrier -|c| sin.
+//
+// Decode (niir.py:102-163) at 3x: band-pass, envelope (pi/2 |x| -> low-pass) = saturation, x / saturation =
+// phase-modulated carrier; each row is demodulated against the carrier of its neighbour row of the field (the
+// previous row; a synthetic carrier at the field top): products with the carrier and with its derivative give
+// sin/cos of the hue after down3, normalisation and rotation by +-line_shift; luma = composite - re-synthesised
+// chroma; the saturation offset is removed last.  3x buffers are stored naturally (odd chunk lengths keep the
+// IIR loads conflict-free, and stride-3 FIR accesses are conflict-free by themselves).
+#pragma once
+#include "cm_common.cuh"
+#include "cm_fir.cuh"
+#include "cm_iir.cuh"
+#include "cm_io.cuh"
+#include "cm_slots.h"
+
+// out[j] = sum_d h[30 - d] in(3j + d), d in [-30, 30] skipping the zero taps, zero outside [0, n3)
+template <typename T, class In>
+__device__ __forceinline__ T down3_at(const T *__restrict__ h, int j, int n3, In in) {
+    const int ctr = 3 * j;
+    T acc = h[30] * in(ctr);
+#pragma unroll 4
+    for (int d = -29; d <= 29; ++d) {
+        if (d % 3 == 0) continue;
+        const int i = ctr + d;
+        if (i >= 0 && i < n3) acc = Real<T>::fma_(h[30 - d], in(i), acc);
+    }
+    return acc;
+}
+
+// x[0..n) natural -> out[0..3n) natural                               h: 61 dense taps
+template <typename T>
+__device__ __forceinline__ void up3_natural(T *__restrict__ out, const T *__restrict__ x, int n, const T *__restrict__ h,
+                                            int tid, int nthr) {
+    const T c0 = h[30];
+    for (int m = tid; m < n; m += nthr) {
+        T a1 = (T)0, a2 = (T)0;
+#pragma unroll
+        for (int k = 0; k < 20; ++k) {
+            const int i = m - 9 + k;
+            const T v = (i >= 0 && i < n) ? x[i] : (T)0;
+            a1 = Real<T>::fma_(h[58 - 3 * k], v, a1);
+            a2 = Real<T>::fma_(h[59 - 3 * k], v, a2);
+        }
+        out[3 * m] = c0 * x[m];
+        out[3 * m + 1] = a1;
+        out[3 * m + 2] = a2;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Encode.  2 warps per row.  smem: R * 3 * N1   (luma | db | dr)
+// ------------------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(CM_NTHREADS)
+k_niir_encode(const __grid_constant__ DevParams<T> p, const __grid_constant__ IoArgs<T> io) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T *sm = reinterpret_cast<T *>(smem_raw);
+    RowGroup g;
+    if (!decode_group(io, g)) return;
+    const int W = p.W, N1 = p.n1p, W4 = W >> 2;
+    const int warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const bool avg = (p.flags & 2) != 0, hue = (p.flags & 4) != 0;
+    for (int k = 0; k < g.count; ++k) {
+        const int row = g.r0 + 2 * k;
+        const int nrow = (row + 2 < io.nrows) ? row + 2 : row;
+        T *ys = sm + (size_t)k * 3 * N1, *bs = ys + N1, *rs_ = bs + N1;
+        for (int q = threadIdx.x; q < W4; q += blockDim.x) {
+            const int x = 4 * q;
+            T r[4], gg[4], b[4], y[4], db[4], dr[4];
+            load_rgb4(io, ((size_t)g.fidx * io.nrows + row) * W + x, r, gg, b);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                y[i] = p.enc[0] * r[i] + p.enc[1] * gg[i] + p.enc[2] * b[i];
+                db[i] = p.enc[3] * r[i] + p.enc[4] * gg[i] + p.enc[5] * b[i];
+                dr[i] = p.enc[6] * r[i] + p.enc[7] * gg[i] + p.enc[8] * b[i];
+            }
+            if (avg || hue) load_rgb4(io, ((size_t)g.fidx * io.nrows + nrow) * W + x, r, gg, b);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                T mag_out, vb = db[i], vr = dr[i];
+                if (hue) {
+                    // niir.py:186-197: hue of the saturation-weighted mean of this row and the next, this row's saturation
+                    const T nb = p.enc[3] * r[i] + p.enc[4] * gg[i] + p.enc[5] * b[i];
+                    const T nr = p.enc[6] * r[i] + p.enc[7] * gg[i] + p.enc[8] * b[i];
+                    const T ls = Real<T>::sqrt_(vb * vb + vr * vr), s = Real<T>::sqrt_(nb * nb + nr * nr);
+                    T div = ls + s;
+                    if (div == (T)0) div = (T)1;
+                    const T ab = (vb * ls + nb * s) / div, ar = (vr * ls + nr * s) / div;
+                    mag_out = ls + (T)0.1;
+                    vb = ab;
+                    vr = ar;
+                } else {
+                    if (avg) {
+                        const T nb = p.enc[3] * r[i] + p.enc[4] * gg[i] + p.enc[5] * b[i];
+                        const T nr = p.enc[6] * r[i] + p.enc[7] * gg[i] + p.enc[8] * b[i];
+                        vb = (T)0.5 * (nb + vb);
+                        vr = (T)0.5 * (nr + vr);
+                    }
+                    mag_out = Real<T>::sqrt_(vb * vb + vr * vr) + (T)0.1;      // niir.py:43
+                }
+                // mag_out * (sin, cos)(atan2(vb, vr));  atan2(0, 0) = 0 -> (0, mag_out)
+                const T m2 = vb * vb + vr * vr;
+                if (m2 > (T)0) {
+                    const T sc = mag_out * Real<T>::rsqrt_(m2);
+                    db[i] = vb * sc;
+                    dr[i] = vr * sc;
+                } else {
+                    db[i] = (T)0;
+                    dr[i] = mag_out;
+                }
+            }
+            st4(ys + x, y);
+            st4(bs + x, db);
+            st4(rs_ + x, dr);
+        }
+    }
+    __syncthreads();
+    for (int k = 0; k < g.count; ++k) cta_fill_tail<T, 1>(sm + (size_t)k * 3 * N1 + N1, (size_t)N1, 2, N1, W, N1);
+    __syncthreads();
+    const FiltHdr &fpre = p.filt[NF_PRE_LP];
+    for (int t = warp; t < 2 * g.count; t += nwarps) {
+        T *buf = sm + (size_t)(t >> 1) * 3 * N1 + (1 + (t & 1)) * N1;
+        warp_iir<T, 1>(p.tab + fpre.off, fpre, [&](int q, int, int) { return buf[q]; },
+                       [&](int j, T v) { buf[j] = v; });
+    }
+    __syncthreads();
+    for (int k = 0; k < g.count; ++k) {
+        const int row = g.r0 + 2 * k, line = io.y0 + row;
+        const T *ys = sm + (size_t)k * 3 * N1, *bs = ys + N1, *rs_ = bs + N1;
+        const unsigned long long ph0 = start_phase(p, g.frame, line);
+        const bool alt = is_alternate(p, g.frame, line);
+        for (int q = threadIdx.x; q < W4; q += blockDim.x) {
+            const int x = 4 * q;
+            T y[4], db[4], dr[4], o[4];
+            ld4(ys + x, y);
+            ld4(bs + x, db);
+            ld4(rs_ + x, dr);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                T s, c;
+                Real<T>::sincos_turns(ph0 + (unsigned long long)(x + i) * p.phases[NP_STEP1X], s, c);
+                o[i] = y[i] + (alt ? -Real<T>::sqrt_(db[i] * db[i] + dr[i] * dr[i]) * s : db[i] * s + dr[i] * c);
+            }
+            store_comp4(io, ((size_t)g.fidx * io.nrows + row) * p.Wc + x, o);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Decode.  smem: taps[128] + (R+1) rows x ( c[N1] | up[N3] | mod->pm[N3] | sat[N3] )
+// ------------------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(CM_NTHREADS)
+k_niir_decode(const __grid_constant__ DevParams<T> p, const __grid_constant__ IoArgs<T> io) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T *sm = reinterpret_cast<T *>(smem_raw);
+    RowGroup g;
+    if (!decode_group(io, g)) return;
+    const int W = p.W, N1 = p.n1p, N3 = 3 * p.hb3, n3 = 3 * W;
+    const int warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    T *taps = sm;
+    T *rows = sm + 128;
+    const size_t per_row = (size_t)N1 + 3 * (size_t)N3;
+    const bool has_prev0 = g.r0 >= 2;
+    const int nin = g.count + 1;                       // row slot 0 = previous row (real or synthetic), slot k+1 = row k
+    const T *hup = taps + p.res[NR_UP3].off, *hdn = taps + p.res[NR_DOWN3].off;
+    auto rowp = [&](int k) { return rows + (size_t)(k + 1) * per_row; };
+    copy_taps(taps, p, 2);
+    for (int k = 0; k < g.count; ++k) load_comp_row(rowp(k), io, g.fidx, g.r0 + 2 * k, W);
+    if (has_prev0) {
+        load_comp_row(rowp(-1), io, g.fidx, g.r0 - 2, W);
+    } else {
+        // niir.py:103-106: synthetic reference carrier of line-2: sin(phi) on normal lines, -sin(phi) on alternate ones
+        const int line = io.y0 + g.r0 - 2;
+        const unsigned long long ph0 = start_phase(p, g.frame, line);
+        const T sgn = is_alternate(p, g.frame, line) ? (T)-1 : (T)1;
+        T *c = rowp(-1);
+        for (int x = threadIdx.x; x < W; x += blockDim.x) {
+            T s, co;
+            Real<T>::sincos_turns(ph0 + (unsigned long long)x * p.phases[NP_STEP1X], s, co);
+            c[x] = sgn * s;
+        }
+    }
+    __syncthreads();
+    for (int k = -1; k < g.count; ++k) up3_natural(rowp(k) + N1, rowp(k), W, hup, threadIdx.x, blockDim.x);
+    __syncthreads();
+    cta_fill_tail<T, 1>(rows + N1, per_row, nin, N3, n3, N3);
+    __syncthreads();
+    const FiltHdr &fbp = p.filt[NF_UP_BP], &flp = p.filt[NF_BASE_LP];
+    for (int t = warp; t < nin; t += nwarps) {          // band-pass: up -> mod
+        const T *u = rows + (size_t)t * per_row + N1;
+        T *m = rows + (size_t)t * per_row + N1 + N3;
+        warp_iir<T, 3>(p.tab + fbp.off, fbp, [&](int q, int ph, int) { return u[3 * q + ph]; },
+                       [&](int j, T v) { m[j] = v; });
+        warp_fill_tail<T, 1>(m, N3, n3, N3);
+    }
+    __syncthreads();
+    // envelope low-pass: sat = LP(pi/2 |mod|).  The synthetic top-of-field carrier is used un-normalised
+    // (niir.py:105-106 stores the band-passed reference itself), so its slot skips this step.
+    for (int t = warp; t < nin; t += nwarps) {
+        if (t == 0 && !has_prev0) continue;
+        const T *m = rows + (size_t)t * per_row + N1 + N3;
+        T *s = rows + (size_t)t * per_row + N1 + 2 * (size_t)N3;
+        warp_iir<T, 3>(p.tab + flp.off, flp,
+                       [&](int q, int ph, int) { return (T)1.57079632679489661923 * Real<T>::abs_(m[3 * q + ph]); },
+                       [&](int j, T v) { s[j] = v; });
+    }
+    __syncthreads();
+    for (int k = -1; k < g.count; ++k) {                // pm = mod / sat in place
+        if (k == -1 && !has_prev0) continue;
+        T *m = rowp(k) + N1 + N3;
+        const T *s = rowp(k) + N1 + 2 * (size_t)N3;
+        for (int j = threadIdx.x; j < n3; j += blockDim.x) m[j] = m[j] / s[j];
+    }
+    __syncthreads();
+    const T inv_step3 = p.scalars[NS_INV_STEP3];
+    T ls_s, ls_c, rot_s, rot_c;
+    Real<T>::sincos_turns(p.phases[NP_LINE_SHIFT], ls_s, ls_c);
+    for (int k = 0; k < g.count; ++k) {
+        const int row = g.r0 + 2 * k, line = io.y0 + row;
+        const bool alt = is_alternate(p, g.frame, line);
+        const T *c = rowp(k);
+        const T *pm = rowp(k) + N1 + N3, *last = rowp(k - 1) + N1 + N3, *satu = rowp(k) + N1 + 2 * (size_t)N3;
+        const T *carrier = alt ? pm : last, *huemod = alt ? last : pm;
+        // rotation by shift = +-line_shift (niir.py:114-121,136-137)
+        const T sh_s = alt ? -ls_s : ls_s, sh_c = ls_c;
+        // luma re-synthesis rotation: (alt ? 0 : line_shift) + pi - bp.phase_shift   (niir.py:146-156)
+        Real<T>::sincos_turns(p.phases[NP_LUMA_ROT] + (alt ? 0ull : p.phases[NP_LINE_SHIFT]), rot_s, rot_c);
+        auto car = [&](int j) { return carrier[j]; };
+        auto altcar = [&](int j) {                       // niir.py:123-125
+            return (j == 0 || j == n3 - 1) ? (T)0 : (T)0.5 * (carrier[j + 1] - carrier[j - 1]) * inv_step3;
+        };
+        for (int q = threadIdx.x; q < (W >> 2); q += blockDim.x) {
+            T y[4], ob[4], orr[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int x = 4 * q + i;
+                T sinphi = down3_at(hdn, x, n3, [&](int j) { return huemod[j] * car(j); });
+                T cosphi = down3_at(hdn, x, n3, [&](int j) { return huemod[j] * altcar(j); });
+                const T norm = Real<T>::sqrt_(cosphi * cosphi + sinphi * sinphi);
+                cosphi = cosphi / norm;
+                sinphi = sinphi / norm;
+                const T sp = -cosphi * sh_s - sinphi * sh_c, cp = sinphi * sh_s - cosphi * sh_c;
+                const T sat = down3_at(hdn, x, n3, [&](int j) { return satu[j]; });
+                T db = sat * sp, dr = sat * cp;
+                const T sincar = down3_at(hdn, x, n3, car), coscar = down3_at(hdn, x, n3, altcar);
+                const T us0 = alt ? -Real<T>::sqrt_(db * db + dr * dr) : db, vs0 = alt ? (T)0 : dr;
+                const T us = us0 * rot_c - vs0 * rot_s, vs = us0 * rot_s + vs0 * rot_c;
+                y[i] = c[x] - (us * sincar + vs * coscar);
+                // niir.py:61-65: remove the saturation offset
+                const T m2 = db * db + dr * dr;
+                if (m2 > (T)0) {
+                    const T mag = Real<T>::sqrt_(m2);
+                    T ns = mag - (T)0.1;
+                    ns = ns > (T)0 ? ns : (T)0;
+                    const T sc = ns / mag;
+                    db *= sc;
+                    dr *= sc;
+                } else {
+                    db = (T)0;
+                    dr = (T)0;
+                }
+                ob[i] = db;
+                orr[i] = dr;
+            }
+            store_rgb4(p, io, g.fidx, row, 4 * q, y, ob, orr);
+        }
+    }
+}

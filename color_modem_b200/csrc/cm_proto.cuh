@@ -1,0 +1,158 @@
+// 819-line AM proto-SECAM kernels.  Reference: color_modem/color/protosecam.py.
+//
+// Encode (protosecam.py:74-90): line-sequential D'R / D'B -> low-pass -> 0.125 (1 + c) cos(phi) on a luma that
+// has had the chroma band removed at 3x (up3 -> band-stop -> down3, optional).
+// Decode (protosecam.py:92-112) at 3x: band-pass -> full-wave rectifier (pi/2 |x|) -> low-pass -> down3 ->
+// 8 c - 1; luma = down3(band-stop(up3)); rows pair their colour-difference signal with the previous row's.
+#pragma once
+#include "cm_niir.cuh"
+
+// Encode.  2 warps per row.  smem: taps[128] + R * (luma[N1] | chroma[N1] | up[N3])
+template <typename T>
+__global__ void __launch_bounds__(CM_NTHREADS)
+k_proto_encode(const __grid_constant__ DevParams<T> p, const __grid_constant__ IoArgs<T> io) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T *sm = reinterpret_cast<T *>(smem_raw);
+    RowGroup g;
+    if (!decode_group(io, g)) return;
+    const int W = p.W, N1 = p.n1p, N3 = 3 * p.hb3, n3 = 3 * W, W4 = W >> 2;
+    const int warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const bool avg = (p.flags & 2) != 0, luma_filter = (p.flags & 256) != 0;
+    T *taps = sm;
+    T *rows = sm + 128;
+    const size_t per_row = 2 * (size_t)N1 + N3;
+    const T *hup = taps + p.res[PR_UP3].off, *hdn = taps + p.res[PR_DOWN3].off;
+    copy_taps(taps, p, 2);
+    for (int k = 0; k < g.count; ++k) {
+        const int row = g.r0 + 2 * k;
+        const int nrow = (row + 2 < io.nrows) ? row + 2 : row;
+        const int ci = is_alternate(p, g.frame, io.y0 + row) ? 6 : 3;      // D'B on alternate lines, else D'R
+        T *ys = rows + k * per_row, *cs = ys + N1;
+        for (int q = threadIdx.x; q < W4; q += blockDim.x) {
+            const int x = 4 * q;
+            T r[4], gg[4], b[4], y[4], c[4];
+            load_rgb4(io, ((size_t)g.fidx * io.nrows + row) * W + x, r, gg, b);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                y[i] = p.enc[0] * r[i] + p.enc[1] * gg[i] + p.enc[2] * b[i];
+                c[i] = p.enc[ci] * r[i] + p.enc[ci + 1] * gg[i] + p.enc[ci + 2] * b[i];
+            }
+            if (avg) {
+                load_rgb4(io, ((size_t)g.fidx * io.nrows + nrow) * W + x, r, gg, b);
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    c[i] = (T)0.5 * ((p.enc[ci] * r[i] + p.enc[ci + 1] * gg[i] + p.enc[ci + 2] * b[i]) + c[i]);
+            }
+            st4(ys + x, y);
+            st4(cs + x, c);
+        }
+    }
+    __syncthreads();
+    for (int k = 0; k < g.count; ++k) {
+        cta_fill_tail<T, 1>(rows + k * per_row + N1, (size_t)N1, 1, N1, W, N1);
+        if (luma_filter) up3_natural(rows + k * per_row + 2 * N1, rows + k * per_row, W, hup, threadIdx.x, blockDim.x);
+    }
+    __syncthreads();
+    if (luma_filter) cta_fill_tail<T, 1>(rows + 2 * N1, per_row, g.count, N3, n3, N3);
+    __syncthreads();
+    for (int t = warp; t < 2 * g.count; t += nwarps) {
+        T *r = rows + (t >> 1) * per_row;
+        if ((t & 1) == 0) {
+            T *cs = r + N1;
+            const FiltHdr &f = p.filt[PF_PRE_LP];
+            warp_iir<T, 1>(p.tab + f.off, f, [&](int q, int, int) { return cs[q]; }, [&](int j, T v) { cs[j] = v; });
+        } else if (luma_filter) {
+            T *u = r + 2 * N1;
+            const FiltHdr &f = p.filt[PF_BS_UP];
+            warp_iir<T, 3>(p.tab + f.off, f, [&](int q, int ph, int) { return u[3 * q + ph]; },
+                           [&](int j, T v) { u[j] = v; });
+        }
+    }
+    __syncthreads();
+    for (int k = 0; k < g.count; ++k) {
+        const int row = g.r0 + 2 * k, line = io.y0 + row;
+        const T *ys = rows + k * per_row, *cs = ys + N1, *u = ys + 2 * N1;
+        const unsigned long long ph0 = start_phase(p, g.frame, line);
+        for (int q = threadIdx.x; q < W4; q += blockDim.x) {
+            T o[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int x = 4 * q + i;
+                const T luma = luma_filter ? down3_at(hdn, x, n3, [&](int j) { return u[j]; }) : ys[x];
+                T s, c;
+                Real<T>::sincos_turns(ph0 + (unsigned long long)x * p.phases[PP_STEP1X], s, c);
+                o[i] = luma + c * ((T)0.125 * ((T)1 + cs[x]));
+            }
+            store_comp4(io, ((size_t)g.fidx * io.nrows + row) * p.Wc + 4 * q, o);
+        }
+    }
+}
+
+// Decode.  smem: taps[128] + (R+1) rows x ( c -> X [N1] | up[N3] | chroma[N3] | luma[N3] )
+template <typename T>
+__global__ void __launch_bounds__(CM_NTHREADS)
+k_proto_decode(const __grid_constant__ DevParams<T> p, const __grid_constant__ IoArgs<T> io) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T *sm = reinterpret_cast<T *>(smem_raw);
+    RowGroup g;
+    if (!decode_group(io, g)) return;
+    const int W = p.W, N1 = p.n1p, N3 = 3 * p.hb3, n3 = 3 * W;
+    const int warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    T *taps = sm;
+    T *rows = sm + 128;
+    const size_t per_row = (size_t)N1 + 3 * (size_t)N3;
+    const bool has_prev0 = g.r0 >= 2;
+    const int k_lo = has_prev0 ? -1 : 0;
+    const int nin = g.count - k_lo;
+    const T *hup = taps + p.res[PR_UP3].off, *hdn = taps + p.res[PR_DOWN3].off;
+    auto rowp = [&](int k) { return rows + (size_t)(k - k_lo) * per_row; };
+    copy_taps(taps, p, 2);
+    for (int k = k_lo; k < g.count; ++k) load_comp_row(rowp(k), io, g.fidx, g.r0 + 2 * k, W);
+    __syncthreads();
+    for (int k = k_lo; k < g.count; ++k) up3_natural(rowp(k) + N1, rowp(k), W, hup, threadIdx.x, blockDim.x);
+    __syncthreads();
+    cta_fill_tail<T, 1>(rows + N1, per_row, nin, N3, n3, N3);
+    __syncthreads();
+    const FiltHdr &fbp = p.filt[PF_BP_UP], &fbs = p.filt[PF_BS_UP], &fpost = p.filt[PF_POST_LP];
+    for (int t = warp; t < 2 * nin; t += nwarps) {
+        T *r = rows + (size_t)(t >> 1) * per_row;
+        const T *u = r + N1;
+        if ((t & 1) == 0) {
+            T *b = r + N1 + N3;
+            warp_iir<T, 3>(p.tab + fbp.off, fbp, [&](int q, int ph, int) { return u[3 * q + ph]; },
+                           [&](int j, T v) { b[j] = v; });
+            warp_fill_tail<T, 1>(b, N3, n3, N3);
+            warp_iir<T, 3>(p.tab + fpost.off, fpost,
+                           [&](int q, int ph, int) { return (T)1.57079632679489661923 * Real<T>::abs_(b[3 * q + ph]); },
+                           [&](int j, T v) { b[j] = v; });
+        } else if ((t >> 1) + k_lo >= 0) {
+            T *l = r + N1 + 2 * (size_t)N3;
+            warp_iir<T, 3>(p.tab + fbs.off, fbs, [&](int q, int ph, int) { return u[3 * q + ph]; },
+                           [&](int j, T v) { l[j] = v; });
+        }
+    }
+    __syncthreads();
+    for (int k = k_lo; k < g.count; ++k) {              // X = 8 down3(chroma_up) - 1 into the (dead) composite buffer
+        T *x = rowp(k);
+        const T *b = rowp(k) + N1 + N3;
+        for (int j = threadIdx.x; j < W; j += blockDim.x)
+            x[j] = (T)8 * down3_at(hdn, j, n3, [&](int i) { return b[i]; }) - (T)1;
+    }
+    __syncthreads();
+    for (int k = 0; k < g.count; ++k) {
+        const int row = g.r0 + 2 * k;
+        const bool alt = is_alternate(p, g.frame, io.y0 + row);
+        const bool hp = (k > 0) || has_prev0;
+        const T *xc = rowp(k), *xp = hp ? rowp(k - 1) : nullptr, *l = rowp(k) + N1 + 2 * (size_t)N3;
+        for (int q = threadIdx.x; q < (W >> 2); q += blockDim.x) {
+            T y[4], a[4], b[4] = {(T)0, (T)0, (T)0, (T)0};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) y[i] = down3_at(hdn, 4 * q + i, n3, [&](int j) { return l[j]; });
+            ld4(xc + 4 * q, a);
+            if (hp) ld4(xp + 4 * q, b);
+            // protosecam.py:105-108: non-alternate rows carry D'R (dr = current, db = previous)
+            if (alt) store_rgb4(p, io, g.fidx, row, 4 * q, y, b, a);
+            else store_rgb4(p, io, g.fidx, row, 4 * q, y, a, b);
+        }
+    }
+}

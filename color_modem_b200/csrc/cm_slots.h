@@ -49,4 +49,32 @@
 #define SS_KD 9
 #define SS_FM_FC 10      /* FmDecoder centre frequency (secam.py:179,187) */
 
+
+/* ---- NIIR / SECAM-IV (niir.py) */
+#define NF_PRE_LP 0      /* _chroma_precorrect_lowpass              niir.py:17   rate 1, n = W  */
+#define NF_BASE_LP 1     /* _demodulate_upsampled_baseband_filter   niir.py:21   rate 3, n = 3W */
+#define NF_UP_BP 2       /* _demodulate_upsampled_filter            niir.py:21   rate 3, n = 3W */
+#define NR_UP3 0
+#define NR_DOWN3 1
+#define NP_STEP1X 0      /* _carrier_phase_step / 2pi = fsc/fs turns per sample (niir.py:12) */
+#define NP_LINE_SHIFT 1  /* line_shift / 2pi                                                  */
+#define NP_LUMA_ROT 2    /* (pi - up_bp.phase_shift) / 2pi   (niir.py:154)                    */
+#define NS_INV_STEP3 0   /* resample_factor / carrier_phase_step = 3 / (2 pi fsc/fs)  (niir.py:124-125) */
+
+/* ---- 819-line AM proto-SECAM (protosecam.py) */
+#define PF_PRE_LP 0      /* _chroma_precorrect_lowpass     protosecam.py:34   rate 1, n = W  */
+#define PF_BP_UP 1       /* _extract_chroma_up             protosecam.py:37   rate 3, n = 3W */
+#define PF_BS_UP 2       /* _remove_chroma_up              protosecam.py:37   rate 3, n = 3W */
+#define PF_POST_LP 3     /* _chroma_up_post_demod_filter   protosecam.py:46   rate 3, n = 3W */
+#define PR_UP3 0
+#define PR_DOWN3 1
+#define PP_STEP1X 0      /* 2 * _carrier_phase_step / 2pi = fsc/fs turns per sample (protosecam.py:33,88) */
+
+/* ---- D2-MAC (mac.py) */
+#define MR_LUMA_IN 0     /* W -> 720          mac.py:47-51  */
+#define MR_CHROMA_IN 1   /* W -> 360          mac.py:48-54  */
+#define MR_OUT 2         /* 1080 -> width     mac.py:70-73  */
+#define MR_COMP_IN 3     /* width -> 1080     mac.py:81-83  */
+#define MR_UP2 4         /* 360 -> 720        mac.py:111    */
+
 #endif

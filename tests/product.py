@@ -1,11 +1,12 @@
 """Build the product (color_modem_b200) modem composition for a test Case — mirrors tests/refload.make_modem."""
 from color_modem_b200.line import LineConfig, LineStandard
 
-BUILT_KINDS = {'ntsc', 'ntsc_comb', 'ntsc_3d', 'pal_s', 'pal_d', 'pal_3d', 'secam'}
+BUILT_KINDS = {'ntsc', 'ntsc_comb', 'ntsc_3d', 'pal_s', 'pal_d', 'pal_3d', 'secam', 'niir', 'niir_hue', 'protosecam',
+               'mac'}
 
 
 def make_modem(c, precision='fp32'):
-    from color_modem_b200.color import ntsc, pal, secam
+    from color_modem_b200.color import ntsc, pal, secam, niir, protosecam, mac
     from color_modem_b200 import comb
     std = getattr(LineStandard, c.standard) if c.standard else None
     lc = LineConfig((c.width, c.height), std)
@@ -20,6 +21,14 @@ def make_modem(c, precision='fp32'):
         m = pal.Pal3DModem(lc, getattr(pal.PalVariant, v), precision=precision)
     elif k == 'secam':
         m = secam.SecamModem(lc, getattr(secam.SecamVariant, v), precision=precision)
+    elif k == 'niir':
+        m = niir.NiirModem(lc, getattr(pal.PalVariant, v), precision=precision)
+    elif k == 'niir_hue':
+        m = niir.HueCorrectingNiirModem(lc, getattr(pal.PalVariant, v), precision=precision)
+    elif k == 'protosecam':
+        m = protosecam.ProtoSecamModem(lc, getattr(protosecam.ProtoSecamVariant, v), precision=precision)
+    elif k == 'mac':
+        m = mac.MacModem(lc, getattr(mac.MacVariant, v), precision=precision)
     elif k == 'pal_s':
         m = pal.PalSModem(lc, getattr(pal.PalVariant, v), precision=precision)
     elif k == 'pal_d':
