@@ -125,6 +125,7 @@ static int upload(const std::vector<double> &src, void **dst) {
 }
 
 extern "C" int cm_abi_version(void) { return CM_ABI_VERSION; }
+extern "C" int cm_sizeof_desc(void) { return (int)sizeof(cm_desc); }
 extern "C" const char *cm_last_error(void) { return g_err; }
 extern "C" int64_t cm_launch_count(void) { return g_launches.load(); }
 

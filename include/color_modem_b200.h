@@ -141,6 +141,8 @@ enum cm_window_mode {
 };
 
 int cm_abi_version(void);
+/* sizeof(cm_desc) as compiled into the library (lets a foreign-language binding verify its struct layout). */
+int cm_sizeof_desc(void);
 const char *cm_last_error(void);
 int cm_device_info(int *sm_count, int *cc_major, int *cc_minor);
 
