@@ -59,7 +59,7 @@ MODE_DEFAULT, MODE_BANDSPLIT_NOSTRIP = 0, 1
 
 EXPORTS = ['cm_abi_version', 'cm_sizeof_desc', 'cm_last_error', 'cm_device_info', 'cm_create', 'cm_destroy', 'cm_encode_frames',
            'cm_decode_frames', 'cm_encode_ex', 'cm_decode_ex', 'cm_encode_frames_host', 'cm_decode_frames_host',
-           'cm_launch_count', 'cm_timing_enable', 'cm_timing_reset', 'cm_timing_read']
+           'cm_launch_count', 'cm_timing_enable', 'cm_timing_reset', 'cm_timing_read', 'cm_phase_profile']
 
 K_ENCODE, K_BANDSPLIT, K_PALD, K_COMB, K_DECODE_OTHER = 0, 1, 2, 3, 4
 
@@ -94,6 +94,7 @@ def load():
     lib.cm_launch_count.restype = C.c_int64
     lib.cm_timing_enable.argtypes = [vp, C.c_int]
     lib.cm_timing_reset.argtypes = [vp]
+    lib.cm_phase_profile.argtypes = [vp, vp]
     lib.cm_timing_read.argtypes = [vp, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int64)]
     if lib.cm_sizeof_desc() != C.sizeof(Desc):
         raise NativeUnavailable('cm_desc layout mismatch between %s and the Python binding' % LIB_NAME)

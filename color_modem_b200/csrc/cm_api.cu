@@ -58,7 +58,7 @@ static void build_filter(const cm_filter &f, FiltHdr &h, std::vector<double> &ta
         const double *c = f.sos[s];
         std::vector<double> sec(CM_SEC_STRIDE, 0.0);
         for (int i = 0; i < 5; ++i) sec[i] = c[i];
-        const double A[4] = {-c[3], 1.0, -c[4], 0.0};
+        const double A[4] = {-c[3], -c[4], 1.0, 0.0};     // (y[-1], y[-2]) -> one step of the homogeneous recursion
         double M[4] = {1.0, 0.0, 0.0, 1.0};
         for (int i = 0; i < L; ++i) {                     // M = A^L
             double Q[4];
@@ -222,8 +222,11 @@ extern "C" void cm_destroy(cm_modem *m) {
     if (!m) return;
     cudaFree(m->d_tab);
     cudaFree(m->d_taps);
-    cudaFree(m->d_in);
-    cudaFree(m->d_out);
+    for (int i = 0; i < cm_modem::kHostStreams; ++i) {
+        cudaFree(m->d_in[i]);
+        cudaFree(m->d_out[i]);
+        if (m->hs[i]) cudaStreamDestroy(m->hs[i]);
+    }
     cm_timing_reset(m);
     delete m;
 }
@@ -234,6 +237,12 @@ extern "C" void cm_destroy(cm_modem *m) {
 extern "C" int cm_timing_enable(cm_modem *m, int on) {
     if (!m) return fail(CM_ERR_INVALID, "null handle%s");
     m->timing = on != 0;
+    return CM_OK;
+}
+
+extern "C" int cm_phase_profile(cm_modem *m, void *device_counters) {
+    if (!m) return fail(CM_ERR_INVALID, "null handle%s");
+    m->phase_prof = (unsigned long long *)device_counters;
     return CM_OK;
 }
 
@@ -324,6 +333,7 @@ static int run_ex(cm_modem *m, bool encode, const cm_window *win, const uint8_t 
     io.out_f = (T *)out_f;
     io.first_frame = first_frame;
     io.nframes = nframes;
+    io.prof = m->phase_prof;
     if (win) {
         if (win->nrows <= 0 || win->out_begin < 0 || win->out_count < 0 || win->out_begin + win->out_count > win->nrows)
             return fail(CM_ERR_INVALID, "bad cm_window%s");
@@ -380,36 +390,53 @@ static int ensure(void **buf, size_t *cap, size_t need) {
     return CM_OK;
 }
 
+// Host-buffer path shared by encode and decode: chunked, triple-buffered over three streams.  With pinned host
+// memory the H2D copy of the next chunk, the kernels of the current one and the D2H copy of the previous one run
+// concurrently (two copy engines + SMs); with pageable memory it is still correct, just serialised by the driver.
+static int run_host(cm_modem *m, bool encode, const uint8_t *in, uint8_t *out, size_t in_frame, size_t out_frame,
+                    int64_t first_frame, int32_t nframes) {
+    if (!m || !in || !out) return fail(CM_ERR_INVALID, "null argument%s");
+    if (nframes < 0) return fail(CM_ERR_INVALID, "bad frame count%s");
+    if (nframes == 0) return CM_OK;
+    CUDA_TRY(cudaSetDevice(m->device));
+    int chunk = 16;
+    if (const char *e = getenv("CM_HOST_CHUNK")) {
+        int v = atoi(e);
+        if (v >= 1) chunk = v;
+    }
+    if (chunk > nframes) chunk = nframes;
+    for (int s = 0; s < cm_modem::kHostStreams; ++s) {
+        if (!m->hs[s]) CUDA_TRY(cudaStreamCreateWithFlags(&m->hs[s], cudaStreamNonBlocking));
+        int rc = ensure(&m->d_in[s], &m->in_cap[s], (size_t)chunk * in_frame);
+        if (!rc) rc = ensure(&m->d_out[s], &m->out_cap[s], (size_t)chunk * out_frame);
+        if (rc) return rc;
+    }
+    int rc = CM_OK;
+    for (int f = 0, i = 0; f < nframes && rc == CM_OK; f += chunk, ++i) {
+        const int s = i % cm_modem::kHostStreams;
+        const int n = nframes - f < chunk ? nframes - f : chunk;
+        cudaStream_t st = m->hs[s];
+        CUDA_TRY(cudaMemcpyAsync(m->d_in[s], in + (size_t)f * in_frame, (size_t)n * in_frame, cudaMemcpyHostToDevice, st));
+        rc = encode ? cm_encode_frames(m, (const uint8_t *)m->d_in[s], (uint8_t *)m->d_out[s], first_frame + f, n, st)
+                    : cm_decode_frames(m, (const uint8_t *)m->d_in[s], (uint8_t *)m->d_out[s], first_frame + f, n, st);
+        if (rc == CM_OK)
+            CUDA_TRY(cudaMemcpyAsync(out + (size_t)f * out_frame, m->d_out[s], (size_t)n * out_frame,
+                                     cudaMemcpyDeviceToHost, st));
+    }
+    for (int s = 0; s < cm_modem::kHostStreams; ++s) CUDA_TRY(cudaStreamSynchronize(m->hs[s]));
+    return rc;
+}
+
 extern "C" int cm_encode_frames_host(cm_modem *m, const uint8_t *rgb, uint8_t *comp, int64_t first_frame,
                                      int32_t nframes) {
-    if (!m || !rgb || !comp) return fail(CM_ERR_INVALID, "null argument%s");
-    CUDA_TRY(cudaSetDevice(m->device));
-    size_t in_b = (size_t)nframes * m->desc.height * m->desc.width * 3;
-    size_t out_b = (size_t)nframes * m->desc.height * m->desc.comp_width;
-    int rc = ensure(&m->d_in, &m->in_cap, in_b);
-    if (!rc) rc = ensure(&m->d_out, &m->out_cap, out_b);
-    if (rc) return rc;
-    CUDA_TRY(cudaMemcpyAsync(m->d_in, rgb, in_b, cudaMemcpyHostToDevice, 0));
-    rc = cm_encode_frames(m, (const uint8_t *)m->d_in, (uint8_t *)m->d_out, first_frame, nframes, nullptr);
-    if (rc) return rc;
-    CUDA_TRY(cudaMemcpyAsync(comp, m->d_out, out_b, cudaMemcpyDeviceToHost, 0));
-    CUDA_TRY(cudaStreamSynchronize(0));
-    return CM_OK;
+    if (!m) return fail(CM_ERR_INVALID, "null handle%s");
+    return run_host(m, true, rgb, comp, (size_t)m->desc.height * m->desc.width * 3,
+                    (size_t)m->desc.height * m->desc.comp_width, first_frame, nframes);
 }
 
 extern "C" int cm_decode_frames_host(cm_modem *m, const uint8_t *comp, uint8_t *rgb, int64_t first_frame,
                                      int32_t nframes) {
-    if (!m || !rgb || !comp) return fail(CM_ERR_INVALID, "null argument%s");
-    CUDA_TRY(cudaSetDevice(m->device));
-    size_t in_b = (size_t)nframes * m->desc.height * m->desc.comp_width;
-    size_t out_b = (size_t)nframes * m->desc.height * m->desc.out_width * 3;
-    int rc = ensure(&m->d_in, &m->in_cap, in_b);
-    if (!rc) rc = ensure(&m->d_out, &m->out_cap, out_b);
-    if (rc) return rc;
-    CUDA_TRY(cudaMemcpyAsync(m->d_in, comp, in_b, cudaMemcpyHostToDevice, 0));
-    rc = cm_decode_frames(m, (const uint8_t *)m->d_in, (uint8_t *)m->d_out, first_frame, nframes, nullptr);
-    if (rc) return rc;
-    CUDA_TRY(cudaMemcpyAsync(rgb, m->d_out, out_b, cudaMemcpyDeviceToHost, 0));
-    CUDA_TRY(cudaStreamSynchronize(0));
-    return CM_OK;
+    if (!m) return fail(CM_ERR_INVALID, "null handle%s");
+    return run_host(m, false, comp, rgb, (size_t)m->desc.height * m->desc.comp_width,
+                    (size_t)m->desc.height * m->desc.out_width * 3, first_frame, nframes);
 }

@@ -66,6 +66,25 @@ struct IoArgs {
     int out_begin, out_count;
     int rows_per_cta; // R
     int groups_per_field;
+    unsigned long long *prof;   // optional per-phase cycle counters (tuning aid, cm_phase_profile); nullptr normally
+};
+
+// Phase timer: thread 0 of every CTA accumulates the cycles between consecutive marks.
+struct PhaseClock {
+    unsigned long long *prof;
+    long long t;
+    int idx;
+    __device__ __forceinline__ PhaseClock(unsigned long long *p) : prof(p), t(0), idx(0) {
+        if (prof && threadIdx.x == 0) t = clock64();
+    }
+    __device__ __forceinline__ void mark() {
+        if (prof && threadIdx.x == 0) {
+            const long long now = clock64();
+            atomicAdd(prof + idx, (unsigned long long)(now - t));
+            t = now;
+        }
+        ++idx;
+    }
 };
 
 // ------------------------------------------------------------------------------------------------------------

@@ -43,17 +43,17 @@ __device__ __forceinline__ void st4<float>(float *p, const float *src) {
     *reinterpret_cast<float4 *>(p) = make_float4(src[0], src[1], src[2], src[3]);
 }
 
-// 28-sample window x[m0-12 .. m0+16) with zeros outside [0, n); fast path = 7 aligned 128-bit loads.
+// 28-sample window x[m0-12 .. m0+16) with zeros outside [0, n).  n and m0 are multiples of 4, so every aligned
+// 4-vector is either entirely inside or entirely outside the line: 7 predicated 128-bit loads, no divergence.
 template <typename T>
 __device__ __forceinline__ void load_window28(const T *__restrict__ x, int n, int m0, T *w) {
-    if (m0 >= 12 && m0 + 16 <= n) {
 #pragma unroll
-        for (int v = 0; v < 7; ++v) ld4(x + m0 - 12 + 4 * v, w + 4 * v);
-    } else {
-#pragma unroll
-        for (int v = 0; v < 28; ++v) {
-            const int i = m0 - 12 + v;
-            w[v] = (i >= 0 && i < n) ? x[i] : (T)0;
+    for (int v = 0; v < 7; ++v) {
+        const int i = m0 - 12 + 4 * v;
+        if (i >= 0 && i < n) {
+            ld4(x + i, w + 4 * v);
+        } else {
+            w[4 * v] = w[4 * v + 1] = w[4 * v + 2] = w[4 * v + 3] = (T)0;
         }
     }
 }

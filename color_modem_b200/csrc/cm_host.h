@@ -1,6 +1,7 @@
 // Host-side internals shared by the translation units of libcolormodem_b200.so (not part of the C ABI).
 #pragma once
 #include <cuda_runtime.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <vector>
@@ -28,11 +29,15 @@ struct cm_modem {
     void *d_tab = nullptr;
     void *d_taps = nullptr;
     bool timing = false;
+    unsigned long long *phase_prof = nullptr;
     struct Ev { cudaEvent_t a, b; int id; };
     std::vector<Ev> events;
-    // scratch for the *_host entry points
-    void *d_in = nullptr, *d_out = nullptr;
-    size_t in_cap = 0, out_cap = 0;
+    // *_host entry points: the batch is cut into chunks that ping-pong over CM_HOST_STREAMS streams so that the
+    // host->device copy of chunk i+1, the kernels of chunk i and the device->host copy of chunk i-1 overlap
+    static const int kHostStreams = 3;
+    cudaStream_t hs[kHostStreams] = {nullptr, nullptr, nullptr};
+    void *d_in[kHostStreams] = {nullptr, nullptr, nullptr}, *d_out[kHostStreams] = {nullptr, nullptr, nullptr};
+    size_t in_cap[kHostStreams] = {0, 0, 0}, out_cap[kHostStreams] = {0, 0, 0};
 };
 
 struct LaunchTimer {
@@ -67,8 +72,13 @@ static int set_smem(K kernel, size_t bytes) {
 }
 
 // Largest R in [1, rmax] whose shared-memory footprint fits `budget`; 0 if even R = 1 does not fit.
+// CM_ROWS_MAX (environment, tuning aid) lowers rmax.
 template <class F>
 static int pick_rows(int rmax, size_t budget, F bytes_for) {
+    if (const char *e = getenv("CM_ROWS_MAX")) {
+        int v = atoi(e);
+        if (v >= 1 && v < rmax) rmax = v;
+    }
     for (int r = rmax; r >= 1; --r)
         if (bytes_for(r) <= budget) return r;
     return 0;

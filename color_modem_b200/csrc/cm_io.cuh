@@ -49,7 +49,8 @@ __device__ __forceinline__ void load_comp_row(T *dst, const IoArgs<T> &io, int f
         } else {
             const uint32_t w = __ldg(reinterpret_cast<const uint32_t *>(io.in_u8 + base + x));
 #pragma unroll
-            for (int i = 0; i < 4; ++i) v[i] = ((T)5 * Real<T>::from_u8((w >> (8 * i)) & 0xff) - (T)1) / (T)3;
+            for (int i = 0; i < 4; ++i)
+                v[i] = ((T)5 * Real<T>::from_u8((w >> (8 * i)) & 0xff) - (T)1) * (T)(1.0 / 3.0);
         }
         st4(dst + x, v);
     }

@@ -267,6 +267,7 @@ k_pald_combed(const __grid_constant__ DevParams<T> p, const __grid_constant__ Io
     T *sm = reinterpret_cast<T *>(smem_raw);
     RowGroup g;
     if (!decode_group(io, g)) return;
+    PhaseClock pc(io.prof);
     const int W = p.W, W2 = 2 * W, N1 = p.n1p, hb = p.hb2, N2 = 2 * hb;
     const int warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     const int R = io.rows_per_cta;
@@ -279,13 +280,16 @@ k_pald_combed(const __grid_constant__ DevParams<T> p, const __grid_constant__ Io
     copy_taps(taps, p, 2);
     for (int k = 0; k < nin; ++k) load_comp_row(cbuf + (size_t)k * N1, io, g.fidx, g.r0 + 2 * (k - 1), W);
     __syncthreads();
+    pc.mark();
     for (int k = 0; k < nin; ++k) {
         T *b = gbuf + (size_t)k * N2;
         fir_up2(b, b + hb, cbuf + (size_t)k * N1, W, hup, threadIdx.x, blockDim.x);
     }
     __syncthreads();
+    pc.mark();
     cta_fill_tail<T, 2>(gbuf, (size_t)N2, nin, hb, W2, N2);
     __syncthreads();
+    pc.mark();
     for (int t = warp; t < nin; t += nwarps) {          // band-pass in place
         T *be = gbuf + (size_t)t * N2, *bo = be + hb;
         const FiltHdr &f = p.filt[QF_BP2X];
@@ -293,19 +297,23 @@ k_pald_combed(const __grid_constant__ DevParams<T> p, const __grid_constant__ Io
                        [&](int j, T v) { ((j & 1) ? bo : be)[j >> 1] = v; });
     }
     __syncthreads();
+    pc.mark();
     for (int k = 0; k < nin; ++k) {                     // E = down2(b2) -> work[k][0..W)
         T *e = work + (size_t)k * N1;
         const T *b = gbuf + (size_t)k * N2;
         fir_down2(b, b + hb, W, hdn, threadIdx.x, blockDim.x, [&](int j0, const T *y) { st4(e + j0, y); });
     }
     __syncthreads();
+    pc.mark();
     for (int k = 0; k < nin; ++k) {                     // G = up2(E)
         T *b = gbuf + (size_t)k * N2;
         fir_up2(b, b + hb, work + (size_t)k * N1, W, hup, threadIdx.x, blockDim.x);
     }
     __syncthreads();
+    pc.mark();
     cta_fill_tail<T, 2>(gbuf, (size_t)N2, nin, hb, W2, N2);
     __syncthreads();
+    pc.mark();
     for (int t = warp; t < 2 * g.count; t += nwarps) {  // AM demodulation low-pass of sum / difference
         const int k = t >> 1;
         const T *gce = gbuf + (size_t)(k + 1) * N2, *gco = gce + hb;
@@ -325,6 +333,7 @@ k_pald_combed(const __grid_constant__ DevParams<T> p, const __grid_constant__ Io
                        [&](int j, T v) { ((j & 1) ? dod : de)[j >> 1] = v; });
     }
     __syncthreads();
+    pc.mark();
     // S, D at 1x -> gbuf rows (G is dead): S at [k][0..N1), D at [k][N1..2 N1)
     for (int k = 0; k < g.count; ++k) {
         T *so = gbuf + (size_t)k * N2, *dout = so + N1;
@@ -333,6 +342,7 @@ k_pald_combed(const __grid_constant__ DevParams<T> p, const __grid_constant__ Io
         fir_down2(wd, wd + hb, W, hdn, threadIdx.x, blockDim.x, [&](int j0, const T *y) { st4(dout + j0, y); });
     }
     __syncthreads();
+    pc.mark();
     const T sf = p.scalars[QS_PALD_SIN], cf = p.scalars[QS_PALD_COS];
     for (int k = 0; k < g.count; ++k) {                 // rotate (S, D) -> (u, v) in place, V switch
         T *so = gbuf + (size_t)k * N2;
@@ -345,8 +355,10 @@ k_pald_combed(const __grid_constant__ DevParams<T> p, const __grid_constant__ Io
         }
     }
     __syncthreads();
+    pc.mark();
     for (int k = 0; k < g.count; ++k) cta_fill_tail<T, 1>(gbuf + (size_t)k * N2, (size_t)N1, 2, N1, W, N1);
     __syncthreads();
+    pc.mark();
     const FiltHdr &fpre = p.filt[QF_PRE_LP];
     for (int t = warp; t < 2 * g.count; t += nwarps) {  // encoder pre-lowpass for the re-modulation
         const T *src = gbuf + (size_t)(t >> 1) * N2 + (t & 1) * N1;
@@ -355,11 +367,13 @@ k_pald_combed(const __grid_constant__ DevParams<T> p, const __grid_constant__ Io
                        [&](int j, T v) { dst[j] = v; });
     }
     __syncthreads();
+    pc.mark();
     T rs, rc;
     Real<T>::sincos_turns(p.phases[QP_STEP1X], rs, rc);
     for (int k = 0; k < g.count; ++k)
         remod_store_row(p, io, g, k, cbuf + (size_t)(k + 1) * N1, work + (size_t)(2 * k) * N1,
                         work + (size_t)(2 * k + 1) * N1, gbuf + (size_t)k * N2, gbuf + (size_t)k * N2 + N1, rs, rc);
+    pc.mark();
 }
 
 // ------------------------------------------------------------------------------------------------------------

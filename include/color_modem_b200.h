@@ -188,6 +188,10 @@ int cm_timing_reset(cm_modem *m);
 /* Waits for the recorded events; returns summed milliseconds and number of launches of kernel `id`. */
 int cm_timing_read(cm_modem *m, int id, double *total_ms, int64_t *launches);
 
+/* Tuning aid: when `device_counters` (>= 32 zeroed uint64 on the device) is non-NULL, instrumented kernels add the
+ * cycles thread 0 of every CTA spends between consecutive barriers to counters[phase].  NULL switches it off. */
+int cm_phase_profile(cm_modem *m, void *device_counters);
+
 /* Number of kernel launches issued by this library in the calling process (bench.py's gpu_launches). */
 int64_t cm_launch_count(void);
 
