@@ -144,7 +144,8 @@ k_qam_bandsplit(const __grid_constant__ DevParams<T> p, const __grid_constant__ 
     const size_t per_row = (size_t)N1 + 4 * (size_t)N2;     // c | a2 | b2 | l2 | v2
     const T *hup = taps + p.res[QR_UP2].off, *hdn = taps + p.res[QR_DOWN2].off;
     copy_taps(taps, p, 2);
-    for (int k = 0; k < g.count; ++k) load_comp_row(rows + k * per_row, io, g.fidx, g.r0 + 2 * k, W);
+    load_comp_rows(io, g.fidx, g.count, W, [&](int k) { return rows + k * per_row; },
+                   [&](int k) { return g.r0 + 2 * k; });
     __syncthreads();
     for (int k = 0; k < g.count; ++k) {
         T *c = rows + k * per_row, *a2 = c + N1;
@@ -161,13 +162,13 @@ k_qam_bandsplit(const __grid_constant__ DevParams<T> p, const __grid_constant__ 
             T *be = c + N1 + N2, *bo = be + hb;
             const FiltHdr &f = p.filt[QF_BP2X];
             warp_iir<T, 2>(p.tab + f.off, f, [&](int q, int ph, int) { return (ph ? ao : ae)[q]; },
-                           [&](int j, T v) { ((j & 1) ? bo : be)[j >> 1] = v; });
+                           Poly2Out<T>{be, bo});
             warp_fill_tail<T, 2>(be, hb, W2, N2);
         } else if (luma_mode == 0) {
             T *le = c + N1 + 2 * N2, *lo = le + hb;
             const FiltHdr &f = p.filt[QF_BS2X];
             warp_iir<T, 2>(p.tab + f.off, f, [&](int q, int ph, int) { return (ph ? ao : ae)[q]; },
-                           [&](int j, T v) { ((j & 1) ? lo : le)[j >> 1] = v; });
+                           Poly2Out<T>{le, lo});
         }
     }
     __syncthreads();
@@ -184,10 +185,10 @@ k_qam_bandsplit(const __grid_constant__ DevParams<T> p, const __grid_constant__ 
         const FiltHdr &f = p.filt[QF_DEMOD_LP];
         warp_iir<T, 2>(p.tab + f.off, f,
                        [&](int q, int ph, int i) {
-                           car.at(2 * q + ph, i == 0);
+                           car.at(2 * q + ph, i);
                            return (T)2 * car.s * (ph ? bo : be)[q];
                        },
-                       [&](int j, T v) { ((j & 1) ? dod : de)[j >> 1] = v; });
+                       Poly2Out<T>{de, dod});
     }
     __syncthreads();
     // down2 of u2, v2 -> u, v at 1x into the b2 region (dead now): u at [0, N1), v at [N1, 2 N1)
@@ -278,7 +279,8 @@ k_pald_combed(const __grid_constant__ DevParams<T> p, const __grid_constant__ Io
     const int nin = g.count + 1;
     const T *hup = taps + p.res[QR_UP2].off, *hdn = taps + p.res[QR_DOWN2].off;
     copy_taps(taps, p, 2);
-    for (int k = 0; k < nin; ++k) load_comp_row(cbuf + (size_t)k * N1, io, g.fidx, g.r0 + 2 * (k - 1), W);
+    load_comp_rows(io, g.fidx, nin, W, [&](int k) { return cbuf + (size_t)k * N1; },
+                   [&](int k) { return g.r0 + 2 * (k - 1); });
     __syncthreads();
     pc.mark();
     for (int k = 0; k < nin; ++k) {
@@ -294,7 +296,7 @@ k_pald_combed(const __grid_constant__ DevParams<T> p, const __grid_constant__ Io
         T *be = gbuf + (size_t)t * N2, *bo = be + hb;
         const FiltHdr &f = p.filt[QF_BP2X];
         warp_iir<T, 2>(p.tab + f.off, f, [&](int q, int ph, int) { return (ph ? bo : be)[q]; },
-                       [&](int j, T v) { ((j & 1) ? bo : be)[j >> 1] = v; });
+                       Poly2Out<T>{be, bo});
     }
     __syncthreads();
     pc.mark();
@@ -327,10 +329,10 @@ k_pald_combed(const __grid_constant__ DevParams<T> p, const __grid_constant__ Io
         const FiltHdr &f = p.filt[QF_PALD_LP];
         warp_iir<T, 2>(p.tab + f.off, f,
                        [&](int q, int ph, int i) {
-                           car.at(2 * q + ph, i == 0);
+                           car.at(2 * q + ph, i);
                            return Real<T>::fma_(sgn, (ph ? glo : gle)[q], (ph ? gco : gce)[q]) * car.s;
                        },
-                       [&](int j, T v) { ((j & 1) ? dod : de)[j >> 1] = v; });
+                       Poly2Out<T>{de, dod});
     }
     __syncthreads();
     pc.mark();
@@ -416,7 +418,8 @@ k_qam_comb(const __grid_constant__ DevParams<T> p, const __grid_constant__ IoArg
     const int nin = k_hi - k_lo + 1;
     const T *hup = taps + p.res[QR_UP2].off, *hdn = taps + p.res[QR_DOWN2].off;
     copy_taps(taps, p, 2);
-    for (int k = k_lo; k <= k_hi; ++k) load_comp_row(cbuf + (size_t)(k + 1) * N1, io, g.fidx, g.r0 + 2 * k, W);
+    load_comp_rows(io, g.fidx, nin, W, [&](int k) { return cbuf + (size_t)(k_lo + k + 1) * N1; },
+                   [&](int k) { return g.r0 + 2 * (k_lo + k); });
     __syncthreads();
     for (int k = k_lo; k <= k_hi; ++k) {
         T *b = bbuf + (size_t)(k + 1) * N2;
@@ -429,7 +432,7 @@ k_qam_comb(const __grid_constant__ DevParams<T> p, const __grid_constant__ IoArg
         T *be = bbuf + (size_t)(k_lo + t + 1) * N2, *bo = be + hb;
         const FiltHdr &f = p.filt[QF_BP2X];
         warp_iir<T, 2>(p.tab + f.off, f, [&](int q, int ph, int) { return (ph ? bo : be)[q]; },
-                       [&](int j, T v) { ((j & 1) ? bo : be)[j >> 1] = v; });
+                       Poly2Out<T>{be, bo});
         warp_fill_tail<T, 2>(be, hb, W2, N2);
     }
     __syncthreads();
@@ -445,7 +448,7 @@ k_qam_comb(const __grid_constant__ DevParams<T> p, const __grid_constant__ IoArg
         const T *bpe = bbuf + (size_t)(hp ? k : k + 1) * N2, *bpo = bpe + hb;
         const T *bne = bbuf + (size_t)(hn ? k + 2 : k + 1) * N2, *bno = bne + hb;
         T *de = work + (size_t)t * N2, *dod = de + hb;
-        auto st = [&](int j, T v) { ((j & 1) ? dod : de)[j >> 1] = v; };
+        auto st = Poly2Out<T>{de, dod};
         const unsigned long long psi = start_phase(p, g.frame, line) + p.phases[QP_BP_SHIFT];
         if (MODE == COMB_NTSC2) {
             const T f2 = (T)2 * p.scalars[QS_NTSC_FACTOR];
@@ -454,7 +457,7 @@ k_qam_comb(const __grid_constant__ DevParams<T> p, const __grid_constant__ IoArg
             const T amp = is_v ? -f2 : f2;
             warp_iir<T, 2>(p.tab + flp.off, flp,
                            [&](int q, int ph, int i) {
-                               car.at(2 * q + ph, i == 0);
+                               car.at(2 * q + ph, i);
                                return amp * car.s * ((ph ? bco : bce)[q] - (ph ? bpo : bpe)[q]);
                            },
                            st);
@@ -469,11 +472,11 @@ k_qam_comb(const __grid_constant__ DevParams<T> p, const __grid_constant__ IoArg
             warp_iir<T, 2>(p.tab + flp.off, flp,
                            [&](int q, int ph, int i) {
                                const int j = 2 * q + ph;
-                               car.at(j, i == 0);
+                               car.at(j, i);
                                const T bc = (ph ? bco : bce)[q];
                                T acc = hp ? amp * car.s * (bc - (ph ? bpo : bpe)[q]) : car.s * bc;
                                if (hn) {
-                                   carn.at(j, i == 0);
+                                   carn.at(j, i);
                                    acc = Real<T>::fma_(amp * carn.s, (ph ? bno : bne)[q] - bc, acc);
                                }
                                return acc;
@@ -485,7 +488,7 @@ k_qam_comb(const __grid_constant__ DevParams<T> p, const __grid_constant__ IoArg
             Carrier<T> car(psi, step, W2);
             warp_iir<T, 2>(p.tab + flp.off, flp,
                            [&](int q, int ph, int i) {
-                               car.at(2 * q + ph, i == 0);
+                               car.at(2 * q + ph, i);
                                const T bc = (ph ? bco : bce)[q];
                                const T curr_diff = (ph ? bno : bne)[q] - bc, last_diff = bc - (ph ? bpo : bpe)[q];
                                const T ssig = curr_diff + last_diff, dsig = curr_diff - last_diff;

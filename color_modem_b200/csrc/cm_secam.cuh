@@ -251,10 +251,10 @@ k_secam_decode(const __grid_constant__ DevParams<T> p, const __grid_constant__ I
         Carrier<T> car((t & 1) ? 0ull : CM_QUARTER_TURN, p.phases[SP_FM_STEP2X], n2);   // I: cos, Q: sin
         warp_iir<T, 2>(p.tab + flp.off, flp,
                        [&](int q, int ph, int i) {
-                           car.at(2 * q + ph, i == 0);
+                           car.at(2 * q + ph, i);
                            return car.s * (ph ? uo : ue)[q];
                        },
-                       [&](int j, T v) { ((j & 1) ? dod : de)[j >> 1] = v; });
+                       Poly2Out<T>{de, dod});
     }
     __syncthreads();
     // discriminator: wrapped phase step of z = I - jQ between consecutive 2x samples, first step 0 (secam.py:143-148)
