@@ -106,54 +106,92 @@ __device__ __forceinline__ void fir_down2(const T *__restrict__ E, const T *__re
     }
 }
 
-// x[0..n) natural -> out[0..3n) natural (3x paths are not on the headline configs; kept simple)   h: 61 taps
+// ---- x3 / :3, polyphase [P0 | P1 | P2] (P_r[m] = x3[3m + r]), 61 dense taps, every tap at a non-zero multiple of 3
+// from the centre is zero:
+//     up3:    P0[m] = h[30] x[m]     P1[m] = sum_k h[58-3k] x[m-9+k]     P2[m] = sum_k h[59-3k] x[m-9+k]   k = 0..19
+//     down3:  y[j]  = h[30] P0[j] + sum_a ( h[29-3a] P1[j+a] + h[28-3a] P2[j+a] ),  a = -10..9
 template <typename T>
-__device__ __forceinline__ void fir_up3(T *__restrict__ out, const T *__restrict__ x, int n, const T *__restrict__ h,
-                                        int tid, int nthr) {
+__device__ __forceinline__ void fir_up3(T *__restrict__ P0, T *__restrict__ P1, T *__restrict__ P2,
+                                        const T *__restrict__ x, int n, const T *__restrict__ h, int tid, int nthr) {
+    T g1[20], g2[20];
+#pragma unroll
+    for (int k = 0; k < 20; ++k) { g1[k] = h[58 - 3 * k]; g2[k] = h[59 - 3 * k]; }
     const T c0 = h[30];
-    for (int m = tid; m < n; m += nthr) {
-        T a1 = (T)0, a2 = (T)0;
-        if (m >= 9 && m + 10 < n) {
+    for (int m0 = 4 * tid; m0 < n; m0 += 4 * nthr) {
+        T w[28], p0[4], p1[4], p2[4];
+        load_window28(x, n, m0, w);
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            p0[r] = c0 * w[12 + r];
+            T a1 = (T)0, a2 = (T)0;
 #pragma unroll
             for (int k = 0; k < 20; ++k) {
-                T v = x[m - 9 + k];
-                a1 = Real<T>::fma_(h[58 - 3 * k], v, a1);
-                a2 = Real<T>::fma_(h[59 - 3 * k], v, a2);
+                a1 = Real<T>::fma_(g1[k], w[3 + r + k], a1);
+                a2 = Real<T>::fma_(g2[k], w[3 + r + k], a2);
             }
-        } else {
-#pragma unroll
-            for (int k = 0; k < 20; ++k) {
-                int i = m - 9 + k;
-                if (i >= 0 && i < n) {
-                    T v = x[i];
-                    a1 = Real<T>::fma_(h[58 - 3 * k], v, a1);
-                    a2 = Real<T>::fma_(h[59 - 3 * k], v, a2);
-                }
-            }
+            p1[r] = a1;
+            p2[r] = a2;
         }
-        out[3 * m] = c0 * x[m];
-        out[3 * m + 1] = a1;
-        out[3 * m + 2] = a2;
+        st4(P0 + m0, p0);
+        st4(P1 + m0, p1);
+        st4(P2 + m0, p2);
     }
 }
 
-// x[0..n) natural -> ceil(n/3) outputs   h: 61 dense taps
-template <typename T, class Post>
-__device__ __forceinline__ void fir_down3(const T *__restrict__ x, int n, const T *__restrict__ h, int tid, int nthr,
-                                          Post post) {
-    const int n_out = (n + 2) / 3;
-    for (int j = tid; j < n_out; j += nthr) {
-        const int ctr = 3 * j;
-        T acc = h[30] * x[ctr];
-        const bool inner = (ctr >= 29 && ctr + 29 < n);
+// Taps of down3 in window order: t1[k] multiplies P1[j0 + r - 10 + k], t2[k] multiplies P2[j0 + r - 10 + k]
+template <typename T>
+struct Down3Taps {
+    T t1[20], t2[20], c0;
+    __device__ __forceinline__ explicit Down3Taps(const T *__restrict__ h) {
 #pragma unroll
-        for (int d = -29; d <= 29; ++d) {
-            if (d % 3 == 0) continue;
-            int i = ctr + d;
-            if (inner || (i >= 0 && i < n)) acc = Real<T>::fma_(h[30 - d], x[i], acc);
-        }
-        post(j, acc);
+        for (int k = 0; k < 20; ++k) { t1[k] = h[59 - 3 * k]; t2[k] = h[58 - 3 * k]; }   // a = k - 10
+        c0 = h[30];
     }
+    // w1 / w2: 28-sample windows of P1 / P2 starting at j0 - 12; e: P0[j0 .. j0+3]
+    __device__ __forceinline__ void apply(const T *w1, const T *w2, const T *e, T *y) const {
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            T acc = c0 * e[r];
+#pragma unroll
+            for (int k = 0; k < 20; ++k) {
+                acc = Real<T>::fma_(t1[k], w1[2 + r + k], acc);
+                acc = Real<T>::fma_(t2[k], w2[2 + r + k], acc);
+            }
+            y[r] = acc;
+        }
+    }
+};
+
+// plain down3 of a polyphase buffer: 4 outputs y[j0..j0+3]
+template <typename T>
+__device__ __forceinline__ void down3_quad(const Down3Taps<T> &tp, const T *P0, const T *P1, const T *P2, int n, int j0,
+                                           T *y) {
+    T w1[28], w2[28], e[4];
+    load_window28(P1, n, j0, w1);
+    load_window28(P2, n, j0, w2);
+    ld4(P0 + j0, e);
+    tp.apply(w1, w2, e, y);
+}
+
+// down3 of the elementwise product of two polyphase buffers A * B
+template <typename T>
+__device__ __forceinline__ void down3_quad_prod(const Down3Taps<T> &tp, const T *A, const T *B, int hb, int n, int j0,
+                                                T *y) {
+    T w1[28], w2[28], e[4], t[28];
+    load_window28(A + hb, n, j0, w1);
+    load_window28(B + hb, n, j0, t);
+#pragma unroll
+    for (int i = 0; i < 28; ++i) w1[i] *= t[i];
+    load_window28(A + 2 * hb, n, j0, w2);
+    load_window28(B + 2 * hb, n, j0, t);
+#pragma unroll
+    for (int i = 0; i < 28; ++i) w2[i] *= t[i];
+    T ea[4], eb[4];
+    ld4(A + j0, ea);
+    ld4(B + j0, eb);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) e[i] = ea[i] * eb[i];
+    tp.apply(w1, w2, e, y);
 }
 
 // General rational resampler (MAC: 3/8, 3/16, 2/3, 3/2, ...).  x[0..n) -> n_out outputs.

@@ -18,39 +18,9 @@
 #include "cm_io.cuh"
 #include "cm_slots.h"
 
-// out[j] = sum_d h[30 - d] in(3j + d), d in [-30, 30] skipping the zero taps, zero outside [0, n3)
-template <typename T, class In>
-__device__ __forceinline__ T down3_at(const T *__restrict__ h, int j, int n3, In in) {
-    const int ctr = 3 * j;
-    T acc = h[30] * in(ctr);
-#pragma unroll 4
-    for (int d = -29; d <= 29; ++d) {
-        if (d % 3 == 0) continue;
-        const int i = ctr + d;
-        if (i >= 0 && i < n3) acc = Real<T>::fma_(h[30 - d], in(i), acc);
-    }
-    return acc;
-}
-
-// x[0..n) natural -> out[0..3n) natural                               h: 61 dense taps
+// sample j of a polyphase 3x buffer
 template <typename T>
-__device__ __forceinline__ void up3_natural(T *__restrict__ out, const T *__restrict__ x, int n, const T *__restrict__ h,
-                                            int tid, int nthr) {
-    const T c0 = h[30];
-    for (int m = tid; m < n; m += nthr) {
-        T a1 = (T)0, a2 = (T)0;
-#pragma unroll
-        for (int k = 0; k < 20; ++k) {
-            const int i = m - 9 + k;
-            const T v = (i >= 0 && i < n) ? x[i] : (T)0;
-            a1 = Real<T>::fma_(h[58 - 3 * k], v, a1);
-            a2 = Real<T>::fma_(h[59 - 3 * k], v, a2);
-        }
-        out[3 * m] = c0 * x[m];
-        out[3 * m + 1] = a1;
-        out[3 * m + 2] = a2;
-    }
-}
+__device__ __forceinline__ T &poly3(T *buf, int hb, int j) { return buf[(j % 3) * hb + j / 3]; }
 
 // ------------------------------------------------------------------------------------------------------------
 // Encode.  2 warps per row.  smem: R * 3 * N1   (luma | db | dr)
@@ -152,7 +122,7 @@ k_niir_encode(const __grid_constant__ DevParams<T> p, const __grid_constant__ Io
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// Decode.  smem: taps[128] + (R+1) rows x ( c[N1] | up[N3] | mod->pm[N3] | sat[N3] )
+// Decode.  smem: taps[128] + (R+1) rows x ( c[N1] | up[N3] | mod->pm[N3] | sat[N3] ), 3x buffers polyphase
 // ------------------------------------------------------------------------------------------------------------
 template <typename T>
 __global__ void __launch_bounds__(CM_NTHREADS)
@@ -161,7 +131,7 @@ k_niir_decode(const __grid_constant__ DevParams<T> p, const __grid_constant__ Io
     T *sm = reinterpret_cast<T *>(smem_raw);
     RowGroup g;
     if (!decode_group(io, g)) return;
-    const int W = p.W, N1 = p.n1p, N3 = 3 * p.hb3, n3 = 3 * W;
+    const int W = p.W, N1 = p.n1p, hb = p.hb3, N3 = 3 * hb, n3 = 3 * W;
     const int warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     T *taps = sm;
     T *rows = sm + 128;
@@ -171,10 +141,10 @@ k_niir_decode(const __grid_constant__ DevParams<T> p, const __grid_constant__ Io
     const T *hup = taps + p.res[NR_UP3].off, *hdn = taps + p.res[NR_DOWN3].off;
     auto rowp = [&](int k) { return rows + (size_t)(k + 1) * per_row; };
     copy_taps(taps, p, 2);
-    for (int k = 0; k < g.count; ++k) load_comp_row(rowp(k), io, g.fidx, g.r0 + 2 * k, W);
-    if (has_prev0) {
-        load_comp_row(rowp(-1), io, g.fidx, g.r0 - 2, W);
-    } else {
+    load_comp_rows(io, g.fidx, has_prev0 ? nin : g.count, W,
+                   [&](int k) { return rowp(has_prev0 ? k - 1 : k); },
+                   [&](int k) { return g.r0 + 2 * (has_prev0 ? k - 1 : k); });
+    if (!has_prev0) {
         // niir.py:103-106: synthetic reference carrier of line-2: sin(phi) on normal lines, -sin(phi) on alternate ones
         const int line = io.y0 + g.r0 - 2;
         const unsigned long long ph0 = start_phase(p, g.frame, line);
@@ -187,17 +157,20 @@ k_niir_decode(const __grid_constant__ DevParams<T> p, const __grid_constant__ Io
         }
     }
     __syncthreads();
-    for (int k = -1; k < g.count; ++k) up3_natural(rowp(k) + N1, rowp(k), W, hup, threadIdx.x, blockDim.x);
+    for (int k = -1; k < g.count; ++k) {
+        T *u = rowp(k) + N1;
+        fir_up3(u, u + hb, u + 2 * hb, rowp(k), W, hup, threadIdx.x, blockDim.x);
+    }
     __syncthreads();
-    cta_fill_tail<T, 1>(rows + N1, per_row, nin, N3, n3, N3);
+    cta_fill_tail<T, 3>(rows + N1, per_row, nin, hb, n3, N3);
     __syncthreads();
     const FiltHdr &fbp = p.filt[NF_UP_BP], &flp = p.filt[NF_BASE_LP];
     for (int t = warp; t < nin; t += nwarps) {          // band-pass: up -> mod
         const T *u = rows + (size_t)t * per_row + N1;
         T *m = rows + (size_t)t * per_row + N1 + N3;
-        warp_iir<T, 3>(p.tab + fbp.off, fbp, [&](int q, int ph, int) { return u[3 * q + ph]; },
-                       [&](int j, T v) { m[j] = v; });
-        warp_fill_tail<T, 1>(m, N3, n3, N3);
+        warp_iir<T, 3>(p.tab + fbp.off, fbp, [&](int q, int ph, int) { return u[ph * hb + q]; },
+                       [&](int j, T v) { poly3(m, hb, j) = v; });
+        warp_fill_tail<T, 3>(m, hb, n3, N3);
     }
     __syncthreads();
     // envelope low-pass: sat = LP(pi/2 |mod|).  The synthetic top-of-field carrier is used un-normalised
@@ -207,53 +180,65 @@ k_niir_decode(const __grid_constant__ DevParams<T> p, const __grid_constant__ Io
         const T *m = rows + (size_t)t * per_row + N1 + N3;
         T *s = rows + (size_t)t * per_row + N1 + 2 * (size_t)N3;
         warp_iir<T, 3>(p.tab + flp.off, flp,
-                       [&](int q, int ph, int) { return (T)1.57079632679489661923 * Real<T>::abs_(m[3 * q + ph]); },
-                       [&](int j, T v) { s[j] = v; });
+                       [&](int q, int ph, int) { return (T)1.57079632679489661923 * Real<T>::abs_(m[ph * hb + q]); },
+                       [&](int j, T v) { poly3(s, hb, j) = v; });
     }
     __syncthreads();
     for (int k = -1; k < g.count; ++k) {                // pm = mod / sat in place
         if (k == -1 && !has_prev0) continue;
         T *m = rowp(k) + N1 + N3;
         const T *s = rowp(k) + N1 + 2 * (size_t)N3;
-        for (int j = threadIdx.x; j < n3; j += blockDim.x) m[j] = m[j] / s[j];
+        for (int i = threadIdx.x; i < 3 * W; i += blockDim.x) {
+            const int ph = i / W, q = i - ph * W;
+            m[ph * hb + q] = m[ph * hb + q] / s[ph * hb + q];
+        }
     }
     __syncthreads();
-    const T inv_step3 = p.scalars[NS_INV_STEP3];
-    T ls_s, ls_c, rot_s, rot_c;
+    // derivative of the carrier (niir.py:123-125) into the (dead) `up` buffer of each output row
+    const T inv_step3 = p.scalars[NS_INV_STEP3] * (T)0.5;
+    for (int k = 0; k < g.count; ++k) {
+        const bool alt = is_alternate(p, g.frame, io.y0 + g.r0 + 2 * k);
+        const T *car = (alt ? rowp(k) : rowp(k - 1)) + N1 + N3;
+        const T *c0 = car, *c1 = car + hb, *c2 = car + 2 * hb;
+        T *a = rowp(k) + N1;
+        for (int m = threadIdx.x; m < W; m += blockDim.x) {
+            a[m] = m > 0 ? (c1[m] - c2[m - 1]) * inv_step3 : (T)0;                 // j = 3m
+            a[hb + m] = (c2[m] - c0[m]) * inv_step3;                               // j = 3m + 1
+            a[2 * hb + m] = m + 1 < W ? (c0[m + 1] - c1[m]) * inv_step3 : (T)0;    // j = 3m + 2
+        }
+    }
+    __syncthreads();
+    const Down3Taps<T> tp(hdn);
+    T ls_s, ls_c;
     Real<T>::sincos_turns(p.phases[NP_LINE_SHIFT], ls_s, ls_c);
     for (int k = 0; k < g.count; ++k) {
         const int row = g.r0 + 2 * k, line = io.y0 + row;
         const bool alt = is_alternate(p, g.frame, line);
         const T *c = rowp(k);
         const T *pm = rowp(k) + N1 + N3, *last = rowp(k - 1) + N1 + N3, *satu = rowp(k) + N1 + 2 * (size_t)N3;
-        const T *carrier = alt ? pm : last, *huemod = alt ? last : pm;
-        // rotation by shift = +-line_shift (niir.py:114-121,136-137)
-        const T sh_s = alt ? -ls_s : ls_s, sh_c = ls_c;
-        // luma re-synthesis rotation: (alt ? 0 : line_shift) + pi - bp.phase_shift   (niir.py:146-156)
+        const T *carrier = alt ? pm : last, *huemod = alt ? last : pm, *altc = rowp(k) + N1;
+        const T sh_s = alt ? -ls_s : ls_s, sh_c = ls_c;                           // niir.py:114-121,136-137
+        T rot_s, rot_c;                                                           // niir.py:146-156
         Real<T>::sincos_turns(p.phases[NP_LUMA_ROT] + (alt ? 0ull : p.phases[NP_LINE_SHIFT]), rot_s, rot_c);
-        auto car = [&](int j) { return carrier[j]; };
-        auto altcar = [&](int j) {                       // niir.py:123-125
-            return (j == 0 || j == n3 - 1) ? (T)0 : (T)0.5 * (carrier[j + 1] - carrier[j - 1]) * inv_step3;
-        };
         for (int q = threadIdx.x; q < (W >> 2); q += blockDim.x) {
-            T y[4], ob[4], orr[4];
+            const int j0 = 4 * q;
+            T sinphi[4], cosphi[4], sat[4], sincar[4], coscar[4], y[4], ob[4], orr[4], cc[4];
+            down3_quad_prod(tp, huemod, carrier, hb, W, j0, sinphi);
+            down3_quad_prod(tp, huemod, altc, hb, W, j0, cosphi);
+            down3_quad(tp, satu, satu + hb, satu + 2 * hb, W, j0, sat);
+            down3_quad(tp, carrier, carrier + hb, carrier + 2 * hb, W, j0, sincar);
+            down3_quad(tp, altc, altc + hb, altc + 2 * hb, W, j0, coscar);
+            ld4(c + j0, cc);
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                const int x = 4 * q + i;
-                T sinphi = down3_at(hdn, x, n3, [&](int j) { return huemod[j] * car(j); });
-                T cosphi = down3_at(hdn, x, n3, [&](int j) { return huemod[j] * altcar(j); });
-                const T norm = Real<T>::sqrt_(cosphi * cosphi + sinphi * sinphi);
-                cosphi = cosphi / norm;
-                sinphi = sinphi / norm;
-                const T sp = -cosphi * sh_s - sinphi * sh_c, cp = sinphi * sh_s - cosphi * sh_c;
-                const T sat = down3_at(hdn, x, n3, [&](int j) { return satu[j]; });
-                T db = sat * sp, dr = sat * cp;
-                const T sincar = down3_at(hdn, x, n3, car), coscar = down3_at(hdn, x, n3, altcar);
+                const T norm = Real<T>::sqrt_(cosphi[i] * cosphi[i] + sinphi[i] * sinphi[i]);
+                const T cp0 = cosphi[i] / norm, sp0 = sinphi[i] / norm;
+                const T sp = -cp0 * sh_s - sp0 * sh_c, cp = sp0 * sh_s - cp0 * sh_c;
+                T db = sat[i] * sp, dr = sat[i] * cp;
                 const T us0 = alt ? -Real<T>::sqrt_(db * db + dr * dr) : db, vs0 = alt ? (T)0 : dr;
                 const T us = us0 * rot_c - vs0 * rot_s, vs = us0 * rot_s + vs0 * rot_c;
-                y[i] = c[x] - (us * sincar + vs * coscar);
-                // niir.py:61-65: remove the saturation offset
-                const T m2 = db * db + dr * dr;
+                y[i] = cc[i] - (us * sincar[i] + vs * coscar[i]);
+                const T m2 = db * db + dr * dr;                                   // niir.py:61-65
                 if (m2 > (T)0) {
                     const T mag = Real<T>::sqrt_(m2);
                     T ns = mag - (T)0.1;
@@ -268,7 +253,7 @@ k_niir_decode(const __grid_constant__ DevParams<T> p, const __grid_constant__ Io
                 ob[i] = db;
                 orr[i] = dr;
             }
-            store_rgb4(p, io, g.fidx, row, 4 * q, y, ob, orr);
+            store_rgb4(p, io, g.fidx, row, j0, y, ob, orr);
         }
     }
 }

@@ -15,7 +15,7 @@ k_proto_encode(const __grid_constant__ DevParams<T> p, const __grid_constant__ I
     T *sm = reinterpret_cast<T *>(smem_raw);
     RowGroup g;
     if (!decode_group(io, g)) return;
-    const int W = p.W, N1 = p.n1p, N3 = 3 * p.hb3, n3 = 3 * W, W4 = W >> 2;
+    const int W = p.W, N1 = p.n1p, hb = p.hb3, N3 = 3 * hb, n3 = 3 * W, W4 = W >> 2;
     const int warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     const bool avg = (p.flags & 2) != 0, luma_filter = (p.flags & 256) != 0;
     T *taps = sm;
@@ -50,10 +50,13 @@ k_proto_encode(const __grid_constant__ DevParams<T> p, const __grid_constant__ I
     __syncthreads();
     for (int k = 0; k < g.count; ++k) {
         cta_fill_tail<T, 1>(rows + k * per_row + N1, (size_t)N1, 1, N1, W, N1);
-        if (luma_filter) up3_natural(rows + k * per_row + 2 * N1, rows + k * per_row, W, hup, threadIdx.x, blockDim.x);
+        if (luma_filter) {
+            T *u = rows + k * per_row + 2 * N1;
+            fir_up3(u, u + hb, u + 2 * hb, rows + k * per_row, W, hup, threadIdx.x, blockDim.x);
+        }
     }
     __syncthreads();
-    if (luma_filter) cta_fill_tail<T, 1>(rows + 2 * N1, per_row, g.count, N3, n3, N3);
+    if (luma_filter) cta_fill_tail<T, 3>(rows + 2 * N1, per_row, g.count, hb, n3, N3);
     __syncthreads();
     for (int t = warp; t < 2 * g.count; t += nwarps) {
         T *r = rows + (t >> 1) * per_row;
@@ -64,24 +67,26 @@ k_proto_encode(const __grid_constant__ DevParams<T> p, const __grid_constant__ I
         } else if (luma_filter) {
             T *u = r + 2 * N1;
             const FiltHdr &f = p.filt[PF_BS_UP];
-            warp_iir<T, 3>(p.tab + f.off, f, [&](int q, int ph, int) { return u[3 * q + ph]; },
-                           [&](int j, T v) { u[j] = v; });
+            warp_iir<T, 3>(p.tab + f.off, f, [&](int q, int ph, int) { return u[ph * hb + q]; },
+                           [&](int j, T v) { poly3(u, hb, j) = v; });
         }
     }
     __syncthreads();
+    const Down3Taps<T> tp(hdn);
     for (int k = 0; k < g.count; ++k) {
         const int row = g.r0 + 2 * k, line = io.y0 + row;
         const T *ys = rows + k * per_row, *cs = ys + N1, *u = ys + 2 * N1;
         const unsigned long long ph0 = start_phase(p, g.frame, line);
         for (int q = threadIdx.x; q < W4; q += blockDim.x) {
-            T o[4];
+            T o[4], luma[4];
+            if (luma_filter) down3_quad(tp, u, u + hb, u + 2 * hb, W, 4 * q, luma);
+            else ld4(ys + 4 * q, luma);
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 const int x = 4 * q + i;
-                const T luma = luma_filter ? down3_at(hdn, x, n3, [&](int j) { return u[j]; }) : ys[x];
                 T s, c;
                 Real<T>::sincos_turns(ph0 + (unsigned long long)x * p.phases[PP_STEP1X], s, c);
-                o[i] = luma + c * ((T)0.125 * ((T)1 + cs[x]));
+                o[i] = luma[i] + c * ((T)0.125 * ((T)1 + cs[x]));
             }
             store_comp4(io, ((size_t)g.fidx * io.nrows + row) * p.Wc + 4 * q, o);
         }
@@ -96,7 +101,7 @@ k_proto_decode(const __grid_constant__ DevParams<T> p, const __grid_constant__ I
     T *sm = reinterpret_cast<T *>(smem_raw);
     RowGroup g;
     if (!decode_group(io, g)) return;
-    const int W = p.W, N1 = p.n1p, N3 = 3 * p.hb3, n3 = 3 * W;
+    const int W = p.W, N1 = p.n1p, hb = p.hb3, N3 = 3 * hb, n3 = 3 * W;
     const int warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     T *taps = sm;
     T *rows = sm + 128;
@@ -107,11 +112,14 @@ k_proto_decode(const __grid_constant__ DevParams<T> p, const __grid_constant__ I
     const T *hup = taps + p.res[PR_UP3].off, *hdn = taps + p.res[PR_DOWN3].off;
     auto rowp = [&](int k) { return rows + (size_t)(k - k_lo) * per_row; };
     copy_taps(taps, p, 2);
-    for (int k = k_lo; k < g.count; ++k) load_comp_row(rowp(k), io, g.fidx, g.r0 + 2 * k, W);
+    load_comp_rows(io, g.fidx, nin, W, [&](int k) { return rowp(k_lo + k); }, [&](int k) { return g.r0 + 2 * (k_lo + k); });
     __syncthreads();
-    for (int k = k_lo; k < g.count; ++k) up3_natural(rowp(k) + N1, rowp(k), W, hup, threadIdx.x, blockDim.x);
+    for (int k = k_lo; k < g.count; ++k) {
+        T *u = rowp(k) + N1;
+        fir_up3(u, u + hb, u + 2 * hb, rowp(k), W, hup, threadIdx.x, blockDim.x);
+    }
     __syncthreads();
-    cta_fill_tail<T, 1>(rows + N1, per_row, nin, N3, n3, N3);
+    cta_fill_tail<T, 3>(rows + N1, per_row, nin, hb, n3, N3);
     __syncthreads();
     const FiltHdr &fbp = p.filt[PF_BP_UP], &fbs = p.filt[PF_BS_UP], &fpost = p.filt[PF_POST_LP];
     for (int t = warp; t < 2 * nin; t += nwarps) {
@@ -119,24 +127,30 @@ k_proto_decode(const __grid_constant__ DevParams<T> p, const __grid_constant__ I
         const T *u = r + N1;
         if ((t & 1) == 0) {
             T *b = r + N1 + N3;
-            warp_iir<T, 3>(p.tab + fbp.off, fbp, [&](int q, int ph, int) { return u[3 * q + ph]; },
-                           [&](int j, T v) { b[j] = v; });
-            warp_fill_tail<T, 1>(b, N3, n3, N3);
+            warp_iir<T, 3>(p.tab + fbp.off, fbp, [&](int q, int ph, int) { return u[ph * hb + q]; },
+                           [&](int j, T v) { poly3(b, hb, j) = v; });
+            warp_fill_tail<T, 3>(b, hb, n3, N3);
             warp_iir<T, 3>(p.tab + fpost.off, fpost,
-                           [&](int q, int ph, int) { return (T)1.57079632679489661923 * Real<T>::abs_(b[3 * q + ph]); },
-                           [&](int j, T v) { b[j] = v; });
+                           [&](int q, int ph, int) { return (T)1.57079632679489661923 * Real<T>::abs_(b[ph * hb + q]); },
+                           [&](int j, T v) { poly3(b, hb, j) = v; });
         } else if ((t >> 1) + k_lo >= 0) {
             T *l = r + N1 + 2 * (size_t)N3;
-            warp_iir<T, 3>(p.tab + fbs.off, fbs, [&](int q, int ph, int) { return u[3 * q + ph]; },
-                           [&](int j, T v) { l[j] = v; });
+            warp_iir<T, 3>(p.tab + fbs.off, fbs, [&](int q, int ph, int) { return u[ph * hb + q]; },
+                           [&](int j, T v) { poly3(l, hb, j) = v; });
         }
     }
     __syncthreads();
+    const Down3Taps<T> tp(hdn);
     for (int k = k_lo; k < g.count; ++k) {              // X = 8 down3(chroma_up) - 1 into the (dead) composite buffer
         T *x = rowp(k);
         const T *b = rowp(k) + N1 + N3;
-        for (int j = threadIdx.x; j < W; j += blockDim.x)
-            x[j] = (T)8 * down3_at(hdn, j, n3, [&](int i) { return b[i]; }) - (T)1;
+        for (int q = threadIdx.x; q < (W >> 2); q += blockDim.x) {
+            T y[4];
+            down3_quad(tp, b, b + hb, b + 2 * hb, W, 4 * q, y);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) y[i] = (T)8 * y[i] - (T)1;
+            st4(x + 4 * q, y);
+        }
     }
     __syncthreads();
     for (int k = 0; k < g.count; ++k) {
@@ -146,8 +160,7 @@ k_proto_decode(const __grid_constant__ DevParams<T> p, const __grid_constant__ I
         const T *xc = rowp(k), *xp = hp ? rowp(k - 1) : nullptr, *l = rowp(k) + N1 + 2 * (size_t)N3;
         for (int q = threadIdx.x; q < (W >> 2); q += blockDim.x) {
             T y[4], a[4], b[4] = {(T)0, (T)0, (T)0, (T)0};
-#pragma unroll
-            for (int i = 0; i < 4; ++i) y[i] = down3_at(hdn, 4 * q + i, n3, [&](int j) { return l[j]; });
+            down3_quad(tp, l, l + hb, l + 2 * hb, W, 4 * q, y);
             ld4(xc + 4 * q, a);
             if (hp) ld4(xp + 4 * q, b);
             // protosecam.py:105-108: non-alternate rows carry D'R (dr = current, db = previous)
