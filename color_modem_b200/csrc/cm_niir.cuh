@@ -125,7 +125,7 @@ k_niir_encode(const __grid_constant__ DevParams<T> p, const __grid_constant__ Io
 // Decode.  smem: taps[128] + (R+1) rows x ( c[N1] | up[N3] | mod->pm[N3] | sat[N3] ), 3x buffers polyphase
 // ------------------------------------------------------------------------------------------------------------
 template <typename T>
-__global__ void __launch_bounds__(CM_NTHREADS)
+__global__ void __launch_bounds__(192, 2)
 k_niir_decode(const __grid_constant__ DevParams<T> p, const __grid_constant__ IoArgs<T> io) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     T *sm = reinterpret_cast<T *>(smem_raw);

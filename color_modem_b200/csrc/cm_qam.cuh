@@ -398,7 +398,7 @@ k_pald_combed(const __grid_constant__ DevParams<T> p, const __grid_constant__ Io
 enum { COMB_NTSC2 = 0, COMB_NTSC3 = 1, COMB_PAL3 = 2 };
 
 template <typename T, int MODE>
-__global__ void __launch_bounds__(CM_NTHREADS)
+__global__ void __launch_bounds__(CM_NTHREADS, 2)
 k_qam_comb(const __grid_constant__ DevParams<T> p, const __grid_constant__ IoArgs<T> io) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     T *sm = reinterpret_cast<T *>(smem_raw);
