@@ -84,6 +84,14 @@ static int pick_rows(int rmax, size_t budget, F bytes_for) {
     return 0;
 }
 
+// Threads per CTA for `tasks` concurrent warp-level IIR tasks: one warp per task, but never fewer than 4 warps so
+// that the sample-parallel FIR / elementwise phases of wide lines (few rows per CTA) still have threads to spread over.
+static inline int cta_threads(int tasks) {
+    int warps = tasks < 4 ? 4 : tasks;
+    if (warps > CM_NWARPS) warps = CM_NWARPS;
+    return 32 * warps;
+}
+
 template <typename T>
 static void set_groups(IoArgs<T> &io, int R) {
     io.rows_per_cta = R;

@@ -14,8 +14,7 @@ static int launch_rows(cm_modem *m, IoArgs<T> io, cudaStream_t st, K kernel, F b
     int rc = set_smem(kernel, bytes(R));
     if (rc) return rc;
     dim3 grid((unsigned)(io.nframes * 2 * io.groups_per_field));
-    int threads = 32 * warps_per_row * (R + extra_rows);
-    if (threads > CM_NTHREADS) threads = CM_NTHREADS;
+    int threads = cta_threads(warps_per_row * (R + extra_rows));
     {
         LaunchTimer lt(m, timer_id, st);
         kernel<<<grid, threads, bytes(R), st>>>(params_of<T>(m), io);

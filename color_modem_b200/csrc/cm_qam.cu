@@ -15,7 +15,7 @@ int qam_encode(cm_modem *m, IoArgs<T> io, cudaStream_t st) {
     dim3 grid((unsigned)(io.nframes * 2 * io.groups_per_field));
     {
         LaunchTimer lt(m, CM_K_ENCODE, st);
-        k_qam_encode<T><<<grid, 64 * R, bytes(R), st>>>(p, io);
+        k_qam_encode<T><<<grid, cta_threads(2 * R), bytes(R), st>>>(p, io);
     }
     cm_count_launch();
     CUDA_TRY(cudaGetLastError());
@@ -36,7 +36,7 @@ static int launch_bandsplit(cm_modem *m, IoArgs<T> io, int luma_mode, cudaStream
     dim3 grid((unsigned)(io.nframes * 2 * io.groups_per_field));
     {
         LaunchTimer lt(m, CM_K_BANDSPLIT, st);
-        k_qam_bandsplit<T><<<grid, 64 * R, bytes(R), st>>>(p, io, luma_mode);
+        k_qam_bandsplit<T><<<grid, cta_threads(2 * R), bytes(R), st>>>(p, io, luma_mode);
     }
     cm_count_launch();
     CUDA_TRY(cudaGetLastError());
@@ -59,7 +59,7 @@ static int launch_pald(cm_modem *m, IoArgs<T> io, cudaStream_t st) {
     dim3 grid((unsigned)(io.nframes * 2 * io.groups_per_field));
     {
         LaunchTimer lt(m, CM_K_PALD, st);
-        k_pald_combed<T><<<grid, 64 * R, bytes(R), st>>>(p, io);
+        k_pald_combed<T><<<grid, cta_threads(2 * R), bytes(R), st>>>(p, io);
     }
     cm_count_launch();
     CUDA_TRY(cudaGetLastError());
@@ -82,7 +82,7 @@ static int launch_comb(cm_modem *m, IoArgs<T> io, cudaStream_t st) {
     dim3 grid((unsigned)(io.nframes * 2 * io.groups_per_field));
     {
         LaunchTimer lt(m, CM_K_COMB, st);
-        k_qam_comb<T, MODE><<<grid, 64 * R, bytes(R), st>>>(p, io);
+        k_qam_comb<T, MODE><<<grid, cta_threads(2 * R), bytes(R), st>>>(p, io);
     }
     cm_count_launch();
     CUDA_TRY(cudaGetLastError());

@@ -15,7 +15,7 @@ int secam_encode(cm_modem *m, IoArgs<T> io, cudaStream_t st) {
     dim3 grid((unsigned)(io.nframes * 2 * io.groups_per_field));
     {
         LaunchTimer lt(m, CM_K_ENCODE, st);
-        k_secam_encode<T><<<grid, 32 * R, bytes(R), st>>>(p, io);
+        k_secam_encode<T><<<grid, cta_threads(R), bytes(R), st>>>(p, io);
     }
     cm_count_launch();
     CUDA_TRY(cudaGetLastError());
@@ -36,7 +36,7 @@ int secam_decode(cm_modem *m, IoArgs<T> io, cudaStream_t st) {
     dim3 grid((unsigned)(io.nframes * 2 * io.groups_per_field));
     {
         LaunchTimer lt(m, CM_K_DECODE_OTHER, st);
-        k_secam_decode<T><<<grid, 64 * (R + 1), bytes(R), st>>>(p, io);
+        k_secam_decode<T><<<grid, cta_threads(2 * (R + 1)), bytes(R), st>>>(p, io);
     }
     cm_count_launch();
     CUDA_TRY(cudaGetLastError());
