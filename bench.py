@@ -92,7 +92,7 @@ def run_reference(args):
     if rank != 0:
         return
     pool, cores = cpu_pool()
-    nframes = args.cpu_frames or max(cores, 32)
+    nframes = args.cpu_frames or 2 * cores            # a whole number of frames per worker
     for _ in range(args.warmup):
         cpu_sample(pool, cores, cores)
     t0 = time.perf_counter()
@@ -194,7 +194,7 @@ def run_ours(args):
         # CPU baseline beside the GPU number (N=1 only): oracle port on all host cores, bounded sample.  Taken before
         # CUDA is initialised so the worker processes can be forked safely.
         pool, cores = cpu_pool()
-        nfr = args.cpu_frames or max(cores, 32)
+        nfr = args.cpu_frames or 2 * cores
         cfps, wall, cpu_s = cpu_sample(pool, cores, nfr)
         pool.close()
         pool.join()
