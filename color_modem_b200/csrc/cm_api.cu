@@ -349,8 +349,23 @@ static int run_ex(cm_modem *m, bool encode, const cm_window *win, const uint8_t 
     }
     CUDA_TRY(cudaSetDevice(m->device));
     const int mode = win ? win->mode : CM_MODE_DEFAULT;
-    return encode ? dispatch_encode<T>(m, io, (cudaStream_t)stream)
-                  : dispatch_decode<T>(m, io, mode, (cudaStream_t)stream);
+    // gridDim.z carries the frame index: at most 65535 frames per launch
+    const size_t in_w = encode ? (size_t)m->desc.width * 3 : (size_t)m->desc.comp_width;
+    const size_t out_w = encode ? (size_t)m->desc.comp_width : (size_t)m->desc.out_width * 3;
+    for (int32_t base = 0; base < nframes; base += 65535) {
+        IoArgs<T> part = io;
+        part.nframes = nframes - base < 65535 ? nframes - base : 65535;
+        part.first_frame = first_frame + base;
+        const size_t in_off = (size_t)base * io.nrows * in_w, out_off = (size_t)base * io.nrows * out_w;
+        if (part.in_u8) part.in_u8 += in_off;
+        if (part.in_f) part.in_f += in_off;
+        if (part.out_u8) part.out_u8 += out_off;
+        if (part.out_f) part.out_f += out_off;
+        int rc = encode ? dispatch_encode<T>(m, part, (cudaStream_t)stream)
+                        : dispatch_decode<T>(m, part, mode, (cudaStream_t)stream);
+        if (rc) return rc;
+    }
+    return CM_OK;
 }
 
 extern "C" int cm_encode_ex(cm_modem *m, const cm_window *win, const uint8_t *rgb_u8, const void *rgb_float,

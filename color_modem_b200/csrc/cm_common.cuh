@@ -163,16 +163,13 @@ struct RowGroup {
 };
 
 // Output rows [out_begin, out_begin+out_count) split by parity into two "fields"; each field into groups of R.
+// Grid: x = group inside the field, y = field, z = frame of the batch (no integer divisions in the prologue).
 template <typename T>
 __device__ __forceinline__ bool decode_group(const IoArgs<T> &io, RowGroup &g) {
-    int per_frame = 2 * io.groups_per_field;
-    int f = blockIdx.x / per_frame;
-    int rem = blockIdx.x - f * per_frame;
-    int field = rem / io.groups_per_field;
-    int gi = rem - field * io.groups_per_field;
-    int first = io.out_begin + field;                         // first row of this parity class
-    int rows_in_field = (io.out_count - field + 1) >> 1;      // rows out_begin+field, +2, ... < out_begin+out_count
-    int start = gi * io.rows_per_cta;
+    const int field = blockIdx.y, gi = blockIdx.x, f = blockIdx.z;
+    const int first = io.out_begin + field;                         // first row of this parity class
+    const int rows_in_field = (io.out_count - field + 1) >> 1;      // rows out_begin+field, +2, ... < out_begin+out_count
+    const int start = gi * io.rows_per_cta;
     g.fidx = f;
     g.frame = io.first_frame + f;
     g.r0 = first + 2 * start;

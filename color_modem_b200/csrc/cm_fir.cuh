@@ -106,6 +106,40 @@ __device__ __forceinline__ void fir_down2(const T *__restrict__ E, const T *__re
     }
 }
 
+// Two down2's at once (same taps): post(j0, y1[4], y2[4]).  Used where two demodulated signals are combined
+// sample by sample right after the decimation (PAL-D: (S, D) -> (u, v)).
+template <typename T, class Post>
+__device__ __forceinline__ void fir_down2_pair(const T *__restrict__ E1, const T *__restrict__ O1,
+                                               const T *__restrict__ E2, const T *__restrict__ O2, int n,
+                                               const T *__restrict__ h, int tid, int nthr, Post post) {
+    T g[20];
+#pragma unroll
+    for (int k = 0; k < 20; ++k) g[k] = h[39 - 2 * k];
+    const T c0 = h[20];
+    for (int j0 = 4 * tid; j0 < n; j0 += 4 * nthr) {
+        T w[28], e[4], y1[4], y2[4];
+        load_window28(O1, n, j0, w);
+        ld4(E1 + j0, e);
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            T acc = c0 * e[r];
+#pragma unroll
+            for (int k = 0; k < 20; ++k) acc = Real<T>::fma_(g[k], w[2 + r + k], acc);
+            y1[r] = acc;
+        }
+        load_window28(O2, n, j0, w);
+        ld4(E2 + j0, e);
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            T acc = c0 * e[r];
+#pragma unroll
+            for (int k = 0; k < 20; ++k) acc = Real<T>::fma_(g[k], w[2 + r + k], acc);
+            y2[r] = acc;
+        }
+        post(j0, y1, y2);
+    }
+}
+
 // ---- x3 / :3, polyphase [P0 | P1 | P2] (P_r[m] = x3[3m + r]), 61 dense taps, every tap at a non-zero multiple of 3
 // from the centre is zero:
 //     up3:    P0[m] = h[30] x[m]     P1[m] = sum_k h[58-3k] x[m-9+k]     P2[m] = sum_k h[59-3k] x[m-9+k]   k = 0..19

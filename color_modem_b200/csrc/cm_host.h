@@ -99,6 +99,12 @@ static void set_groups(IoArgs<T> &io, int R) {
     io.groups_per_field = (rows_in_field + R - 1) / R;
 }
 
+// grid of a row-group kernel: x = groups per field, y = 2 fields, z = frames (run_ex keeps nframes <= 65535 per launch)
+template <typename T>
+static dim3 cm_grid(const IoArgs<T> &io) {
+    return dim3((unsigned)io.groups_per_field, 2u, (unsigned)io.nframes);
+}
+
 // rows of [begin, begin+count) that have no predecessor in the window (r < 2) / that have one (r >= 2)
 template <typename T>
 static void split_top(const IoArgs<T> &io, IoArgs<T> &top, IoArgs<T> &rest) {

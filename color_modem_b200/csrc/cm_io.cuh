@@ -56,37 +56,33 @@ __device__ __forceinline__ void load_comp_row(T *dst, const IoArgs<T> &io, int f
     }
 }
 
-// Several composite rows at once: all global loads of a thread are issued back to back before any conversion, so
-// the DRAM latency is paid once per CTA instead of once per row.  dst(k) -> shared row of index k in [0, nrows),
-// src_row(k) -> buffer row number.
+// Several composite rows at once (at most 6): all global loads of a thread are issued back to back before any
+// conversion, so the DRAM latency is paid once per CTA instead of once per row.  dst(k) -> shared row of index k in
+// [0, nrows), src_row(k) -> buffer row number.
 template <typename T, class Dst, class SrcRow>
 __device__ __forceinline__ void load_comp_rows(const IoArgs<T> &io, int fidx, int nrows, int Wc, Dst dst, SrcRow src_row) {
-    const int q_per_row = Wc >> 2, total = nrows * q_per_row;
-    constexpr int kBatch = 4;
-    for (int base = threadIdx.x; base < total; base += kBatch * blockDim.x) {
-        uint32_t w[kBatch];
-        T vf[kBatch][4];
+    constexpr int kMaxRows = 6;
+    const size_t frame_base = (size_t)fidx * io.nrows;
+    for (int x = 4 * threadIdx.x; x < Wc; x += 4 * blockDim.x) {
+        uint32_t w[kMaxRows];
+        T vf[kMaxRows][4];
 #pragma unroll
-        for (int b = 0; b < kBatch; ++b) {
-            const int idx = base + b * blockDim.x;
-            if (idx < total) {
-                const int k = idx / q_per_row, x = 4 * (idx - k * q_per_row);
-                const size_t off = ((size_t)fidx * io.nrows + src_row(k)) * Wc + x;
-                if (io.in_f) ld4(io.in_f + off, vf[b]);
-                else w[b] = __ldg(reinterpret_cast<const uint32_t *>(io.in_u8 + off));
+        for (int k = 0; k < kMaxRows; ++k) {
+            if (k < nrows) {
+                const size_t off = (frame_base + src_row(k)) * Wc + x;
+                if (io.in_f) ld4(io.in_f + off, vf[k]);
+                else w[k] = __ldg(reinterpret_cast<const uint32_t *>(io.in_u8 + off));
             }
         }
 #pragma unroll
-        for (int b = 0; b < kBatch; ++b) {
-            const int idx = base + b * blockDim.x;
-            if (idx < total) {
-                const int k = idx / q_per_row, x = 4 * (idx - k * q_per_row);
+        for (int k = 0; k < kMaxRows; ++k) {
+            if (k < nrows) {
                 if (!io.in_f) {
 #pragma unroll
                     for (int i = 0; i < 4; ++i)
-                        vf[b][i] = ((T)5 * Real<T>::from_u8((w[b] >> (8 * i)) & 0xff) - (T)1) * (T)(1.0 / 3.0);
+                        vf[k][i] = ((T)5 * Real<T>::from_u8((w[k] >> (8 * i)) & 0xff) - (T)1) * (T)(1.0 / 3.0);
                 }
-                st4(dst(k) + x, vf[b]);
+                st4(dst(k) + x, vf[k]);
             }
         }
     }

@@ -20,7 +20,7 @@ int mac_encode(cm_modem *m, IoArgs<T> io, cudaStream_t st) {
     set_groups(io, R);
     int rc = set_smem(k_mac_encode<T>, bytes(R));
     if (rc) return rc;
-    dim3 grid((unsigned)(io.nframes * 2 * io.groups_per_field));
+    dim3 grid = cm_grid(io);
     {
         LaunchTimer lt(m, CM_K_ENCODE, st);
         k_mac_encode<T><<<grid, CM_NTHREADS, bytes(R), st>>>(p, io, tl);
@@ -43,7 +43,7 @@ int mac_decode(cm_modem *m, IoArgs<T> io, cudaStream_t st) {
     set_groups(io, R);
     int rc = set_smem(k_mac_decode<T>, bytes(R));
     if (rc) return rc;
-    dim3 grid((unsigned)(io.nframes * 2 * io.groups_per_field));
+    dim3 grid = cm_grid(io);
     {
         LaunchTimer lt(m, CM_K_DECODE_OTHER, st);
         k_mac_decode<T><<<grid, CM_NTHREADS, bytes(R), st>>>(p, io, tl);

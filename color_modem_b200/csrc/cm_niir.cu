@@ -13,7 +13,7 @@ static int launch_rows(cm_modem *m, IoArgs<T> io, cudaStream_t st, K kernel, F b
     set_groups(io, R);
     int rc = set_smem(kernel, bytes(R));
     if (rc) return rc;
-    dim3 grid((unsigned)(io.nframes * 2 * io.groups_per_field));
+    dim3 grid = cm_grid(io);
     int threads = cta_threads(warps_per_row * (R + extra_rows));
     {
         LaunchTimer lt(m, timer_id, st);

@@ -12,7 +12,7 @@ int qam_encode(cm_modem *m, IoArgs<T> io, cudaStream_t st) {
     set_groups(io, R);
     int rc = set_smem(k_qam_encode<T>, bytes(R));
     if (rc) return rc;
-    dim3 grid((unsigned)(io.nframes * 2 * io.groups_per_field));
+    dim3 grid = cm_grid(io);
     {
         LaunchTimer lt(m, CM_K_ENCODE, st);
         k_qam_encode<T><<<grid, cta_threads(2 * R), bytes(R), st>>>(p, io);
@@ -33,7 +33,7 @@ static int launch_bandsplit(cm_modem *m, IoArgs<T> io, int luma_mode, cudaStream
     set_groups(io, R);
     int rc = set_smem(k_qam_bandsplit<T>, bytes(R));
     if (rc) return rc;
-    dim3 grid((unsigned)(io.nframes * 2 * io.groups_per_field));
+    dim3 grid = cm_grid(io);
     {
         LaunchTimer lt(m, CM_K_BANDSPLIT, st);
         k_qam_bandsplit<T><<<grid, cta_threads(2 * R), bytes(R), st>>>(p, io, luma_mode);
@@ -56,7 +56,7 @@ static int launch_pald(cm_modem *m, IoArgs<T> io, cudaStream_t st) {
     set_groups(io, R);
     int rc = set_smem(k_pald_combed<T>, bytes(R));
     if (rc) return rc;
-    dim3 grid((unsigned)(io.nframes * 2 * io.groups_per_field));
+    dim3 grid = cm_grid(io);
     {
         LaunchTimer lt(m, CM_K_PALD, st);
         k_pald_combed<T><<<grid, cta_threads(2 * R), bytes(R), st>>>(p, io);
@@ -79,7 +79,7 @@ static int launch_comb(cm_modem *m, IoArgs<T> io, cudaStream_t st) {
     set_groups(io, R);
     int rc = set_smem(k_qam_comb<T, MODE>, bytes(R));
     if (rc) return rc;
-    dim3 grid((unsigned)(io.nframes * 2 * io.groups_per_field));
+    dim3 grid = cm_grid(io);
     {
         LaunchTimer lt(m, CM_K_COMB, st);
         k_qam_comb<T, MODE><<<grid, cta_threads(2 * R), bytes(R), st>>>(p, io);

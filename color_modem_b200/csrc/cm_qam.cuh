@@ -336,25 +336,23 @@ k_pald_combed(const __grid_constant__ DevParams<T> p, const __grid_constant__ Io
     }
     __syncthreads();
     pc.mark();
-    // S, D at 1x -> gbuf rows (G is dead): S at [k][0..N1), D at [k][N1..2 N1)
-    for (int k = 0; k < g.count; ++k) {
-        T *so = gbuf + (size_t)k * N2, *dout = so + N1;
-        const T *ws = work + (size_t)(2 * k) * N2, *wd = work + (size_t)(2 * k + 1) * N2;
-        fir_down2(ws, ws + hb, W, hdn, threadIdx.x, blockDim.x, [&](int j0, const T *y) { st4(so + j0, y); });
-        fir_down2(wd, wd + hb, W, hdn, threadIdx.x, blockDim.x, [&](int j0, const T *y) { st4(dout + j0, y); });
-    }
-    __syncthreads();
-    pc.mark();
+    // S, D at 1x, rotated to (u, v) with the V switch (pal.py:121-125), into the gbuf rows (G is dead):
+    // u at [k][0..N1), v at [k][N1..2 N1)
     const T sf = p.scalars[QS_PALD_SIN], cf = p.scalars[QS_PALD_COS];
-    for (int k = 0; k < g.count; ++k) {                 // rotate (S, D) -> (u, v) in place, V switch
-        T *so = gbuf + (size_t)k * N2;
-        const bool alt = is_alternate(p, g.frame, io.y0 + g.r0 + 2 * k);
-        for (int x = threadIdx.x; x < W; x += blockDim.x) {
-            const T s = so[x], d = so[N1 + x];
-            const T v = d * cf - s * sf;
-            so[x] = d * sf + s * cf;
-            so[N1 + x] = alt ? -v : v;
-        }
+    for (int k = 0; k < g.count; ++k) {
+        T *uo = gbuf + (size_t)k * N2, *vo = uo + N1;
+        const T *ws = work + (size_t)(2 * k) * N2, *wd = work + (size_t)(2 * k + 1) * N2;
+        const T vsgn = is_alternate(p, g.frame, io.y0 + g.r0 + 2 * k) ? (T)-1 : (T)1;
+        fir_down2_pair(ws, ws + hb, wd, wd + hb, W, hdn, threadIdx.x, blockDim.x, [&](int j0, const T *s, const T *d) {
+            T u[4], v[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                u[i] = d[i] * sf + s[i] * cf;
+                v[i] = vsgn * (d[i] * cf - s[i] * sf);
+            }
+            st4(uo + j0, u);
+            st4(vo + j0, v);
+        });
     }
     __syncthreads();
     pc.mark();

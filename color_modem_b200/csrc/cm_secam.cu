@@ -12,7 +12,7 @@ int secam_encode(cm_modem *m, IoArgs<T> io, cudaStream_t st) {
     set_groups(io, R);
     int rc = set_smem(k_secam_encode<T>, bytes(R));
     if (rc) return rc;
-    dim3 grid((unsigned)(io.nframes * 2 * io.groups_per_field));
+    dim3 grid = cm_grid(io);
     {
         LaunchTimer lt(m, CM_K_ENCODE, st);
         k_secam_encode<T><<<grid, cta_threads(R), bytes(R), st>>>(p, io);
@@ -33,7 +33,7 @@ int secam_decode(cm_modem *m, IoArgs<T> io, cudaStream_t st) {
     set_groups(io, R);
     int rc = set_smem(k_secam_decode<T>, bytes(R));
     if (rc) return rc;
-    dim3 grid((unsigned)(io.nframes * 2 * io.groups_per_field));
+    dim3 grid = cm_grid(io);
     {
         LaunchTimer lt(m, CM_K_DECODE_OTHER, st);
         k_secam_decode<T><<<grid, cta_threads(2 * (R + 1)), bytes(R), st>>>(p, io);
