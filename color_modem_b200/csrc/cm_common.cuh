@@ -127,8 +127,7 @@ __device__ __forceinline__ unsigned to_u8(T v) {
 }
 template <>
 __device__ __forceinline__ unsigned to_u8<float>(float v) {
-    v = fminf(fmaxf(v, 0.0f), 1.0f);
-    return (unsigned)__float2int_rn(v * 255.0f);
+    return (unsigned)__float2int_rn(__saturatef(v) * 255.0f);
 }
 
 // ------------------------------------------------------------------------------------------------------------

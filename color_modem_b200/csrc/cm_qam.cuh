@@ -27,7 +27,7 @@ __device__ __forceinline__ void carrier4(unsigned long long ph_x0, T rs, T rc, T
 // optional ColorAveragingModem front end (comb.py:141-152).     smem: R * 3 * N1
 // ------------------------------------------------------------------------------------------------------------
 template <typename T>
-__global__ void __launch_bounds__(CM_NTHREADS)
+__global__ void __launch_bounds__(CM_NTHREADS, 3)
 k_qam_encode(const __grid_constant__ DevParams<T> p, const __grid_constant__ IoArgs<T> io) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     T *sm = reinterpret_cast<T *>(smem_raw);
