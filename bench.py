@@ -41,6 +41,7 @@ def parse():
     ap.add_argument('--frames', type=int, default=256, help='frames per GPU per step')
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--cpu-frames', type=int, default=0, help='frames in the CPU sample (0 = auto)')
+    ap.add_argument('--no-extras', action='store_true', help='skip the short runs of the other BASELINE configs')
     return ap.parse_args()
 
 
@@ -281,6 +282,39 @@ def run_ours(args):
     e2e_s = float(t.item())
     checksum = int(np_out[0, :4, :4].sum())     # device->host read of the step's result
 
+    # ---- the other BASELINE configs, briefly (rank 0, device-resident, CUDA events): context for the headline --------
+    others = []
+    if rank == 0 and not args.no_extras:
+        from color_modem_b200 import comb
+        from color_modem_b200.color import ntsc, secam, niir
+        lc480 = LineConfig((720, 480))
+        extra = [('Simple3DCombModem(NtscCombModem) NTSC 720x480 (BASELINE configs[2], north_star 480i target)',
+                  lambda: comb.Simple3DCombModem(ntsc.NtscCombModem(lc480)), 480),
+                 ('NtscModem NTSC 720x480 (BASELINE configs[0])', lambda: ntsc.NtscModem(lc480), 480),
+                 ('ColorAveragingModem(SecamModem) SECAM 720x576 (BASELINE configs[3])',
+                  lambda: comb.ColorAveragingModem(secam.SecamModem(LineConfig((W, H)))), H),
+                 ('HueCorrectingNiirModem 720x576 (BASELINE configs[3])',
+                  lambda: niir.HueCorrectingNiirModem(LineConfig((W, H))), H)]
+        for name, make, hh in extra:
+            mm = make()
+            fr = 128
+            xr = torch.from_numpy(synth_frames_u8(8, hh, W, seed=2)).repeat(fr // 8, 1, 1, 1).contiguous().to(dev)
+            xc = mm.encode_frames(xr)
+            xo = mm.decode_frames(xc)
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(5):
+                mm.encode_frames(xr, out=xc)
+                mm.decode_frames(xc, out=xo)
+            b.record()
+            torch.cuda.synchronize()
+            fps_x = 5 * fr / (a.elapsed_time(b) * 1e-3)
+            bytes_x = 3 * W * hh + 2 * mm.composite_width * hh + 3 * mm.output_width * hh
+            others.append({'workload': name, 'frames_per_s': fps_x, 'frames_per_step': fr,
+                           'hbm_roofline_frac': fps_x * bytes_x / 1e9 / measured_peak_gbs()[0]})
+            del mm, xr, xc, xo
+
     if rank == 0:
         total_frames = F * world * args.steps
         fps = total_frames / (ms * 1e-3)
@@ -303,6 +337,7 @@ def run_ours(args):
                     'steps': e2e_steps, 'api': 'ImageModem.modulate_batch -> demodulate_batch (pinned host buffers)',
                     'result_checksum': checksum},
             'gpu_launches': launches,
+            'other_workloads': others,
             'roofline': {'bound': 'hbm', 'kernel': 'k_pald_combed<float>', 'achieved': achieved, 'peak': peak,
                          'unit': 'GB/s', 'frac': achieved / peak, 'traffic': None, 'peak_source': peak_src,
                          'algorithmic_bytes_per_launch': F * DECODE_BYTES_PER_FRAME,

@@ -71,6 +71,30 @@ static void build_filter(const cm_filter &f, FiltHdr &h, std::vector<double> &ta
             mat_mul(M, M, Q);
             memcpy(M, Q, sizeof(M));
         }
+        // DF-II-T tables of the multi-warp path: state (s1, s2), one step = [[-a1, 1], [-a2, 0]]
+        const double At[4] = {-c[3], 1.0, -c[4], 0.0};
+        double Mt[4] = {1.0, 0.0, 0.0, 1.0};
+        for (int i = 0; i < L; ++i) {
+            double Q[4];
+            mat_mul(At, Mt, Q);
+            memcpy(Mt, Q, sizeof(Mt));
+        }
+        double Pw[4] = {1.0, 0.0, 0.0, 1.0};              // (A^L)^t
+        for (int t = 0; t < 32; ++t) {
+            for (int i = 0; i < 4; ++i) sec[CM_SEC_T_LANE + 4 * t + i] = Pw[i];
+            double Q[4];
+            mat_mul(Mt, Pw, Q);
+            memcpy(Pw, Q, sizeof(Pw));
+        }
+        for (int i = 0; i < 4; ++i) sec[CM_SEC_T_M32 + i] = Pw[i];      // (A^L)^32
+        double Sq[4];
+        memcpy(Sq, Mt, sizeof(Sq));
+        for (int k = 0; k < 5; ++k) {
+            for (int i = 0; i < 4; ++i) sec[CM_SEC_T_MPOW + 4 * k + i] = Sq[i];
+            double Q[4];
+            mat_mul(Sq, Sq, Q);
+            memcpy(Sq, Q, sizeof(Sq));
+        }
         tab.insert(tab.end(), sec.begin(), sec.end());
     }
 }

@@ -2,20 +2,30 @@
 #include "cm_host.h"
 #include "cm_qam.cuh"
 
+// true when some IIR use-site of the handle spans several super-chunks (long lines): use the multi-warp kernels
+template <typename T>
+static bool needs_teams(const DevParams<T> &p) {
+    for (int i = 0; i < CM_NFILT; ++i)
+        if (p.filt[i].nsec && p.filt[i].nsuper > 1) return true;
+    return false;
+}
+
 template <typename T>
 int qam_encode(cm_modem *m, IoArgs<T> io, cudaStream_t st) {
     const DevParams<T> &p = params_of<T>(m);
     if (io.out_count <= 0) return CM_OK;
-    auto bytes = [&](int r) { return (size_t)r * 3 * p.n1p * sizeof(T); };
+    auto bytes = [&](int r) { return (64 + (size_t)r * 3 * p.n1p) * sizeof(T); };
     int R = pick_rows(4, (size_t)m->smem_optin / 2, bytes);
     if (!R) return cm_fail(CM_ERR_UNSUPPORTED, "line too wide for the encode kernel%s");
     set_groups(io, R);
-    int rc = set_smem(k_qam_encode<T>, bytes(R));
+    const bool teams = needs_teams(p);
+    int rc = teams ? set_smem(k_qam_encode<T, true>, bytes(R)) : set_smem(k_qam_encode<T, false>, bytes(R));
     if (rc) return rc;
     dim3 grid = cm_grid(io);
     {
         LaunchTimer lt(m, CM_K_ENCODE, st);
-        k_qam_encode<T><<<grid, cta_threads(2 * R), bytes(R), st>>>(p, io);
+        if (teams) k_qam_encode<T, true><<<grid, CM_NTHREADS, bytes(R), st>>>(p, io);
+        else k_qam_encode<T, false><<<grid, cta_threads(2 * R), bytes(R), st>>>(p, io);
     }
     cm_count_launch();
     CUDA_TRY(cudaGetLastError());
@@ -26,17 +36,19 @@ template <typename T>
 static int launch_bandsplit(cm_modem *m, IoArgs<T> io, int luma_mode, cudaStream_t st) {
     const DevParams<T> &p = params_of<T>(m);
     if (io.out_count <= 0) return CM_OK;
-    auto bytes = [&](int r) { return (128 + (size_t)r * (p.n1p + 8 * (size_t)p.hb2)) * sizeof(T); };
+    auto bytes = [&](int r) { return (CM_TAPS_ELEMS + (size_t)r * (p.n1p + 8 * (size_t)p.hb2)) * sizeof(T); };
     int R = pick_rows(4, (size_t)m->smem_optin / 2, bytes);
     if (!R) R = pick_rows(1, (size_t)m->smem_optin, bytes);
     if (!R) return cm_fail(CM_ERR_UNSUPPORTED, "line too wide for the band-split kernel%s");
     set_groups(io, R);
-    int rc = set_smem(k_qam_bandsplit<T>, bytes(R));
+    const bool teams = needs_teams(p);
+    int rc = teams ? set_smem(k_qam_bandsplit<T, true>, bytes(R)) : set_smem(k_qam_bandsplit<T, false>, bytes(R));
     if (rc) return rc;
     dim3 grid = cm_grid(io);
     {
         LaunchTimer lt(m, CM_K_BANDSPLIT, st);
-        k_qam_bandsplit<T><<<grid, cta_threads(2 * R), bytes(R), st>>>(p, io, luma_mode);
+        if (teams) k_qam_bandsplit<T, true><<<grid, CM_NTHREADS, bytes(R), st>>>(p, io, luma_mode);
+        else k_qam_bandsplit<T, false><<<grid, cta_threads(2 * R), bytes(R), st>>>(p, io, luma_mode);
     }
     cm_count_launch();
     CUDA_TRY(cudaGetLastError());
@@ -48,18 +60,20 @@ static int launch_pald(cm_modem *m, IoArgs<T> io, cudaStream_t st) {
     const DevParams<T> &p = params_of<T>(m);
     if (io.out_count <= 0) return CM_OK;
     auto bytes = [&](int r) {
-        return (128 + (size_t)(r + 1) * (p.n1p + 2 * (size_t)p.hb2) + (size_t)r * 4 * p.hb2) * sizeof(T);
+        return (CM_TAPS_ELEMS + (size_t)(r + 1) * (p.n1p + 2 * (size_t)p.hb2) + (size_t)r * 4 * p.hb2) * sizeof(T);
     };
     int R = pick_rows(4, (size_t)m->smem_optin / 2, bytes);
     if (!R) R = pick_rows(2, (size_t)m->smem_optin, bytes);
     if (!R) return cm_fail(CM_ERR_UNSUPPORTED, "line too wide for the PAL-D kernel%s");
     set_groups(io, R);
-    int rc = set_smem(k_pald_combed<T>, bytes(R));
+    const bool teams = needs_teams(p);
+    int rc = teams ? set_smem(k_pald_combed<T, true>, bytes(R)) : set_smem(k_pald_combed<T, false>, bytes(R));
     if (rc) return rc;
     dim3 grid = cm_grid(io);
     {
         LaunchTimer lt(m, CM_K_PALD, st);
-        k_pald_combed<T><<<grid, cta_threads(2 * R), bytes(R), st>>>(p, io);
+        if (teams) k_pald_combed<T, true><<<grid, CM_NTHREADS, bytes(R), st>>>(p, io);
+        else k_pald_combed<T, false><<<grid, cta_threads(2 * R), bytes(R), st>>>(p, io);
     }
     cm_count_launch();
     CUDA_TRY(cudaGetLastError());
@@ -71,18 +85,20 @@ static int launch_comb(cm_modem *m, IoArgs<T> io, cudaStream_t st) {
     const DevParams<T> &p = params_of<T>(m);
     if (io.out_count <= 0) return CM_OK;
     auto bytes = [&](int r) {
-        return (128 + (size_t)(r + 2) * (p.n1p + 2 * (size_t)p.hb2) + (size_t)r * 4 * p.hb2) * sizeof(T);
+        return (CM_TAPS_ELEMS + (size_t)(r + 2) * (p.n1p + 2 * (size_t)p.hb2) + (size_t)r * 4 * p.hb2) * sizeof(T);
     };
     int R = pick_rows(4, (size_t)m->smem_optin / 2, bytes);
     if (!R) R = pick_rows(2, (size_t)m->smem_optin, bytes);
     if (!R) return cm_fail(CM_ERR_UNSUPPORTED, "line too wide for the comb kernel%s");
     set_groups(io, R);
-    int rc = set_smem(k_qam_comb<T, MODE>, bytes(R));
+    const bool teams = needs_teams(p);
+    int rc = teams ? set_smem(k_qam_comb<T, MODE, true>, bytes(R)) : set_smem(k_qam_comb<T, MODE, false>, bytes(R));
     if (rc) return rc;
     dim3 grid = cm_grid(io);
     {
         LaunchTimer lt(m, CM_K_COMB, st);
-        k_qam_comb<T, MODE><<<grid, cta_threads(2 * R), bytes(R), st>>>(p, io);
+        if (teams) k_qam_comb<T, MODE, true><<<grid, CM_NTHREADS, bytes(R), st>>>(p, io);
+        else k_qam_comb<T, MODE, false><<<grid, cta_threads(2 * R), bytes(R), st>>>(p, io);
     }
     cm_count_launch();
     CUDA_TRY(cudaGetLastError());

@@ -26,11 +26,11 @@ __device__ __forceinline__ void carrier4(unsigned long long ph_x0, T rs, T rc, T
 // Encode: RGB -> Y + sin(phi) LP(U) + cos(phi) LP(+-V)          qam.py:20-32, ntsc.py:27-45, pal.py:32-52
 // optional ColorAveragingModem front end (comb.py:141-152).     smem: R * 3 * N1
 // ------------------------------------------------------------------------------------------------------------
-template <typename T>
+template <typename T, bool TEAMS>
 __global__ void __launch_bounds__(CM_NTHREADS, 3)
 k_qam_encode(const __grid_constant__ DevParams<T> p, const __grid_constant__ IoArgs<T> io) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    T *sm = reinterpret_cast<T *>(smem_raw);
+    T *sm = reinterpret_cast<T *>(smem_raw) + 64;          // [0, 64): IIR team scratch
     RowGroup g;
     if (!decode_group(io, g)) return;
     const int W = p.W, N1 = p.n1p, W4 = W >> 2;
@@ -70,11 +70,11 @@ k_qam_encode(const __grid_constant__ DevParams<T> p, const __grid_constant__ IoA
     for (int k = 0; k < g.count; ++k) cta_fill_tail<T, 1>(sm + (size_t)k * 3 * N1 + N1, (size_t)N1, 2, N1, W, N1);
     __syncthreads();
     const FiltHdr &fpre = p.filt[QF_PRE_LP];
-    for (int t = warp; t < 2 * g.count; t += nwarps) {
+    for_each_iir_task<T, TEAMS>(fpre, 2 * g.count, sm - 64, [&](int t, const IirTeam<T> &tm) {
         T *buf = sm + (size_t)(t >> 1) * 3 * N1 + (1 + (t & 1)) * N1;
-        warp_iir<T, 1>(p.tab + fpre.off, fpre, [&](int q, int, int) { return buf[q]; },
-                       [&](int j, T v) { buf[j] = v; });
-    }
+        team_iir<T, 1, TEAMS>(p.tab + fpre.off, fpre, [&](int q, int, int) { return buf[q]; },
+                       [&](int j, T v) { buf[j] = v; }, tm);
+    });
     __syncthreads();
     T rs, rc;
     Real<T>::sincos_turns(p.phases[QP_STEP1X], rs, rc);
@@ -130,8 +130,8 @@ __device__ __forceinline__ void remod_store_row(const DevParams<T> &p, const IoA
 //                                                decoders, CM_MODE_BANDSPLIT_NOSTRIP)
 // 2 warps per row.  smem: taps[128] + R * (c[N1] + 4 x [N2])
 // ------------------------------------------------------------------------------------------------------------
-template <typename T>
-__global__ void __launch_bounds__(CM_NTHREADS)
+template <typename T, bool TEAMS>
+__global__ void __launch_bounds__(CM_NTHREADS, 2)
 k_qam_bandsplit(const __grid_constant__ DevParams<T> p, const __grid_constant__ IoArgs<T> io, int luma_mode) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     T *sm = reinterpret_cast<T *>(smem_raw);
@@ -140,7 +140,7 @@ k_qam_bandsplit(const __grid_constant__ DevParams<T> p, const __grid_constant__ 
     const int W = p.W, W2 = 2 * W, N1 = p.n1p, hb = p.hb2, N2 = 2 * hb;
     const int warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     T *taps = sm;
-    T *rows = sm + 128;
+    T *rows = sm + CM_TAPS_ELEMS, *scratch = sm + 128;
     const size_t per_row = (size_t)N1 + 4 * (size_t)N2;     // c | a2 | b2 | l2 | v2
     const T *hup = taps + p.res[QR_UP2].off, *hdn = taps + p.res[QR_DOWN2].off;
     copy_taps(taps, p, 2);
@@ -155,25 +155,29 @@ k_qam_bandsplit(const __grid_constant__ DevParams<T> p, const __grid_constant__ 
     cta_fill_tail<T, 2>(rows + N1, per_row, g.count, hb, W2, N2);
     __syncthreads();
     // IIR phase 1: band-pass a2 -> b2, band-stop a2 -> l2
-    for (int t = warp; t < 2 * g.count; t += nwarps) {
-        T *c = rows + (t >> 1) * per_row;
-        const T *ae = c + N1, *ao = ae + hb;
-        if ((t & 1) == 0) {
+    {
+        const FiltHdr &fbp = p.filt[QF_BP2X], &fbs = p.filt[QF_BS2X];
+        for_each_iir_task<T, TEAMS>(fbp, g.count, scratch, [&](int k, const IirTeam<T> &tm) {
+            T *c = rows + k * per_row;
+            const T *ae = c + N1, *ao = ae + hb;
             T *be = c + N1 + N2, *bo = be + hb;
-            const FiltHdr &f = p.filt[QF_BP2X];
-            warp_iir<T, 2>(p.tab + f.off, f, [&](int q, int ph, int) { return (ph ? ao : ae)[q]; },
-                           Poly2Out<T>{be, bo});
-            warp_fill_tail<T, 2>(be, hb, W2, N2);
-        } else if (luma_mode == 0) {
-            T *le = c + N1 + 2 * N2, *lo = le + hb;
-            const FiltHdr &f = p.filt[QF_BS2X];
-            warp_iir<T, 2>(p.tab + f.off, f, [&](int q, int ph, int) { return (ph ? ao : ae)[q]; },
-                           Poly2Out<T>{le, lo});
-        }
+            team_iir<T, 2, TEAMS>(p.tab + fbp.off, fbp, [&](int q, int ph, int) { return (ph ? ao : ae)[q]; },
+                           Poly2Out<T>{be, bo}, tm);
+        });
+        if (luma_mode == 0)
+            for_each_iir_task<T, TEAMS>(fbs, g.count, scratch, [&](int k, const IirTeam<T> &tm) {
+                T *c = rows + k * per_row;
+                const T *ae = c + N1, *ao = ae + hb;
+                T *le = c + N1 + 2 * N2, *lo = le + hb;
+                team_iir<T, 2, TEAMS>(p.tab + fbs.off, fbs, [&](int q, int ph, int) { return (ph ? ao : ae)[q]; },
+                               Poly2Out<T>{le, lo}, tm);
+            }, g.count);
     }
     __syncthreads();
+    cta_fill_tail<T, 2>(rows + N1 + N2, per_row, g.count, hb, W2, N2);      // b2 feeds the low-pass stage
+    __syncthreads();
     // IIR phase 2: product demodulation + low-pass.  u2 -> a2 (dead), v2 -> 4th buffer
-    for (int t = warp; t < 2 * g.count; t += nwarps) {
+    for_each_iir_task<T, TEAMS>(p.filt[QF_DEMOD_LP], 2 * g.count, scratch, [&](int t, const IirTeam<T> &tm) {
         const int k = t >> 1;
         T *c = rows + k * per_row;
         const T *be = c + N1 + N2, *bo = be + hb;
@@ -183,13 +187,13 @@ k_qam_bandsplit(const __grid_constant__ DevParams<T> p, const __grid_constant__ 
         Carrier<T> car(start_phase(p, g.frame, line) + p.phases[QP_BP_SHIFT] + ((t & 1) ? CM_QUARTER_TURN : 0ull),
                        p.phases[QP_STEP2X], W2);
         const FiltHdr &f = p.filt[QF_DEMOD_LP];
-        warp_iir<T, 2>(p.tab + f.off, f,
+        team_iir<T, 2, TEAMS>(p.tab + f.off, f,
                        [&](int q, int ph, int i) {
                            car.at(2 * q + ph, i);
                            return (T)2 * car.s * (ph ? bo : be)[q];
                        },
-                       Poly2Out<T>{de, dod});
-    }
+                       Poly2Out<T>{de, dod}, tm);
+    });
     __syncthreads();
     // down2 of u2, v2 -> u, v at 1x into the b2 region (dead now): u at [0, N1), v at [N1, 2 N1)
     for (int k = 0; k < g.count; ++k) {
@@ -236,13 +240,13 @@ k_qam_bandsplit(const __grid_constant__ DevParams<T> p, const __grid_constant__ 
     for (int k = 0; k < g.count; ++k) cta_fill_tail<T, 1>(rows + k * per_row + N1 + N2, (size_t)N1, 2, N1, W, N1);
     __syncthreads();
     const FiltHdr &fpre = p.filt[QF_PRE_LP];
-    for (int t = warp; t < 2 * g.count; t += nwarps) {
+    for_each_iir_task<T, TEAMS>(fpre, 2 * g.count, scratch, [&](int t, const IirTeam<T> &tm) {
         T *c = rows + (t >> 1) * per_row;
         const T *src = c + N1 + N2 + (t & 1) * N1;
         T *dst = c + N1 + (t & 1) * N1;
-        warp_iir<T, 1>(p.tab + fpre.off, fpre, [&](int q, int, int) { return src[q]; },
-                       [&](int j, T v) { dst[j] = v; });
-    }
+        team_iir<T, 1, TEAMS>(p.tab + fpre.off, fpre, [&](int q, int, int) { return src[q]; },
+                       [&](int j, T v) { dst[j] = v; }, tm);
+    });
     __syncthreads();
     T rs, rc;
     Real<T>::sincos_turns(p.phases[QP_STEP1X], rs, rc);
@@ -261,8 +265,8 @@ k_qam_bandsplit(const __grid_constant__ DevParams<T> p, const __grid_constant__ 
 //   y = c - (sin(phi) LP_pre(u) + cos(phi) LP_pre(+-v))
 // smem: taps[128] + (R+1) * (c[N1] + G[N2]) + 2R * [N2] work
 // ------------------------------------------------------------------------------------------------------------
-template <typename T>
-__global__ void __launch_bounds__(CM_NTHREADS)
+template <typename T, bool TEAMS>
+__global__ void __launch_bounds__(CM_NTHREADS, 2)
 k_pald_combed(const __grid_constant__ DevParams<T> p, const __grid_constant__ IoArgs<T> io) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     T *sm = reinterpret_cast<T *>(smem_raw);
@@ -273,7 +277,8 @@ k_pald_combed(const __grid_constant__ DevParams<T> p, const __grid_constant__ Io
     const int warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     const int R = io.rows_per_cta;
     T *taps = sm;
-    T *cbuf = sm + 128;                          // (R+1) x N1    composite rows, index k+1
+    T *scratch = sm + 128;
+    T *cbuf = sm + CM_TAPS_ELEMS;                          // (R+1) x N1    composite rows, index k+1
     T *gbuf = cbuf + (size_t)(R + 1) * N1;       // (R+1) x N2    G rows, index k+1
     T *work = gbuf + (size_t)(R + 1) * N2;       // 2R x N2
     const int nin = g.count + 1;
@@ -292,12 +297,12 @@ k_pald_combed(const __grid_constant__ DevParams<T> p, const __grid_constant__ Io
     cta_fill_tail<T, 2>(gbuf, (size_t)N2, nin, hb, W2, N2);
     __syncthreads();
     pc.mark();
-    for (int t = warp; t < nin; t += nwarps) {          // band-pass in place
+    for_each_iir_task<T, TEAMS>(p.filt[QF_BP2X], nin, scratch, [&](int t, const IirTeam<T> &tm) {   // band-pass in place
         T *be = gbuf + (size_t)t * N2, *bo = be + hb;
         const FiltHdr &f = p.filt[QF_BP2X];
-        warp_iir<T, 2>(p.tab + f.off, f, [&](int q, int ph, int) { return (ph ? bo : be)[q]; },
-                       Poly2Out<T>{be, bo});
-    }
+        team_iir<T, 2, TEAMS>(p.tab + f.off, f, [&](int q, int ph, int) { return (ph ? bo : be)[q]; },
+                       Poly2Out<T>{be, bo}, tm);
+    });
     __syncthreads();
     pc.mark();
     for (int k = 0; k < nin; ++k) {                     // E = down2(b2) -> work[k][0..W)
@@ -316,7 +321,8 @@ k_pald_combed(const __grid_constant__ DevParams<T> p, const __grid_constant__ Io
     cta_fill_tail<T, 2>(gbuf, (size_t)N2, nin, hb, W2, N2);
     __syncthreads();
     pc.mark();
-    for (int t = warp; t < 2 * g.count; t += nwarps) {  // AM demodulation low-pass of sum / difference
+    for_each_iir_task<T, TEAMS>(p.filt[QF_PALD_LP], 2 * g.count, scratch, [&](int t, const IirTeam<T> &tm) {
+        // AM demodulation low-pass of sum / difference
         const int k = t >> 1;
         const T *gce = gbuf + (size_t)(k + 1) * N2, *gco = gce + hb;
         const T *gle = gbuf + (size_t)k * N2, *glo = gle + hb;
@@ -327,13 +333,13 @@ k_pald_combed(const __grid_constant__ DevParams<T> p, const __grid_constant__ Io
                            ((t & 1) ? CM_QUARTER_TURN : 0ull),
                        p.phases[QP_STEP2X], W2);
         const FiltHdr &f = p.filt[QF_PALD_LP];
-        warp_iir<T, 2>(p.tab + f.off, f,
+        team_iir<T, 2, TEAMS>(p.tab + f.off, f,
                        [&](int q, int ph, int i) {
                            car.at(2 * q + ph, i);
                            return Real<T>::fma_(sgn, (ph ? glo : gle)[q], (ph ? gco : gce)[q]) * car.s;
                        },
-                       Poly2Out<T>{de, dod});
-    }
+                       Poly2Out<T>{de, dod}, tm);
+    });
     __syncthreads();
     pc.mark();
     // S, D at 1x, rotated to (u, v) with the V switch (pal.py:121-125), into the gbuf rows (G is dead):
@@ -360,12 +366,13 @@ k_pald_combed(const __grid_constant__ DevParams<T> p, const __grid_constant__ Io
     __syncthreads();
     pc.mark();
     const FiltHdr &fpre = p.filt[QF_PRE_LP];
-    for (int t = warp; t < 2 * g.count; t += nwarps) {  // encoder pre-lowpass for the re-modulation
+    for_each_iir_task<T, TEAMS>(fpre, 2 * g.count, scratch, [&](int t, const IirTeam<T> &tm) {
+        // encoder pre-lowpass for the re-modulation
         const T *src = gbuf + (size_t)(t >> 1) * N2 + (t & 1) * N1;
         T *dst = work + (size_t)t * N1;
-        warp_iir<T, 1>(p.tab + fpre.off, fpre, [&](int q, int, int) { return src[q]; },
-                       [&](int j, T v) { dst[j] = v; });
-    }
+        team_iir<T, 1, TEAMS>(p.tab + fpre.off, fpre, [&](int q, int, int) { return src[q]; },
+                       [&](int j, T v) { dst[j] = v; }, tm);
+    });
     __syncthreads();
     pc.mark();
     T rs, rc;
@@ -395,7 +402,7 @@ k_pald_combed(const __grid_constant__ DevParams<T> p, const __grid_constant__ Io
 // ------------------------------------------------------------------------------------------------------------
 enum { COMB_NTSC2 = 0, COMB_NTSC3 = 1, COMB_PAL3 = 2 };
 
-template <typename T, int MODE>
+template <typename T, int MODE, bool TEAMS>
 __global__ void __launch_bounds__(CM_NTHREADS, 2)
 k_qam_comb(const __grid_constant__ DevParams<T> p, const __grid_constant__ IoArgs<T> io) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -406,7 +413,8 @@ k_qam_comb(const __grid_constant__ DevParams<T> p, const __grid_constant__ IoArg
     const int warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     const int R = io.rows_per_cta;
     T *taps = sm;
-    T *cbuf = sm + 128;                          // (R+2) x N1    index k+1, k = -1 .. R
+    T *scratch = sm + 128;
+    T *cbuf = sm + CM_TAPS_ELEMS;                          // (R+2) x N1    index k+1, k = -1 .. R
     T *bbuf = cbuf + (size_t)(R + 2) * N1;       // (R+2) x N2
     T *work = bbuf + (size_t)(R + 2) * N2;       // 2R x N2
     const bool has_prev0 = g.r0 >= 2;                               // row k = -1 exists
@@ -426,17 +434,18 @@ k_qam_comb(const __grid_constant__ DevParams<T> p, const __grid_constant__ IoArg
     __syncthreads();
     cta_fill_tail<T, 2>(bbuf + (size_t)(k_lo + 1) * N2, (size_t)N2, nin, hb, W2, N2);
     __syncthreads();
-    for (int t = warp; t < nin; t += nwarps) {
+    for_each_iir_task<T, TEAMS>(p.filt[QF_BP2X], nin, scratch, [&](int t, const IirTeam<T> &tm) {
         T *be = bbuf + (size_t)(k_lo + t + 1) * N2, *bo = be + hb;
         const FiltHdr &f = p.filt[QF_BP2X];
-        warp_iir<T, 2>(p.tab + f.off, f, [&](int q, int ph, int) { return (ph ? bo : be)[q]; },
-                       Poly2Out<T>{be, bo});
-        warp_fill_tail<T, 2>(be, hb, W2, N2);
-    }
+        team_iir<T, 2, TEAMS>(p.tab + f.off, f, [&](int q, int ph, int) { return (ph ? bo : be)[q]; },
+                       Poly2Out<T>{be, bo}, tm);
+    });
+    __syncthreads();
+    cta_fill_tail<T, 2>(bbuf + (size_t)(k_lo + 1) * N2, (size_t)N2, nin, hb, W2, N2);
     __syncthreads();
     const unsigned long long step = p.phases[QP_STEP2X];
     const FiltHdr &flp = p.filt[QF_DEMOD_LP];
-    for (int t = warp; t < 2 * g.count; t += nwarps) {
+    for_each_iir_task<T, TEAMS>(flp, 2 * g.count, scratch, [&](int t, const IirTeam<T> &tm) {
         const int k = t >> 1;
         const bool is_v = (t & 1) != 0;
         const int line = io.y0 + g.r0 + 2 * k;
@@ -453,12 +462,12 @@ k_qam_comb(const __grid_constant__ DevParams<T> p, const __grid_constant__ IoArg
             // u: f 2 cos(phi) d = f2 sin(phi + 1/4) d;   v: -f 2 sin(phi) d
             Carrier<T> car(psi - p.phases[QP_HALF_LS] + (is_v ? 0ull : CM_QUARTER_TURN), step, W2);
             const T amp = is_v ? -f2 : f2;
-            warp_iir<T, 2>(p.tab + flp.off, flp,
+            team_iir<T, 2, TEAMS>(p.tab + flp.off, flp,
                            [&](int q, int ph, int i) {
                                car.at(2 * q + ph, i);
                                return amp * car.s * ((ph ? bco : bce)[q] - (ph ? bpo : bpe)[q]);
                            },
-                           st);
+                           st, tm);
         } else if (MODE == COMB_NTSC3) {
             const T f = p.scalars[QS_NTSC_FACTOR];      // 0.5 * (2 f ...) = f ...
             const unsigned long long quarter = is_v ? 0ull : CM_QUARTER_TURN;
@@ -467,7 +476,7 @@ k_qam_comb(const __grid_constant__ DevParams<T> p, const __grid_constant__ IoArg
             Carrier<T> carn(start_phase(p, g.frame, line + 2) + p.phases[QP_BP_SHIFT] - p.phases[QP_HALF_LS] + quarter,
                             step, W2);
             const T amp = is_v ? -f : f;
-            warp_iir<T, 2>(p.tab + flp.off, flp,
+            team_iir<T, 2, TEAMS>(p.tab + flp.off, flp,
                            [&](int q, int ph, int i) {
                                const int j = 2 * q + ph;
                                car.at(j, i);
@@ -479,12 +488,12 @@ k_qam_comb(const __grid_constant__ DevParams<T> p, const __grid_constant__ IoArg
                                }
                                return acc;
                            },
-                           st);
+                           st, tm);
         } else {
             const T a_ss = (T)2 * p.scalars[QS_P3D_SINSUM];
             const T a_c = (T)2 * (is_v ? p.scalars[QS_P3D_COSV] : p.scalars[QS_P3D_COSU]);
             Carrier<T> car(psi, step, W2);
-            warp_iir<T, 2>(p.tab + flp.off, flp,
+            team_iir<T, 2, TEAMS>(p.tab + flp.off, flp,
                            [&](int q, int ph, int i) {
                                car.at(2 * q + ph, i);
                                const T bc = (ph ? bco : bce)[q];
@@ -493,9 +502,9 @@ k_qam_comb(const __grid_constant__ DevParams<T> p, const __grid_constant__ IoArg
                                return is_v ? (a_ss * car.s * ssig + a_c * car.c * dsig)
                                            : (a_ss * car.c * ssig + a_c * car.s * dsig);
                            },
-                           st);
+                           st, tm);
         }
-    }
+    });
     __syncthreads();
     // u, v at 1x into bbuf rows (the B's are dead): u at [k+1][0..N1), v at [k+1][N1..2 N1)
     for (int t = 0; t < 2 * g.count; ++t) {
@@ -514,12 +523,12 @@ k_qam_comb(const __grid_constant__ DevParams<T> p, const __grid_constant__ IoArg
     for (int k = 0; k < g.count; ++k) cta_fill_tail<T, 1>(bbuf + (size_t)(k + 1) * N2, (size_t)N1, 2, N1, W, N1);
     __syncthreads();
     const FiltHdr &fpre = p.filt[QF_PRE_LP];
-    for (int t = warp; t < 2 * g.count; t += nwarps) {
+    for_each_iir_task<T, TEAMS>(fpre, 2 * g.count, scratch, [&](int t, const IirTeam<T> &tm) {
         const T *src = bbuf + (size_t)((t >> 1) + 1) * N2 + (t & 1) * N1;
         T *dst = work + (size_t)t * N1;
-        warp_iir<T, 1>(p.tab + fpre.off, fpre, [&](int q, int, int) { return src[q]; },
-                       [&](int j, T v) { dst[j] = v; });
-    }
+        team_iir<T, 1, TEAMS>(p.tab + fpre.off, fpre, [&](int q, int, int) { return src[q]; },
+                       [&](int j, T v) { dst[j] = v; }, tm);
+    });
     __syncthreads();
     T rs, rc;
     Real<T>::sincos_turns(p.phases[QP_STEP1X], rs, rc);
