@@ -19,7 +19,7 @@
 #define CM_NRES 6
 #define CM_NSCAL 48
 #define CM_NPHASE 16
-#define CM_TAPS_ELEMS 192   // head of every decode kernel's shared memory: resampler taps [0,128) + IIR team scratch [128,192)
+#define CM_TAPS_ELEMS 256   // head of every decode kernel's shared memory: resampler taps [0,128) + IIR team scratch [128,256)
 #define CM_QUARTER_TURN 0x4000000000000000ull
 
 struct FiltHdr {

@@ -14,7 +14,7 @@ template <typename T>
 int qam_encode(cm_modem *m, IoArgs<T> io, cudaStream_t st) {
     const DevParams<T> &p = params_of<T>(m);
     if (io.out_count <= 0) return CM_OK;
-    auto bytes = [&](int r) { return (64 + (size_t)r * 3 * p.n1p) * sizeof(T); };
+    auto bytes = [&](int r) { return (128 + (size_t)r * 3 * p.n1p) * sizeof(T); };
     int R = pick_rows(4, (size_t)m->smem_optin / 2, bytes);
     if (!R) return cm_fail(CM_ERR_UNSUPPORTED, "line too wide for the encode kernel%s");
     set_groups(io, R);

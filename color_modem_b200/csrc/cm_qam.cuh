@@ -30,7 +30,7 @@ template <typename T, bool TEAMS>
 __global__ void __launch_bounds__(CM_NTHREADS, 3)
 k_qam_encode(const __grid_constant__ DevParams<T> p, const __grid_constant__ IoArgs<T> io) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    T *sm = reinterpret_cast<T *>(smem_raw) + 64;          // [0, 64): IIR team scratch
+    T *sm = reinterpret_cast<T *>(smem_raw) + 128;         // [0, 128): IIR team scratch
     RowGroup g;
     if (!decode_group(io, g)) return;
     const int W = p.W, N1 = p.n1p, W4 = W >> 2;
@@ -70,7 +70,7 @@ k_qam_encode(const __grid_constant__ DevParams<T> p, const __grid_constant__ IoA
     for (int k = 0; k < g.count; ++k) cta_fill_tail<T, 1>(sm + (size_t)k * 3 * N1 + N1, (size_t)N1, 2, N1, W, N1);
     __syncthreads();
     const FiltHdr &fpre = p.filt[QF_PRE_LP];
-    for_each_iir_task<T, TEAMS>(fpre, 2 * g.count, sm - 64, [&](int t, const IirTeam<T> &tm) {
+    for_each_iir_task<T, TEAMS>(fpre, 2 * g.count, sm - 128, [&](int t, const IirTeam<T> &tm) {
         T *buf = sm + (size_t)(t >> 1) * 3 * N1 + (1 + (t & 1)) * N1;
         team_iir<T, 1, TEAMS>(p.tab + fpre.off, fpre, [&](int q, int, int) { return buf[q]; },
                        [&](int j, T v) { buf[j] = v; }, tm);

@@ -26,17 +26,20 @@ template <typename T>
 int secam_decode(cm_modem *m, IoArgs<T> io, cudaStream_t st) {
     const DevParams<T> &p = params_of<T>(m);
     if (io.out_count <= 0) return CM_OK;
-    auto bytes = [&](int r) { return (128 + (size_t)(r + 1) * (2 * (size_t)p.n1p + 6 * (size_t)p.hb2)) * sizeof(T); };
+    auto bytes = [&](int r) { return (CM_TAPS_ELEMS + (size_t)(r + 1) * (2 * (size_t)p.n1p + 6 * (size_t)p.hb2)) * sizeof(T); };
     int R = pick_rows(3, (size_t)m->smem_optin / 2, bytes);
     if (!R) R = pick_rows(1, (size_t)m->smem_optin, bytes);
     if (!R) return cm_fail(CM_ERR_UNSUPPORTED, "line too wide for the SECAM decode kernel%s");
     set_groups(io, R);
-    int rc = set_smem(k_secam_decode<T>, bytes(R));
+    bool teams = false;
+    for (int i = 0; i < CM_NFILT; ++i) teams = teams || (p.filt[i].nsec && p.filt[i].nsuper > 1);
+    int rc = teams ? set_smem(k_secam_decode<T, true>, bytes(R)) : set_smem(k_secam_decode<T, false>, bytes(R));
     if (rc) return rc;
     dim3 grid = cm_grid(io);
     {
         LaunchTimer lt(m, CM_K_DECODE_OTHER, st);
-        k_secam_decode<T><<<grid, cta_threads(2 * (R + 1)), bytes(R), st>>>(p, io);
+        if (teams) k_secam_decode<T, true><<<grid, CM_NTHREADS, bytes(R), st>>>(p, io);
+        else k_secam_decode<T, false><<<grid, cta_threads(2 * (R + 1)), bytes(R), st>>>(p, io);
     }
     cm_count_launch();
     CUDA_TRY(cudaGetLastError());

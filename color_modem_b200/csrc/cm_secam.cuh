@@ -176,8 +176,8 @@ k_secam_encode(const __grid_constant__ DevParams<T> p, const __grid_constant__ I
 //   cc : warm-up prefix + composite -> band-passed chroma -> later the colour-difference signal X
 //   U2 : up2(chroma), later the instantaneous frequency at 2x
 // ------------------------------------------------------------------------------------------------------------
-template <typename T>
-__global__ void __launch_bounds__(CM_NTHREADS)
+template <typename T, bool TEAMS>
+__global__ void __launch_bounds__(CM_NTHREADS, 2)
 k_secam_decode(const __grid_constant__ DevParams<T> p, const __grid_constant__ IoArgs<T> io) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     T *sm = reinterpret_cast<T *>(smem_raw);
@@ -187,8 +187,8 @@ k_secam_decode(const __grid_constant__ DevParams<T> p, const __grid_constant__ I
     const int warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     const int pre = W / 40 - 1;                 // samples of flipped warm-up (secam.py:283)
     const int ncc = W + pre, ncc4 = (ncc + 3) & ~3, n2 = 2 * ncc;
-    T *taps = sm;
-    T *rows = sm + 128;
+    T *taps = sm, *scratch = sm + 128;
+    T *rows = sm + CM_TAPS_ELEMS;
     const size_t per_row = 2 * (size_t)N1 + 3 * (size_t)N2;
     const bool has_prev0 = g.r0 >= 2;
     const int k_lo = has_prev0 ? -1 : 0;
@@ -215,24 +215,34 @@ k_secam_decode(const __grid_constant__ DevParams<T> p, const __grid_constant__ I
     }
     __syncthreads();
     // IIR phase 1: luma band-stop (rows k >= 0, in place) and chroma band-pass (+ anti-bell) on cc (all rows)
-    for (int t = warp; t < g.count + nin; t += nwarps) {
-        if (t < g.count) {
+    {
+        const FiltHdr &fl = p.filt[SF_LUMA_BS], &fc = p.filt[SF_CHROMA_BP];
+        for_each_iir_task<T, TEAMS>(fl, g.count, scratch, [&](int t, const IirTeam<T> &tm) {
             T *c = rowp(t);
-            const FiltHdr &f = p.filt[SF_LUMA_BS];
-            warp_iir<T, 1>(p.tab + f.off, f, [&](int q, int, int) { return c[q]; }, [&](int j, T v) { c[j] = v; });
-        } else {
-            T *cc = rowp(k_lo + (t - g.count)) + N1;
-            const FiltHdr &f = p.filt[SF_CHROMA_BP];
-            warp_iir<T, 1>(p.tab + f.off, f, [&](int q, int, int) { return cc[q]; }, [&](int j, T v) { cc[j] = v; });
-            if (p.flags & 64) {
-                warp_fill_tail<T, 1>(cc, N1, ncc, N1);
-                const FiltHdr &fb = p.filt[SF_ANTI_BELL];
-                warp_iir<T, 1>(p.tab + fb.off, fb, [&](int q, int, int) { return cc[q]; },
-                               [&](int j, T v) { cc[j] = v; });
-            }
-            __syncwarp();
-            for (int i = ncc + (threadIdx.x & 31); i < ncc4; i += 32) cc[i] = (T)0;   // zero pad for the resampler
-        }
+            team_iir<T, 1, TEAMS>(p.tab + fl.off, fl, [&](int q, int, int) { return c[q]; },
+                                  [&](int j, T v) { c[j] = v; }, tm);
+        });
+        for_each_iir_task<T, TEAMS>(fc, nin, scratch, [&](int t, const IirTeam<T> &tm) {
+            T *cc = rowp(k_lo + t) + N1;
+            team_iir<T, 1, TEAMS>(p.tab + fc.off, fc, [&](int q, int, int) { return cc[q]; },
+                                  [&](int j, T v) { cc[j] = v; }, tm);
+        }, g.count);
+    }
+    __syncthreads();
+    if (p.flags & 64) {
+        cta_fill_tail<T, 1>(rows + N1, per_row, nin, N1, ncc, N1);
+        __syncthreads();
+        const FiltHdr &fb = p.filt[SF_ANTI_BELL];
+        for_each_iir_task<T, TEAMS>(fb, nin, scratch, [&](int t, const IirTeam<T> &tm) {
+            T *cc = rowp(k_lo + t) + N1;
+            team_iir<T, 1, TEAMS>(p.tab + fb.off, fb, [&](int q, int, int) { return cc[q]; },
+                                  [&](int j, T v) { cc[j] = v; }, tm);
+        });
+        __syncthreads();
+    }
+    for (int idx = threadIdx.x; idx < nin * (ncc4 - ncc); idx += blockDim.x) {   // zero pad for the resampler
+        const int r = idx / (ncc4 - ncc), i = ncc + idx - r * (ncc4 - ncc);
+        rows[(size_t)r * per_row + N1 + i] = (T)0;
     }
     __syncthreads();
     for (int k = k_lo; k < g.count; ++k) {
@@ -244,18 +254,18 @@ k_secam_decode(const __grid_constant__ DevParams<T> p, const __grid_constant__ I
     __syncthreads();
     // IIR phase 2: mix to baseband and low-pass: I = LP(x cos), Q = LP(x sin)        secam.py:137-142
     const FiltHdr &flp = p.filt[SF_FM_LP];
-    for (int t = warp; t < 2 * nin; t += nwarps) {
+    for_each_iir_task<T, TEAMS>(flp, 2 * nin, scratch, [&](int t, const IirTeam<T> &tm) {
         T *r = rows + (size_t)(t >> 1) * per_row;
         const T *ue = r + 2 * N1, *uo = ue + hb;
         T *de = r + 2 * N1 + ((t & 1) ? 2 : 1) * (size_t)N2, *dod = de + hb;
         Carrier<T> car((t & 1) ? 0ull : CM_QUARTER_TURN, p.phases[SP_FM_STEP2X], n2);   // I: cos, Q: sin
-        warp_iir<T, 2>(p.tab + flp.off, flp,
-                       [&](int q, int ph, int i) {
-                           car.at(2 * q + ph, i);
-                           return car.s * (ph ? uo : ue)[q];
-                       },
-                       Poly2Out<T>{de, dod});
-    }
+        team_iir<T, 2, TEAMS>(p.tab + flp.off, flp,
+                              [&](int q, int ph, int i) {
+                                  car.at(2 * q + ph, i);
+                                  return car.s * (ph ? uo : ue)[q];
+                              },
+                              Poly2Out<T>{de, dod}, tm);
+    });
     __syncthreads();
     // discriminator: wrapped phase step of z = I - jQ between consecutive 2x samples, first step 0 (secam.py:143-148)
     const T fc = p.scalars[SS_FM_FC];
@@ -308,10 +318,11 @@ k_secam_decode(const __grid_constant__ DevParams<T> p, const __grid_constant__ I
     __syncthreads();
     if (p.flags & 128) {
         const FiltHdr &fd = p.filt[SF_DE_EMPH];
-        for (int t = warp; t < nin; t += nwarps) {
+        for_each_iir_task<T, TEAMS>(fd, nin, scratch, [&](int t, const IirTeam<T> &tm) {
             T *x = rows + (size_t)t * per_row + N1;
-            warp_iir<T, 1>(p.tab + fd.off, fd, [&](int q, int, int) { return x[q]; }, [&](int j, T v) { x[j] = v; });
-        }
+            team_iir<T, 1, TEAMS>(p.tab + fd.off, fd, [&](int q, int, int) { return x[q]; },
+                                  [&](int j, T v) { x[j] = v; }, tm);
+        });
         __syncthreads();
     }
     for (int k = 0; k < g.count; ++k) {
