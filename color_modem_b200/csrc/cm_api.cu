@@ -251,6 +251,7 @@ extern "C" void cm_destroy(cm_modem *m) {
         cudaFree(m->d_out[i]);
         if (m->hs[i]) cudaStreamDestroy(m->hs[i]);
     }
+    for (int i = 0; i < 4; ++i) cudaFree(m->d_aux[i]);
     cm_timing_reset(m);
     delete m;
 }
@@ -258,6 +259,20 @@ extern "C" void cm_destroy(cm_modem *m) {
 // ------------------------------------------------------------------------------------------------------------
 // launches
 // ------------------------------------------------------------------------------------------------------------
+void *cm_ensure_aux(cm_modem *m, size_t bytes) {
+    const int k = m->aux_slot;
+    if (m->aux_cap[k] >= bytes) return m->d_aux[k];
+    // the old buffer may still be in use by kernels already queued on some stream
+    if (cudaDeviceSynchronize() != cudaSuccess) { fail(CM_ERR_CUDA, "cudaDeviceSynchronize failed%s"); return nullptr; }
+    cudaFree(m->d_aux[k]);
+    m->d_aux[k] = nullptr;
+    m->aux_cap[k] = 0;
+    cudaError_t e = cudaMalloc(&m->d_aux[k], bytes);
+    if (e != cudaSuccess) { fail(CM_ERR_NOMEM, "cudaMalloc(aux): %s", cudaGetErrorString(e)); return nullptr; }
+    m->aux_cap[k] = bytes;
+    return m->d_aux[k];
+}
+
 extern "C" int cm_timing_enable(cm_modem *m, int on) {
     if (!m) return fail(CM_ERR_INVALID, "null handle%s");
     m->timing = on != 0;
@@ -456,8 +471,10 @@ static int run_host(cm_modem *m, bool encode, const uint8_t *in, uint8_t *out, s
         const int n = nframes - f < chunk ? nframes - f : chunk;
         cudaStream_t st = m->hs[s];
         CUDA_TRY(cudaMemcpyAsync(m->d_in[s], in + (size_t)f * in_frame, (size_t)n * in_frame, cudaMemcpyHostToDevice, st));
+        m->aux_slot = 1 + s;
         rc = encode ? cm_encode_frames(m, (const uint8_t *)m->d_in[s], (uint8_t *)m->d_out[s], first_frame + f, n, st)
                     : cm_decode_frames(m, (const uint8_t *)m->d_in[s], (uint8_t *)m->d_out[s], first_frame + f, n, st);
+        m->aux_slot = 0;
         if (rc == CM_OK)
             CUDA_TRY(cudaMemcpyAsync(out + (size_t)f * out_frame, m->d_out[s], (size_t)n * out_frame,
                                      cudaMemcpyDeviceToHost, st));

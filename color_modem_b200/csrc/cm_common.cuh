@@ -67,6 +67,7 @@ struct IoArgs {
     int out_begin, out_count;
     int rows_per_cta; // R
     int groups_per_field;
+    T *aux;                 // kernel-specific scratch in global memory (line-sequential decoders: per-row luma | chroma)
     unsigned long long *prof;   // optional per-phase cycle counters (tuning aid, cm_phase_profile); nullptr normally
 };
 

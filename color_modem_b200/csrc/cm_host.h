@@ -30,6 +30,11 @@ struct cm_modem {
     void *d_taps = nullptr;
     bool timing = false;
     unsigned long long *phase_prof = nullptr;
+    // pairing scratch of the line-sequential decoders (grown on demand); one per host-path stream (+ slot 0 for
+    // caller-provided streams: a handle must not be used from two streams at once)
+    void *d_aux[4] = {nullptr, nullptr, nullptr, nullptr};
+    size_t aux_cap[4] = {0, 0, 0, 0};
+    int aux_slot = 0;
     struct Ev { cudaEvent_t a, b; int id; };
     std::vector<Ev> events;
     // *_host entry points: the batch is cut into chunks that ping-pong over CM_HOST_STREAMS streams so that the
@@ -117,6 +122,9 @@ static void split_top(const IoArgs<T> &io, IoArgs<T> &top, IoArgs<T> &rest) {
     rest.out_begin = rest_begin;
     rest.out_count = end > rest_begin ? end - rest_begin : 0;
 }
+
+// Grow-only device scratch of a handle (stream-ordered use only).
+void *cm_ensure_aux(cm_modem *m, size_t bytes);   // nullptr on failure (cm_last_error set)
 
 // per-family entry points (explicitly instantiated for float and double in cm_<family>.cu)
 template <typename T> int qam_encode(cm_modem *m, IoArgs<T> io, cudaStream_t st);

@@ -126,3 +126,32 @@ __device__ __forceinline__ void store_rgb4(const DevParams<T> &p, const IoArgs<T
         dst[2] = w[2];
     }
 }
+
+// ------------------------------------------------------------------------------------------------------------
+// Line-sequential colour systems (SECAM, proto-SECAM, MAC): every row carries ONE colour-difference signal X and
+// the decoder pairs it with the X of the previous row of the field (zeros at the field top), e.g. secam.py:297-300.
+// The heavy per-row kernel writes (luma, X) of each row once to a float scratch in HBM (aux: [frame][row][2][Wo]);
+// this light kernel pairs neighbouring rows, applies the inverse matrix and stores RGB.  Compared with recomputing
+// the previous row as a halo inside the heavy kernel this trades 20 B/pixel of HBM traffic (the kernels use < 3 %
+// of the HBM bandwidth) for 25-100 % less arithmetic.
+// ------------------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) k_pair_rows_store(const __grid_constant__ DevParams<T> p,
+                                                         const __grid_constant__ IoArgs<T> io) {
+    const int Wo = p.Wo, q_per_row = Wo >> 2;
+    const int f = blockIdx.z, row = io.out_begin + blockIdx.y;
+    const long long frame = io.first_frame + f;
+    const bool alt = is_alternate(p, frame, io.y0 + row);
+    const bool hp = row >= 2;
+    const T *cur = io.aux + ((size_t)f * io.nrows + row) * 2 * Wo;
+    const T *prev = io.aux + ((size_t)f * io.nrows + (hp ? row - 2 : row)) * 2 * Wo;
+    for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < q_per_row; q += gridDim.x * blockDim.x) {
+        T y[4], a[4], b[4] = {(T)0, (T)0, (T)0, (T)0};
+        ld4(cur + 4 * q, y);
+        ld4(cur + Wo + 4 * q, a);
+        if (hp) ld4(prev + Wo + 4 * q, b);
+        // non-alternate rows carry D'R (dr = current, db = previous), alternate rows D'B
+        if (alt) store_rgb4(p, io, f, row, 4 * q, y, b, a);
+        else store_rgb4(p, io, f, row, 4 * q, y, a, b);
+    }
+}

@@ -171,7 +171,7 @@ k_secam_encode(const __grid_constant__ DevParams<T> p, const __grid_constant__ I
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// Decode.  smem: taps[128] + (R+1) rows x ( c[N1] | cc[N1] | U2[N2] | I2[N2] | Q2[N2] )
+// Decode, per row (no coupling between rows).  smem: taps/scratch[256] + R rows x ( c[N1] | cc[N1] | U2[N2] | I2[N2] | Q2[N2] )
 //   c  : composite, then luma (band-stop in place)
 //   cc : warm-up prefix + composite -> band-passed chroma -> later the colour-difference signal X
 //   U2 : up2(chroma), later the instantaneous frequency at 2x
@@ -190,13 +190,12 @@ k_secam_decode(const __grid_constant__ DevParams<T> p, const __grid_constant__ I
     T *taps = sm, *scratch = sm + 128;
     T *rows = sm + CM_TAPS_ELEMS;
     const size_t per_row = 2 * (size_t)N1 + 3 * (size_t)N2;
-    const bool has_prev0 = g.r0 >= 2;
-    const int k_lo = has_prev0 ? -1 : 0;
-    const int nin = g.count - k_lo;
+    const int k_lo = 0;                          // rows are independent here: pairing with the previous row happens
+    const int nin = g.count;                     // in k_pair_rows_store
     const T *hup = taps + p.res[SR_UP2].off, *hdn = taps + p.res[SR_DOWN2].off;
-    auto rowp = [&](int k) { return rows + (size_t)(k - k_lo) * per_row; };
+    auto rowp = [&](int k) { return rows + (size_t)k * per_row; };
     copy_taps(taps, p, 2);
-    for (int k = k_lo; k < g.count; ++k) load_comp_row(rowp(k), io, g.fidx, g.r0 + 2 * k, W);
+    load_comp_rows(io, g.fidx, nin, W, [&](int k) { return rowp(k); }, [&](int k) { return g.r0 + 2 * k; });
     __syncthreads();
     for (int k = k_lo; k < g.count; ++k) {
         const T *c = rowp(k);
@@ -325,19 +324,17 @@ k_secam_decode(const __grid_constant__ DevParams<T> p, const __grid_constant__ I
         });
         __syncthreads();
     }
+    // (luma, X) of every row to the pairing scratch; k_pair_rows_store combines rows y and y-2 (secam.py:297-300)
     for (int k = 0; k < g.count; ++k) {
         const int row = g.r0 + 2 * k;
-        const bool alt = is_alternate(p, g.frame, io.y0 + row);
-        const bool hp = (k > 0) || has_prev0;
-        const T *luma = rowp(k), *xc = rowp(k) + N1, *xp = hp ? rowp(k - 1) + N1 : nullptr;
+        const T *luma = rowp(k), *xc = rowp(k) + N1;
+        T *dst = io.aux + ((size_t)g.fidx * io.nrows + row) * 2 * W;
         for (int q = threadIdx.x; q < (W >> 2); q += blockDim.x) {
-            T y[4], a[4], b[4] = {(T)0, (T)0, (T)0, (T)0};
+            T y[4], a[4];
             ld4(luma + 4 * q, y);
             ld4(xc + 4 * q, a);
-            if (hp) ld4(xp + 4 * q, b);
-            // secam.py:297-300: non-alternate rows carry D'R (dr = current, db = previous), alternate rows D'B
-            if (alt) store_rgb4(p, io, g.fidx, row, 4 * q, y, b, a);
-            else store_rgb4(p, io, g.fidx, row, 4 * q, y, a, b);
+            st4(dst + 4 * q, y);
+            st4(dst + W + 4 * q, a);
         }
     }
 }
