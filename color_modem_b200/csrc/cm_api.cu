@@ -65,6 +65,17 @@ static void build_filter(const cm_filter &f, FiltHdr &h, std::vector<double> &ta
             mat_mul(A, M, Q);
             memcpy(M, Q, sizeof(M));
         }
+        {   // packed fp32 path (two half-chunks per lane): A^ceil(L/2), A^floor(L/2)
+            double Mh[4] = {1.0, 0.0, 0.0, 1.0};
+            for (int i = 0; i < (L + 1) / 2; ++i) {
+                if (i == L / 2) memcpy(&sec[CM_SEC_MHALF + 4], Mh, sizeof(Mh));
+                double Q[4];
+                mat_mul(A, Mh, Q);
+                memcpy(Mh, Q, sizeof(Mh));
+            }
+            memcpy(&sec[CM_SEC_MHALF], Mh, sizeof(Mh));
+            if ((L & 1) == 0) memcpy(&sec[CM_SEC_MHALF + 4], Mh, sizeof(Mh));
+        }
         for (int k = 0; k < 5; ++k) {                     // M, M^2, M^4, M^8, M^16
             for (int i = 0; i < 4; ++i) sec[CM_SEC_MPOW + 4 * k + i] = M[i];
             double Q[4];
@@ -137,6 +148,9 @@ static void fill_params(const cm_desc &d, DevParams<T> &p, const FiltHdr *fh, co
     for (int i = 0; i < CM_NRES; ++i) p.res[i] = rh[i];
     p.tab = (const T *)tab;
     p.taps = (const T *)taps;
+    for (int r = 0; r < 2; ++r)
+        if (d.resamplers[r].ntaps > 0 && d.resamplers[r].ntaps <= 64)
+            for (int i = 0; i < d.resamplers[r].ntaps; ++i) p.firc[r][i] = (T)d.resamplers[r].taps[i];
 }
 
 template <typename T>

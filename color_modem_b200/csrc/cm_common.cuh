@@ -51,6 +51,11 @@ struct DevParams {
     ResHdr res[CM_NRES];
     const T *tab;
     const T *taps;
+    // dense taps of resampler slots 0 and 1 (the x2 / x3 half-band pair of every family except MAC), zero-filled:
+    // read with compile-time indices they become constant-bank operands of the FIR FMAs (FFMA R, R, c[0][..], R
+    // issues at full rate; with the tap in a third register the sm_100 register file caps FFMA at ~0.7 / clk,
+    // tools/ubench/fma_forms.cu)
+    T firc[2][64];
 };
 
 // Launch geometry / buffers of one call.

@@ -62,20 +62,18 @@ __device__ __forceinline__ void load_window28(const T *__restrict__ x, int n, in
 template <typename T>
 __device__ __forceinline__ void fir_up2(T *__restrict__ E, T *__restrict__ O, const T *__restrict__ x, int n,
                                         const T *__restrict__ h, int tid, int nthr) {
-    T g[20];
-#pragma unroll
-    for (int k = 0; k < 20; ++k) g[k] = h[39 - 2 * k];
-    const T c0 = h[20];
+    // taps are read with compile-time indices right in the FMA loops: for h in the kernel-parameter constant
+    // bank (DevParams::firc) they become constant operands instead of 21 registers
     for (int m0 = 4 * tid; m0 < n; m0 += 4 * nthr) {
         T w[28];
         load_window28(x, n, m0, w);
         T e[4], o[4];
 #pragma unroll
         for (int r = 0; r < 4; ++r) {
-            e[r] = c0 * w[12 + r];
+            e[r] = h[20] * w[12 + r];
             T acc = (T)0;
 #pragma unroll
-            for (int k = 0; k < 20; ++k) acc = Real<T>::fma_(g[k], w[3 + r + k], acc);   // x[m0+r-9+k]
+            for (int k = 0; k < 20; ++k) acc = Real<T>::fma_(h[39 - 2 * k], w[3 + r + k], acc);   // x[m0+r-9+k]
             o[r] = acc;
         }
         st4(E + m0, e);
@@ -87,19 +85,17 @@ __device__ __forceinline__ void fir_up2(T *__restrict__ E, T *__restrict__ O, co
 template <typename T, class Post>
 __device__ __forceinline__ void fir_down2(const T *__restrict__ E, const T *__restrict__ O, int n,
                                           const T *__restrict__ h, int tid, int nthr, Post post) {
-    T g[20];
-#pragma unroll
-    for (int k = 0; k < 20; ++k) g[k] = h[39 - 2 * k];
-    const T c0 = h[20];
+    // taps are read with compile-time indices right in the FMA loops: for h in the kernel-parameter constant
+    // bank (DevParams::firc) they become constant operands instead of 21 registers
     for (int j0 = 4 * tid; j0 < n; j0 += 4 * nthr) {
         T w[28], e[4], y[4];
         load_window28(O, n, j0, w);
         ld4(E + j0, e);
 #pragma unroll
         for (int r = 0; r < 4; ++r) {
-            T acc = c0 * e[r];
+            T acc = h[20] * e[r];
 #pragma unroll
-            for (int k = 0; k < 20; ++k) acc = Real<T>::fma_(g[k], w[2 + r + k], acc);   // O[j0+r-10+k]
+            for (int k = 0; k < 20; ++k) acc = Real<T>::fma_(h[39 - 2 * k], w[2 + r + k], acc);   // O[j0+r-10+k]
             y[r] = acc;
         }
         post(j0, y);
@@ -112,28 +108,26 @@ template <typename T, class Post>
 __device__ __forceinline__ void fir_down2_pair(const T *__restrict__ E1, const T *__restrict__ O1,
                                                const T *__restrict__ E2, const T *__restrict__ O2, int n,
                                                const T *__restrict__ h, int tid, int nthr, Post post) {
-    T g[20];
-#pragma unroll
-    for (int k = 0; k < 20; ++k) g[k] = h[39 - 2 * k];
-    const T c0 = h[20];
+    // taps are read with compile-time indices right in the FMA loops: for h in the kernel-parameter constant
+    // bank (DevParams::firc) they become constant operands instead of 21 registers
     for (int j0 = 4 * tid; j0 < n; j0 += 4 * nthr) {
         T w[28], e[4], y1[4], y2[4];
         load_window28(O1, n, j0, w);
         ld4(E1 + j0, e);
 #pragma unroll
         for (int r = 0; r < 4; ++r) {
-            T acc = c0 * e[r];
+            T acc = h[20] * e[r];
 #pragma unroll
-            for (int k = 0; k < 20; ++k) acc = Real<T>::fma_(g[k], w[2 + r + k], acc);
+            for (int k = 0; k < 20; ++k) acc = Real<T>::fma_(h[39 - 2 * k], w[2 + r + k], acc);
             y1[r] = acc;
         }
         load_window28(O2, n, j0, w);
         ld4(E2 + j0, e);
 #pragma unroll
         for (int r = 0; r < 4; ++r) {
-            T acc = c0 * e[r];
+            T acc = h[20] * e[r];
 #pragma unroll
-            for (int k = 0; k < 20; ++k) acc = Real<T>::fma_(g[k], w[2 + r + k], acc);
+            for (int k = 0; k < 20; ++k) acc = Real<T>::fma_(h[39 - 2 * k], w[2 + r + k], acc);
             y2[r] = acc;
         }
         post(j0, y1, y2);
@@ -147,21 +141,17 @@ __device__ __forceinline__ void fir_down2_pair(const T *__restrict__ E1, const T
 template <typename T>
 __device__ __forceinline__ void fir_up3(T *__restrict__ P0, T *__restrict__ P1, T *__restrict__ P2,
                                         const T *__restrict__ x, int n, const T *__restrict__ h, int tid, int nthr) {
-    T g1[20], g2[20];
-#pragma unroll
-    for (int k = 0; k < 20; ++k) { g1[k] = h[58 - 3 * k]; g2[k] = h[59 - 3 * k]; }
-    const T c0 = h[30];
     for (int m0 = 4 * tid; m0 < n; m0 += 4 * nthr) {
         T w[28], p0[4], p1[4], p2[4];
         load_window28(x, n, m0, w);
 #pragma unroll
         for (int r = 0; r < 4; ++r) {
-            p0[r] = c0 * w[12 + r];
+            p0[r] = h[30] * w[12 + r];
             T a1 = (T)0, a2 = (T)0;
 #pragma unroll
             for (int k = 0; k < 20; ++k) {
-                a1 = Real<T>::fma_(g1[k], w[3 + r + k], a1);
-                a2 = Real<T>::fma_(g2[k], w[3 + r + k], a2);
+                a1 = Real<T>::fma_(h[58 - 3 * k], w[3 + r + k], a1);
+                a2 = Real<T>::fma_(h[59 - 3 * k], w[3 + r + k], a2);
             }
             p1[r] = a1;
             p2[r] = a2;
@@ -172,24 +162,20 @@ __device__ __forceinline__ void fir_up3(T *__restrict__ P0, T *__restrict__ P1, 
     }
 }
 
-// Taps of down3 in window order: t1[k] multiplies P1[j0 + r - 10 + k], t2[k] multiplies P2[j0 + r - 10 + k]
+// Taps of down3 in window order: h[59 - 3k] multiplies P1[j0 + r - 10 + k], h[58 - 3k] multiplies P2[j0 + r - 10 + k]
 template <typename T>
 struct Down3Taps {
-    T t1[20], t2[20], c0;
-    __device__ __forceinline__ explicit Down3Taps(const T *__restrict__ h) {
-#pragma unroll
-        for (int k = 0; k < 20; ++k) { t1[k] = h[59 - 3 * k]; t2[k] = h[58 - 3 * k]; }   // a = k - 10
-        c0 = h[30];
-    }
+    const T *h;       // 61 dense taps (constant bank): h[59 - 3k] multiplies P1, h[58 - 3k] multiplies P2   (a = k - 10)
+    __device__ __forceinline__ explicit Down3Taps(const T *__restrict__ h_) : h(h_) {}
     // w1 / w2: 28-sample windows of P1 / P2 starting at j0 - 12; e: P0[j0 .. j0+3]
     __device__ __forceinline__ void apply(const T *w1, const T *w2, const T *e, T *y) const {
 #pragma unroll
         for (int r = 0; r < 4; ++r) {
-            T acc = c0 * e[r];
+            T acc = h[30] * e[r];
 #pragma unroll
             for (int k = 0; k < 20; ++k) {
-                acc = Real<T>::fma_(t1[k], w1[2 + r + k], acc);
-                acc = Real<T>::fma_(t2[k], w2[2 + r + k], acc);
+                acc = Real<T>::fma_(h[59 - 3 * k], w1[2 + r + k], acc);
+                acc = Real<T>::fma_(h[58 - 3 * k], w2[2 + r + k], acc);
             }
             y[r] = acc;
         }

@@ -126,6 +126,16 @@ static void split_top(const IoArgs<T> &io, IoArgs<T> &top, IoArgs<T> &rest) {
 // Grow-only device scratch of a handle (stream-ordered use only).
 void *cm_ensure_aux(cm_modem *m, size_t bytes);   // nullptr on failure (cm_last_error set)
 
+// Explicit instantiation of the float / double variants; the build may compile a unit once per type
+// (-DCM_INST_F32 / -DCM_INST_F64) so that the two halves compile in parallel.
+#if defined(CM_INST_F32)
+#define CM_INSTANTIATE(f32, f64) f32
+#elif defined(CM_INST_F64)
+#define CM_INSTANTIATE(f32, f64) f64
+#else
+#define CM_INSTANTIATE(f32, f64) f32 f64
+#endif
+
 // per-family entry points (explicitly instantiated for float and double in cm_<family>.cu)
 template <typename T> int qam_encode(cm_modem *m, IoArgs<T> io, cudaStream_t st);
 template <typename T> int qam_decode(cm_modem *m, IoArgs<T> io, int mode, cudaStream_t st);

@@ -53,7 +53,7 @@ int mac_decode(cm_modem *m, IoArgs<T> io, cudaStream_t st) {
     return CM_OK;
 }
 
-template int mac_encode<float>(cm_modem *, IoArgs<float>, cudaStream_t);
-template int mac_encode<double>(cm_modem *, IoArgs<double>, cudaStream_t);
-template int mac_decode<float>(cm_modem *, IoArgs<float>, cudaStream_t);
-template int mac_decode<double>(cm_modem *, IoArgs<double>, cudaStream_t);
+CM_INSTANTIATE(template int mac_encode<float>(cm_modem *, IoArgs<float>, cudaStream_t);,
+               template int mac_encode<double>(cm_modem *, IoArgs<double>, cudaStream_t);)
+CM_INSTANTIATE(template int mac_decode<float>(cm_modem *, IoArgs<float>, cudaStream_t);,
+               template int mac_decode<double>(cm_modem *, IoArgs<double>, cudaStream_t);)

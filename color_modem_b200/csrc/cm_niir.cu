@@ -52,9 +52,9 @@ int proto_decode(cm_modem *m, IoArgs<T> io, cudaStream_t st) {
     return launch_rows<T>(m, io, st, k_proto_decode<T>, bytes, 3, 2, 1, CM_K_DECODE_OTHER, "proto-SECAM decode");
 }
 
-#define CM_INST(fn)                                                      \
-    template int fn<float>(cm_modem *, IoArgs<float>, cudaStream_t);     \
-    template int fn<double>(cm_modem *, IoArgs<double>, cudaStream_t);
+#define CM_INST(fn)                                                                     \
+    CM_INSTANTIATE(template int fn<float>(cm_modem *, IoArgs<float>, cudaStream_t);,     \
+                   template int fn<double>(cm_modem *, IoArgs<double>, cudaStream_t);)
 CM_INST(niir_encode)
 CM_INST(niir_decode)
 CM_INST(proto_encode)

@@ -1,6 +1,20 @@
 // Launchers of the QAM family (NTSC / PAL): kernels in cm_qam.cuh.
+//
+// The build compiles this file several times (__graft_entry__.py: UNIT_VARIANTS): -DCM_QAM_PART=0 encoder and
+// band-split kernels, 1 PAL-D kernel, 2 line-comb kernels, 3 the dispatchers; -DCM_INST_F32 / -DCM_INST_F64 keep one
+// arithmetic type.  Without the macros everything lands in one object.
 #include "cm_host.h"
 #include "cm_qam.cuh"
+
+#ifdef CM_QAM_PART
+#define CM_PART(n) (CM_QAM_PART == (n))
+#else
+#define CM_PART(n) 1
+#endif
+
+template <typename T> int launch_bandsplit(cm_modem *m, IoArgs<T> io, int luma_mode, cudaStream_t st);
+template <typename T> int launch_pald(cm_modem *m, IoArgs<T> io, cudaStream_t st);
+template <typename T, int MODE> int launch_comb(cm_modem *m, IoArgs<T> io, cudaStream_t st);
 
 // true when some IIR use-site of the handle spans several super-chunks (long lines): use the multi-warp kernels
 template <typename T>
@@ -10,6 +24,7 @@ static bool needs_teams(const DevParams<T> &p) {
     return false;
 }
 
+#if CM_PART(0)
 template <typename T>
 int qam_encode(cm_modem *m, IoArgs<T> io, cudaStream_t st) {
     const DevParams<T> &p = params_of<T>(m);
@@ -33,7 +48,7 @@ int qam_encode(cm_modem *m, IoArgs<T> io, cudaStream_t st) {
 }
 
 template <typename T>
-static int launch_bandsplit(cm_modem *m, IoArgs<T> io, int luma_mode, cudaStream_t st) {
+int launch_bandsplit(cm_modem *m, IoArgs<T> io, int luma_mode, cudaStream_t st) {
     const DevParams<T> &p = params_of<T>(m);
     if (io.out_count <= 0) return CM_OK;
     auto bytes = [&](int r) { return (CM_TAPS_ELEMS + (size_t)r * (p.n1p + 8 * (size_t)p.hb2)) * sizeof(T); };
@@ -55,8 +70,60 @@ static int launch_bandsplit(cm_modem *m, IoArgs<T> io, int luma_mode, cudaStream
     return CM_OK;
 }
 
+CM_INSTANTIATE(template int qam_encode<float>(cm_modem *, IoArgs<float>, cudaStream_t);,
+               template int qam_encode<double>(cm_modem *, IoArgs<double>, cudaStream_t);)
+CM_INSTANTIATE(template int launch_bandsplit<float>(cm_modem *, IoArgs<float>, int, cudaStream_t);,
+               template int launch_bandsplit<double>(cm_modem *, IoArgs<double>, int, cudaStream_t);)
+#endif
+
+#if CM_PART(1)
+// Two-pass PAL-D over independent rows (cm_qam.cuh: k_pald_rows / k_pald_pair).  The batch is cut into chunks of
+// CM_PALD_CHUNK frames so that the (a, b) scratch stays modest (64 frames of 720x576: 212 MB, largely L2-resident
+// between the passes).
 template <typename T>
-static int launch_pald(cm_modem *m, IoArgs<T> io, cudaStream_t st) {
+static int launch_pald_rows(cm_modem *m, IoArgs<T> io, cudaStream_t st) {
+    const DevParams<T> &p = params_of<T>(m);
+    const size_t b1 = ((size_t)p.n1p + 6 * (size_t)p.hb2) * sizeof(T), b2 = 4 * (size_t)p.n1p * sizeof(T);
+    int rc = set_smem(k_pald_rows<T>, b1);
+    if (rc) return rc;
+    rc = set_smem(k_pald_pair<T>, b2);
+    if (rc) return rc;
+    const int kChunk = 64;
+    const int chunk = io.nframes < kChunk ? io.nframes : kChunk;
+    const size_t frame_elems = (size_t)io.nrows * 2 * p.W;
+    T *aux = (T *)cm_ensure_aux(m, (size_t)chunk * frame_elems * sizeof(T));
+    if (!aux) return CM_ERR_NOMEM;
+    const size_t in_frame = (size_t)io.nrows * p.Wc, out_frame = (size_t)io.nrows * p.Wo * 3;
+    for (int f0 = 0; f0 < io.nframes; f0 += chunk) {
+        IoArgs<T> c = io;
+        c.nframes = io.nframes - f0 < chunk ? io.nframes - f0 : chunk;
+        c.first_frame = io.first_frame + f0;
+        c.aux = aux;
+        if (c.in_u8) c.in_u8 += (size_t)f0 * in_frame;
+        if (c.in_f) c.in_f += (size_t)f0 * in_frame;
+        if (c.out_u8) c.out_u8 += (size_t)f0 * out_frame;
+        if (c.out_f) c.out_f += (size_t)f0 * out_frame;
+        IoArgs<T> a = c;                                   // pass 1 also covers the two rows above the output rows
+        a.out_begin = c.out_begin >= 2 ? c.out_begin - 2 : 0;
+        a.out_count = c.out_begin + c.out_count - a.out_begin;
+        {
+            LaunchTimer lt(m, CM_K_PALD, st);
+            k_pald_rows<T><<<dim3((unsigned)a.out_count, 1u, (unsigned)c.nframes), CM_ROW_THREADS, b1, st>>>(p, a);
+        }
+        cm_count_launch();
+        CUDA_TRY(cudaGetLastError());
+        {
+            LaunchTimer lt(m, CM_K_DECODE_OTHER, st);
+            k_pald_pair<T><<<dim3((unsigned)c.out_count, 1u, (unsigned)c.nframes), CM_ROW_THREADS, b2, st>>>(p, c);
+        }
+        cm_count_launch();
+        CUDA_TRY(cudaGetLastError());
+    }
+    return CM_OK;
+}
+
+template <typename T>
+int launch_pald(cm_modem *m, IoArgs<T> io, cudaStream_t st) {
     const DevParams<T> &p = params_of<T>(m);
     if (io.out_count <= 0) return CM_OK;
     auto bytes = [&](int r) {
@@ -65,8 +132,9 @@ static int launch_pald(cm_modem *m, IoArgs<T> io, cudaStream_t st) {
     int R = pick_rows(4, (size_t)m->smem_optin / 2, bytes);
     if (!R) R = pick_rows(2, (size_t)m->smem_optin, bytes);
     if (!R) return cm_fail(CM_ERR_UNSUPPORTED, "line too wide for the PAL-D kernel%s");
-    set_groups(io, R);
     const bool teams = needs_teams(p);
+    if (!teams && !io.prof && !getenv("CM_PALD_ONEPASS")) return launch_pald_rows<T>(m, io, st);
+    set_groups(io, R);
     int rc = teams ? set_smem(k_pald_combed<T, true>, bytes(R)) : set_smem(k_pald_combed<T, false>, bytes(R));
     if (rc) return rc;
     dim3 grid = cm_grid(io);
@@ -80,8 +148,13 @@ static int launch_pald(cm_modem *m, IoArgs<T> io, cudaStream_t st) {
     return CM_OK;
 }
 
+CM_INSTANTIATE(template int launch_pald<float>(cm_modem *, IoArgs<float>, cudaStream_t);,
+               template int launch_pald<double>(cm_modem *, IoArgs<double>, cudaStream_t);)
+#endif
+
+#if CM_PART(2)
 template <typename T, int MODE>
-static int launch_comb(cm_modem *m, IoArgs<T> io, cudaStream_t st) {
+int launch_comb(cm_modem *m, IoArgs<T> io, cudaStream_t st) {
     const DevParams<T> &p = params_of<T>(m);
     if (io.out_count <= 0) return CM_OK;
     auto bytes = [&](int r) {
@@ -105,6 +178,14 @@ static int launch_comb(cm_modem *m, IoArgs<T> io, cudaStream_t st) {
     return CM_OK;
 }
 
+#define CM_COMB_INST(T)                                                                        \
+    template int launch_comb<T, COMB_NTSC2>(cm_modem *, IoArgs<T>, cudaStream_t);              \
+    template int launch_comb<T, COMB_NTSC3>(cm_modem *, IoArgs<T>, cudaStream_t);              \
+    template int launch_comb<T, COMB_PAL3>(cm_modem *, IoArgs<T>, cudaStream_t);
+CM_INSTANTIATE(CM_COMB_INST(float), CM_COMB_INST(double))
+#endif
+
+#if CM_PART(3)
 template <typename T>
 int qam_decode(cm_modem *m, IoArgs<T> io, int mode, cudaStream_t st) {
     const DevParams<T> &p = params_of<T>(m);
@@ -139,7 +220,6 @@ int qam_decode(cm_modem *m, IoArgs<T> io, int mode, cudaStream_t st) {
     }
 }
 
-template int qam_encode<float>(cm_modem *, IoArgs<float>, cudaStream_t);
-template int qam_encode<double>(cm_modem *, IoArgs<double>, cudaStream_t);
-template int qam_decode<float>(cm_modem *, IoArgs<float>, int, cudaStream_t);
-template int qam_decode<double>(cm_modem *, IoArgs<double>, int, cudaStream_t);
+CM_INSTANTIATE(template int qam_decode<float>(cm_modem *, IoArgs<float>, int, cudaStream_t);,
+               template int qam_decode<double>(cm_modem *, IoArgs<double>, int, cudaStream_t);)
+#endif

@@ -142,8 +142,7 @@ k_qam_bandsplit(const __grid_constant__ DevParams<T> p, const __grid_constant__ 
     T *taps = sm;
     T *rows = sm + CM_TAPS_ELEMS, *scratch = sm + 128;
     const size_t per_row = (size_t)N1 + 4 * (size_t)N2;     // c | a2 | b2 | l2 | v2
-    const T *hup = taps + p.res[QR_UP2].off, *hdn = taps + p.res[QR_DOWN2].off;
-    copy_taps(taps, p, 2);
+    const T *hup = p.firc[QR_UP2], *hdn = p.firc[QR_DOWN2];   // constant bank (kernel parameter)
     load_comp_rows(io, g.fidx, g.count, W, [&](int k) { return rows + k * per_row; },
                    [&](int k) { return g.r0 + 2 * k; });
     __syncthreads();
@@ -282,8 +281,7 @@ k_pald_combed(const __grid_constant__ DevParams<T> p, const __grid_constant__ Io
     T *gbuf = cbuf + (size_t)(R + 1) * N1;       // (R+1) x N2    G rows, index k+1
     T *work = gbuf + (size_t)(R + 1) * N2;       // 2R x N2
     const int nin = g.count + 1;
-    const T *hup = taps + p.res[QR_UP2].off, *hdn = taps + p.res[QR_DOWN2].off;
-    copy_taps(taps, p, 2);
+    const T *hup = p.firc[QR_UP2], *hdn = p.firc[QR_DOWN2];   // constant bank (kernel parameter)
     load_comp_rows(io, g.fidx, nin, W, [&](int k) { return cbuf + (size_t)k * N1; },
                    [&](int k) { return g.r0 + 2 * (k - 1); });
     __syncthreads();
@@ -384,6 +382,143 @@ k_pald_combed(const __grid_constant__ DevParams<T> p, const __grid_constant__ Io
 }
 
 // ------------------------------------------------------------------------------------------------------------
+// PAL-D in two passes over independent rows (the path taken when every IIR use-site fits one super-chunk, i.e.
+// 720-sample lines).  The AM demodulation of the line sum / difference (pal.py:116-119) is linear in the lines, and
+// the carrier of row k is the carrier of row k-1 advanced by the line shift LS, so with the per-row quadrature pair
+//     a_k = down2(LP(sin(psi_k) G_k)),   b_k = down2(LP(cos(psi_k) G_k)),   psi_k = start_phase(k) + bp_shift - LS/2
+// (G_k = up2(down2(BP(up2 c_k))) as above) the sum / difference channels are
+//     S_k = a_k + cos(LS) a_{k-1} + sin(LS) b_{k-1},     D_k = b_k - cos(LS) b_{k-1} + sin(LS) a_{k-1}.
+// Pass 1 (k_pald_rows, all the arithmetic: 1 row per CTA of two warps, ~21 KB of shared memory, 11 CTAs per SM, no
+// halo row, no idle warps) writes (a_k, b_k) to an fp32 scratch in HBM / L2; pass 2 (k_pald_pair) combines
+// neighbouring rows, rotates to (u, v), re-modulates through the encoder low-pass and stores RGB.
+// ------------------------------------------------------------------------------------------------------------
+#define CM_ROW_THREADS 64
+#ifndef CM_ROWS_MINB
+#define CM_ROWS_MINB 10
+#endif
+#ifndef CM_PAIR_MINB
+#define CM_PAIR_MINB 12
+#endif
+
+template <typename T>
+__global__ void __launch_bounds__(CM_ROW_THREADS, CM_ROWS_MINB)
+k_pald_rows(const __grid_constant__ DevParams<T> p, const __grid_constant__ IoArgs<T> io) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T *sm = reinterpret_cast<T *>(smem_raw);
+    const int W = p.W, W2 = 2 * W, N1 = p.n1p, hb = p.hb2, N2 = 2 * hb;
+    const int warp = threadIdx.x >> 5;
+    const int row = io.out_begin + blockIdx.x, f = blockIdx.z;
+    const long long frame = io.first_frame + f;
+    T *cb = sm;                       // N1: composite row, later E = down2(BP(up2 c))
+    T *g = cb + N1;                   // N2: up2(c), band-passed in place, later G = up2(E)
+    T *wa = g + N2, *wb = wa + N2;    // N2 each: LP(sin G), LP(cos G)
+    const T *hup = p.firc[QR_UP2], *hdn = p.firc[QR_DOWN2];
+    load_comp_row(cb, io, f, row, W);
+    __syncthreads();
+    fir_up2(g, g + hb, cb, W, hup, threadIdx.x, blockDim.x);
+    __syncthreads();
+    if (warp == 0) {
+        const FiltHdr &fb = p.filt[QF_BP2X];
+        warp_fill_tail<T, 2>(g, hb, W2, N2);
+        T *ge = g, *go = g + hb;
+        warp_iir<T, 2>(p.tab + fb.off, fb, [&](int q, int ph, int) { return (ph ? go : ge)[q]; }, Poly2Out<T>{ge, go});
+    }
+    __syncthreads();
+    fir_down2(g, g + hb, W, hdn, threadIdx.x, blockDim.x, [&](int j0, const T *y) { st4(cb + j0, y); });
+    __syncthreads();
+    fir_up2(g, g + hb, cb, W, hup, threadIdx.x, blockDim.x);
+    __syncthreads();
+    {
+        const FiltHdr &fl = p.filt[QF_PALD_LP];
+        warp_fill_tail<T, 2>(g, hb, W2, N2);          // both warps write the same values
+        const T *ge = g, *go = g + hb;
+        T *de = warp ? wb : wa, *dod = de + hb;
+        Carrier<T> car(start_phase(p, frame, io.y0 + row) + p.phases[QP_BP_SHIFT] - p.phases[QP_HALF_LS] +
+                           (warp ? CM_QUARTER_TURN : 0ull),
+                       p.phases[QP_STEP2X], W2);
+        warp_iir<T, 2>(p.tab + fl.off, fl,
+                       [&](int q, int ph, int i) {
+                           car.at(2 * q + ph, i);
+                           return (ph ? go : ge)[q] * car.s;
+                       },
+                       Poly2Out<T>{de, dod});
+    }
+    __syncthreads();
+    T *dst = io.aux + ((size_t)f * io.nrows + row) * 2 * W;
+    fir_down2_pair(wa, wa + hb, wb, wb + hb, W, hdn, threadIdx.x, blockDim.x, [&](int j0, const T *a, const T *b) {
+        st4(dst + j0, a);
+        st4(dst + W + j0, b);
+    });
+}
+
+template <typename T>
+__global__ void __launch_bounds__(CM_ROW_THREADS, CM_PAIR_MINB)
+k_pald_pair(const __grid_constant__ DevParams<T> p, const __grid_constant__ IoArgs<T> io) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T *sm = reinterpret_cast<T *>(smem_raw);
+    const int W = p.W, N1 = p.n1p, W4 = W >> 2;
+    const int warp = threadIdx.x >> 5;
+    const int row = io.out_begin + blockIdx.x, f = blockIdx.z;      // row >= 2: it has a predecessor in its field
+    const long long frame = io.first_frame + f;
+    const int line = io.y0 + row;
+    T *u = sm, *v = u + N1, *ulp = v + N1, *vlp = ulp + N1;
+    const T *ak = io.aux + ((size_t)f * io.nrows + row) * 2 * W, *bk = ak + W;
+    const T *ap = io.aux + ((size_t)f * io.nrows + row - 2) * 2 * W, *bp = ap + W;
+    const T sf = p.scalars[QS_PALD_SIN], cf = p.scalars[QS_PALD_COS];
+    const T cl = cf * cf - sf * sf, sl = (T)2 * sf * cf;             // cos(LS), sin(LS) from the half-angle factors
+    const bool alt = is_alternate(p, frame, line);
+    const T vsgn = alt ? (T)-1 : (T)1;
+    for (int q = threadIdx.x; q < W4; q += blockDim.x) {
+        T a1[4], b1[4], a0[4], b0[4], uu[4], vv[4];
+        ld4(ak + 4 * q, a1);
+        ld4(bk + 4 * q, b1);
+        ld4(ap + 4 * q, a0);
+        ld4(bp + 4 * q, b0);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const T s = a1[i] + (cl * a0[i] + sl * b0[i]);
+            const T d = b1[i] - (cl * b0[i] - sl * a0[i]);
+            uu[i] = d * sf + s * cf;                                  // pal.py:121-125
+            vv[i] = vsgn * (d * cf - s * sf);
+        }
+        st4(u + 4 * q, uu);
+        st4(v + 4 * q, vv);
+    }
+    __syncthreads();
+    {
+        const FiltHdr &fpre = p.filt[QF_PRE_LP];                      // encoder pre-lowpass for the re-modulation
+        T *src = warp ? v : u, *dstp = warp ? vlp : ulp;
+        warp_fill_tail<T, 1>(src, N1, W, N1);
+        warp_iir<T, 1>(p.tab + fpre.off, fpre, [&](int q, int, int) { return src[q]; }, [&](int j, T x) { dstp[j] = x; });
+    }
+    __syncthreads();
+    T rs, rc;
+    Real<T>::sincos_turns(p.phases[QP_STEP1X], rs, rc);
+    const unsigned long long ph0 = start_phase(p, frame, line);
+    const bool neg = (p.flags & 1) && alt;
+    const size_t cbase = ((size_t)f * io.nrows + row) * W;
+    for (int q = threadIdx.x; q < W4; q += blockDim.x) {
+        const int x = 4 * q;
+        T cc[4], a[4], b[4], uu[4], vv[4], s[4], co[4], y[4];
+        if (io.in_f) {
+            ld4(io.in_f + cbase + x, cc);
+        } else {
+            const uint32_t w = __ldg(reinterpret_cast<const uint32_t *>(io.in_u8 + cbase + x));
+#pragma unroll
+            for (int i = 0; i < 4; ++i) cc[i] = ((T)5 * Real<T>::from_u8((w >> (8 * i)) & 0xff) - (T)1) * (T)(1.0 / 3.0);
+        }
+        ld4(ulp + x, a);
+        ld4(vlp + x, b);
+        ld4(u + x, uu);
+        ld4(v + x, vv);
+        carrier4(ph0 + (unsigned long long)x * p.phases[QP_STEP1X], rs, rc, s, co);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) y[i] = cc[i] - (s[i] * a[i] + co[i] * (neg ? -b[i] : b[i]));
+        store_rgb4(p, io, f, row, x, y, uu, vv);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
 // Line-comb decoders that work on the band-passed 2x signal B[k] = BP(up2 c[k]) of neighbouring rows.
 // qam.demodulate (qam.py:43-58) is linear in its composite argument, so demodulating a line difference equals
 // combining the B's first; likewise the wrappers' 0.5*(a+b) averages commute with the low-pass and down2.
@@ -422,8 +557,7 @@ k_qam_comb(const __grid_constant__ DevParams<T> p, const __grid_constant__ IoArg
     const int k_lo = has_prev0 ? -1 : 0;
     const int k_hi = (MODE != COMB_NTSC2 && has_next_last) ? g.count : g.count - 1;
     const int nin = k_hi - k_lo + 1;
-    const T *hup = taps + p.res[QR_UP2].off, *hdn = taps + p.res[QR_DOWN2].off;
-    copy_taps(taps, p, 2);
+    const T *hup = p.firc[QR_UP2], *hdn = p.firc[QR_DOWN2];   // constant bank (kernel parameter)
     load_comp_rows(io, g.fidx, nin, W, [&](int k) { return cbuf + (size_t)(k_lo + k + 1) * N1; },
                    [&](int k) { return g.r0 + 2 * (k_lo + k); });
     __syncthreads();

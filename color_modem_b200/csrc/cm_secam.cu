@@ -61,7 +61,7 @@ int secam_decode(cm_modem *m, IoArgs<T> io, cudaStream_t st) {
     return CM_OK;
 }
 
-template int secam_encode<float>(cm_modem *, IoArgs<float>, cudaStream_t);
-template int secam_encode<double>(cm_modem *, IoArgs<double>, cudaStream_t);
-template int secam_decode<float>(cm_modem *, IoArgs<float>, cudaStream_t);
-template int secam_decode<double>(cm_modem *, IoArgs<double>, cudaStream_t);
+CM_INSTANTIATE(template int secam_encode<float>(cm_modem *, IoArgs<float>, cudaStream_t);,
+               template int secam_encode<double>(cm_modem *, IoArgs<double>, cudaStream_t);)
+CM_INSTANTIATE(template int secam_decode<float>(cm_modem *, IoArgs<float>, cudaStream_t);,
+               template int secam_decode<double>(cm_modem *, IoArgs<double>, cudaStream_t);)
