@@ -19,7 +19,8 @@ FLAG_PAL3D_SIN, FLAG_PAL3D_COS, FLAG_SECAM_BELL, FLAG_SECAM_LF, FLAG_PROTO_LUMA 
 FP32, FP64 = 0, 1
 
 LIB_NAME = 'libcolormodem_b200.so'
-LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), LIB_NAME)
+# CM_B200_LIB: tuning aid, load an alternative build of the same library (tools/variants.sh)
+LIB_PATH = os.environ.get('CM_B200_LIB') or os.path.join(os.path.dirname(os.path.abspath(__file__)), LIB_NAME)
 
 
 class NativeUnavailable(RuntimeError):

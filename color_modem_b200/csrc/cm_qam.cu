@@ -76,17 +76,23 @@ CM_INSTANTIATE(template int launch_bandsplit<float>(cm_modem *, IoArgs<float>, i
                template int launch_bandsplit<double>(cm_modem *, IoArgs<double>, int, cudaStream_t);)
 #endif
 
-#if CM_PART(1)
-// Two-pass PAL-D over independent rows (cm_qam.cuh: k_pald_rows / k_pald_pair).  The batch is cut into chunks of
-// CM_PALD_CHUNK frames so that the (a, b) scratch stays modest (64 frames of 720x576: 212 MB, largely L2-resident
-// between the passes).
-template <typename T>
-static int launch_pald_rows(cm_modem *m, IoArgs<T> io, cudaStream_t st) {
+#if CM_PART(1) || CM_PART(2)
+// Two-pass decoders over independent rows (cm_qam.cuh: k_pald_rows / k_qam_rows, then k_qam_pair<MODE>).  The batch
+// is cut into chunks of 64 frames so that the (a, b) scratch stays modest (64 frames of 720x576: 212 MB, partly
+// L2-resident between the passes).
+template <typename T, int MODE>
+int launch_rows_pair(cm_modem *m, IoArgs<T> io, cudaStream_t st) {
     const DevParams<T> &p = params_of<T>(m);
-    const size_t b1 = ((size_t)p.n1p + 6 * (size_t)p.hb2) * sizeof(T), b2 = 4 * (size_t)p.n1p * sizeof(T);
-    int rc = set_smem(k_pald_rows<T>, b1);
+    if (io.out_count <= 0) return CM_OK;
+    const size_t b1 = ((size_t)p.n1p + 6 * (size_t)p.hb2) * sizeof(T);
+    auto bytes2 = [&](int r) { return (128 + (size_t)r * 4 * p.n1p) * sizeof(T); };
+    int R = pick_rows(4, (size_t)m->smem_optin / 3, bytes2);
+    if (!R) R = pick_rows(1, (size_t)m->smem_optin, bytes2);
+    if (!R || b1 > (size_t)m->smem_optin) return cm_fail(CM_ERR_UNSUPPORTED, "line too wide for the row kernels%s");
+    auto pass1 = MODE == PAIR_PALD ? k_pald_rows<T> : k_qam_rows<T>;
+    int rc = set_smem(pass1, b1);
     if (rc) return rc;
-    rc = set_smem(k_pald_pair<T>, b2);
+    rc = set_smem(k_qam_pair<T, MODE>, bytes2(R));
     if (rc) return rc;
     const int kChunk = 64;
     const int chunk = io.nframes < kChunk ? io.nframes : kChunk;
@@ -103,25 +109,30 @@ static int launch_pald_rows(cm_modem *m, IoArgs<T> io, cudaStream_t st) {
         if (c.in_f) c.in_f += (size_t)f0 * in_frame;
         if (c.out_u8) c.out_u8 += (size_t)f0 * out_frame;
         if (c.out_f) c.out_f += (size_t)f0 * out_frame;
-        IoArgs<T> a = c;                                   // pass 1 also covers the two rows above the output rows
+        IoArgs<T> a = c;                      // pass 1 also covers the neighbour rows the combination reads
         a.out_begin = c.out_begin >= 2 ? c.out_begin - 2 : 0;
-        a.out_count = c.out_begin + c.out_count - a.out_begin;
+        int end = c.out_begin + c.out_count + (MODE >= PAIR_NTSC3 ? 2 : 0);
+        if (end > c.nrows) end = c.nrows;
+        a.out_count = end - a.out_begin;
         {
-            LaunchTimer lt(m, CM_K_PALD, st);
-            k_pald_rows<T><<<dim3((unsigned)a.out_count, 1u, (unsigned)c.nframes), CM_ROW_THREADS, b1, st>>>(p, a);
+            LaunchTimer lt(m, MODE == PAIR_PALD ? CM_K_PALD : CM_K_COMB, st);
+            pass1<<<dim3((unsigned)a.out_count, 1u, (unsigned)c.nframes), CM_ROW_THREADS, b1, st>>>(p, a);
         }
         cm_count_launch();
         CUDA_TRY(cudaGetLastError());
+        set_groups(c, R);
         {
             LaunchTimer lt(m, CM_K_DECODE_OTHER, st);
-            k_pald_pair<T><<<dim3((unsigned)c.out_count, 1u, (unsigned)c.nframes), CM_ROW_THREADS, b2, st>>>(p, c);
+            k_qam_pair<T, MODE><<<cm_grid(c), cta_threads(2 * R), bytes2(R), st>>>(p, c);
         }
         cm_count_launch();
         CUDA_TRY(cudaGetLastError());
     }
     return CM_OK;
 }
+#endif
 
+#if CM_PART(1)
 template <typename T>
 int launch_pald(cm_modem *m, IoArgs<T> io, cudaStream_t st) {
     const DevParams<T> &p = params_of<T>(m);
@@ -133,7 +144,7 @@ int launch_pald(cm_modem *m, IoArgs<T> io, cudaStream_t st) {
     if (!R) R = pick_rows(2, (size_t)m->smem_optin, bytes);
     if (!R) return cm_fail(CM_ERR_UNSUPPORTED, "line too wide for the PAL-D kernel%s");
     const bool teams = needs_teams(p);
-    if (!teams && !io.prof && !getenv("CM_PALD_ONEPASS")) return launch_pald_rows<T>(m, io, st);
+    if (!teams && !io.prof && !getenv("CM_ONEPASS")) return launch_rows_pair<T, PAIR_PALD>(m, io, st);
     set_groups(io, R);
     int rc = teams ? set_smem(k_pald_combed<T, true>, bytes(R)) : set_smem(k_pald_combed<T, false>, bytes(R));
     if (rc) return rc;
@@ -163,8 +174,10 @@ int launch_comb(cm_modem *m, IoArgs<T> io, cudaStream_t st) {
     int R = pick_rows(4, (size_t)m->smem_optin / 2, bytes);
     if (!R) R = pick_rows(2, (size_t)m->smem_optin, bytes);
     if (!R) return cm_fail(CM_ERR_UNSUPPORTED, "line too wide for the comb kernel%s");
-    set_groups(io, R);
     const bool teams = needs_teams(p);
+    if (!teams && !getenv("CM_ONEPASS"))
+        return launch_rows_pair<T, MODE == COMB_NTSC2 ? PAIR_NTSC2 : (MODE == COMB_NTSC3 ? PAIR_NTSC3 : PAIR_PAL3)>(m, io, st);
+    set_groups(io, R);
     int rc = teams ? set_smem(k_qam_comb<T, MODE, true>, bytes(R)) : set_smem(k_qam_comb<T, MODE, false>, bytes(R));
     if (rc) return rc;
     dim3 grid = cm_grid(io);

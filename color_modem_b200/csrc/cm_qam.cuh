@@ -394,7 +394,7 @@ k_pald_combed(const __grid_constant__ DevParams<T> p, const __grid_constant__ Io
 // ------------------------------------------------------------------------------------------------------------
 #define CM_ROW_THREADS 64
 #ifndef CM_ROWS_MINB
-#define CM_ROWS_MINB 10
+#define CM_ROWS_MINB 8
 #endif
 #ifndef CM_PAIR_MINB
 #define CM_PAIR_MINB 12
@@ -451,70 +451,179 @@ k_pald_rows(const __grid_constant__ DevParams<T> p, const __grid_constant__ IoAr
     });
 }
 
+// Pass 1 of the line-comb decoders (NTSC 2-line / 3-line, PAL 3-line): per-row quadrature demodulation of the
+// band-passed 2x signal B_k = BP(up2 c_k) at the row's own phase psi_k = start_phase(k) + bp_shift,
+//     a_k = down2(LP(sin(psi_k) B_k)),   b_k = down2(LP(cos(psi_k) B_k))          (qam.py:43-58 without the factor 2)
+// k_qam_pair rotates these to the phase each comb needs (multiples of LS/2) and combines neighbouring rows.
 template <typename T>
-__global__ void __launch_bounds__(CM_ROW_THREADS, CM_PAIR_MINB)
-k_pald_pair(const __grid_constant__ DevParams<T> p, const __grid_constant__ IoArgs<T> io) {
+__global__ void __launch_bounds__(CM_ROW_THREADS, CM_ROWS_MINB)
+k_qam_rows(const __grid_constant__ DevParams<T> p, const __grid_constant__ IoArgs<T> io) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     T *sm = reinterpret_cast<T *>(smem_raw);
-    const int W = p.W, N1 = p.n1p, W4 = W >> 2;
+    const int W = p.W, W2 = 2 * W, N1 = p.n1p, hb = p.hb2, N2 = 2 * hb;
     const int warp = threadIdx.x >> 5;
-    const int row = io.out_begin + blockIdx.x, f = blockIdx.z;      // row >= 2: it has a predecessor in its field
+    const int row = io.out_begin + blockIdx.x, f = blockIdx.z;
     const long long frame = io.first_frame + f;
-    const int line = io.y0 + row;
-    T *u = sm, *v = u + N1, *ulp = v + N1, *vlp = ulp + N1;
-    const T *ak = io.aux + ((size_t)f * io.nrows + row) * 2 * W, *bk = ak + W;
-    const T *ap = io.aux + ((size_t)f * io.nrows + row - 2) * 2 * W, *bp = ap + W;
-    const T sf = p.scalars[QS_PALD_SIN], cf = p.scalars[QS_PALD_COS];
-    const T cl = cf * cf - sf * sf, sl = (T)2 * sf * cf;             // cos(LS), sin(LS) from the half-angle factors
-    const bool alt = is_alternate(p, frame, line);
-    const T vsgn = alt ? (T)-1 : (T)1;
-    for (int q = threadIdx.x; q < W4; q += blockDim.x) {
-        T a1[4], b1[4], a0[4], b0[4], uu[4], vv[4];
-        ld4(ak + 4 * q, a1);
-        ld4(bk + 4 * q, b1);
-        ld4(ap + 4 * q, a0);
-        ld4(bp + 4 * q, b0);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const T s = a1[i] + (cl * a0[i] + sl * b0[i]);
-            const T d = b1[i] - (cl * b0[i] - sl * a0[i]);
-            uu[i] = d * sf + s * cf;                                  // pal.py:121-125
-            vv[i] = vsgn * (d * cf - s * sf);
-        }
-        st4(u + 4 * q, uu);
-        st4(v + 4 * q, vv);
+    T *cb = sm;                       // N1: composite row
+    T *g = cb + N1;                   // N2: up2(c), band-passed in place
+    T *wa = g + N2, *wb = wa + N2;    // N2 each: LP(sin B), LP(cos B)
+    const T *hup = p.firc[QR_UP2], *hdn = p.firc[QR_DOWN2];
+    load_comp_row(cb, io, f, row, W);
+    __syncthreads();
+    fir_up2(g, g + hb, cb, W, hup, threadIdx.x, blockDim.x);
+    __syncthreads();
+    if (warp == 0) {
+        const FiltHdr &fb = p.filt[QF_BP2X];
+        warp_fill_tail<T, 2>(g, hb, W2, N2);
+        T *ge = g, *go = g + hb;
+        warp_iir<T, 2>(p.tab + fb.off, fb, [&](int q, int ph, int) { return (ph ? go : ge)[q]; }, Poly2Out<T>{ge, go});
     }
     __syncthreads();
     {
-        const FiltHdr &fpre = p.filt[QF_PRE_LP];                      // encoder pre-lowpass for the re-modulation
-        T *src = warp ? v : u, *dstp = warp ? vlp : ulp;
-        warp_fill_tail<T, 1>(src, N1, W, N1);
-        warp_iir<T, 1>(p.tab + fpre.off, fpre, [&](int q, int, int) { return src[q]; }, [&](int j, T x) { dstp[j] = x; });
+        const FiltHdr &fl = p.filt[QF_DEMOD_LP];
+        warp_fill_tail<T, 2>(g, hb, W2, N2);          // both warps write the same values
+        const T *ge = g, *go = g + hb;
+        T *de = warp ? wb : wa, *dod = de + hb;
+        Carrier<T> car(start_phase(p, frame, io.y0 + row) + p.phases[QP_BP_SHIFT] + (warp ? CM_QUARTER_TURN : 0ull),
+                       p.phases[QP_STEP2X], W2);
+        warp_iir<T, 2>(p.tab + fl.off, fl,
+                       [&](int q, int ph, int i) {
+                           car.at(2 * q + ph, i);
+                           return (ph ? go : ge)[q] * car.s;
+                       },
+                       Poly2Out<T>{de, dod});
     }
+    __syncthreads();
+    T *dst = io.aux + ((size_t)f * io.nrows + row) * 2 * W;
+    fir_down2_pair(wa, wa + hb, wb, wb + hb, W, hdn, threadIdx.x, blockDim.x, [&](int j0, const T *a, const T *b) {
+        st4(dst + j0, a);
+        st4(dst + W + j0, b);
+    });
+}
+
+// Pass 2: combine the per-row pairs (a, b) of neighbouring rows of a field into (u, v), run the encoder low-pass for
+// the re-modulation, y = c - remod(u, v), inverse matrix, store.  R rows per CTA (the pairs of R + 1 or R + 2 rows are
+// read once), 8 warps.  With ch/sh = cos/sin(LS/2), cl/sl = cos/sin(LS) and D[.] = down2(LP(.)):
+//     D[sin(psi_k + t) B_k] = cos(t) a_k + sin(t) b_k,     D[cos(psi_k + t) B_k] = cos(t) b_k - sin(t) a_k,
+// and psi_{k+1} = psi_k + LS.
+//   PAIR_PALD   pal.py:113-125   S = a_k + D[sin(psi_k) G_{k-1}],  D = b_k - D[cos(psi_k) G_{k-1}]
+//   PAIR_NTSC2  ntsc.py:74-81    phase psi_k - LS/2 on the line difference, u from cos, v from -sin
+//   PAIR_NTSC3  comb.py:96-113   average of the 2-line chroma of this row (band-split chroma at a field top) and of
+//                                the next row (nothing at the bottom, where the driver re-feeds the row, image.py:51-53)
+//   PAIR_PAL3   pal.py:198-226   sums / differences of three rows at the phase of the middle one
+enum { PAIR_PALD = 0, PAIR_NTSC2 = 1, PAIR_NTSC3 = 2, PAIR_PAL3 = 3 };
+
+template <typename T, int MODE>
+__global__ void __launch_bounds__(CM_NTHREADS, 3)
+k_qam_pair(const __grid_constant__ DevParams<T> p, const __grid_constant__ IoArgs<T> io) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T *sm = reinterpret_cast<T *>(smem_raw);
+    RowGroup g;
+    if (!decode_group(io, g)) return;
+    const int W = p.W, N1 = p.n1p, W4 = W >> 2;
+    T *scratch = sm, *rows = sm + 128;                     // per row: u | v | ulp | vlp
+    const size_t per_row = 4 * (size_t)N1;
+    const bool has_prev0 = g.r0 >= 2;
+    const bool has_next_last = g.r0 + 2 * g.count < io.nrows;
+    T sh, ch, sl, cl;
+    Real<T>::sincos_turns(p.phases[QP_HALF_LS], sh, ch);
+    Real<T>::sincos_turns(p.line_shift, sl, cl);
+    const T sf = p.scalars[QS_PALD_SIN], cf = p.scalars[QS_PALD_COS];
+    const T fac = p.scalars[QS_NTSC_FACTOR];
+    const T a_ss = (T)2 * p.scalars[QS_P3D_SINSUM], a_cu = (T)2 * p.scalars[QS_P3D_COSU],
+            a_cv = (T)2 * p.scalars[QS_P3D_COSV];
+    const T *aux = io.aux + (size_t)g.fidx * io.nrows * 2 * W;
+    auto ldab = [&](int row, int x, T *a, T *b) {
+        ld4(aux + (size_t)row * 2 * W + x, a);
+        ld4(aux + (size_t)row * 2 * W + W + x, b);
+    };
+    for (int q = threadIdx.x; q < W4; q += blockDim.x) {
+        const int x = 4 * q;
+        T ap[4], bp[4], ac[4], bc[4], an[4], bn[4];
+        if (has_prev0) ldab(g.r0 - 2, x, ap, bp);
+        ldab(g.r0, x, ac, bc);
+        for (int k = 0; k < g.count; ++k) {
+            const int row = g.r0 + 2 * k;
+            const bool hp = (k > 0) || has_prev0;
+            const bool hn = (k + 1 < g.count) || has_next_last;
+            if (MODE >= PAIR_NTSC3 && hn) ldab(row + 2, x, an, bn);
+            else if (MODE < PAIR_NTSC3 && k + 1 < g.count) ldab(row + 2, x, an, bn);
+            const bool alt = is_alternate(p, g.frame, io.y0 + row);
+            T u[4], v[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                if (MODE == PAIR_PALD) {
+                    const T s = ac[i] + (cl * ap[i] + sl * bp[i]);
+                    const T d = bc[i] - (cl * bp[i] - sl * ap[i]);
+                    u[i] = d * sf + s * cf;
+                    v[i] = (alt ? (T)-1 : (T)1) * (d * cf - s * sf);
+                } else if (MODE == PAIR_NTSC2) {
+                    const T f2 = (T)2 * fac;
+                    u[i] = f2 * ((ch * bc[i] + sh * ac[i]) - (ch * bp[i] - sh * ap[i]));
+                    v[i] = -f2 * ((ch * ac[i] - sh * bc[i]) - (ch * ap[i] + sh * bp[i]));
+                } else if (MODE == PAIR_NTSC3) {
+                    const T f2 = (T)2 * fac;
+                    T uu = hp ? f2 * ((ch * bc[i] + sh * ac[i]) - (ch * bp[i] - sh * ap[i])) : (T)2 * ac[i];
+                    T vv = hp ? -f2 * ((ch * ac[i] - sh * bc[i]) - (ch * ap[i] + sh * bp[i])) : (T)2 * bc[i];
+                    if (hn) {
+                        uu += f2 * ((ch * bn[i] + sh * an[i]) - (ch * bc[i] - sh * ac[i]));
+                        vv -= f2 * ((ch * an[i] - sh * bn[i]) - (ch * ac[i] + sh * bc[i]));
+                    }
+                    u[i] = (T)0.5 * uu;
+                    v[i] = (T)0.5 * vv;
+                } else {
+                    const T sin_n = hn ? cl * an[i] - sl * bn[i] : ac[i], cos_n = hn ? cl * bn[i] + sl * an[i] : bc[i];
+                    const T sin_p = cl * ap[i] + sl * bp[i], cos_p = cl * bp[i] - sl * ap[i];
+                    u[i] = a_ss * (cos_n - cos_p) + a_cu * (sin_n - (T)2 * ac[i] + sin_p);
+                    const T vv = a_ss * (sin_n - sin_p) + a_cv * (cos_n - (T)2 * bc[i] + cos_p);
+                    v[i] = alt ? -vv : vv;
+                }
+            }
+            T *ur = rows + (size_t)k * per_row;
+            st4(ur + x, u);
+            st4(ur + N1 + x, v);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { ap[i] = ac[i]; bp[i] = bc[i]; ac[i] = an[i]; bc[i] = bn[i]; }
+        }
+    }
+    __syncthreads();
+    const FiltHdr &fpre = p.filt[QF_PRE_LP];
+    for_each_iir_task<T, false>(fpre, 2 * g.count, scratch, [&](int t, const IirTeam<T> &tm) {
+        T *src = rows + (size_t)(t >> 1) * per_row + (t & 1) * N1;
+        T *dstp = src + 2 * N1;
+        warp_fill_tail<T, 1>(src, N1, W, N1);
+        team_iir<T, 1, false>(p.tab + fpre.off, fpre, [&](int q, int, int) { return src[q]; },
+                              [&](int j, T x) { dstp[j] = x; }, tm);
+    });
     __syncthreads();
     T rs, rc;
     Real<T>::sincos_turns(p.phases[QP_STEP1X], rs, rc);
-    const unsigned long long ph0 = start_phase(p, frame, line);
-    const bool neg = (p.flags & 1) && alt;
-    const size_t cbase = ((size_t)f * io.nrows + row) * W;
-    for (int q = threadIdx.x; q < W4; q += blockDim.x) {
-        const int x = 4 * q;
-        T cc[4], a[4], b[4], uu[4], vv[4], s[4], co[4], y[4];
-        if (io.in_f) {
-            ld4(io.in_f + cbase + x, cc);
-        } else {
-            const uint32_t w = __ldg(reinterpret_cast<const uint32_t *>(io.in_u8 + cbase + x));
+    for (int k = 0; k < g.count; ++k) {
+        const int row = g.r0 + 2 * k, line = io.y0 + row;
+        const T *ur = rows + (size_t)k * per_row;
+        const unsigned long long ph0 = start_phase(p, g.frame, line);
+        const bool neg = (p.flags & 1) && is_alternate(p, g.frame, line);
+        const size_t cbase = ((size_t)g.fidx * io.nrows + row) * W;
+        for (int q = threadIdx.x; q < W4; q += blockDim.x) {
+            const int x = 4 * q;
+            T cc[4], a[4], b[4], uu[4], vv[4], s[4], co[4], y[4];
+            if (io.in_f) {
+                ld4(io.in_f + cbase + x, cc);
+            } else {
+                const uint32_t w = __ldg(reinterpret_cast<const uint32_t *>(io.in_u8 + cbase + x));
 #pragma unroll
-            for (int i = 0; i < 4; ++i) cc[i] = ((T)5 * Real<T>::from_u8((w >> (8 * i)) & 0xff) - (T)1) * (T)(1.0 / 3.0);
+                for (int i = 0; i < 4; ++i)
+                    cc[i] = ((T)5 * Real<T>::from_u8((w >> (8 * i)) & 0xff) - (T)1) * (T)(1.0 / 3.0);
+            }
+            ld4(ur + x, uu);
+            ld4(ur + N1 + x, vv);
+            ld4(ur + 2 * N1 + x, a);
+            ld4(ur + 3 * N1 + x, b);
+            carrier4(ph0 + (unsigned long long)x * p.phases[QP_STEP1X], rs, rc, s, co);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) y[i] = cc[i] - (s[i] * a[i] + co[i] * (neg ? -b[i] : b[i]));
+            store_rgb4(p, io, g.fidx, row, x, y, uu, vv);
         }
-        ld4(ulp + x, a);
-        ld4(vlp + x, b);
-        ld4(u + x, uu);
-        ld4(v + x, vv);
-        carrier4(ph0 + (unsigned long long)x * p.phases[QP_STEP1X], rs, rc, s, co);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) y[i] = cc[i] - (s[i] * a[i] + co[i] * (neg ? -b[i] : b[i]));
-        store_rgb4(p, io, f, row, x, y, uu, vv);
     }
 }
 
