@@ -150,7 +150,10 @@ static void fill_params(const cm_desc &d, DevParams<T> &p, const FiltHdr *fh, co
     p.taps = (const T *)taps;
     for (int r = 0; r < 2; ++r)
         if (d.resamplers[r].ntaps > 0 && d.resamplers[r].ntaps <= 64)
-            for (int i = 0; i < d.resamplers[r].ntaps; ++i) p.firc[r][i] = (T)d.resamplers[r].taps[i];
+            for (int i = 0; i < d.resamplers[r].ntaps; ++i) {
+                p.firc[r][i] = (T)d.resamplers[r].taps[i];
+                p.fircp[r][i][0] = p.fircp[r][i][1] = (float)d.resamplers[r].taps[i];
+            }
 }
 
 template <typename T>

@@ -56,7 +56,11 @@ struct DevParams {
     // issues at full rate; with the tap in a third register the sm_100 register file caps FFMA at ~0.7 / clk,
     // tools/ubench/fma_forms.cu)
     T firc[2][64];
+    float fircp[2][64][2];     // the same taps duplicated (h, h): 64-bit uniform operands of the packed f32x2 FIRs
 };
+
+template <typename T> struct IsF32 { static const bool value = false; };
+template <> struct IsF32<float> { static const bool value = true; };
 
 // Launch geometry / buffers of one call.
 template <typename T>

@@ -58,10 +58,89 @@ __device__ __forceinline__ void load_window28(const T *__restrict__ x, int n, in
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// fp32: packed f32x2 versions (FFMA2: one issue slot for two FMAs).  The window is held as the 14 naturally aligned
+// pairs W2[i] = (w[2i], w[2i+1]) that the 128-bit loads deliver; a pair of neighbouring outputs (r, r+1) needs, for
+// tap k, the pair (w[c+r+k], w[c+r+k+1]), which is aligned for every other tap.  Five accumulator pairs
+//     (0,1), (2,3) over the taps of one parity  +  (-1,0), (1,2), (3,4) over the taps of the other parity
+// give the four outputs with 50 FFMA2 instead of 80 FFMA (the outer halves of (-1,0) and (3,4) are discarded).
+// The taps are (h, h) pairs in the kernel-parameter constant bank (DevParams::fircp), `hp` points at one of them and
+// must be indexed with compile-time constants.
+// ------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void load_window28_f2(const float *__restrict__ x, int n, int m0, float2 *w2) {
+#pragma unroll
+    for (int v = 0; v < 7; ++v) {
+        const int i = m0 - 12 + 4 * v;
+        if (i >= 0 && i < n) {
+            const float4 t = *reinterpret_cast<const float4 *>(x + i);
+            w2[2 * v] = make_float2(t.x, t.y);
+            w2[2 * v + 1] = make_float2(t.z, t.w);
+        } else {
+            w2[2 * v] = w2[2 * v + 1] = make_float2(0.f, 0.f);
+        }
+    }
+}
+
+// out[r] (+)= sum_{k<20} h[T0 - TS k] w[C + r + k],  r = 0..3;  C = 3 (up) or 2 (down).  a01 / a23 carry the initial
+// values of the outputs (0,1) / (2,3).
+template <int C, int T0, int TS>
+__device__ __forceinline__ void fir4_f2(const float (*hp)[2], const float2 *w2, float2 a01, float2 a23, float *out) {
+    constexpr int PA = (C & 1) ? 1 : 0;      // parity of the taps whose (r, r+1) pairs are aligned for even r
+    float2 bm = make_float2(0.f, 0.f), b12 = bm, b34 = bm;
+#pragma unroll
+    for (int kk = 0; kk < 10; ++kk) {
+        const int k = 2 * kk + PA;
+        const float2 g = make_float2(hp[T0 - TS * k][0], hp[T0 - TS * k][1]);
+        a01 = __ffma2_rn(g, w2[(C + k) / 2], a01);
+        a23 = __ffma2_rn(g, w2[(C + 2 + k) / 2], a23);
+    }
+#pragma unroll
+    for (int kk = 0; kk < 10; ++kk) {
+        const int k = 2 * kk + (1 - PA);
+        const float2 g = make_float2(hp[T0 - TS * k][0], hp[T0 - TS * k][1]);
+        bm = __ffma2_rn(g, w2[(C - 1 + k) / 2], bm);
+        b12 = __ffma2_rn(g, w2[(C + 1 + k) / 2], b12);
+        b34 = __ffma2_rn(g, w2[(C + 3 + k) / 2], b34);
+    }
+    out[0] = a01.x + bm.y;
+    out[1] = a01.y + b12.x;
+    out[2] = a23.x + b12.y;
+    out[3] = a23.y + b34.x;
+}
+
+// Taps of one resampler: dense taps h (shared or constant memory) and, for the packed fp32 path, the duplicated
+// pairs in the constant bank (nullptr: scalar path, e.g. the MAC kernels whose taps live in shared memory).
+template <typename T>
+struct FirTaps {
+    const T *h;
+    const float (*hp)[2];
+#ifdef CM_NO_PACKED_FIR
+    __device__ __forceinline__ FirTaps(const T *h_, const float (*)[2]) : h(h_), hp(nullptr) {}
+#else
+    __device__ __forceinline__ FirTaps(const T *h_, const float (*hp_)[2]) : h(h_), hp(hp_) {}
+#endif
+};
+
 // x[0..n) natural -> E[0..n), O[0..n).  n % 4 == 0, buffers 16-byte aligned.      h: 41 dense taps
 template <typename T>
 __device__ __forceinline__ void fir_up2(T *__restrict__ E, T *__restrict__ O, const T *__restrict__ x, int n,
-                                        const T *__restrict__ h, int tid, int nthr) {
+                                        const FirTaps<T> tp, int tid, int nthr) {
+    const T *__restrict__ h = tp.h;
+    if constexpr (IsF32<T>::value) {
+        if (tp.hp) {
+            for (int m0 = 4 * tid; m0 < n; m0 += 4 * nthr) {
+                float2 w2[14];
+                load_window28_f2(x, n, m0, w2);
+                const float2 c0 = make_float2(tp.hp[20][0], tp.hp[20][1]), z = make_float2(0.f, 0.f);
+                const float2 e01 = __fmul2_rn(c0, w2[6]), e23 = __fmul2_rn(c0, w2[7]);
+                float o[4];
+                fir4_f2<3, 39, 2>(tp.hp, w2, z, z, o);
+                *reinterpret_cast<float4 *>(E + m0) = make_float4(e01.x, e01.y, e23.x, e23.y);
+                *reinterpret_cast<float4 *>(O + m0) = make_float4(o[0], o[1], o[2], o[3]);
+            }
+            return;
+        }
+    }
     // taps are read with compile-time indices right in the FMA loops: for h in the kernel-parameter constant
     // bank (DevParams::firc) they become constant operands instead of 21 registers
     for (int m0 = 4 * tid; m0 < n; m0 += 4 * nthr) {
@@ -81,10 +160,31 @@ __device__ __forceinline__ void fir_up2(T *__restrict__ E, T *__restrict__ O, co
     }
 }
 
+// packed down2 of one quad: y[r] = h[20] E[j0+r] + sum_k h[39-2k] O[j0+r-10+k]
+__device__ __forceinline__ void down2_quad_f2(const float (*hp)[2], const float *__restrict__ E,
+                                              const float *__restrict__ O, int n, int j0, float *y) {
+    float2 w2[14];
+    load_window28_f2(O, n, j0, w2);
+    const float4 e = *reinterpret_cast<const float4 *>(E + j0);
+    const float2 c0 = make_float2(hp[20][0], hp[20][1]);
+    fir4_f2<2, 39, 2>(hp, w2, __fmul2_rn(c0, make_float2(e.x, e.y)), __fmul2_rn(c0, make_float2(e.z, e.w)), y);
+}
+
 // E[0..n), O[0..n) -> n outputs; post(j0, y[4]) consumes outputs j0..j0+3.       h: 41 dense taps
 template <typename T, class Post>
 __device__ __forceinline__ void fir_down2(const T *__restrict__ E, const T *__restrict__ O, int n,
-                                          const T *__restrict__ h, int tid, int nthr, Post post) {
+                                          const FirTaps<T> tp, int tid, int nthr, Post post) {
+    const T *__restrict__ h = tp.h;
+    if constexpr (IsF32<T>::value) {
+        if (tp.hp) {
+            for (int j0 = 4 * tid; j0 < n; j0 += 4 * nthr) {
+                float y[4];
+                down2_quad_f2(tp.hp, E, O, n, j0, y);
+                post(j0, y);
+            }
+            return;
+        }
+    }
     // taps are read with compile-time indices right in the FMA loops: for h in the kernel-parameter constant
     // bank (DevParams::firc) they become constant operands instead of 21 registers
     for (int j0 = 4 * tid; j0 < n; j0 += 4 * nthr) {
@@ -107,7 +207,19 @@ __device__ __forceinline__ void fir_down2(const T *__restrict__ E, const T *__re
 template <typename T, class Post>
 __device__ __forceinline__ void fir_down2_pair(const T *__restrict__ E1, const T *__restrict__ O1,
                                                const T *__restrict__ E2, const T *__restrict__ O2, int n,
-                                               const T *__restrict__ h, int tid, int nthr, Post post) {
+                                               const FirTaps<T> tp, int tid, int nthr, Post post) {
+    const T *__restrict__ h = tp.h;
+    if constexpr (IsF32<T>::value) {
+        if (tp.hp) {
+            for (int j0 = 4 * tid; j0 < n; j0 += 4 * nthr) {
+                float y1[4], y2[4];
+                down2_quad_f2(tp.hp, E1, O1, n, j0, y1);
+                down2_quad_f2(tp.hp, E2, O2, n, j0, y2);
+                post(j0, y1, y2);
+            }
+            return;
+        }
+    }
     // taps are read with compile-time indices right in the FMA loops: for h in the kernel-parameter constant
     // bank (DevParams::firc) they become constant operands instead of 21 registers
     for (int j0 = 4 * tid; j0 < n; j0 += 4 * nthr) {
@@ -140,7 +252,25 @@ __device__ __forceinline__ void fir_down2_pair(const T *__restrict__ E1, const T
 //     down3:  y[j]  = h[30] P0[j] + sum_a ( h[29-3a] P1[j+a] + h[28-3a] P2[j+a] ),  a = -10..9
 template <typename T>
 __device__ __forceinline__ void fir_up3(T *__restrict__ P0, T *__restrict__ P1, T *__restrict__ P2,
-                                        const T *__restrict__ x, int n, const T *__restrict__ h, int tid, int nthr) {
+                                        const T *__restrict__ x, int n, const FirTaps<T> tp, int tid, int nthr) {
+    const T *__restrict__ h = tp.h;
+    if constexpr (IsF32<T>::value) {
+        if (tp.hp) {
+            for (int m0 = 4 * tid; m0 < n; m0 += 4 * nthr) {
+                float2 w2[14];
+                load_window28_f2(x, n, m0, w2);
+                const float2 c0 = make_float2(tp.hp[30][0], tp.hp[30][1]), z = make_float2(0.f, 0.f);
+                const float2 e01 = __fmul2_rn(c0, w2[6]), e23 = __fmul2_rn(c0, w2[7]);
+                float o1[4], o2[4];
+                fir4_f2<3, 58, 3>(tp.hp, w2, z, z, o1);
+                fir4_f2<3, 59, 3>(tp.hp, w2, z, z, o2);
+                *reinterpret_cast<float4 *>(P0 + m0) = make_float4(e01.x, e01.y, e23.x, e23.y);
+                *reinterpret_cast<float4 *>(P1 + m0) = make_float4(o1[0], o1[1], o1[2], o1[3]);
+                *reinterpret_cast<float4 *>(P2 + m0) = make_float4(o2[0], o2[1], o2[2], o2[3]);
+            }
+            return;
+        }
+    }
     for (int m0 = 4 * tid; m0 < n; m0 += 4 * nthr) {
         T w[28], p0[4], p1[4], p2[4];
         load_window28(x, n, m0, w);
@@ -166,9 +296,25 @@ __device__ __forceinline__ void fir_up3(T *__restrict__ P0, T *__restrict__ P1, 
 template <typename T>
 struct Down3Taps {
     const T *h;       // 61 dense taps (constant bank): h[59 - 3k] multiplies P1, h[58 - 3k] multiplies P2   (a = k - 10)
-    __device__ __forceinline__ explicit Down3Taps(const T *__restrict__ h_) : h(h_) {}
+    const float (*hp)[2];
+    __device__ __forceinline__ explicit Down3Taps(const FirTaps<T> tp) : h(tp.h), hp(tp.hp) {}
     // w1 / w2: 28-sample windows of P1 / P2 starting at j0 - 12; e: P0[j0 .. j0+3]
     __device__ __forceinline__ void apply(const T *w1, const T *w2, const T *e, T *y) const {
+        if constexpr (IsF32<T>::value) {
+            if (hp) {
+                float2 p1[14], p2[14];
+#pragma unroll
+                for (int i = 0; i < 14; ++i) {
+                    p1[i] = make_float2(w1[2 * i], w1[2 * i + 1]);
+                    p2[i] = make_float2(w2[2 * i], w2[2 * i + 1]);
+                }
+                const float2 c0 = make_float2(hp[30][0], hp[30][1]);
+                float t[4];
+                fir4_f2<2, 59, 3>(hp, p1, __fmul2_rn(c0, make_float2(e[0], e[1])), __fmul2_rn(c0, make_float2(e[2], e[3])), t);
+                fir4_f2<2, 58, 3>(hp, p2, make_float2(t[0], t[1]), make_float2(t[2], t[3]), y);
+                return;
+            }
+        }
 #pragma unroll
         for (int r = 0; r < 4; ++r) {
             T acc = h[30] * e[r];

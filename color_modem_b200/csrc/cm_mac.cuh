@@ -161,7 +161,7 @@ k_mac_decode(const __grid_constant__ DevParams<T> p, const __grid_constant__ IoA
         }
     }
     __syncthreads();
-    const T *hup = taps + p.res[MR_UP2].off;
+    const FirTaps<T> hup{taps + p.res[MR_UP2].off, nullptr};
     for (int k = k_lo; k < g.count; ++k) {
         T *ch = rowp(k) + Wc + 1080 + 720, *xe = ch + 360, *xo = xe + 360;
         fir_up2(xe, xo, ch, 360, hup, threadIdx.x, blockDim.x);

@@ -138,7 +138,7 @@ k_niir_decode(const __grid_constant__ DevParams<T> p, const __grid_constant__ Io
     const size_t per_row = (size_t)N1 + 3 * (size_t)N3;
     const bool has_prev0 = g.r0 >= 2;
     const int nin = g.count + 1;                       // row slot 0 = previous row (real or synthetic), slot k+1 = row k
-    const T *hup = p.firc[NR_UP3], *hdn = p.firc[NR_DOWN3];   // constant bank (kernel parameter)
+    const FirTaps<T> hup{p.firc[NR_UP3], p.fircp[NR_UP3]}, hdn{p.firc[NR_DOWN3], p.fircp[NR_DOWN3]};   // constant bank (kernel parameter)
     auto rowp = [&](int k) { return rows + (size_t)(k + 1) * per_row; };
     load_comp_rows(io, g.fidx, has_prev0 ? nin : g.count, W,
                    [&](int k) { return rowp(has_prev0 ? k - 1 : k); },

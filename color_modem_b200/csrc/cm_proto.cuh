@@ -21,7 +21,7 @@ k_proto_encode(const __grid_constant__ DevParams<T> p, const __grid_constant__ I
     T *taps = sm;
     T *rows = sm + 128;
     const size_t per_row = 2 * (size_t)N1 + N3;
-    const T *hup = p.firc[PR_UP3], *hdn = p.firc[PR_DOWN3];   // constant bank (kernel parameter)
+    const FirTaps<T> hup{p.firc[PR_UP3], p.fircp[PR_UP3]}, hdn{p.firc[PR_DOWN3], p.fircp[PR_DOWN3]};   // constant bank (kernel parameter)
     for (int k = 0; k < g.count; ++k) {
         const int row = g.r0 + 2 * k;
         const int nrow = (row + 2 < io.nrows) ? row + 2 : row;
@@ -108,7 +108,7 @@ k_proto_decode(const __grid_constant__ DevParams<T> p, const __grid_constant__ I
     const bool has_prev0 = g.r0 >= 2;
     const int k_lo = has_prev0 ? -1 : 0;
     const int nin = g.count - k_lo;
-    const T *hup = p.firc[PR_UP3], *hdn = p.firc[PR_DOWN3];   // constant bank (kernel parameter)
+    const FirTaps<T> hup{p.firc[PR_UP3], p.fircp[PR_UP3]}, hdn{p.firc[PR_DOWN3], p.fircp[PR_DOWN3]};   // constant bank (kernel parameter)
     auto rowp = [&](int k) { return rows + (size_t)(k - k_lo) * per_row; };
     load_comp_rows(io, g.fidx, nin, W, [&](int k) { return rowp(k_lo + k); }, [&](int k) { return g.r0 + 2 * (k_lo + k); });
     __syncthreads();

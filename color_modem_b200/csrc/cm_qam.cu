@@ -78,25 +78,21 @@ CM_INSTANTIATE(template int launch_bandsplit<float>(cm_modem *, IoArgs<float>, i
 
 #if CM_PART(1) || CM_PART(2)
 // Two-pass decoders over independent rows (cm_qam.cuh: k_pald_rows / k_qam_rows, then k_qam_pair<MODE>).  The batch
-// is cut into chunks of 64 frames so that the (a, b) scratch stays modest (64 frames of 720x576: 212 MB, partly
+// is cut into chunks of 64 frames so that the (a, b) scratch stays modest (64 frames of 720x576: 425 MB, partly
 // L2-resident between the passes).
 template <typename T, int MODE>
 int launch_rows_pair(cm_modem *m, IoArgs<T> io, cudaStream_t st) {
     const DevParams<T> &p = params_of<T>(m);
     if (io.out_count <= 0) return CM_OK;
     const size_t b1 = ((size_t)p.n1p + 6 * (size_t)p.hb2) * sizeof(T);
-    auto bytes2 = [&](int r) { return (128 + (size_t)r * 4 * p.n1p) * sizeof(T); };
-    int R = pick_rows(4, (size_t)m->smem_optin / 3, bytes2);
-    if (!R) R = pick_rows(1, (size_t)m->smem_optin, bytes2);
-    if (!R || b1 > (size_t)m->smem_optin) return cm_fail(CM_ERR_UNSUPPORTED, "line too wide for the row kernels%s");
+    if (b1 > (size_t)m->smem_optin) return cm_fail(CM_ERR_UNSUPPORTED, "line too wide for the row kernels%s");
     auto pass1 = MODE == PAIR_PALD ? k_pald_rows<T> : k_qam_rows<T>;
     int rc = set_smem(pass1, b1);
     if (rc) return rc;
-    rc = set_smem(k_qam_pair<T, MODE>, bytes2(R));
-    if (rc) return rc;
-    const int kChunk = 64;
+    int kChunk = 64;
+    if (const char *e = getenv("CM_CHUNK")) kChunk = atoi(e) > 0 ? atoi(e) : kChunk;     // tuning aid
     const int chunk = io.nframes < kChunk ? io.nframes : kChunk;
-    const size_t frame_elems = (size_t)io.nrows * 2 * p.W;
+    const size_t frame_elems = (size_t)io.nrows * 4 * p.W;
     T *aux = (T *)cm_ensure_aux(m, (size_t)chunk * frame_elems * sizeof(T));
     if (!aux) return CM_ERR_NOMEM;
     const size_t in_frame = (size_t)io.nrows * p.Wc, out_frame = (size_t)io.nrows * p.Wo * 3;
@@ -120,10 +116,11 @@ int launch_rows_pair(cm_modem *m, IoArgs<T> io, cudaStream_t st) {
         }
         cm_count_launch();
         CUDA_TRY(cudaGetLastError());
-        set_groups(c, R);
         {
             LaunchTimer lt(m, CM_K_DECODE_OTHER, st);
-            k_qam_pair<T, MODE><<<cm_grid(c), cta_threads(2 * R), bytes2(R), st>>>(p, c);
+            const int segs = (((c.out_count + 1) >> 1) + CM_SEG - 1) / CM_SEG, threads = 128;
+            dim3 grid((unsigned)((segs * (p.W >> 2) + threads - 1) / threads), 2u, (unsigned)c.nframes);
+            k_qam_combine<T, MODE><<<grid, threads, 0, st>>>(p, c);
         }
         cm_count_launch();
         CUDA_TRY(cudaGetLastError());

@@ -142,7 +142,7 @@ k_qam_bandsplit(const __grid_constant__ DevParams<T> p, const __grid_constant__ 
     T *taps = sm;
     T *rows = sm + CM_TAPS_ELEMS, *scratch = sm + 128;
     const size_t per_row = (size_t)N1 + 4 * (size_t)N2;     // c | a2 | b2 | l2 | v2
-    const T *hup = p.firc[QR_UP2], *hdn = p.firc[QR_DOWN2];   // constant bank (kernel parameter)
+    const FirTaps<T> hup{p.firc[QR_UP2], p.fircp[QR_UP2]}, hdn{p.firc[QR_DOWN2], p.fircp[QR_DOWN2]};   // constant bank (kernel parameter)
     load_comp_rows(io, g.fidx, g.count, W, [&](int k) { return rows + k * per_row; },
                    [&](int k) { return g.r0 + 2 * k; });
     __syncthreads();
@@ -281,7 +281,7 @@ k_pald_combed(const __grid_constant__ DevParams<T> p, const __grid_constant__ Io
     T *gbuf = cbuf + (size_t)(R + 1) * N1;       // (R+1) x N2    G rows, index k+1
     T *work = gbuf + (size_t)(R + 1) * N2;       // 2R x N2
     const int nin = g.count + 1;
-    const T *hup = p.firc[QR_UP2], *hdn = p.firc[QR_DOWN2];   // constant bank (kernel parameter)
+    const FirTaps<T> hup{p.firc[QR_UP2], p.fircp[QR_UP2]}, hdn{p.firc[QR_DOWN2], p.fircp[QR_DOWN2]};   // constant bank (kernel parameter)
     load_comp_rows(io, g.fidx, nin, W, [&](int k) { return cbuf + (size_t)k * N1; },
                    [&](int k) { return g.r0 + 2 * (k - 1); });
     __syncthreads();
@@ -393,6 +393,43 @@ k_pald_combed(const __grid_constant__ DevParams<T> p, const __grid_constant__ Io
 // neighbouring rows, rotates to (u, v), re-modulates through the encoder low-pass and stores RGB.
 // ------------------------------------------------------------------------------------------------------------
 #define CM_ROW_THREADS 64
+
+// Common tail of the pass-1 row kernels.  wa / wb hold LP(sin X), LP(cos X) at 2x (polyphase).  Writes four planes of
+// the row to the scratch  aux[frame][row][4][W]:
+//     a = down2(wa),  b = down2(wb),  alpha = LPpre(a),  beta = LPpre(b)
+// LPpre is the encoder's chroma low-pass (qam.py:16) that the comb decoders apply to (u, v) before re-modulating
+// (comb.py:53).  (u, v) are fixed linear combinations of the (a, b) of neighbouring rows and the filter is linear, so
+// filtering a and b here, where both warps of the CTA are free, leaves pass 2 purely elementwise.
+template <typename T>
+__device__ __forceinline__ void rows_epilogue(const DevParams<T> &p, const IoArgs<T> &io, int f, int row, T *cb, T *g,
+                                              T *wa, T *wb) {
+    const int W = p.W, N1 = p.n1p, hb = p.hb2;
+    const int warp = threadIdx.x >> 5;
+    const FirTaps<T> hdn{p.firc[QR_DOWN2], p.fircp[QR_DOWN2]};
+    T *dst = io.aux + ((size_t)f * io.nrows + row) * 4 * W;
+    T *sa = cb, *sb = g;                                   // both dead by now; g holds two N1 rows
+    fir_down2_pair(wa, wa + hb, wb, wb + hb, W, hdn, threadIdx.x, blockDim.x, [&](int j0, const T *a, const T *b) {
+        st4(dst + j0, a);
+        st4(dst + W + j0, b);
+        st4(sa + j0, a);
+        st4(sb + j0, b);
+    });
+    __syncthreads();
+    {
+        const FiltHdr &fpre = p.filt[QF_PRE_LP];
+        T *src = warp ? sb : sa, *out = warp ? wb : wa;
+        warp_fill_tail<T, 1>(src, N1, W, N1);
+        warp_iir<T, 1>(p.tab + fpre.off, fpre, [&](int q, int, int) { return src[q]; }, [&](int j, T x) { out[j] = x; });
+    }
+    __syncthreads();
+    for (int x = 4 * threadIdx.x; x < W; x += 4 * blockDim.x) {
+        T v[4];
+        ld4(wa + x, v);
+        st4(dst + 2 * W + x, v);
+        ld4(wb + x, v);
+        st4(dst + 3 * W + x, v);
+    }
+}
 #ifndef CM_ROWS_MINB
 #define CM_ROWS_MINB 8
 #endif
@@ -412,7 +449,7 @@ k_pald_rows(const __grid_constant__ DevParams<T> p, const __grid_constant__ IoAr
     T *cb = sm;                       // N1: composite row, later E = down2(BP(up2 c))
     T *g = cb + N1;                   // N2: up2(c), band-passed in place, later G = up2(E)
     T *wa = g + N2, *wb = wa + N2;    // N2 each: LP(sin G), LP(cos G)
-    const T *hup = p.firc[QR_UP2], *hdn = p.firc[QR_DOWN2];
+    const FirTaps<T> hup{p.firc[QR_UP2], p.fircp[QR_UP2]}, hdn{p.firc[QR_DOWN2], p.fircp[QR_DOWN2]};   // constant bank (kernel parameter)
     load_comp_row(cb, io, f, row, W);
     __syncthreads();
     fir_up2(g, g + hb, cb, W, hup, threadIdx.x, blockDim.x);
@@ -444,11 +481,7 @@ k_pald_rows(const __grid_constant__ DevParams<T> p, const __grid_constant__ IoAr
                        Poly2Out<T>{de, dod});
     }
     __syncthreads();
-    T *dst = io.aux + ((size_t)f * io.nrows + row) * 2 * W;
-    fir_down2_pair(wa, wa + hb, wb, wb + hb, W, hdn, threadIdx.x, blockDim.x, [&](int j0, const T *a, const T *b) {
-        st4(dst + j0, a);
-        st4(dst + W + j0, b);
-    });
+    rows_epilogue(p, io, f, row, cb, g, wa, wb);
 }
 
 // Pass 1 of the line-comb decoders (NTSC 2-line / 3-line, PAL 3-line): per-row quadrature demodulation of the
@@ -467,7 +500,7 @@ k_qam_rows(const __grid_constant__ DevParams<T> p, const __grid_constant__ IoArg
     T *cb = sm;                       // N1: composite row
     T *g = cb + N1;                   // N2: up2(c), band-passed in place
     T *wa = g + N2, *wb = wa + N2;    // N2 each: LP(sin B), LP(cos B)
-    const T *hup = p.firc[QR_UP2], *hdn = p.firc[QR_DOWN2];
+    const FirTaps<T> hup{p.firc[QR_UP2], p.fircp[QR_UP2]}, hdn{p.firc[QR_DOWN2], p.fircp[QR_DOWN2]};   // constant bank (kernel parameter)
     load_comp_row(cb, io, f, row, W);
     __syncthreads();
     fir_up2(g, g + hb, cb, W, hup, threadIdx.x, blockDim.x);
@@ -494,16 +527,14 @@ k_qam_rows(const __grid_constant__ DevParams<T> p, const __grid_constant__ IoArg
                        Poly2Out<T>{de, dod});
     }
     __syncthreads();
-    T *dst = io.aux + ((size_t)f * io.nrows + row) * 2 * W;
-    fir_down2_pair(wa, wa + hb, wb, wb + hb, W, hdn, threadIdx.x, blockDim.x, [&](int j0, const T *a, const T *b) {
-        st4(dst + j0, a);
-        st4(dst + W + j0, b);
-    });
+    rows_epilogue(p, io, f, row, cb, g, wa, wb);
 }
 
-// Pass 2: combine the per-row pairs (a, b) of neighbouring rows of a field into (u, v), run the encoder low-pass for
-// the re-modulation, y = c - remod(u, v), inverse matrix, store.  R rows per CTA (the pairs of R + 1 or R + 2 rows are
-// read once), 8 warps.  With ch/sh = cos/sin(LS/2), cl/sl = cos/sin(LS) and D[.] = down2(LP(.)):
+// Pass 2 (elementwise): combine the planes of neighbouring rows of a field into (u, v) and the low-passed (u, v) the
+// re-modulation needs, y = c - remod, inverse matrix, store.  A thread owns 4 consecutive samples of CM_SEG consecutive
+// rows of one field and walks down the rows keeping the previous rows' planes in registers, so every plane is read
+// ~once; the carrier of the next row is the carrier of this row rotated by LS.
+// With ch/sh = cos/sin(LS/2), cl/sl = cos/sin(LS) and D[.] = down2(LP(.)):
 //     D[sin(psi_k + t) B_k] = cos(t) a_k + sin(t) b_k,     D[cos(psi_k + t) B_k] = cos(t) b_k - sin(t) a_k,
 // and psi_{k+1} = psi_k + LS.
 //   PAIR_PALD   pal.py:113-125   S = a_k + D[sin(psi_k) G_{k-1}],  D = b_k - D[cos(psi_k) G_{k-1}]
@@ -512,117 +543,117 @@ k_qam_rows(const __grid_constant__ DevParams<T> p, const __grid_constant__ IoArg
 //                                the next row (nothing at the bottom, where the driver re-feeds the row, image.py:51-53)
 //   PAIR_PAL3   pal.py:198-226   sums / differences of three rows at the phase of the middle one
 enum { PAIR_PALD = 0, PAIR_NTSC2 = 1, PAIR_NTSC3 = 2, PAIR_PAL3 = 3 };
+#define CM_SEG 8
+
+template <typename T>
+struct PairCoef {
+    T sh, ch, sl, cl, sf, cf, f2, a_ss, a_cu, a_cv;
+};
+
+// (u, v) of one sample from the (a, b) of the previous / current / next row of the field
+template <typename T, int MODE>
+__device__ __forceinline__ void pair_uv(const PairCoef<T> &k, bool hp, bool hn, bool alt, T ap, T bp, T ac, T bc, T an,
+                                        T bn, T &u, T &v) {
+    if (MODE == PAIR_PALD) {
+        const T s = ac + (k.cl * ap + k.sl * bp);
+        const T d = bc - (k.cl * bp - k.sl * ap);
+        u = d * k.sf + s * k.cf;
+        v = d * k.cf - s * k.sf;
+        v = alt ? -v : v;
+    } else if (MODE == PAIR_NTSC2) {
+        u = k.f2 * ((k.ch * bc + k.sh * ac) - (k.ch * bp - k.sh * ap));
+        v = -k.f2 * ((k.ch * ac - k.sh * bc) - (k.ch * ap + k.sh * bp));
+    } else if (MODE == PAIR_NTSC3) {
+        T uu = hp ? k.f2 * ((k.ch * bc + k.sh * ac) - (k.ch * bp - k.sh * ap)) : (T)2 * ac;
+        T vv = hp ? -k.f2 * ((k.ch * ac - k.sh * bc) - (k.ch * ap + k.sh * bp)) : (T)2 * bc;
+        if (hn) {
+            uu += k.f2 * ((k.ch * bn + k.sh * an) - (k.ch * bc - k.sh * ac));
+            vv -= k.f2 * ((k.ch * an - k.sh * bn) - (k.ch * ac + k.sh * bc));
+        }
+        u = (T)0.5 * uu;
+        v = (T)0.5 * vv;
+    } else {
+        const T sin_n = hn ? k.cl * an - k.sl * bn : ac, cos_n = hn ? k.cl * bn + k.sl * an : bc;
+        const T sin_p = k.cl * ap + k.sl * bp, cos_p = k.cl * bp - k.sl * ap;
+        u = k.a_ss * (cos_n - cos_p) + k.a_cu * (sin_n - (T)2 * ac + sin_p);
+        v = k.a_ss * (sin_n - sin_p) + k.a_cv * (cos_n - (T)2 * bc + cos_p);
+        v = alt ? -v : v;
+    }
+}
 
 template <typename T, int MODE>
-__global__ void __launch_bounds__(CM_NTHREADS, 3)
-k_qam_pair(const __grid_constant__ DevParams<T> p, const __grid_constant__ IoArgs<T> io) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    T *sm = reinterpret_cast<T *>(smem_raw);
-    RowGroup g;
-    if (!decode_group(io, g)) return;
-    const int W = p.W, N1 = p.n1p, W4 = W >> 2;
-    T *scratch = sm, *rows = sm + 128;                     // per row: u | v | ulp | vlp
-    const size_t per_row = 4 * (size_t)N1;
-    const bool has_prev0 = g.r0 >= 2;
-    const bool has_next_last = g.r0 + 2 * g.count < io.nrows;
-    T sh, ch, sl, cl;
-    Real<T>::sincos_turns(p.phases[QP_HALF_LS], sh, ch);
-    Real<T>::sincos_turns(p.line_shift, sl, cl);
-    const T sf = p.scalars[QS_PALD_SIN], cf = p.scalars[QS_PALD_COS];
-    const T fac = p.scalars[QS_NTSC_FACTOR];
-    const T a_ss = (T)2 * p.scalars[QS_P3D_SINSUM], a_cu = (T)2 * p.scalars[QS_P3D_COSU],
-            a_cv = (T)2 * p.scalars[QS_P3D_COSV];
-    const T *aux = io.aux + (size_t)g.fidx * io.nrows * 2 * W;
-    auto ldab = [&](int row, int x, T *a, T *b) {
-        ld4(aux + (size_t)row * 2 * W + x, a);
-        ld4(aux + (size_t)row * 2 * W + W + x, b);
+__global__ void __launch_bounds__(128)
+k_qam_combine(const __grid_constant__ DevParams<T> p, const __grid_constant__ IoArgs<T> io) {
+    const int W = p.W, W4 = W >> 2;
+    const int field = blockIdx.y, f = blockIdx.z;
+    const int first = io.out_begin + field;
+    const int rows_in_field = (io.out_count - field + 1) >> 1;
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    const int seg = idx / W4, q = idx - seg * W4;
+    const int k0 = seg * CM_SEG;
+    if (k0 >= rows_in_field) return;
+    const int k1 = min(k0 + CM_SEG, rows_in_field);
+    const int x = 4 * q;
+    const long long frame = io.first_frame + f;
+    PairCoef<T> kc;
+    Real<T>::sincos_turns(p.phases[QP_HALF_LS], kc.sh, kc.ch);
+    Real<T>::sincos_turns(p.line_shift, kc.sl, kc.cl);
+    kc.sf = p.scalars[QS_PALD_SIN];
+    kc.cf = p.scalars[QS_PALD_COS];
+    kc.f2 = (T)2 * p.scalars[QS_NTSC_FACTOR];
+    kc.a_ss = (T)2 * p.scalars[QS_P3D_SINSUM];
+    kc.a_cu = (T)2 * p.scalars[QS_P3D_COSU];
+    kc.a_cv = (T)2 * p.scalars[QS_P3D_COSV];
+    const T *aux = io.aux + (size_t)f * io.nrows * 4 * W + x;
+    // planes of a row: [0] a, [1] b, [2] alpha, [3] beta
+    T P[4][4], C[4][4], Nx[4][4];
+    auto ldrow = [&](int row, T (*dst)[4]) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) ld4(aux + ((size_t)row * 4 + j) * W, dst[j]);
     };
-    for (int q = threadIdx.x; q < W4; q += blockDim.x) {
-        const int x = 4 * q;
-        T ap[4], bp[4], ac[4], bc[4], an[4], bn[4];
-        if (has_prev0) ldab(g.r0 - 2, x, ap, bp);
-        ldab(g.r0, x, ac, bc);
-        for (int k = 0; k < g.count; ++k) {
-            const int row = g.r0 + 2 * k;
-            const bool hp = (k > 0) || has_prev0;
-            const bool hn = (k + 1 < g.count) || has_next_last;
-            if (MODE >= PAIR_NTSC3 && hn) ldab(row + 2, x, an, bn);
-            else if (MODE < PAIR_NTSC3 && k + 1 < g.count) ldab(row + 2, x, an, bn);
-            const bool alt = is_alternate(p, g.frame, io.y0 + row);
-            T u[4], v[4];
+    int row = first + 2 * k0;
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                if (MODE == PAIR_PALD) {
-                    const T s = ac[i] + (cl * ap[i] + sl * bp[i]);
-                    const T d = bc[i] - (cl * bp[i] - sl * ap[i]);
-                    u[i] = d * sf + s * cf;
-                    v[i] = (alt ? (T)-1 : (T)1) * (d * cf - s * sf);
-                } else if (MODE == PAIR_NTSC2) {
-                    const T f2 = (T)2 * fac;
-                    u[i] = f2 * ((ch * bc[i] + sh * ac[i]) - (ch * bp[i] - sh * ap[i]));
-                    v[i] = -f2 * ((ch * ac[i] - sh * bc[i]) - (ch * ap[i] + sh * bp[i]));
-                } else if (MODE == PAIR_NTSC3) {
-                    const T f2 = (T)2 * fac;
-                    T uu = hp ? f2 * ((ch * bc[i] + sh * ac[i]) - (ch * bp[i] - sh * ap[i])) : (T)2 * ac[i];
-                    T vv = hp ? -f2 * ((ch * ac[i] - sh * bc[i]) - (ch * ap[i] + sh * bp[i])) : (T)2 * bc[i];
-                    if (hn) {
-                        uu += f2 * ((ch * bn[i] + sh * an[i]) - (ch * bc[i] - sh * ac[i]));
-                        vv -= f2 * ((ch * an[i] - sh * bn[i]) - (ch * ac[i] + sh * bc[i]));
-                    }
-                    u[i] = (T)0.5 * uu;
-                    v[i] = (T)0.5 * vv;
-                } else {
-                    const T sin_n = hn ? cl * an[i] - sl * bn[i] : ac[i], cos_n = hn ? cl * bn[i] + sl * an[i] : bc[i];
-                    const T sin_p = cl * ap[i] + sl * bp[i], cos_p = cl * bp[i] - sl * ap[i];
-                    u[i] = a_ss * (cos_n - cos_p) + a_cu * (sin_n - (T)2 * ac[i] + sin_p);
-                    const T vv = a_ss * (sin_n - sin_p) + a_cv * (cos_n - (T)2 * bc[i] + cos_p);
-                    v[i] = alt ? -vv : vv;
-                }
-            }
-            T *ur = rows + (size_t)k * per_row;
-            st4(ur + x, u);
-            st4(ur + N1 + x, v);
+    for (int j = 0; j < 4; ++j)
 #pragma unroll
-            for (int i = 0; i < 4; ++i) { ap[i] = ac[i]; bp[i] = bc[i]; ac[i] = an[i]; bc[i] = bn[i]; }
-        }
-    }
-    __syncthreads();
-    const FiltHdr &fpre = p.filt[QF_PRE_LP];
-    for_each_iir_task<T, false>(fpre, 2 * g.count, scratch, [&](int t, const IirTeam<T> &tm) {
-        T *src = rows + (size_t)(t >> 1) * per_row + (t & 1) * N1;
-        T *dstp = src + 2 * N1;
-        warp_fill_tail<T, 1>(src, N1, W, N1);
-        team_iir<T, 1, false>(p.tab + fpre.off, fpre, [&](int q, int, int) { return src[q]; },
-                              [&](int j, T x) { dstp[j] = x; }, tm);
-    });
-    __syncthreads();
-    T rs, rc;
+        for (int i = 0; i < 4; ++i) P[j][i] = Nx[j][i] = (T)0;
+    if (row >= 2) ldrow(row - 2, P);
+    ldrow(row, C);
+    T rs, rc, s[4], co[4];
     Real<T>::sincos_turns(p.phases[QP_STEP1X], rs, rc);
-    for (int k = 0; k < g.count; ++k) {
-        const int row = g.r0 + 2 * k, line = io.y0 + row;
-        const T *ur = rows + (size_t)k * per_row;
-        const unsigned long long ph0 = start_phase(p, g.frame, line);
-        const bool neg = (p.flags & 1) && is_alternate(p, g.frame, line);
-        const size_t cbase = ((size_t)g.fidx * io.nrows + row) * W;
-        for (int q = threadIdx.x; q < W4; q += blockDim.x) {
-            const int x = 4 * q;
-            T cc[4], a[4], b[4], uu[4], vv[4], s[4], co[4], y[4];
-            if (io.in_f) {
-                ld4(io.in_f + cbase + x, cc);
-            } else {
-                const uint32_t w = __ldg(reinterpret_cast<const uint32_t *>(io.in_u8 + cbase + x));
+    carrier4(start_phase(p, frame, io.y0 + row) + (unsigned long long)x * p.phases[QP_STEP1X], rs, rc, s, co);
+    for (int k = k0; k < k1; ++k, row += 2) {
+        const bool hp = row >= 2, hn = row + 2 < io.nrows;
+        const bool need_next = (MODE >= PAIR_NTSC3) ? hn : (k + 1 < k1);
+        if (need_next) ldrow(row + 2, Nx);
+        const int line = io.y0 + row;
+        const bool alt = is_alternate(p, frame, line);
+        const bool neg = (p.flags & 1) && alt;
+        T cc[4], y[4], u[4], v[4];
+        const size_t cbase = ((size_t)f * io.nrows + row) * W + x;
+        if (io.in_f) {
+            ld4(io.in_f + cbase, cc);
+        } else {
+            const uint32_t w = __ldg(reinterpret_cast<const uint32_t *>(io.in_u8 + cbase));
 #pragma unroll
-                for (int i = 0; i < 4; ++i)
-                    cc[i] = ((T)5 * Real<T>::from_u8((w >> (8 * i)) & 0xff) - (T)1) * (T)(1.0 / 3.0);
-            }
-            ld4(ur + x, uu);
-            ld4(ur + N1 + x, vv);
-            ld4(ur + 2 * N1 + x, a);
-            ld4(ur + 3 * N1 + x, b);
-            carrier4(ph0 + (unsigned long long)x * p.phases[QP_STEP1X], rs, rc, s, co);
+            for (int i = 0; i < 4; ++i) cc[i] = ((T)5 * Real<T>::from_u8((w >> (8 * i)) & 0xff) - (T)1) * (T)(1.0 / 3.0);
+        }
 #pragma unroll
-            for (int i = 0; i < 4; ++i) y[i] = cc[i] - (s[i] * a[i] + co[i] * (neg ? -b[i] : b[i]));
-            store_rgb4(p, io, g.fidx, row, x, y, uu, vv);
+        for (int i = 0; i < 4; ++i) {
+            T ul, vl;
+            pair_uv<T, MODE>(kc, hp, hn, alt, P[0][i], P[1][i], C[0][i], C[1][i], Nx[0][i], Nx[1][i], u[i], v[i]);
+            pair_uv<T, MODE>(kc, hp, hn, alt, P[2][i], P[3][i], C[2][i], C[3][i], Nx[2][i], Nx[3][i], ul, vl);
+            y[i] = cc[i] - (s[i] * ul + co[i] * (neg ? -vl : vl));
+        }
+        store_rgb4(p, io, f, row, x, y, u, v);
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { P[j][i] = C[j][i]; C[j][i] = Nx[j][i]; }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {          // carrier of the next row of the field: advance by LS
+            const T ns = Real<T>::fma_(s[i], kc.cl, co[i] * kc.sl);
+            co[i] = Real<T>::fma_(co[i], kc.cl, -(s[i] * kc.sl));
+            s[i] = ns;
         }
     }
 }
@@ -666,7 +697,7 @@ k_qam_comb(const __grid_constant__ DevParams<T> p, const __grid_constant__ IoArg
     const int k_lo = has_prev0 ? -1 : 0;
     const int k_hi = (MODE != COMB_NTSC2 && has_next_last) ? g.count : g.count - 1;
     const int nin = k_hi - k_lo + 1;
-    const T *hup = p.firc[QR_UP2], *hdn = p.firc[QR_DOWN2];   // constant bank (kernel parameter)
+    const FirTaps<T> hup{p.firc[QR_UP2], p.fircp[QR_UP2]}, hdn{p.firc[QR_DOWN2], p.fircp[QR_DOWN2]};   // constant bank (kernel parameter)
     load_comp_rows(io, g.fidx, nin, W, [&](int k) { return cbuf + (size_t)(k_lo + k + 1) * N1; },
                    [&](int k) { return g.r0 + 2 * (k_lo + k); });
     __syncthreads();

@@ -192,7 +192,7 @@ k_secam_decode(const __grid_constant__ DevParams<T> p, const __grid_constant__ I
     const size_t per_row = 2 * (size_t)N1 + 3 * (size_t)N2;
     const int k_lo = 0;                          // rows are independent here: pairing with the previous row happens
     const int nin = g.count;                     // in k_pair_rows_store
-    const T *hup = p.firc[SR_UP2], *hdn = p.firc[SR_DOWN2];   // constant bank (kernel parameter)
+    const FirTaps<T> hup{p.firc[SR_UP2], p.fircp[SR_UP2]}, hdn{p.firc[SR_DOWN2], p.fircp[SR_DOWN2]};   // constant bank (kernel parameter)
     auto rowp = [&](int k) { return rows + (size_t)k * per_row; };
     load_comp_rows(io, g.fidx, nin, W, [&](int k) { return rowp(k); }, [&](int k) { return g.r0 + 2 * k; });
     __syncthreads();

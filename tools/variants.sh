@@ -1,6 +1,6 @@
 #!/bin/bash
-# Tuning aid: build variants of the library with extra -D flags into build/variants/<name>.so
-#   tools/variants.sh name1 "-DFOO=1 -DBAR=2" name2 "..."      (then: CM_B200_LIB=build/variants/name1.so python tools/kt.py)
+# Tuning aid: build variants of the library with extra -D flags into tools/variants/<name>.so (objects under build/variants/<name>/)
+#   tools/variants.sh name1 "-DFOO=1 -DBAR=2" name2 "..."      (then: CM_B200_LIB=tools/variants/name1.so python tools/kt.py)
 set -e
 cd "$(dirname "$0")/.."
 FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 --expt-extended-lambda -Xcompiler -fPIC"
@@ -17,6 +17,7 @@ while [ $# -ge 2 ]; do
     nvcc $FLAGS $defs -DCM_QAM_PART=3 -c -o $d/qam_3.o color_modem_b200/csrc/cm_qam.cu &
     wait
   ) 2>&1 | grep -E "error" || true
-  nvcc -shared -o build/variants/$name.so $d/*.o
-  echo built build/variants/$name.so
+  mkdir -p tools/variants
+  nvcc -shared -o tools/variants/$name.so $d/*.o
+  echo built tools/variants/$name.so
 done
