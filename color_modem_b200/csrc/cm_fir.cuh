@@ -170,34 +170,38 @@ __device__ __forceinline__ void down2_quad_f2(const float (*hp)[2], const float 
     fir4_f2<2, 39, 2>(hp, w2, __fmul2_rn(c0, make_float2(e.x, e.y)), __fmul2_rn(c0, make_float2(e.z, e.w)), y);
 }
 
-// E[0..n), O[0..n) -> n outputs; post(j0, y[4]) consumes outputs j0..j0+3.       h: 41 dense taps
-template <typename T, class Post>
-__device__ __forceinline__ void fir_down2(const T *__restrict__ E, const T *__restrict__ O, int n,
-                                          const FirTaps<T> tp, int tid, int nthr, Post post) {
-    const T *__restrict__ h = tp.h;
+// One quad of a down2: y[r] = h[20] E[j0+r] + sum_k h[39-2k] O[j0+r-10+k], r = 0..3.        h: 41 dense taps
+// (taps are read with compile-time indices right in the FMA loops: in the kernel-parameter constant bank,
+// DevParams::firc, they become constant operands instead of 21 registers)
+template <typename T>
+__device__ __forceinline__ void down2_quad(const FirTaps<T> tp, const T *__restrict__ E, const T *__restrict__ O, int n,
+                                           int j0, T *y) {
     if constexpr (IsF32<T>::value) {
         if (tp.hp) {
-            for (int j0 = 4 * tid; j0 < n; j0 += 4 * nthr) {
-                float y[4];
-                down2_quad_f2(tp.hp, E, O, n, j0, y);
-                post(j0, y);
-            }
+            down2_quad_f2(tp.hp, E, O, n, j0, y);
             return;
         }
     }
-    // taps are read with compile-time indices right in the FMA loops: for h in the kernel-parameter constant
-    // bank (DevParams::firc) they become constant operands instead of 21 registers
+    const T *__restrict__ h = tp.h;
+    T w[28], e[4];
+    load_window28(O, n, j0, w);
+    ld4(E + j0, e);
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        T acc = h[20] * e[r];
+#pragma unroll
+        for (int k = 0; k < 20; ++k) acc = Real<T>::fma_(h[39 - 2 * k], w[2 + r + k], acc);   // O[j0+r-10+k]
+        y[r] = acc;
+    }
+}
+
+// E[0..n), O[0..n) -> n outputs; post(j0, y[4]) consumes outputs j0..j0+3.
+template <typename T, class Post>
+__device__ __forceinline__ void fir_down2(const T *__restrict__ E, const T *__restrict__ O, int n,
+                                          const FirTaps<T> tp, int tid, int nthr, Post post) {
     for (int j0 = 4 * tid; j0 < n; j0 += 4 * nthr) {
-        T w[28], e[4], y[4];
-        load_window28(O, n, j0, w);
-        ld4(E + j0, e);
-#pragma unroll
-        for (int r = 0; r < 4; ++r) {
-            T acc = h[20] * e[r];
-#pragma unroll
-            for (int k = 0; k < 20; ++k) acc = Real<T>::fma_(h[39 - 2 * k], w[2 + r + k], acc);   // O[j0+r-10+k]
-            y[r] = acc;
-        }
+        T y[4];
+        down2_quad(tp, E, O, n, j0, y);
         post(j0, y);
     }
 }
@@ -208,40 +212,10 @@ template <typename T, class Post>
 __device__ __forceinline__ void fir_down2_pair(const T *__restrict__ E1, const T *__restrict__ O1,
                                                const T *__restrict__ E2, const T *__restrict__ O2, int n,
                                                const FirTaps<T> tp, int tid, int nthr, Post post) {
-    const T *__restrict__ h = tp.h;
-    if constexpr (IsF32<T>::value) {
-        if (tp.hp) {
-            for (int j0 = 4 * tid; j0 < n; j0 += 4 * nthr) {
-                float y1[4], y2[4];
-                down2_quad_f2(tp.hp, E1, O1, n, j0, y1);
-                down2_quad_f2(tp.hp, E2, O2, n, j0, y2);
-                post(j0, y1, y2);
-            }
-            return;
-        }
-    }
-    // taps are read with compile-time indices right in the FMA loops: for h in the kernel-parameter constant
-    // bank (DevParams::firc) they become constant operands instead of 21 registers
     for (int j0 = 4 * tid; j0 < n; j0 += 4 * nthr) {
-        T w[28], e[4], y1[4], y2[4];
-        load_window28(O1, n, j0, w);
-        ld4(E1 + j0, e);
-#pragma unroll
-        for (int r = 0; r < 4; ++r) {
-            T acc = h[20] * e[r];
-#pragma unroll
-            for (int k = 0; k < 20; ++k) acc = Real<T>::fma_(h[39 - 2 * k], w[2 + r + k], acc);
-            y1[r] = acc;
-        }
-        load_window28(O2, n, j0, w);
-        ld4(E2 + j0, e);
-#pragma unroll
-        for (int r = 0; r < 4; ++r) {
-            T acc = h[20] * e[r];
-#pragma unroll
-            for (int k = 0; k < 20; ++k) acc = Real<T>::fma_(h[39 - 2 * k], w[2 + r + k], acc);
-            y2[r] = acc;
-        }
+        T y1[4], y2[4];
+        down2_quad(tp, E1, O1, n, j0, y1);
+        down2_quad(tp, E2, O2, n, j0, y2);
         post(j0, y1, y2);
     }
 }

@@ -55,8 +55,20 @@ int launch_bandsplit(cm_modem *m, IoArgs<T> io, int luma_mode, cudaStream_t st) 
     int R = pick_rows(4, (size_t)m->smem_optin / 2, bytes);
     if (!R) R = pick_rows(1, (size_t)m->smem_optin, bytes);
     if (!R) return cm_fail(CM_ERR_UNSUPPORTED, "line too wide for the band-split kernel%s");
-    set_groups(io, R);
     const bool teams = needs_teams(p);
+    if (!teams && luma_mode == 0 && !getenv("CM_ONEPASS")) {       // one row per CTA of two warps
+        const size_t b1 = ((size_t)p.n1p + 8 * (size_t)p.hb2) * sizeof(T);
+        int rc1 = set_smem(k_qam_bs_row<T>, b1);
+        if (rc1) return rc1;
+        {
+            LaunchTimer lt(m, CM_K_BANDSPLIT, st);
+            k_qam_bs_row<T><<<dim3((unsigned)io.out_count, 1u, (unsigned)io.nframes), CM_ROW_THREADS, b1, st>>>(p, io);
+        }
+        cm_count_launch();
+        CUDA_TRY(cudaGetLastError());
+        return CM_OK;
+    }
+    set_groups(io, R);
     int rc = teams ? set_smem(k_qam_bandsplit<T, true>, bytes(R)) : set_smem(k_qam_bandsplit<T, false>, bytes(R));
     if (rc) return rc;
     dim3 grid = cm_grid(io);

@@ -530,6 +530,61 @@ k_qam_rows(const __grid_constant__ DevParams<T> p, const __grid_constant__ IoArg
     rows_epilogue(p, io, f, row, cb, g, wa, wb);
 }
 
+// Band-split decode (qam.py:43-58 with strip_chroma=True: NtscModem, PalSModem) of one row per CTA of two warps:
+// the two IIR stages are pairs of independent tasks (band-pass || band-stop, then the u || v low-pass), so both warps
+// are busy in every phase; 26.5 KB of shared memory, 8 CTAs per SM.
+template <typename T>
+__global__ void __launch_bounds__(CM_ROW_THREADS, CM_ROWS_MINB)
+k_qam_bs_row(const __grid_constant__ DevParams<T> p, const __grid_constant__ IoArgs<T> io) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T *sm = reinterpret_cast<T *>(smem_raw);
+    const int W = p.W, W2 = 2 * W, N1 = p.n1p, hb = p.hb2, N2 = 2 * hb;
+    const int warp = threadIdx.x >> 5;
+    const int row = io.out_begin + blockIdx.x, f = blockIdx.z;
+    const long long frame = io.first_frame + f;
+    T *cb = sm;                                       // N1: composite row
+    T *a2 = cb + N1, *b2 = a2 + N2, *l2 = b2 + N2, *v2 = l2 + N2;
+    T *u2 = a2;                                       // up2(c) is dead once both filters have read it
+    const FirTaps<T> hup{p.firc[QR_UP2], p.fircp[QR_UP2]}, hdn{p.firc[QR_DOWN2], p.fircp[QR_DOWN2]};
+    load_comp_row(cb, io, f, row, W);
+    __syncthreads();
+    fir_up2(a2, a2 + hb, cb, W, hup, threadIdx.x, blockDim.x);
+    __syncthreads();
+    {
+        const FiltHdr &ff = warp ? p.filt[QF_BS2X] : p.filt[QF_BP2X];
+        warp_fill_tail<T, 2>(a2, hb, W2, N2);          // both warps write the same values
+        const T *ae = a2, *ao = a2 + hb;
+        T *de = warp ? l2 : b2, *dod = de + hb;
+        warp_iir<T, 2>(p.tab + ff.off, ff, [&](int q, int ph, int) { return (ph ? ao : ae)[q]; }, Poly2Out<T>{de, dod});
+    }
+    __syncthreads();
+    {
+        const FiltHdr &fl = p.filt[QF_DEMOD_LP];
+        warp_fill_tail<T, 2>(b2, hb, W2, N2);
+        const T *be = b2, *bo = b2 + hb;
+        T *de = warp ? v2 : u2, *dod = de + hb;
+        Carrier<T> car(start_phase(p, frame, io.y0 + row) + p.phases[QP_BP_SHIFT] + (warp ? CM_QUARTER_TURN : 0ull),
+                       p.phases[QP_STEP2X], W2);
+        warp_iir<T, 2>(p.tab + fl.off, fl,
+                       [&](int q, int ph, int i) {
+                           car.at(2 * q + ph, i);
+                           return (T)2 * car.s * (ph ? bo : be)[q];
+                       },
+                       Poly2Out<T>{de, dod});
+    }
+    __syncthreads();
+    const bool alt = (p.flags & 1) && is_alternate(p, frame, io.y0 + row);
+    for (int j0 = 4 * threadIdx.x; j0 < W; j0 += 4 * blockDim.x) {
+        T y[4], u[4], v[4];
+        down2_quad(hdn, u2, u2 + hb, W, j0, u);
+        down2_quad(hdn, v2, v2 + hb, W, j0, v);
+        down2_quad(hdn, l2, l2 + hb, W, j0, y);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) v[i] = alt ? -v[i] : v[i];
+        store_rgb4(p, io, f, row, j0, y, u, v);
+    }
+}
+
 // Pass 2 (elementwise): combine the planes of neighbouring rows of a field into (u, v) and the low-passed (u, v) the
 // re-modulation needs, y = c - remod, inverse matrix, store.  A thread owns 4 consecutive samples of CM_SEG consecutive
 // rows of one field and walks down the rows keeping the previous rows' planes in registers, so every plane is read
