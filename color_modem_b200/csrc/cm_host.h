@@ -89,10 +89,13 @@ static int pick_rows(int rmax, size_t budget, F bytes_for) {
     return 0;
 }
 
-// Threads per CTA for `tasks` concurrent warp-level IIR tasks: one warp per task, but never fewer than 4 warps so
-// that the sample-parallel FIR / elementwise phases of wide lines (few rows per CTA) still have threads to spread over.
+// Threads per CTA for `tasks` concurrent warp-level IIR tasks: one warp per task, at least two.  Small CTAs win on
+// B200 for these kernels (measured sweep of rows per CTA x warps): many independent CTAs per SM
+// in different phases overlap better than a few large ones that synchronise 8 warps at every phase boundary.
 static inline int cta_threads(int tasks) {
-    int warps = tasks < 4 ? 4 : tasks;
+    int minw = 2;
+    if (const char *e = getenv("CM_MIN_WARPS")) minw = atoi(e) > 0 ? atoi(e) : minw;     // tuning aid
+    int warps = tasks < minw ? minw : tasks;
     if (warps > CM_NWARPS) warps = CM_NWARPS;
     return 32 * warps;
 }

@@ -28,28 +28,28 @@ template <typename T>
 int niir_encode(cm_modem *m, IoArgs<T> io, cudaStream_t st) {
     const DevParams<T> &p = params_of<T>(m);
     auto bytes = [&](int r) { return (size_t)r * 3 * p.n1p * sizeof(T); };
-    return launch_rows<T>(m, io, st, k_niir_encode<T>, bytes, 4, 2, 0, CM_K_ENCODE, "NIIR encode");
+    return launch_rows<T>(m, io, st, k_niir_encode<T>, bytes, 1, 2, 0, CM_K_ENCODE, "NIIR encode");
 }
 
 template <typename T>
 int niir_decode(cm_modem *m, IoArgs<T> io, cudaStream_t st) {
     const DevParams<T> &p = params_of<T>(m);
     auto bytes = [&](int r) { return (128 + (size_t)(r + 1) * (p.n1p + 9 * (size_t)p.hb3)) * sizeof(T); };
-    return launch_rows<T>(m, io, st, k_niir_decode<T>, bytes, 3, 2, 1, CM_K_DECODE_OTHER, "NIIR decode");
+    return launch_rows<T>(m, io, st, k_niir_decode<T>, bytes, 2, 2, 1, CM_K_DECODE_OTHER, "NIIR decode");
 }
 
 template <typename T>
 int proto_encode(cm_modem *m, IoArgs<T> io, cudaStream_t st) {
     const DevParams<T> &p = params_of<T>(m);
     auto bytes = [&](int r) { return (128 + (size_t)r * (2 * (size_t)p.n1p + 3 * (size_t)p.hb3)) * sizeof(T); };
-    return launch_rows<T>(m, io, st, k_proto_encode<T>, bytes, 4, 2, 0, CM_K_ENCODE, "proto-SECAM encode");
+    return launch_rows<T>(m, io, st, k_proto_encode<T>, bytes, 1, 2, 0, CM_K_ENCODE, "proto-SECAM encode");
 }
 
 template <typename T>
 int proto_decode(cm_modem *m, IoArgs<T> io, cudaStream_t st) {
     const DevParams<T> &p = params_of<T>(m);
     auto bytes = [&](int r) { return (128 + (size_t)(r + 1) * (p.n1p + 9 * (size_t)p.hb3)) * sizeof(T); };
-    return launch_rows<T>(m, io, st, k_proto_decode<T>, bytes, 3, 2, 1, CM_K_DECODE_OTHER, "proto-SECAM decode");
+    return launch_rows<T>(m, io, st, k_proto_decode<T>, bytes, 2, 2, 1, CM_K_DECODE_OTHER, "proto-SECAM decode");
 }
 
 #define CM_INST(fn)                                                                     \

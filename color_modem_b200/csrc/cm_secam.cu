@@ -7,7 +7,7 @@ int secam_encode(cm_modem *m, IoArgs<T> io, cudaStream_t st) {
     const DevParams<T> &p = params_of<T>(m);
     if (io.out_count <= 0) return CM_OK;
     auto bytes = [&](int r) { return (size_t)r * 2 * p.n1p * sizeof(T); };
-    int R = pick_rows(8, (size_t)m->smem_optin / 2, bytes);
+    int R = pick_rows(2, (size_t)m->smem_optin / 2, bytes);
     if (!R) return cm_fail(CM_ERR_UNSUPPORTED, "line too wide for the SECAM encode kernel%s");
     set_groups(io, R);
     int rc = set_smem(k_secam_encode<T>, bytes(R));
@@ -35,7 +35,7 @@ int secam_decode(cm_modem *m, IoArgs<T> io, cudaStream_t st) {
     a.out_begin = io.out_begin >= 2 ? io.out_begin - 2 : 0;
     a.out_count = io.out_begin + io.out_count - a.out_begin;
     auto bytes = [&](int r) { return (CM_TAPS_ELEMS + (size_t)r * (2 * (size_t)p.n1p + 6 * (size_t)p.hb2)) * sizeof(T); };
-    int R = pick_rows(4, (size_t)m->smem_optin / 2, bytes);
+    int R = pick_rows(2, (size_t)m->smem_optin / 2, bytes);
     if (!R) R = pick_rows(1, (size_t)m->smem_optin, bytes);
     if (!R) return cm_fail(CM_ERR_UNSUPPORTED, "line too wide for the SECAM decode kernel%s");
     set_groups(a, R);
