@@ -6,10 +6,12 @@
 Workload (BASELINE.json configs[1], the configuration the metric is quoted on): standard 625-line PAL, PAL-D
 decoder, 720x576 frames.  A *step* is one pass of the hot path over one batch of F synthetic frames per GPU:
     composite = encode(rgb)      k_qam_encode
-    rgb'      = decode(composite)   k_qam_bandsplit (2 field-top rows per frame) + k_pald_combed
+    rgb'      = decode(composite)   k_qam_bs_row (2 field-top rows per frame) + k_pald_rows (all the filtering, one row
+                                    per CTA) + k_qam_combine (elementwise pairing of neighbouring rows), per 64 frames
 `value` is whole-job frames/s with the batch resident in HBM; `e2e` is the same metric through the public host
 API (ImageModem.modulate_batch / demodulate_batch -> cm_encode_frames_host / cm_decode_frames_host) with pinned
-HOST buffers, copies inside the timed region.  Frames are sharded over ranks in contiguous ranges (rank r owns
+HOST buffers, copies inside the timed region: two host threads keep both PCIe directions busy (batch i is demodulated
+while batch i+1 is modulated); `e2e.sequential` is the same without the overlap.  Frames are sharded over ranks in contiguous ranges (rank r owns
 absolute frames [r*F, (r+1)*F)); the path needs no inter-GPU traffic, so scaling is "weak".
 
 `--impl reference` times the CPU restatement of the reference (oracle/, float64 numpy/scipy — the reference is
@@ -254,7 +256,8 @@ def run_ours(args):
     ms = float(t.item())
     clocks = sampler.stop(t_begin, t_end) if rank == 0 else None
     k_ms = {name: modem.timing_read(kid) for name, kid in
-            (('encode', N.K_ENCODE), ('bandsplit', N.K_BANDSPLIT), ('pald', N.K_PALD))}
+            (('encode', N.K_ENCODE), ('bandsplit_top_rows', N.K_BANDSPLIT), ('pald_rows', N.K_PALD),
+             ('combine', N.K_DECODE_OTHER))}
     modem.timing(False)
 
     # ---- end-to-end through the public host API, pinned host buffers, copies inside the timed region --------
@@ -267,19 +270,45 @@ def run_ours(args):
         img.modulate_batch(np_rgb, first_frame, out=np_comp)
         img.demodulate_batch(np_comp, first_frame, out=np_out)
 
+    def timed(fn, n):
+        barrier()
+        t0 = time.perf_counter()
+        fn(n)
+        barrier()
+        dt = time.perf_counter() - t0
+        tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return float(tt.item())
+
     e2e_steps = max(2, min(args.steps, 5))
     for _ in range(2):
         e2e_step()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        e2e_step()
-    barrier()
-    e2e_s = time.perf_counter() - t0
-    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_s = float(t.item())
+    e2e_seq_s = timed(lambda n: [e2e_step() for _ in range(n)], e2e_steps)
+
+    # pipelined: a second modem handle (own streams and staging buffers) demodulates batch i while batch i+1 is being
+    # modulated, so the H2D-heavy encode and the D2H-heavy decode share the full-duplex link.  Every timed step still
+    # moves one batch of RGB in, its composite out and in again, and the decoded RGB out.
+    from concurrent.futures import ThreadPoolExecutor
+    img2 = ImageModem(PalDModem(LineConfig((W, H))))
+    host_comp2 = torch.empty((F, H, W), dtype=torch.uint8).pin_memory()
+    np_comp2 = host_comp2.numpy()
+    comps = [np_comp, np_comp2]
+    pool2 = ThreadPoolExecutor(max_workers=2)
+
+    img2._modem._handle()                          # create the second native handle on this rank's device
+    img.modulate_batch(np_rgb, first_frame, out=comps[0])              # pipeline fill (untimed)
+
+    def e2e_pipelined(n):
+        for i in range(n):
+            a = pool2.submit(img.modulate_batch, np_rgb, first_frame, comps[(i + 1) & 1])
+            b = pool2.submit(img2.demodulate_batch, comps[i & 1], first_frame, np_out)
+            a.result()
+            b.result()
+
+    e2e_pipelined(2)
+    e2e_s = timed(e2e_pipelined, e2e_steps)
+    pool2.shutdown()
     checksum = int(np_out[0, :4, :4].sum())     # device->host read of the step's result
 
     # ---- the other BASELINE configs, briefly (rank 0, device-resident, CUDA events): context for the headline --------
@@ -319,9 +348,18 @@ def run_ours(args):
         total_frames = F * world * args.steps
         fps = total_frames / (ms * 1e-3)
         peak, peak_src = measured_peak_gbs()
-        pald_ms, pald_n = k_ms['pald']
+        pald_ms, pald_n = k_ms['pald_rows']
+        comb_ms, comb_n = k_ms['combine']
         per_launch_ms = pald_ms / max(pald_n, 1)
-        achieved = (F * DECODE_BYTES_PER_FRAME) / (per_launch_ms * 1e-3) / 1e9 if per_launch_ms > 0 else 0.0
+        frames_per_launch = F * args.steps / max(pald_n, 1)
+        achieved = (frames_per_launch * DECODE_BYTES_PER_FRAME) / (per_launch_ms * 1e-3) / 1e9 if per_launch_ms > 0 else 0.0
+        pair_ms = (pald_ms + comb_ms) / max(pald_n, 1)
+        traffic = None
+        try:
+            with open(os.path.join(ROOT, 'profiles', 'r1_traffic.json')) as tf:
+                traffic = json.load(tf)
+        except Exception:
+            pass
         step_ms = ms / args.steps
         shares = {k: (v[0] / max(v[1], 1)) * (v[1] / args.steps) / step_ms for k, v in k_ms.items()}
         line = {
@@ -334,14 +372,25 @@ def run_ours(args):
             'clocks': clocks,
             'e2e': {'value': F * world * e2e_steps / e2e_s, 'unit': 'frames/s',
                     'h2d_bytes_per_step': F * (3 * W * H + W * H), 'd2h_bytes_per_step': F * (W * H + 3 * W * H),
-                    'steps': e2e_steps, 'api': 'ImageModem.modulate_batch -> demodulate_batch (pinned host buffers)',
+                    'steps': e2e_steps,
+                    'api': 'ImageModem.modulate_batch / demodulate_batch on pinned host buffers; two host threads: '
+                           'batch i is demodulated while batch i+1 is modulated',
+                    'sequential': F * world * e2e_steps / e2e_seq_s,
                     'result_checksum': checksum},
             'gpu_launches': launches,
             'other_workloads': others,
-            'roofline': {'bound': 'hbm', 'kernel': 'k_pald_combed<float>', 'achieved': achieved, 'peak': peak,
-                         'unit': 'GB/s', 'frac': achieved / peak, 'traffic': None, 'peak_source': peak_src,
-                         'algorithmic_bytes_per_launch': F * DECODE_BYTES_PER_FRAME,
-                         'avg_launch_ms': per_launch_ms, 'kernel_share_of_step': shares,
+            'roofline': {'bound': 'hbm', 'kernel': 'k_pald_rows<float>', 'achieved': achieved, 'peak': peak,
+                         'unit': 'GB/s', 'frac': achieved / peak,
+                         'traffic': traffic['k_pald_rows']['dram_bytes_per_launch'] if traffic else None,
+                         'traffic_source': traffic['source'] if traffic else None,
+                         'peak_source': peak_src,
+                         'algorithmic_bytes_per_launch': frames_per_launch * DECODE_BYTES_PER_FRAME,
+                         'frames_per_launch': frames_per_launch,
+                         'avg_launch_ms': per_launch_ms,
+                         'decode_pair': {'kernels': 'k_pald_rows + k_qam_combine', 'avg_ms': pair_ms,
+                                         'achieved': (frames_per_launch * DECODE_BYTES_PER_FRAME) / (pair_ms * 1e-3) / 1e9
+                                         if pair_ms > 0 else 0.0},
+                         'kernel_share_of_step': shares,
                          'whole_chain_frac': fps / world * BYTES_PER_FRAME / 1e9 / peak,
                          'note': 'the decode chain is FMA-bound, not HBM-bound (SURVEY.md §0 fact 5, DESIGN.md §5)'},
         }

@@ -24,6 +24,16 @@ static bool needs_teams(const DevParams<T> &p) {
     return false;
 }
 
+// threads of a one-row CTA: two concurrent IIR tasks, each run by a team of `nsuper` warps (at most 4, cm_iir.cuh)
+template <typename T>
+static int row_threads(const DevParams<T> &p) {
+    int ts = 1;
+    for (int i = 0; i < CM_NFILT; ++i)
+        if (p.filt[i].nsec && p.filt[i].nsuper > ts) ts = p.filt[i].nsuper;
+    if (ts > 4) ts = 1;
+    return 64 * ts;
+}
+
 #if CM_PART(0)
 template <typename T>
 int qam_encode(cm_modem *m, IoArgs<T> io, cudaStream_t st) {
@@ -56,17 +66,21 @@ int launch_bandsplit(cm_modem *m, IoArgs<T> io, int luma_mode, cudaStream_t st) 
     if (!R) R = pick_rows(1, (size_t)m->smem_optin, bytes);
     if (!R) return cm_fail(CM_ERR_UNSUPPORTED, "line too wide for the band-split kernel%s");
     const bool teams = needs_teams(p);
-    if (!teams && luma_mode == 0 && !getenv("CM_ONEPASS")) {       // one row per CTA of two warps
-        const size_t b1 = ((size_t)p.n1p + 8 * (size_t)p.hb2) * sizeof(T);
-        int rc1 = set_smem(k_qam_bs_row<T>, b1);
-        if (rc1) return rc1;
-        {
-            LaunchTimer lt(m, CM_K_BANDSPLIT, st);
-            k_qam_bs_row<T><<<dim3((unsigned)io.out_count, 1u, (unsigned)io.nframes), CM_ROW_THREADS, b1, st>>>(p, io);
+    if (luma_mode == 0 && !getenv("CM_ONEPASS")) {       // one row per CTA: two IIR tasks, one warp (team) each
+        const size_t b1 = (128 + (size_t)p.n1p + 8 * (size_t)p.hb2) * sizeof(T);
+        if (b1 <= (size_t)m->smem_optin) {
+            int rc1 = teams ? set_smem(k_qam_bs_row<T, true>, b1) : set_smem(k_qam_bs_row<T, false>, b1);
+            if (rc1) return rc1;
+            const dim3 grid((unsigned)io.out_count, 1u, (unsigned)io.nframes);
+            {
+                LaunchTimer lt(m, CM_K_BANDSPLIT, st);
+                if (teams) k_qam_bs_row<T, true><<<grid, row_threads(p), b1, st>>>(p, io);
+                else k_qam_bs_row<T, false><<<grid, CM_ROW_THREADS, b1, st>>>(p, io);
+            }
+            cm_count_launch();
+            CUDA_TRY(cudaGetLastError());
+            return CM_OK;
         }
-        cm_count_launch();
-        CUDA_TRY(cudaGetLastError());
-        return CM_OK;
     }
     set_groups(io, R);
     int rc = teams ? set_smem(k_qam_bandsplit<T, true>, bytes(R)) : set_smem(k_qam_bandsplit<T, false>, bytes(R));
@@ -96,9 +110,12 @@ template <typename T, int MODE>
 int launch_rows_pair(cm_modem *m, IoArgs<T> io, cudaStream_t st) {
     const DevParams<T> &p = params_of<T>(m);
     if (io.out_count <= 0) return CM_OK;
-    const size_t b1 = ((size_t)p.n1p + 6 * (size_t)p.hb2) * sizeof(T);
+    const size_t b1 = (128 + (size_t)p.n1p + 6 * (size_t)p.hb2) * sizeof(T);
     if (b1 > (size_t)m->smem_optin) return cm_fail(CM_ERR_UNSUPPORTED, "line too wide for the row kernels%s");
-    auto pass1 = MODE == PAIR_PALD ? k_pald_rows<T> : k_qam_rows<T>;
+    const bool teams = needs_teams(p);
+    auto pass1 = MODE == PAIR_PALD ? (teams ? k_pald_rows<T, true> : k_pald_rows<T, false>)
+                                   : (teams ? k_qam_rows<T, true> : k_qam_rows<T, false>);
+    const int threads1 = teams ? row_threads(p) : CM_ROW_THREADS;
     int rc = set_smem(pass1, b1);
     if (rc) return rc;
     int kChunk = 64;
@@ -124,7 +141,7 @@ int launch_rows_pair(cm_modem *m, IoArgs<T> io, cudaStream_t st) {
         a.out_count = end - a.out_begin;
         {
             LaunchTimer lt(m, MODE == PAIR_PALD ? CM_K_PALD : CM_K_COMB, st);
-            pass1<<<dim3((unsigned)a.out_count, 1u, (unsigned)c.nframes), CM_ROW_THREADS, b1, st>>>(p, a);
+            pass1<<<dim3((unsigned)a.out_count, 1u, (unsigned)c.nframes), threads1, b1, st>>>(p, a);
         }
         cm_count_launch();
         CUDA_TRY(cudaGetLastError());
@@ -146,6 +163,9 @@ template <typename T>
 int launch_pald(cm_modem *m, IoArgs<T> io, cudaStream_t st) {
     const DevParams<T> &p = params_of<T>(m);
     if (io.out_count <= 0) return CM_OK;
+    if (!io.prof && !getenv("CM_ONEPASS") &&
+        (128 + (size_t)p.n1p + 6 * (size_t)p.hb2) * sizeof(T) <= (size_t)m->smem_optin)
+        return launch_rows_pair<T, PAIR_PALD>(m, io, st);
     auto bytes = [&](int r) {
         return (CM_TAPS_ELEMS + (size_t)(r + 1) * (p.n1p + 2 * (size_t)p.hb2) + (size_t)r * 4 * p.hb2) * sizeof(T);
     };
@@ -153,7 +173,6 @@ int launch_pald(cm_modem *m, IoArgs<T> io, cudaStream_t st) {
     if (!R) R = pick_rows(2, (size_t)m->smem_optin, bytes);
     if (!R) return cm_fail(CM_ERR_UNSUPPORTED, "line too wide for the PAL-D kernel%s");
     const bool teams = needs_teams(p);
-    if (!teams && !io.prof && !getenv("CM_ONEPASS")) return launch_rows_pair<T, PAIR_PALD>(m, io, st);
     set_groups(io, R);
     int rc = teams ? set_smem(k_pald_combed<T, true>, bytes(R)) : set_smem(k_pald_combed<T, false>, bytes(R));
     if (rc) return rc;
@@ -177,6 +196,8 @@ template <typename T, int MODE>
 int launch_comb(cm_modem *m, IoArgs<T> io, cudaStream_t st) {
     const DevParams<T> &p = params_of<T>(m);
     if (io.out_count <= 0) return CM_OK;
+    if (!getenv("CM_ONEPASS") && (128 + (size_t)p.n1p + 6 * (size_t)p.hb2) * sizeof(T) <= (size_t)m->smem_optin)
+        return launch_rows_pair<T, MODE == COMB_NTSC2 ? PAIR_NTSC2 : (MODE == COMB_NTSC3 ? PAIR_NTSC3 : PAIR_PAL3)>(m, io, st);
     auto bytes = [&](int r) {
         return (CM_TAPS_ELEMS + (size_t)(r + 2) * (p.n1p + 2 * (size_t)p.hb2) + (size_t)r * 4 * p.hb2) * sizeof(T);
     };
@@ -184,8 +205,6 @@ int launch_comb(cm_modem *m, IoArgs<T> io, cudaStream_t st) {
     if (!R) R = pick_rows(2, (size_t)m->smem_optin, bytes);
     if (!R) return cm_fail(CM_ERR_UNSUPPORTED, "line too wide for the comb kernel%s");
     const bool teams = needs_teams(p);
-    if (!teams && !getenv("CM_ONEPASS"))
-        return launch_rows_pair<T, MODE == COMB_NTSC2 ? PAIR_NTSC2 : (MODE == COMB_NTSC3 ? PAIR_NTSC3 : PAIR_PAL3)>(m, io, st);
     set_groups(io, R);
     int rc = teams ? set_smem(k_qam_comb<T, MODE, true>, bytes(R)) : set_smem(k_qam_comb<T, MODE, false>, bytes(R));
     if (rc) return rc;

@@ -400,11 +400,10 @@ k_pald_combed(const __grid_constant__ DevParams<T> p, const __grid_constant__ Io
 // LPpre is the encoder's chroma low-pass (qam.py:16) that the comb decoders apply to (u, v) before re-modulating
 // (comb.py:53).  (u, v) are fixed linear combinations of the (a, b) of neighbouring rows and the filter is linear, so
 // filtering a and b here, where both warps of the CTA are free, leaves pass 2 purely elementwise.
-template <typename T>
-__device__ __forceinline__ void rows_epilogue(const DevParams<T> &p, const IoArgs<T> &io, int f, int row, T *cb, T *g,
-                                              T *wa, T *wb) {
+template <typename T, bool TEAMS>
+__device__ __forceinline__ void rows_epilogue(const DevParams<T> &p, const IoArgs<T> &io, int f, int row, T *scratch,
+                                              T *cb, T *g, T *wa, T *wb) {
     const int W = p.W, N1 = p.n1p, hb = p.hb2;
-    const int warp = threadIdx.x >> 5;
     const FirTaps<T> hdn{p.firc[QR_DOWN2], p.fircp[QR_DOWN2]};
     T *dst = io.aux + ((size_t)f * io.nrows + row) * 4 * W;
     T *sa = cb, *sb = g;                                   // both dead by now; g holds two N1 rows
@@ -417,9 +416,12 @@ __device__ __forceinline__ void rows_epilogue(const DevParams<T> &p, const IoArg
     __syncthreads();
     {
         const FiltHdr &fpre = p.filt[QF_PRE_LP];
-        T *src = warp ? sb : sa, *out = warp ? wb : wa;
-        warp_fill_tail<T, 1>(src, N1, W, N1);
-        warp_iir<T, 1>(p.tab + fpre.off, fpre, [&](int q, int, int) { return src[q]; }, [&](int j, T x) { out[j] = x; });
+        for_row_tasks<T, TEAMS>(fpre, 2, scratch, [&](int t, const IirTeam<T> &tm) {
+            T *src = t ? sb : sa, *out = t ? wb : wa;
+            warp_fill_tail<T, 1>(src, N1, W, N1);
+            team_iir<T, 1, TEAMS>(p.tab + fpre.off, fpre, [&](int q, int, int) { return src[q]; },
+                                  [&](int j, T x) { out[j] = x; }, tm);
+        });
     }
     __syncthreads();
     for (int x = 4 * threadIdx.x; x < W; x += 4 * blockDim.x) {
@@ -437,13 +439,12 @@ __device__ __forceinline__ void rows_epilogue(const DevParams<T> &p, const IoArg
 #define CM_PAIR_MINB 12
 #endif
 
-template <typename T>
-__global__ void __launch_bounds__(CM_ROW_THREADS, CM_ROWS_MINB)
+template <typename T, bool TEAMS>
+__global__ void __launch_bounds__(TEAMS ? CM_NTHREADS : CM_ROW_THREADS, TEAMS ? 2 : CM_ROWS_MINB)
 k_pald_rows(const __grid_constant__ DevParams<T> p, const __grid_constant__ IoArgs<T> io) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    T *sm = reinterpret_cast<T *>(smem_raw);
+    T *scratch = reinterpret_cast<T *>(smem_raw), *sm = scratch + 128;      // [0, 128): IIR team scratch
     const int W = p.W, W2 = 2 * W, N1 = p.n1p, hb = p.hb2, N2 = 2 * hb;
-    const int warp = threadIdx.x >> 5;
     const int row = io.out_begin + blockIdx.x, f = blockIdx.z;
     const long long frame = io.first_frame + f;
     T *cb = sm;                       // N1: composite row, later E = down2(BP(up2 c))
@@ -454,11 +455,14 @@ k_pald_rows(const __grid_constant__ DevParams<T> p, const __grid_constant__ IoAr
     __syncthreads();
     fir_up2(g, g + hb, cb, W, hup, threadIdx.x, blockDim.x);
     __syncthreads();
-    if (warp == 0) {
+    {
         const FiltHdr &fb = p.filt[QF_BP2X];
-        warp_fill_tail<T, 2>(g, hb, W2, N2);
-        T *ge = g, *go = g + hb;
-        warp_iir<T, 2>(p.tab + fb.off, fb, [&](int q, int ph, int) { return (ph ? go : ge)[q]; }, Poly2Out<T>{ge, go});
+        for_row_tasks<T, TEAMS>(fb, 1, scratch, [&](int, const IirTeam<T> &tm) {
+            warp_fill_tail<T, 2>(g, hb, W2, N2);
+            T *ge = g, *go = g + hb;
+            team_iir<T, 2, TEAMS>(p.tab + fb.off, fb, [&](int q, int ph, int) { return (ph ? go : ge)[q]; },
+                                  Poly2Out<T>{ge, go}, tm);
+        });
     }
     __syncthreads();
     fir_down2(g, g + hb, W, hdn, threadIdx.x, blockDim.x, [&](int j0, const T *y) { st4(cb + j0, y); });
@@ -467,34 +471,35 @@ k_pald_rows(const __grid_constant__ DevParams<T> p, const __grid_constant__ IoAr
     __syncthreads();
     {
         const FiltHdr &fl = p.filt[QF_PALD_LP];
-        warp_fill_tail<T, 2>(g, hb, W2, N2);          // both warps write the same values
-        const T *ge = g, *go = g + hb;
-        T *de = warp ? wb : wa, *dod = de + hb;
-        Carrier<T> car(start_phase(p, frame, io.y0 + row) + p.phases[QP_BP_SHIFT] - p.phases[QP_HALF_LS] +
-                           (warp ? CM_QUARTER_TURN : 0ull),
-                       p.phases[QP_STEP2X], W2);
-        warp_iir<T, 2>(p.tab + fl.off, fl,
-                       [&](int q, int ph, int i) {
-                           car.at(2 * q + ph, i);
-                           return (ph ? go : ge)[q] * car.s;
-                       },
-                       Poly2Out<T>{de, dod});
+        for_row_tasks<T, TEAMS>(fl, 2, scratch, [&](int t, const IirTeam<T> &tm) {
+            warp_fill_tail<T, 2>(g, hb, W2, N2);          // every warp writes the same values
+            const T *ge = g, *go = g + hb;
+            T *de = t ? wb : wa, *dod = de + hb;
+            Carrier<T> car(start_phase(p, frame, io.y0 + row) + p.phases[QP_BP_SHIFT] - p.phases[QP_HALF_LS] +
+                               (t ? CM_QUARTER_TURN : 0ull),
+                           p.phases[QP_STEP2X], W2);
+            team_iir<T, 2, TEAMS>(p.tab + fl.off, fl,
+                                  [&](int q, int ph, int i) {
+                                      car.at(2 * q + ph, i);
+                                      return (ph ? go : ge)[q] * car.s;
+                                  },
+                                  Poly2Out<T>{de, dod}, tm);
+        });
     }
     __syncthreads();
-    rows_epilogue(p, io, f, row, cb, g, wa, wb);
+    rows_epilogue<T, TEAMS>(p, io, f, row, scratch, cb, g, wa, wb);
 }
 
 // Pass 1 of the line-comb decoders (NTSC 2-line / 3-line, PAL 3-line): per-row quadrature demodulation of the
 // band-passed 2x signal B_k = BP(up2 c_k) at the row's own phase psi_k = start_phase(k) + bp_shift,
 //     a_k = down2(LP(sin(psi_k) B_k)),   b_k = down2(LP(cos(psi_k) B_k))          (qam.py:43-58 without the factor 2)
 // k_qam_pair rotates these to the phase each comb needs (multiples of LS/2) and combines neighbouring rows.
-template <typename T>
-__global__ void __launch_bounds__(CM_ROW_THREADS, CM_ROWS_MINB)
+template <typename T, bool TEAMS>
+__global__ void __launch_bounds__(TEAMS ? CM_NTHREADS : CM_ROW_THREADS, TEAMS ? 2 : CM_ROWS_MINB)
 k_qam_rows(const __grid_constant__ DevParams<T> p, const __grid_constant__ IoArgs<T> io) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    T *sm = reinterpret_cast<T *>(smem_raw);
+    T *scratch = reinterpret_cast<T *>(smem_raw), *sm = scratch + 128;      // [0, 128): IIR team scratch
     const int W = p.W, W2 = 2 * W, N1 = p.n1p, hb = p.hb2, N2 = 2 * hb;
-    const int warp = threadIdx.x >> 5;
     const int row = io.out_begin + blockIdx.x, f = blockIdx.z;
     const long long frame = io.first_frame + f;
     T *cb = sm;                       // N1: composite row
@@ -505,41 +510,45 @@ k_qam_rows(const __grid_constant__ DevParams<T> p, const __grid_constant__ IoArg
     __syncthreads();
     fir_up2(g, g + hb, cb, W, hup, threadIdx.x, blockDim.x);
     __syncthreads();
-    if (warp == 0) {
+    {
         const FiltHdr &fb = p.filt[QF_BP2X];
-        warp_fill_tail<T, 2>(g, hb, W2, N2);
-        T *ge = g, *go = g + hb;
-        warp_iir<T, 2>(p.tab + fb.off, fb, [&](int q, int ph, int) { return (ph ? go : ge)[q]; }, Poly2Out<T>{ge, go});
+        for_row_tasks<T, TEAMS>(fb, 1, scratch, [&](int, const IirTeam<T> &tm) {
+            warp_fill_tail<T, 2>(g, hb, W2, N2);
+            T *ge = g, *go = g + hb;
+            team_iir<T, 2, TEAMS>(p.tab + fb.off, fb, [&](int q, int ph, int) { return (ph ? go : ge)[q]; },
+                                  Poly2Out<T>{ge, go}, tm);
+        });
     }
     __syncthreads();
     {
         const FiltHdr &fl = p.filt[QF_DEMOD_LP];
-        warp_fill_tail<T, 2>(g, hb, W2, N2);          // both warps write the same values
-        const T *ge = g, *go = g + hb;
-        T *de = warp ? wb : wa, *dod = de + hb;
-        Carrier<T> car(start_phase(p, frame, io.y0 + row) + p.phases[QP_BP_SHIFT] + (warp ? CM_QUARTER_TURN : 0ull),
-                       p.phases[QP_STEP2X], W2);
-        warp_iir<T, 2>(p.tab + fl.off, fl,
-                       [&](int q, int ph, int i) {
-                           car.at(2 * q + ph, i);
-                           return (ph ? go : ge)[q] * car.s;
-                       },
-                       Poly2Out<T>{de, dod});
+        for_row_tasks<T, TEAMS>(fl, 2, scratch, [&](int t, const IirTeam<T> &tm) {
+            warp_fill_tail<T, 2>(g, hb, W2, N2);          // every warp writes the same values
+            const T *ge = g, *go = g + hb;
+            T *de = t ? wb : wa, *dod = de + hb;
+            Carrier<T> car(start_phase(p, frame, io.y0 + row) + p.phases[QP_BP_SHIFT] + (t ? CM_QUARTER_TURN : 0ull),
+                           p.phases[QP_STEP2X], W2);
+            team_iir<T, 2, TEAMS>(p.tab + fl.off, fl,
+                                  [&](int q, int ph, int i) {
+                                      car.at(2 * q + ph, i);
+                                      return (ph ? go : ge)[q] * car.s;
+                                  },
+                                  Poly2Out<T>{de, dod}, tm);
+        });
     }
     __syncthreads();
-    rows_epilogue(p, io, f, row, cb, g, wa, wb);
+    rows_epilogue<T, TEAMS>(p, io, f, row, scratch, cb, g, wa, wb);
 }
 
 // Band-split decode (qam.py:43-58 with strip_chroma=True: NtscModem, PalSModem) of one row per CTA of two warps:
 // the two IIR stages are pairs of independent tasks (band-pass || band-stop, then the u || v low-pass), so both warps
 // are busy in every phase; 26.5 KB of shared memory, 8 CTAs per SM.
-template <typename T>
-__global__ void __launch_bounds__(CM_ROW_THREADS, CM_ROWS_MINB)
+template <typename T, bool TEAMS>
+__global__ void __launch_bounds__(TEAMS ? CM_NTHREADS : CM_ROW_THREADS, TEAMS ? 2 : CM_ROWS_MINB)
 k_qam_bs_row(const __grid_constant__ DevParams<T> p, const __grid_constant__ IoArgs<T> io) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    T *sm = reinterpret_cast<T *>(smem_raw);
+    T *scratch = reinterpret_cast<T *>(smem_raw), *sm = scratch + 128;      // [0, 128): IIR team scratch
     const int W = p.W, W2 = 2 * W, N1 = p.n1p, hb = p.hb2, N2 = 2 * hb;
-    const int warp = threadIdx.x >> 5;
     const int row = io.out_begin + blockIdx.x, f = blockIdx.z;
     const long long frame = io.first_frame + f;
     T *cb = sm;                                       // N1: composite row
@@ -551,26 +560,45 @@ k_qam_bs_row(const __grid_constant__ DevParams<T> p, const __grid_constant__ IoA
     fir_up2(a2, a2 + hb, cb, W, hup, threadIdx.x, blockDim.x);
     __syncthreads();
     {
-        const FiltHdr &ff = warp ? p.filt[QF_BS2X] : p.filt[QF_BP2X];
-        warp_fill_tail<T, 2>(a2, hb, W2, N2);          // both warps write the same values
+        const FiltHdr &fbp = p.filt[QF_BP2X], &fbs = p.filt[QF_BS2X];
         const T *ae = a2, *ao = a2 + hb;
-        T *de = warp ? l2 : b2, *dod = de + hb;
-        warp_iir<T, 2>(p.tab + ff.off, ff, [&](int q, int ph, int) { return (ph ? ao : ae)[q]; }, Poly2Out<T>{de, dod});
+        if constexpr (!TEAMS) {
+            // one call site for both filters (warp 0: band-pass -> b2, warp 1: band-stop -> l2) keeps the code small
+            const int t = threadIdx.x >> 5;
+            const FiltHdr &ff = t ? fbs : fbp;
+            T *de = t ? l2 : b2;
+            warp_fill_tail<T, 2>(a2, hb, W2, N2);          // both warps write the same values
+            warp_iir<T, 2>(p.tab + ff.off, ff, [&](int q, int ph, int) { return (ph ? ao : ae)[q]; },
+                           Poly2Out<T>{de, de + hb});
+        } else {
+            for_row_tasks<T, TEAMS>(fbp, 1, scratch, [&](int, const IirTeam<T> &tm) {
+                warp_fill_tail<T, 2>(a2, hb, W2, N2);
+                team_iir<T, 2, TEAMS>(p.tab + fbp.off, fbp, [&](int q, int ph, int) { return (ph ? ao : ae)[q]; },
+                                      Poly2Out<T>{b2, b2 + hb}, tm);
+            });
+            for_row_tasks<T, TEAMS>(fbs, 1, scratch, [&](int, const IirTeam<T> &tm) {
+                warp_fill_tail<T, 2>(a2, hb, W2, N2);
+                team_iir<T, 2, TEAMS>(p.tab + fbs.off, fbs, [&](int q, int ph, int) { return (ph ? ao : ae)[q]; },
+                                      Poly2Out<T>{l2, l2 + hb}, tm);
+            }, 1);
+        }
     }
     __syncthreads();
     {
         const FiltHdr &fl = p.filt[QF_DEMOD_LP];
-        warp_fill_tail<T, 2>(b2, hb, W2, N2);
-        const T *be = b2, *bo = b2 + hb;
-        T *de = warp ? v2 : u2, *dod = de + hb;
-        Carrier<T> car(start_phase(p, frame, io.y0 + row) + p.phases[QP_BP_SHIFT] + (warp ? CM_QUARTER_TURN : 0ull),
-                       p.phases[QP_STEP2X], W2);
-        warp_iir<T, 2>(p.tab + fl.off, fl,
-                       [&](int q, int ph, int i) {
-                           car.at(2 * q + ph, i);
-                           return (T)2 * car.s * (ph ? bo : be)[q];
-                       },
-                       Poly2Out<T>{de, dod});
+        for_row_tasks<T, TEAMS>(fl, 2, scratch, [&](int t, const IirTeam<T> &tm) {
+            warp_fill_tail<T, 2>(b2, hb, W2, N2);
+            const T *be = b2, *bo = b2 + hb;
+            T *de = t ? v2 : u2, *dod = de + hb;
+            Carrier<T> car(start_phase(p, frame, io.y0 + row) + p.phases[QP_BP_SHIFT] + (t ? CM_QUARTER_TURN : 0ull),
+                           p.phases[QP_STEP2X], W2);
+            team_iir<T, 2, TEAMS>(p.tab + fl.off, fl,
+                                  [&](int q, int ph, int i) {
+                                      car.at(2 * q + ph, i);
+                                      return (T)2 * car.s * (ph ? bo : be)[q];
+                                  },
+                                  Poly2Out<T>{de, dod}, tm);
+        });
     }
     __syncthreads();
     const bool alt = (p.flags & 1) && is_alternate(p, frame, io.y0 + row);
