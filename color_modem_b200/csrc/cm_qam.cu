@@ -113,8 +113,7 @@ int launch_rows_pair(cm_modem *m, IoArgs<T> io, cudaStream_t st) {
     const size_t b1 = (128 + (size_t)p.n1p + 6 * (size_t)p.hb2) * sizeof(T);
     if (b1 > (size_t)m->smem_optin) return cm_fail(CM_ERR_UNSUPPORTED, "line too wide for the row kernels%s");
     const bool teams = needs_teams(p);
-    auto pass1 = MODE == PAIR_PALD ? (teams ? k_pald_rows<T, true> : k_pald_rows<T, false>)
-                                   : (teams ? k_qam_rows<T, true> : k_qam_rows<T, false>);
+    auto pass1 = teams ? k_qam_rows<T, MODE == PAIR_PALD, true> : k_qam_rows<T, MODE == PAIR_PALD, false>;
     const int threads1 = teams ? row_threads(p) : CM_ROW_THREADS;
     int rc = set_smem(pass1, b1);
     if (rc) return rc;

@@ -401,11 +401,10 @@ k_pald_combed(const __grid_constant__ DevParams<T> p, const __grid_constant__ Io
 // (comb.py:53).  (u, v) are fixed linear combinations of the (a, b) of neighbouring rows and the filter is linear, so
 // filtering a and b here, where both warps of the CTA are free, leaves pass 2 purely elementwise.
 template <typename T, bool TEAMS>
-__device__ __forceinline__ void rows_epilogue(const DevParams<T> &p, const IoArgs<T> &io, int f, int row, T *scratch,
-                                              T *cb, T *g, T *wa, T *wb) {
+__device__ __forceinline__ void rows_epilogue(const DevParams<T> &p, T *__restrict__ dst, T *scratch, T *cb, T *g,
+                                              T *wa, T *wb) {
     const int W = p.W, N1 = p.n1p, hb = p.hb2;
     const FirTaps<T> hdn{p.firc[QR_DOWN2], p.fircp[QR_DOWN2]};
-    T *dst = io.aux + ((size_t)f * io.nrows + row) * 4 * W;
     T *sa = cb, *sb = g;                                   // both dead by now; g holds two N1 rows
     fir_down2_pair(wa, wa + hb, wb, wb + hb, W, hdn, threadIdx.x, blockDim.x, [&](int j0, const T *a, const T *b) {
         st4(dst + j0, a);
@@ -439,18 +438,15 @@ __device__ __forceinline__ void rows_epilogue(const DevParams<T> &p, const IoArg
 #define CM_PAIR_MINB 12
 #endif
 
-template <typename T, bool TEAMS>
-__global__ void __launch_bounds__(TEAMS ? CM_NTHREADS : CM_ROW_THREADS, TEAMS ? 2 : CM_ROWS_MINB)
-k_pald_rows(const __grid_constant__ DevParams<T> p, const __grid_constant__ IoArgs<T> io) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    T *scratch = reinterpret_cast<T *>(smem_raw), *sm = scratch + 128;      // [0, 128): IIR team scratch
-    const int W = p.W, W2 = 2 * W, N1 = p.n1p, hb = p.hb2, N2 = 2 * hb;
-    const int row = io.out_begin + blockIdx.x, f = blockIdx.z;
-    const long long frame = io.first_frame + f;
-    T *cb = sm;                       // N1: composite row, later E = down2(BP(up2 c))
-    T *g = cb + N1;                   // N2: up2(c), band-passed in place, later G = up2(E)
-    T *wa = g + N2, *wb = wa + N2;    // N2 each: LP(sin G), LP(cos G)
-    const FirTaps<T> hup{p.firc[QR_UP2], p.fircp[QR_UP2]}, hdn{p.firc[QR_DOWN2], p.fircp[QR_DOWN2]};   // constant bank (kernel parameter)
+// The planes of one row.  PALD: G-path of pal.py:79-127 (a, b from G = up2(down2(BP(up2 c))) through PalDModem._filter
+// at phase psi - LS/2); otherwise the qam.py:43-58 path (a, b from B = BP(up2 c) through _demod_lowpass at phase psi,
+// without the factor 2).  On return the four planes are in `dst` (global, plane pitch W) and in shared memory at
+// cb (a), g (b), wa (alpha), wb (beta); the CTA is synchronised.
+template <typename T, bool PALD, bool TEAMS>
+__device__ __forceinline__ void row_planes(const DevParams<T> &p, const IoArgs<T> &io, int f, long long frame, int row,
+                                           T *__restrict__ dst, T *scratch, T *cb, T *g, T *wa, T *wb) {
+    const int W = p.W, W2 = 2 * W, hb = p.hb2, N2 = 2 * hb;
+    const FirTaps<T> hup{p.firc[QR_UP2], p.fircp[QR_UP2]}, hdn{p.firc[QR_DOWN2], p.fircp[QR_DOWN2]};
     load_comp_row(cb, io, f, row, W);
     __syncthreads();
     fir_up2(g, g + hb, cb, W, hup, threadIdx.x, blockDim.x);
@@ -465,19 +461,21 @@ k_pald_rows(const __grid_constant__ DevParams<T> p, const __grid_constant__ IoAr
         });
     }
     __syncthreads();
-    fir_down2(g, g + hb, W, hdn, threadIdx.x, blockDim.x, [&](int j0, const T *y) { st4(cb + j0, y); });
-    __syncthreads();
-    fir_up2(g, g + hb, cb, W, hup, threadIdx.x, blockDim.x);
-    __syncthreads();
+    if (PALD) {
+        fir_down2(g, g + hb, W, hdn, threadIdx.x, blockDim.x, [&](int j0, const T *y) { st4(cb + j0, y); });
+        __syncthreads();
+        fir_up2(g, g + hb, cb, W, hup, threadIdx.x, blockDim.x);
+        __syncthreads();
+    }
     {
-        const FiltHdr &fl = p.filt[QF_PALD_LP];
+        const FiltHdr &fl = p.filt[PALD ? QF_PALD_LP : QF_DEMOD_LP];
+        const unsigned long long psi = start_phase(p, frame, io.y0 + row) + p.phases[QP_BP_SHIFT] -
+                                       (PALD ? p.phases[QP_HALF_LS] : 0ull);
         for_row_tasks<T, TEAMS>(fl, 2, scratch, [&](int t, const IirTeam<T> &tm) {
             warp_fill_tail<T, 2>(g, hb, W2, N2);          // every warp writes the same values
             const T *ge = g, *go = g + hb;
             T *de = t ? wb : wa, *dod = de + hb;
-            Carrier<T> car(start_phase(p, frame, io.y0 + row) + p.phases[QP_BP_SHIFT] - p.phases[QP_HALF_LS] +
-                               (t ? CM_QUARTER_TURN : 0ull),
-                           p.phases[QP_STEP2X], W2);
+            Carrier<T> car(psi + (t ? CM_QUARTER_TURN : 0ull), p.phases[QP_STEP2X], W2);
             team_iir<T, 2, TEAMS>(p.tab + fl.off, fl,
                                   [&](int q, int ph, int i) {
                                       car.at(2 * q + ph, i);
@@ -487,57 +485,21 @@ k_pald_rows(const __grid_constant__ DevParams<T> p, const __grid_constant__ IoAr
         });
     }
     __syncthreads();
-    rows_epilogue<T, TEAMS>(p, io, f, row, scratch, cb, g, wa, wb);
+    rows_epilogue<T, TEAMS>(p, dst, scratch, cb, g, wa, wb);
+    __syncthreads();
 }
 
-// Pass 1 of the line-comb decoders (NTSC 2-line / 3-line, PAL 3-line): per-row quadrature demodulation of the
-// band-passed 2x signal B_k = BP(up2 c_k) at the row's own phase psi_k = start_phase(k) + bp_shift,
-//     a_k = down2(LP(sin(psi_k) B_k)),   b_k = down2(LP(cos(psi_k) B_k))          (qam.py:43-58 without the factor 2)
-// k_qam_pair rotates these to the phase each comb needs (multiples of LS/2) and combines neighbouring rows.
-template <typename T, bool TEAMS>
+// Pass 1 of the two-pass decoders: one row per CTA, planes to aux[frame][row][4][W].
+template <typename T, bool PALD, bool TEAMS>
 __global__ void __launch_bounds__(TEAMS ? CM_NTHREADS : CM_ROW_THREADS, TEAMS ? 2 : CM_ROWS_MINB)
 k_qam_rows(const __grid_constant__ DevParams<T> p, const __grid_constant__ IoArgs<T> io) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     T *scratch = reinterpret_cast<T *>(smem_raw), *sm = scratch + 128;      // [0, 128): IIR team scratch
-    const int W = p.W, W2 = 2 * W, N1 = p.n1p, hb = p.hb2, N2 = 2 * hb;
+    const int N1 = p.n1p, N2 = 2 * p.hb2;
     const int row = io.out_begin + blockIdx.x, f = blockIdx.z;
-    const long long frame = io.first_frame + f;
-    T *cb = sm;                       // N1: composite row
-    T *g = cb + N1;                   // N2: up2(c), band-passed in place
-    T *wa = g + N2, *wb = wa + N2;    // N2 each: LP(sin B), LP(cos B)
-    const FirTaps<T> hup{p.firc[QR_UP2], p.fircp[QR_UP2]}, hdn{p.firc[QR_DOWN2], p.fircp[QR_DOWN2]};   // constant bank (kernel parameter)
-    load_comp_row(cb, io, f, row, W);
-    __syncthreads();
-    fir_up2(g, g + hb, cb, W, hup, threadIdx.x, blockDim.x);
-    __syncthreads();
-    {
-        const FiltHdr &fb = p.filt[QF_BP2X];
-        for_row_tasks<T, TEAMS>(fb, 1, scratch, [&](int, const IirTeam<T> &tm) {
-            warp_fill_tail<T, 2>(g, hb, W2, N2);
-            T *ge = g, *go = g + hb;
-            team_iir<T, 2, TEAMS>(p.tab + fb.off, fb, [&](int q, int ph, int) { return (ph ? go : ge)[q]; },
-                                  Poly2Out<T>{ge, go}, tm);
-        });
-    }
-    __syncthreads();
-    {
-        const FiltHdr &fl = p.filt[QF_DEMOD_LP];
-        for_row_tasks<T, TEAMS>(fl, 2, scratch, [&](int t, const IirTeam<T> &tm) {
-            warp_fill_tail<T, 2>(g, hb, W2, N2);          // every warp writes the same values
-            const T *ge = g, *go = g + hb;
-            T *de = t ? wb : wa, *dod = de + hb;
-            Carrier<T> car(start_phase(p, frame, io.y0 + row) + p.phases[QP_BP_SHIFT] + (t ? CM_QUARTER_TURN : 0ull),
-                           p.phases[QP_STEP2X], W2);
-            team_iir<T, 2, TEAMS>(p.tab + fl.off, fl,
-                                  [&](int q, int ph, int i) {
-                                      car.at(2 * q + ph, i);
-                                      return (ph ? go : ge)[q] * car.s;
-                                  },
-                                  Poly2Out<T>{de, dod}, tm);
-        });
-    }
-    __syncthreads();
-    rows_epilogue<T, TEAMS>(p, io, f, row, scratch, cb, g, wa, wb);
+    T *cb = sm, *g = cb + N1, *wa = g + N2, *wb = wa + N2;
+    row_planes<T, PALD, TEAMS>(p, io, f, io.first_frame + f, row, io.aux + ((size_t)f * io.nrows + row) * 4 * p.W,
+                               scratch, cb, g, wa, wb);
 }
 
 // Band-split decode (qam.py:43-58 with strip_chroma=True: NtscModem, PalSModem) of one row per CTA of two warps:

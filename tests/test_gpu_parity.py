@@ -85,3 +85,32 @@ def test_float_planes_against_oracle(c, precision, tol, cuda_required):
         assert np.quantile(err, 0.999) <= tol and err.max() <= 1e-2
     else:
         assert err.max() <= tol
+
+
+# ------------------------------------------------------------------------------------------------------------
+# The QAM comb decoders have two implementations of the same function (csrc/cm_qam.cu: launch_rows_pair): two passes
+# over independent rows (what the tests above run) and the legacy multi-row halo kernels, which remain the fallback for
+# lines whose row buffers exceed the shared memory of one CTA.  CM_ONEPASS forces the legacy path, CM_CHUNK the number
+# of frames per pass; every path must meet the same golden-fixture and oracle bounds.
+# ------------------------------------------------------------------------------------------------------------
+COMB_KINDS = {'ntsc_comb', 'ntsc_3d', 'pal_d', 'pal_3d'}
+PATHS = [('legacy', {'CM_ONEPASS': '1'}), ('chunk2', {'CM_CHUNK': '2'})]
+
+
+@pytest.mark.parametrize('path,env', PATHS, ids=[p[0] for p in PATHS])
+@pytest.mark.parametrize('c', [c for c in CASES if c.kind in COMB_KINDS], ids=case_id)
+def test_comb_decoder_paths(c, path, env, cuda_required, monkeypatch):
+    import torch
+    g, rgb, om = _inputs(c)
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    m = make_modem(c)
+    out = m.decode_frames(torch.from_numpy(g['comp_u8'][None]).cuda(), first_frame=c.frame)[0].cpu().numpy()
+    assert _lsb(out, g['rgb_u8']) <= 1
+    comp_in = oframe.composite_unlevel(g['comp_u8'] / 255.0)
+    err = np.abs(m.decode_frame_float(comp_in, c.frame) - om.decode(c.frame, comp_in))
+    assert err.max() <= FP32_TOL
+    # a batch of frames with different absolute frame numbers through the same path
+    comp3 = np.stack([g['comp_u8']] * 3)
+    out3 = m.decode_frames(torch.from_numpy(comp3).cuda(), first_frame=c.frame - 1)[1].cpu().numpy()
+    assert np.array_equal(out3, out)
