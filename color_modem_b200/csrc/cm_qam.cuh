@@ -440,15 +440,14 @@ __device__ __forceinline__ void rows_epilogue(const DevParams<T> &p, T *__restri
 
 // The planes of one row.  PALD: G-path of pal.py:79-127 (a, b from G = up2(down2(BP(up2 c))) through PalDModem._filter
 // at phase psi - LS/2); otherwise the qam.py:43-58 path (a, b from B = BP(up2 c) through _demod_lowpass at phase psi,
-// without the factor 2).  On return the four planes are in `dst` (global, plane pitch W) and in shared memory at
-// cb (a), g (b), wa (alpha), wb (beta); the CTA is synchronised.
+// without the factor 2).  The composite row must already be staged in cb.  On return the four planes are in `dst`
+// (global, plane pitch W) and in shared memory at cb (a), g (b), wa (alpha), wb (beta); the CTA is synchronised.
 template <typename T, bool PALD, bool TEAMS>
 __device__ __forceinline__ void row_planes(const DevParams<T> &p, const IoArgs<T> &io, int f, long long frame, int row,
                                            T *__restrict__ dst, T *scratch, T *cb, T *g, T *wa, T *wb) {
     const int W = p.W, W2 = 2 * W, hb = p.hb2, N2 = 2 * hb;
     const FirTaps<T> hup{p.firc[QR_UP2], p.fircp[QR_UP2]}, hdn{p.firc[QR_DOWN2], p.fircp[QR_DOWN2]};
-    load_comp_row(cb, io, f, row, W);
-    __syncthreads();
+    // precondition: the composite row is staged in cb and the CTA is synchronised
     fir_up2(g, g + hb, cb, W, hup, threadIdx.x, blockDim.x);
     __syncthreads();
     {
@@ -489,17 +488,57 @@ __device__ __forceinline__ void row_planes(const DevParams<T> &p, const IoArgs<T
     __syncthreads();
 }
 
-// Pass 1 of the two-pass decoders: one row per CTA, planes to aux[frame][row][4][W].
+// u8 composite row held in registers between its (early) global load and its staging into shared memory: the DRAM
+// latency of the row a CTA works on next is hidden behind the row it is working on now.
+struct RowPrefetch {
+    static constexpr int kMaxQuads = 4;          // 4 pixels per quad: rows of up to 16 * blockDim samples
+    uint32_t w[kMaxQuads];
+    template <typename T>
+    __device__ __forceinline__ void fetch(const IoArgs<T> &io, int f, int row, int Wc) {
+        const uint8_t *src = io.in_u8 + ((size_t)f * io.nrows + row) * Wc;
+#pragma unroll
+        for (int q = 0; q < kMaxQuads; ++q) {
+            const int x = 4 * (threadIdx.x + q * blockDim.x);
+            if (x < Wc) w[q] = __ldg(reinterpret_cast<const uint32_t *>(src + x));
+        }
+    }
+    template <typename T>
+    __device__ __forceinline__ void stage(T *dst, int Wc) const {
+#pragma unroll
+        for (int q = 0; q < kMaxQuads; ++q) {
+            const int x = 4 * (threadIdx.x + q * blockDim.x);
+            if (x < Wc) {
+                T v[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) v[i] = ((T)5 * Real<T>::from_u8((w[q] >> (8 * i)) & 0xff) - (T)1) * (T)(1.0 / 3.0);
+                st4(dst + x, v);
+            }
+        }
+    }
+};
+
+// Pass 1 of the two-pass decoders: a CTA works through rows blockIdx.x, blockIdx.x + gridDim.x, ... of one frame (one at
+// a time; the next one is prefetched), planes to aux[frame][row][4][W].
 template <typename T, bool PALD, bool TEAMS>
 __global__ void __launch_bounds__(TEAMS ? CM_NTHREADS : CM_ROW_THREADS, TEAMS ? 2 : CM_ROWS_MINB)
 k_qam_rows(const __grid_constant__ DevParams<T> p, const __grid_constant__ IoArgs<T> io) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     T *scratch = reinterpret_cast<T *>(smem_raw), *sm = scratch + 128;      // [0, 128): IIR team scratch
-    const int N1 = p.n1p, N2 = 2 * p.hb2;
-    const int row = io.out_begin + blockIdx.x, f = blockIdx.z;
+    const int W = p.W, N1 = p.n1p, N2 = 2 * p.hb2;
+    const int f = blockIdx.z, end = io.out_begin + io.out_count;
     T *cb = sm, *g = cb + N1, *wa = g + N2, *wb = wa + N2;
-    row_planes<T, PALD, TEAMS>(p, io, f, io.first_frame + f, row, io.aux + ((size_t)f * io.nrows + row) * 4 * p.W,
-                               scratch, cb, g, wa, wb);
+    const bool pre = io.in_u8 != nullptr && W <= 4 * RowPrefetch::kMaxQuads * (int)blockDim.x;
+    RowPrefetch pf;
+    int row = io.out_begin + blockIdx.x;
+    if (pre && row < end) pf.fetch(io, f, row, W);
+    for (; row < end; row += gridDim.x) {
+        if (pre) pf.stage(cb, W);
+        else load_comp_row(cb, io, f, row, W);
+        __syncthreads();
+        if (pre && row + (int)gridDim.x < end) pf.fetch(io, f, row + gridDim.x, W);
+        row_planes<T, PALD, TEAMS>(p, io, f, io.first_frame + f, row, io.aux + ((size_t)f * io.nrows + row) * 4 * W,
+                                   scratch, cb, g, wa, wb);
+    }
 }
 
 // Band-split decode (qam.py:43-58 with strip_chroma=True: NtscModem, PalSModem) of one row per CTA of two warps:

@@ -1,5 +1,3 @@
-for w in secam niir proto mac pald; do
-  for r in 1 2 3 4 8; do for mw in 2 4; do
-  echo -n "R=$r minw=$mw "; CM_ROWS_MAX=$r CM_MIN_WARPS=$mw python tools/kt.py $w 2>&1 | sed 's/default //; s/(. launches.step)//g' | cut -c1-150
-  done; done
-done
+python -m pytest tests -m gpu -x -q 2>&1 | tail -3
+for rpc in 1 2 4 8; do echo -n "RPC=$rpc "; CM_RPC=$rpc python tools/kt.py pald | cut -c1-230; done
+CM_RPC=4 python tools/kt.py ntsc3d | cut -c1-230
