@@ -48,8 +48,26 @@ int proto_encode(cm_modem *m, IoArgs<T> io, cudaStream_t st) {
 template <typename T>
 int proto_decode(cm_modem *m, IoArgs<T> io, cudaStream_t st) {
     const DevParams<T> &p = params_of<T>(m);
-    auto bytes = [&](int r) { return (128 + (size_t)(r + 1) * (p.n1p + 9 * (size_t)p.hb3)) * sizeof(T); };
-    return launch_rows<T>(m, io, st, k_proto_decode<T>, bytes, 2, 2, 1, CM_K_DECODE_OTHER, "proto-SECAM decode");
+    if (io.out_count <= 0) return CM_OK;
+    // pass 1 (heavy): (luma, X) per row for the output rows and the two rows above them
+    io.aux = (T *)cm_ensure_aux(m, (size_t)io.nframes * io.nrows * 2 * p.Wo * sizeof(T));
+    if (!io.aux) return CM_ERR_NOMEM;
+    IoArgs<T> a = io;
+    a.out_begin = io.out_begin >= 2 ? io.out_begin - 2 : 0;
+    a.out_count = io.out_begin + io.out_count - a.out_begin;
+    auto bytes = [&](int r) { return (128 + (size_t)r * (p.n1p + 9 * (size_t)p.hb3)) * sizeof(T); };
+    // two tasks per row (chroma, luma), each run by a team of up to four warps
+    int rc = launch_rows<T>(m, a, st, k_proto_decode<T>, bytes, 2, 4, 0, CM_K_DECODE_OTHER, "proto-SECAM decode");
+    if (rc) return rc;
+    // pass 2 (light): pair rows y / y-2, inverse matrix, store
+    {
+        LaunchTimer lt(m, CM_K_DECODE_OTHER, st);
+        dim3 grid(1u, (unsigned)io.out_count, (unsigned)io.nframes);
+        k_pair_rows_store<T><<<grid, 192, 0, st>>>(p, io);
+    }
+    cm_count_launch();
+    CUDA_TRY(cudaGetLastError());
+    return CM_OK;
 }
 
 #define CM_INST(fn)                                                                     \

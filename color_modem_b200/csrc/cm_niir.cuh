@@ -164,24 +164,25 @@ k_niir_decode(const __grid_constant__ DevParams<T> p, const __grid_constant__ Io
     cta_fill_tail<T, 3>(rows + N1, per_row, nin, hb, n3, N3);
     __syncthreads();
     const FiltHdr &fbp = p.filt[NF_UP_BP], &flp = p.filt[NF_BASE_LP];
-    for (int t = warp; t < nin; t += nwarps) {          // band-pass: up -> mod
+    // band-pass: up -> mod.  The 3x lines are 2-4 super-chunks long: each task is run by a team of warps (cm_iir.cuh)
+    for_each_iir_task<T, true>(fbp, nin, taps, [&](int t, const IirTeam<T> &tm) {
         const T *u = rows + (size_t)t * per_row + N1;
         T *m = rows + (size_t)t * per_row + N1 + N3;
-        warp_iir<T, 3>(p.tab + fbp.off, fbp, [&](int q, int ph, int) { return u[ph * hb + q]; },
-                       [&](int j, T v) { poly3(m, hb, j) = v; });
-        warp_fill_tail<T, 3>(m, hb, n3, N3);
-    }
+        team_iir<T, 3, true>(p.tab + fbp.off, fbp, [&](int q, int ph, int) { return u[ph * hb + q]; },
+                             [&](int j, T v) { poly3(m, hb, j) = v; }, tm);
+    });
     __syncthreads();
     // envelope low-pass: sat = LP(pi/2 |mod|).  The synthetic top-of-field carrier is used un-normalised
     // (niir.py:105-106 stores the band-passed reference itself), so its slot skips this step.
-    for (int t = warp; t < nin; t += nwarps) {
-        if (t == 0 && !has_prev0) continue;
-        const T *m = rows + (size_t)t * per_row + N1 + N3;
+    for_each_iir_task<T, true>(flp, nin, taps, [&](int t, const IirTeam<T> &tm) {
+        if (t == 0 && !has_prev0) return;
+        T *m = rows + (size_t)t * per_row + N1 + N3;
         T *s = rows + (size_t)t * per_row + N1 + 2 * (size_t)N3;
-        warp_iir<T, 3>(p.tab + flp.off, flp,
-                       [&](int q, int ph, int) { return (T)1.57079632679489661923 * Real<T>::abs_(m[ph * hb + q]); },
-                       [&](int j, T v) { poly3(s, hb, j) = v; });
-    }
+        warp_fill_tail<T, 3>(m, hb, n3, N3);           // every warp of the team writes the same values
+        team_iir<T, 3, true>(p.tab + flp.off, flp,
+                             [&](int q, int ph, int) { return (T)1.57079632679489661923 * Real<T>::abs_(m[ph * hb + q]); },
+                             [&](int j, T v) { poly3(s, hb, j) = v; }, tm);
+    });
     __syncthreads();
     for (int k = -1; k < g.count; ++k) {                // pm = mod / sat in place
         if (k == -1 && !has_prev0) continue;

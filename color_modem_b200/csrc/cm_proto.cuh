@@ -105,9 +105,8 @@ k_proto_decode(const __grid_constant__ DevParams<T> p, const __grid_constant__ I
     T *taps = sm;
     T *rows = sm + 128;
     const size_t per_row = (size_t)N1 + 3 * (size_t)N3;
-    const bool has_prev0 = g.r0 >= 2;
-    const int k_lo = has_prev0 ? -1 : 0;
-    const int nin = g.count - k_lo;
+    const int k_lo = 0;                          // rows are independent here: pairing with the previous row happens
+    const int nin = g.count;                     // in k_pair_rows_store (cm_io.cuh)
     const FirTaps<T> hup{p.firc[PR_UP3], p.fircp[PR_UP3]}, hdn{p.firc[PR_DOWN3], p.fircp[PR_DOWN3]};   // constant bank (kernel parameter)
     auto rowp = [&](int k) { return rows + (size_t)(k - k_lo) * per_row; };
     load_comp_rows(io, g.fidx, nin, W, [&](int k) { return rowp(k_lo + k); }, [&](int k) { return g.r0 + 2 * (k_lo + k); });
@@ -120,23 +119,29 @@ k_proto_decode(const __grid_constant__ DevParams<T> p, const __grid_constant__ I
     cta_fill_tail<T, 3>(rows + N1, per_row, nin, hb, n3, N3);
     __syncthreads();
     const FiltHdr &fbp = p.filt[PF_BP_UP], &fbs = p.filt[PF_BS_UP], &fpost = p.filt[PF_POST_LP];
-    for (int t = warp; t < 2 * nin; t += nwarps) {
-        T *r = rows + (size_t)(t >> 1) * per_row;
+    // chroma band-pass (u -> b) and luma band-stop (u -> l) side by side, each task run by a team of warps
+    for_each_iir_task<T, true>(fbp, nin, taps, [&](int t, const IirTeam<T> &tm) {
+        T *r = rows + (size_t)t * per_row;
         const T *u = r + N1;
-        if ((t & 1) == 0) {
-            T *b = r + N1 + N3;
-            warp_iir<T, 3>(p.tab + fbp.off, fbp, [&](int q, int ph, int) { return u[ph * hb + q]; },
-                           [&](int j, T v) { poly3(b, hb, j) = v; });
-            warp_fill_tail<T, 3>(b, hb, n3, N3);
-            warp_iir<T, 3>(p.tab + fpost.off, fpost,
-                           [&](int q, int ph, int) { return (T)1.57079632679489661923 * Real<T>::abs_(b[ph * hb + q]); },
-                           [&](int j, T v) { poly3(b, hb, j) = v; });
-        } else if ((t >> 1) + k_lo >= 0) {
-            T *l = r + N1 + 2 * (size_t)N3;
-            warp_iir<T, 3>(p.tab + fbs.off, fbs, [&](int q, int ph, int) { return u[ph * hb + q]; },
-                           [&](int j, T v) { poly3(l, hb, j) = v; });
-        }
-    }
+        T *b = r + N1 + N3;
+        team_iir<T, 3, true>(p.tab + fbp.off, fbp, [&](int q, int ph, int) { return u[ph * hb + q]; },
+                             [&](int j, T v) { poly3(b, hb, j) = v; }, tm);
+    });
+    for_each_iir_task<T, true>(fbs, nin, taps, [&](int t, const IirTeam<T> &tm) {
+        T *r = rows + (size_t)t * per_row;
+        const T *u = r + N1;
+        T *l = r + N1 + 2 * (size_t)N3;
+        team_iir<T, 3, true>(p.tab + fbs.off, fbs, [&](int q, int ph, int) { return u[ph * hb + q]; },
+                             [&](int j, T v) { poly3(l, hb, j) = v; }, tm);
+    }, nin);
+    __syncthreads();
+    for_each_iir_task<T, true>(fpost, nin, taps, [&](int t, const IirTeam<T> &tm) {     // rectifier + low-pass, in place
+        T *b = rows + (size_t)t * per_row + N1 + N3;
+        warp_fill_tail<T, 3>(b, hb, n3, N3);           // every warp of the team writes the same values
+        team_iir<T, 3, true>(p.tab + fpost.off, fpost,
+                             [&](int q, int ph, int) { return (T)1.57079632679489661923 * Real<T>::abs_(b[ph * hb + q]); },
+                             [&](int j, T v) { poly3(b, hb, j) = v; }, tm);
+    });
     __syncthreads();
     const Down3Taps<T> tp(hdn);
     for (int k = k_lo; k < g.count; ++k) {              // X = 8 down3(chroma_up) - 1 into the (dead) composite buffer
@@ -151,19 +156,17 @@ k_proto_decode(const __grid_constant__ DevParams<T> p, const __grid_constant__ I
         }
     }
     __syncthreads();
+    // (luma, X) of every row to the pairing scratch; k_pair_rows_store combines rows y and y-2 (protosecam.py:105-108)
     for (int k = 0; k < g.count; ++k) {
         const int row = g.r0 + 2 * k;
-        const bool alt = is_alternate(p, g.frame, io.y0 + row);
-        const bool hp = (k > 0) || has_prev0;
-        const T *xc = rowp(k), *xp = hp ? rowp(k - 1) : nullptr, *l = rowp(k) + N1 + 2 * (size_t)N3;
+        const T *xc = rowp(k), *l = rowp(k) + N1 + 2 * (size_t)N3;
+        T *dst = io.aux + ((size_t)g.fidx * io.nrows + row) * 2 * W;
         for (int q = threadIdx.x; q < (W >> 2); q += blockDim.x) {
-            T y[4], a[4], b[4] = {(T)0, (T)0, (T)0, (T)0};
+            T y[4], a[4];
             down3_quad(tp, l, l + hb, l + 2 * hb, W, 4 * q, y);
             ld4(xc + 4 * q, a);
-            if (hp) ld4(xp + 4 * q, b);
-            // protosecam.py:105-108: non-alternate rows carry D'R (dr = current, db = previous)
-            if (alt) store_rgb4(p, io, g.fidx, row, 4 * q, y, b, a);
-            else store_rgb4(p, io, g.fidx, row, 4 * q, y, a, b);
+            st4(dst + 4 * q, y);
+            st4(dst + W + 4 * q, a);
         }
     }
 }
