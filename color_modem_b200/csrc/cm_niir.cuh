@@ -169,7 +169,7 @@ k_niir_decode(const __grid_constant__ DevParams<T> p, const __grid_constant__ Io
         const T *u = rows + (size_t)t * per_row + N1;
         T *m = rows + (size_t)t * per_row + N1 + N3;
         team_iir<T, 3, true>(p.tab + fbp.off, fbp, [&](int q, int ph, int) { return u[ph * hb + q]; },
-                             [&](int j, T v) { poly3(m, hb, j) = v; }, tm);
+                             Poly3Out<T>{m, hb}, tm);
     });
     __syncthreads();
     // envelope low-pass: sat = LP(pi/2 |mod|).  The synthetic top-of-field carrier is used un-normalised
@@ -181,16 +181,24 @@ k_niir_decode(const __grid_constant__ DevParams<T> p, const __grid_constant__ Io
         warp_fill_tail<T, 3>(m, hb, n3, N3);           // every warp of the team writes the same values
         team_iir<T, 3, true>(p.tab + flp.off, flp,
                              [&](int q, int ph, int) { return (T)1.57079632679489661923 * Real<T>::abs_(m[ph * hb + q]); },
-                             [&](int j, T v) { poly3(s, hb, j) = v; }, tm);
+                             Poly3Out<T>{s, hb}, tm);
     });
     __syncthreads();
     for (int k = -1; k < g.count; ++k) {                // pm = mod / sat in place
         if (k == -1 && !has_prev0) continue;
         T *m = rowp(k) + N1 + N3;
         const T *s = rowp(k) + N1 + 2 * (size_t)N3;
-        for (int i = threadIdx.x; i < 3 * W; i += blockDim.x) {
-            const int ph = i / W, q = i - ph * W;
-            m[ph * hb + q] = m[ph * hb + q] / s[ph * hb + q];
+        for (int ph = 0; ph < 3; ++ph) {
+            T *mp = m + ph * hb;
+            const T *sp = s + ph * hb;
+            for (int q = 4 * threadIdx.x; q < W; q += 4 * blockDim.x) {
+                T a[4], b[4];
+                ld4(mp + q, a);
+                ld4(sp + q, b);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) a[i] = a[i] / b[i];
+                st4(mp + q, a);
+            }
         }
     }
     __syncthreads();

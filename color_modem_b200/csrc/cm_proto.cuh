@@ -67,7 +67,7 @@ k_proto_encode(const __grid_constant__ DevParams<T> p, const __grid_constant__ I
             T *u = r + 2 * N1;
             const FiltHdr &f = p.filt[PF_BS_UP];
             warp_iir<T, 3>(p.tab + f.off, f, [&](int q, int ph, int) { return u[ph * hb + q]; },
-                           [&](int j, T v) { poly3(u, hb, j) = v; });
+                           Poly3Out<T>{u, hb});
         }
     }
     __syncthreads();
@@ -94,7 +94,7 @@ k_proto_encode(const __grid_constant__ DevParams<T> p, const __grid_constant__ I
 
 // Decode.  smem: taps[128] + (R+1) rows x ( c -> X [N1] | up[N3] | chroma[N3] | luma[N3] )
 template <typename T>
-__global__ void __launch_bounds__(CM_NTHREADS)
+__global__ void __launch_bounds__(CM_NTHREADS, 2)
 k_proto_decode(const __grid_constant__ DevParams<T> p, const __grid_constant__ IoArgs<T> io) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     T *sm = reinterpret_cast<T *>(smem_raw);
@@ -125,14 +125,14 @@ k_proto_decode(const __grid_constant__ DevParams<T> p, const __grid_constant__ I
         const T *u = r + N1;
         T *b = r + N1 + N3;
         team_iir<T, 3, true>(p.tab + fbp.off, fbp, [&](int q, int ph, int) { return u[ph * hb + q]; },
-                             [&](int j, T v) { poly3(b, hb, j) = v; }, tm);
+                             Poly3Out<T>{b, hb}, tm);
     });
     for_each_iir_task<T, true>(fbs, nin, taps, [&](int t, const IirTeam<T> &tm) {
         T *r = rows + (size_t)t * per_row;
         const T *u = r + N1;
         T *l = r + N1 + 2 * (size_t)N3;
         team_iir<T, 3, true>(p.tab + fbs.off, fbs, [&](int q, int ph, int) { return u[ph * hb + q]; },
-                             [&](int j, T v) { poly3(l, hb, j) = v; }, tm);
+                             Poly3Out<T>{l, hb}, tm);
     }, nin);
     __syncthreads();
     for_each_iir_task<T, true>(fpost, nin, taps, [&](int t, const IirTeam<T> &tm) {     // rectifier + low-pass, in place
@@ -140,7 +140,7 @@ k_proto_decode(const __grid_constant__ DevParams<T> p, const __grid_constant__ I
         warp_fill_tail<T, 3>(b, hb, n3, N3);           // every warp of the team writes the same values
         team_iir<T, 3, true>(p.tab + fpost.off, fpost,
                              [&](int q, int ph, int) { return (T)1.57079632679489661923 * Real<T>::abs_(b[ph * hb + q]); },
-                             [&](int j, T v) { poly3(b, hb, j) = v; }, tm);
+                             Poly3Out<T>{b, hb}, tm);
     });
     __syncthreads();
     const Down3Taps<T> tp(hdn);
