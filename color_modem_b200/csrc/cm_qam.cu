@@ -42,8 +42,22 @@ int qam_encode(cm_modem *m, IoArgs<T> io, cudaStream_t st) {
     auto bytes = [&](int r) { return (128 + (size_t)r * 3 * p.n1p) * sizeof(T); };
     int R = pick_rows(1, (size_t)m->smem_optin / 2, bytes);     // one row, two warps (u and v low-pass): 1.84 vs 2.64 us/frame
     if (!R) return cm_fail(CM_ERR_UNSUPPORTED, "line too wide for the encode kernel%s");
-    set_groups(io, R);
     const bool teams = needs_teams(p);
+    if (!teams && io.in_u8 && p.W <= 768 && !getenv("CM_ONEPASS")) {        // one row at a time, next row prefetched
+        int rc1 = set_smem(k_qam_encode_row<T>, bytes(1));
+        if (rc1) return rc1;
+        int rpc = 2;
+        if (const char *e = getenv("CM_RPC")) rpc = atoi(e) > 0 ? atoi(e) : rpc;      // tuning aid
+        const int nf = (io.out_count + 1) >> 1;
+        {
+            LaunchTimer lt(m, CM_K_ENCODE, st);
+            k_qam_encode_row<T><<<dim3((unsigned)((nf + rpc - 1) / rpc), 2u, (unsigned)io.nframes), CM_ROW_THREADS, bytes(1), st>>>(p, io);
+        }
+        cm_count_launch();
+        CUDA_TRY(cudaGetLastError());
+        return CM_OK;
+    }
+    set_groups(io, R);
     int rc = teams ? set_smem(k_qam_encode<T, true>, bytes(R)) : set_smem(k_qam_encode<T, false>, bytes(R));
     if (rc) return rc;
     dim3 grid = cm_grid(io);

@@ -10,6 +10,13 @@
 #include "cm_io.cuh"
 #include "cm_slots.h"
 
+// one-row kernels: a CTA of two warps; 8 CTAs per SM at 128 registers per thread (more CTAs at fewer registers spill
+// and lose)
+#define CM_ROW_THREADS 64
+#ifndef CM_ROWS_MINB
+#define CM_ROWS_MINB 8
+#endif
+
 
 // sin/cos of the subcarrier at 4 consecutive 1x samples starting at x0 (exact seed + 3 rotations)
 template <typename T>
@@ -94,6 +101,114 @@ k_qam_encode(const __grid_constant__ DevParams<T> p, const __grid_constant__ IoA
             for (int i = 0; i < 4; ++i) o[i] = y[i] + (s[i] * u[i] + c[i] * (neg ? -v[i] : v[i]));
             store_comp4(io, ((size_t)g.fidx * io.nrows + row) * p.Wc + x, o);
         }
+    }
+}
+
+// Encoder for u8 frames of narrow lines: the same chain, one row at a time per CTA of two warps, the RGB words of the
+// row the CTA works on next (and of its field neighbour for the ColorAveraging front end) prefetched into registers
+// while the current row is filtered — the global-load latency was 24 % of this kernel's warp-stall samples.
+// Grid: x = rows of a field handled round-robin, y = field, z = frame.
+template <typename T>
+__global__ void __launch_bounds__(CM_ROW_THREADS, 8)
+k_qam_encode_row(const __grid_constant__ DevParams<T> p, const __grid_constant__ IoArgs<T> io) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T *scratch = reinterpret_cast<T *>(smem_raw), *sm = scratch + 128;
+    constexpr int kQ = 3;                                   // quads per thread: W <= 4 * 3 * 64 = 768
+    const int W = p.W, N1 = p.n1p, W4 = W >> 2;
+    const int warp = threadIdx.x >> 5;
+    const bool avg = (p.flags & 2) != 0;
+    const int field = blockIdx.y, f = blockIdx.z;
+    const long long frame = io.first_frame + f;
+    const int first = io.out_begin + field, nout = (io.out_count - field + 1) >> 1;
+    T *ys = sm, *us = ys + N1, *vs = us + N1;
+    uint32_t wc[kQ][3], wn[kQ][3];
+    auto fetch = [&](int row) {
+        const int nrow = (row + 2 < io.nrows) ? row + 2 : row;
+        const uint32_t *a = reinterpret_cast<const uint32_t *>(io.in_u8 + ((size_t)f * io.nrows + row) * W * 3);
+        const uint32_t *b = reinterpret_cast<const uint32_t *>(io.in_u8 + ((size_t)f * io.nrows + nrow) * W * 3);
+#pragma unroll
+        for (int j = 0; j < kQ; ++j) {
+            const int q = threadIdx.x + j * CM_ROW_THREADS;
+            if (q < W4) {
+#pragma unroll
+                for (int i = 0; i < 3; ++i) {
+                    wc[j][i] = __ldg(a + 3 * q + i);
+                    if (avg) wn[j][i] = __ldg(b + 3 * q + i);
+                }
+            }
+        }
+    };
+    auto unpack = [&](const uint32_t *w, T *r, T *g, T *b) {
+        unsigned char bytes[12];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            bytes[i] = (w[0] >> (8 * i)) & 0xff;
+            bytes[4 + i] = (w[1] >> (8 * i)) & 0xff;
+            bytes[8 + i] = (w[2] >> (8 * i)) & 0xff;
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            r[i] = Real<T>::from_u8(bytes[3 * i]);
+            g[i] = Real<T>::from_u8(bytes[3 * i + 1]);
+            b[i] = Real<T>::from_u8(bytes[3 * i + 2]);
+        }
+    };
+    T rs, rc;
+    Real<T>::sincos_turns(p.phases[QP_STEP1X], rs, rc);
+    int k = blockIdx.x;
+    if (k < nout) fetch(first + 2 * k);
+    for (; k < nout; k += gridDim.x) {
+        const int row = first + 2 * k, line = io.y0 + row;
+#pragma unroll
+        for (int j = 0; j < kQ; ++j) {
+            const int q = threadIdx.x + j * CM_ROW_THREADS;
+            if (q < W4) {
+                T r[4], gg[4], b[4], y[4], u[4], v[4];
+                unpack(wc[j], r, gg, b);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    y[i] = p.enc[0] * r[i] + p.enc[1] * gg[i] + p.enc[2] * b[i];
+                    u[i] = p.enc[3] * r[i] + p.enc[4] * gg[i] + p.enc[5] * b[i];
+                    v[i] = p.enc[6] * r[i] + p.enc[7] * gg[i] + p.enc[8] * b[i];
+                }
+                if (avg) {
+                    unpack(wn[j], r, gg, b);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const T un = p.enc[3] * r[i] + p.enc[4] * gg[i] + p.enc[5] * b[i];
+                        const T vn = p.enc[6] * r[i] + p.enc[7] * gg[i] + p.enc[8] * b[i];
+                        u[i] = (T)0.5 * (un + u[i]);
+                        v[i] = (T)0.5 * (vn + v[i]);
+                    }
+                }
+                st4(ys + 4 * q, y);
+                st4(us + 4 * q, u);
+                st4(vs + 4 * q, v);
+            }
+        }
+        __syncthreads();
+        if (k + (int)gridDim.x < nout) fetch(first + 2 * (k + gridDim.x));       // in flight during the filtering
+        {
+            const FiltHdr &fpre = p.filt[QF_PRE_LP];
+            T *buf = warp ? vs : us;
+            warp_fill_tail<T, 1>(buf, N1, W, N1);
+            warp_iir<T, 1>(p.tab + fpre.off, fpre, [&](int q, int, int) { return buf[q]; }, [&](int j, T x) { buf[j] = x; });
+        }
+        __syncthreads();
+        const unsigned long long ph0 = start_phase(p, frame, line);
+        const bool neg = (p.flags & 1) && is_alternate(p, frame, line);
+        for (int q = threadIdx.x; q < W4; q += blockDim.x) {
+            const int x = 4 * q;
+            T y[4], u[4], v[4], s[4], c[4], o[4];
+            ld4(ys + x, y);
+            ld4(us + x, u);
+            ld4(vs + x, v);
+            carrier4(ph0 + (unsigned long long)x * p.phases[QP_STEP1X], rs, rc, s, c);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) o[i] = y[i] + (s[i] * u[i] + c[i] * (neg ? -v[i] : v[i]));
+            store_comp4(io, ((size_t)f * io.nrows + row) * p.Wc + x, o);
+        }
+        __syncthreads();
     }
 }
 
@@ -392,7 +507,6 @@ k_pald_combed(const __grid_constant__ DevParams<T> p, const __grid_constant__ Io
 // halo row, no idle warps) writes (a_k, b_k) to an fp32 scratch in HBM / L2; pass 2 (k_pald_pair) combines
 // neighbouring rows, rotates to (u, v), re-modulates through the encoder low-pass and stores RGB.
 // ------------------------------------------------------------------------------------------------------------
-#define CM_ROW_THREADS 64
 
 // Common tail of the pass-1 row kernels.  wa / wb hold LP(sin X), LP(cos X) at 2x (polyphase).  Writes four planes of
 // the row to the scratch  aux[frame][row][4][W]:
@@ -431,12 +545,6 @@ __device__ __forceinline__ void rows_epilogue(const DevParams<T> &p, T *__restri
         st4(dst + 3 * W + x, v);
     }
 }
-#ifndef CM_ROWS_MINB
-#define CM_ROWS_MINB 8
-#endif
-#ifndef CM_PAIR_MINB
-#define CM_PAIR_MINB 12
-#endif
 
 // The planes of one row.  PALD: G-path of pal.py:79-127 (a, b from G = up2(down2(BP(up2 c))) through PalDModem._filter
 // at phase psi - LS/2); otherwise the qam.py:43-58 path (a, b from B = BP(up2 c) through _demod_lowpass at phase psi,
