@@ -39,9 +39,8 @@ class NtscCombModem(NtscModem):
     decoder_rows = 2
 
     def __init__(self, line_config, variant=NtscVariant.NTSC, notch=0.0, precision='fp32'):
-        if notch:
-            raise NotImplementedError('notch= is a non-default knob that is not built (SURVEY.md §8f)')
         super(NtscCombModem, self).__init__(line_config, variant, precision)
+        self._notch_q = float(notch)
         self.backend = self
         sine = numpy.sin(self.line_shift * 0.5)
         self._factor = 0.5 / sine if abs(sine) > 0.05 else float('inf')

@@ -38,9 +38,8 @@ class PalDModem(PalSModem):
     decoder_rows = 2
 
     def __init__(self, line_config, variant=PalVariant.PAL, notch=0.0, precision='fp32'):
-        if notch:
-            raise NotImplementedError('notch= is a non-default knob that is not built (SURVEY.md §8f)')
         super(PalDModem, self).__init__(line_config, variant, precision)
+        self._notch_q = float(notch)
         self.backend = self
         self._sin_factor = numpy.sin(0.5 * self.line_shift)
         self._cos_factor = numpy.cos(0.5 * self.line_shift)

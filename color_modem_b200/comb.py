@@ -41,11 +41,12 @@ class Simple3DCombModem(_Wrapper):
 
     def __init__(self, backend, notch=0.0, avg=None):
         from .color.ntsc import NtscCombModem
-        if notch or avg is not None:
-            raise NotImplementedError('notch= / avg= are non-default knobs that are not built (SURVEY.md §8f)')
+        if avg is not None:
+            raise NotImplementedError('avg= is a non-default knob that is not built (SURVEY.md §8f)')
         if type(backend) is not NtscCombModem:
             raise NotImplementedError('Simple3DCombModem is built for NtscCombModem backends only')
-        impl = _clone(backend, kind=N.KIND_NTSC_3D, decoder_rows=3,
+        # the wrapper's own notch (comb.py:108-109); the backend's is never applied (it is called with strip_chroma=False)
+        impl = _clone(backend, kind=N.KIND_NTSC_3D, decoder_rows=3, _notch_q=float(notch),
                       demodulation_delay=getattr(backend, 'demodulation_delay', 0) + 1)
         super(Simple3DCombModem, self).__init__(backend, impl)
 

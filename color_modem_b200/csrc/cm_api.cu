@@ -268,7 +268,7 @@ extern "C" void cm_destroy(cm_modem *m) {
         cudaFree(m->d_out[i]);
         if (m->hs[i]) cudaStreamDestroy(m->hs[i]);
     }
-    for (int i = 0; i < 4; ++i) cudaFree(m->d_aux[i]);
+    for (int i = 0; i < 8; ++i) cudaFree(m->d_aux[i]);
     cm_timing_reset(m);
     delete m;
 }
@@ -276,8 +276,8 @@ extern "C" void cm_destroy(cm_modem *m) {
 // ------------------------------------------------------------------------------------------------------------
 // launches
 // ------------------------------------------------------------------------------------------------------------
-void *cm_ensure_aux(cm_modem *m, size_t bytes) {
-    const int k = m->aux_slot;
+void *cm_ensure_aux(cm_modem *m, size_t bytes, int which) {
+    const int k = which * 4 + m->aux_slot;
     if (m->aux_cap[k] >= bytes) return m->d_aux[k];
     // the old buffer may still be in use by kernels already queued on some stream
     if (cudaDeviceSynchronize() != cudaSuccess) { fail(CM_ERR_CUDA, "cudaDeviceSynchronize failed%s"); return nullptr; }

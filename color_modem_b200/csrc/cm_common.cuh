@@ -77,6 +77,8 @@ struct IoArgs {
     int rows_per_cta; // R
     int groups_per_field;
     T *aux;                 // kernel-specific scratch in global memory (line-sequential decoders: per-row luma | chroma)
+    T *yuv;                 // non-null: store_rgb4 writes the planes (y, c1, c2) of the row to yuv[frame][row][3][Wo] instead
+                            // of RGB (comb decoders with a luma notch: k_notch_rows finishes the row)
     unsigned long long *prof;   // optional per-phase cycle counters (tuning aid, cm_phase_profile); nullptr normally
 };
 

@@ -32,8 +32,8 @@ struct cm_modem {
     unsigned long long *phase_prof = nullptr;
     // pairing scratch of the line-sequential decoders (grown on demand); one per host-path stream (+ slot 0 for
     // caller-provided streams: a handle must not be used from two streams at once)
-    void *d_aux[4] = {nullptr, nullptr, nullptr, nullptr};
-    size_t aux_cap[4] = {0, 0, 0, 0};
+    void *d_aux[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // [which * 4 + slot]
+    size_t aux_cap[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     int aux_slot = 0;
     struct Ev { cudaEvent_t a, b; int id; };
     std::vector<Ev> events;
@@ -127,7 +127,8 @@ static void split_top(const IoArgs<T> &io, IoArgs<T> &top, IoArgs<T> &rest) {
 }
 
 // Grow-only device scratch of a handle (stream-ordered use only).
-void *cm_ensure_aux(cm_modem *m, size_t bytes);   // nullptr on failure (cm_last_error set)
+// which = 0: pass-1 -> pass-2 planes; 1: (y, u, v) rows waiting for the luma notch
+void *cm_ensure_aux(cm_modem *m, size_t bytes, int which = 0);   // nullptr on failure (cm_last_error set)
 
 // Explicit instantiation of the float / double variants; the build may compile a unit once per type
 // (-DCM_INST_F32 / -DCM_INST_F64) so that the two halves compile in parallel.

@@ -104,6 +104,13 @@ __device__ __forceinline__ void store_comp4(const IoArgs<T> &io, size_t off, con
 template <typename T>
 __device__ __forceinline__ void store_rgb4(const DevParams<T> &p, const IoArgs<T> &io, int fidx, int row, int x0,
                                            const T y[4], const T c1[4], const T c2[4]) {
+    if (io.yuv) {
+        T *dst = io.yuv + ((size_t)fidx * io.nrows + row) * 3 * p.Wo + x0;
+        st4(dst, y);
+        st4(dst + p.Wo, c1);
+        st4(dst + 2 * p.Wo, c2);
+        return;
+    }
     T v[12];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {

@@ -15,6 +15,7 @@
 template <typename T> int launch_bandsplit(cm_modem *m, IoArgs<T> io, int luma_mode, cudaStream_t st);
 template <typename T> int launch_pald(cm_modem *m, IoArgs<T> io, cudaStream_t st);
 template <typename T, int MODE> int launch_comb(cm_modem *m, IoArgs<T> io, cudaStream_t st);
+template <typename T> int qam_decode(cm_modem *m, IoArgs<T> io, int mode, cudaStream_t st);
 
 // true when some IIR use-site of the handle spans several super-chunks (long lines): use the multi-warp kernels
 template <typename T>
@@ -242,12 +243,59 @@ CM_INSTANTIATE(CM_COMB_INST(float), CM_COMB_INST(double))
 #endif
 
 #if CM_PART(3)
+// Comb decoders with a luma notch: run the decoder with the (y, u, v) of the rows that take the notch diverted to a
+// scratch, then k_notch_rows.  2-line decoders notch the rows that have a predecessor (comb.py:48-55), the 3-line
+// decoders every row they keep (comb.py:96-109, pal.py:191-228).
+template <typename T>
+static int qam_decode_notched(cm_modem *m, IoArgs<T> io, cudaStream_t st) {
+    const DevParams<T> &p = params_of<T>(m);
+    if (io.out_count <= 0) return CM_OK;
+    const bool three_line = p.kind == CM_KIND_NTSC_3D ||
+                            (p.kind == CM_KIND_PAL_3D && (p.flags & (CM_FLAG_PAL3D_SIN | CM_FLAG_PAL3D_COS)));
+    const size_t smem = (size_t)p.n1p * sizeof(T);
+    int rc = set_smem(k_notch_rows<T>, smem);
+    if (rc) return rc;
+    const int chunk = io.nframes < 64 ? io.nframes : 64;
+    const size_t frame_elems = (size_t)io.nrows * 3 * p.Wo;
+    T *yuv = (T *)cm_ensure_aux(m, (size_t)chunk * frame_elems * sizeof(T), 1);
+    if (!yuv) return CM_ERR_NOMEM;
+    const size_t in_frame = (size_t)io.nrows * p.Wc, out_frame = (size_t)io.nrows * p.Wo * 3;
+    for (int f0 = 0; f0 < io.nframes; f0 += chunk) {
+        IoArgs<T> c = io;
+        c.nframes = io.nframes - f0 < chunk ? io.nframes - f0 : chunk;
+        c.first_frame = io.first_frame + f0;
+        c.yuv = yuv;
+        if (c.in_u8) c.in_u8 += (size_t)f0 * in_frame;
+        if (c.in_f) c.in_f += (size_t)f0 * in_frame;
+        if (c.out_u8) c.out_u8 += (size_t)f0 * out_frame;
+        if (c.out_f) c.out_f += (size_t)f0 * out_frame;
+        rc = qam_decode<T>(m, c, CM_MODE_DEFAULT, st);
+        if (rc) return rc;
+        IoArgs<T> n = c;
+        if (!three_line && n.out_begin < 2) {
+            n.out_count -= 2 - n.out_begin;
+            n.out_begin = 2;
+        }
+        if (n.out_count <= 0) continue;
+        {
+            LaunchTimer lt(m, CM_K_DECODE_OTHER, st);
+            k_notch_rows<T><<<dim3((unsigned)n.out_count, 1u, (unsigned)n.nframes), CM_ROW_THREADS, smem, st>>>(p, n);
+        }
+        cm_count_launch();
+        CUDA_TRY(cudaGetLastError());
+    }
+    return CM_OK;
+}
+
 template <typename T>
 int qam_decode(cm_modem *m, IoArgs<T> io, int mode, cudaStream_t st) {
     const DevParams<T> &p = params_of<T>(m);
     if (mode == CM_MODE_BANDSPLIT_NOSTRIP) return launch_bandsplit<T>(m, io, 2, st);
+    if ((p.flags & CM_FLAG_NOTCH) && p.kind != CM_KIND_QAM_BANDSPLIT && !io.yuv) return qam_decode_notched<T>(m, io, st);
     IoArgs<T> top, rest;
     split_top(io, top, rest);
+    if (!(p.kind == CM_KIND_PAL_3D && (p.flags & (CM_FLAG_PAL3D_SIN | CM_FLAG_PAL3D_COS))))
+        top.yuv = nullptr;                      // field tops of the 2-line decoders bypass the notch (comb.py:48-49)
     int rc;
     switch (p.kind) {
         case CM_KIND_QAM_BANDSPLIT:

@@ -851,6 +851,43 @@ k_qam_combine(const __grid_constant__ DevParams<T> p, const __grid_constant__ Io
 }
 
 // ------------------------------------------------------------------------------------------------------------
+// Luma notch of the comb decoders (non-default knob notch=Q: comb.py:18-20, 54-55, 108-109, pal.py:227-228).  The
+// decoders above leave (y, u, v) of the rows that take the notch in io.yuv (store_rgb4); this kernel filters y along
+// the row (one biquad at fsc, zero initial state, utils.py:28-36) and finishes with the inverse matrix.  One row per
+// CTA.
+// ------------------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(CM_ROW_THREADS, 8)
+k_notch_rows(const __grid_constant__ DevParams<T> p, const __grid_constant__ IoArgs<T> io) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T *y = reinterpret_cast<T *>(smem_raw);
+    const int W = p.Wo, N1 = p.n1p;
+    const int row = io.out_begin + blockIdx.x, f = blockIdx.z;
+    const T *src = io.yuv + ((size_t)f * io.nrows + row) * 3 * W;
+    for (int x = 4 * threadIdx.x; x < W; x += 4 * blockDim.x) {
+        T v[4];
+        ld4(src + x, v);
+        st4(y + x, v);
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        const FiltHdr &fn = p.filt[QF_NOTCH];
+        warp_fill_tail<T, 1>(y, N1, W, N1);
+        warp_iir<T, 1>(p.tab + fn.off, fn, [&](int q, int, int) { return y[q]; }, [&](int j, T v) { y[j] = v; });
+    }
+    __syncthreads();
+    IoArgs<T> out = io;
+    out.yuv = nullptr;
+    for (int x = 4 * threadIdx.x; x < W; x += 4 * blockDim.x) {
+        T yy[4], u[4], v[4];
+        ld4(y + x, yy);
+        ld4(src + W + x, u);
+        ld4(src + 2 * W + x, v);
+        store_rgb4(p, out, f, row, x, yy, u, v);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
 // Line-comb decoders that work on the band-passed 2x signal B[k] = BP(up2 c[k]) of neighbouring rows.
 // qam.demodulate (qam.py:43-58) is linear in its composite argument, so demodulating a line difference equals
 // combining the B's first; likewise the wrappers' 0.5*(a+b) averages commute with the low-pass and down2.

@@ -9,6 +9,7 @@
 #define QF_BS2X 2        /* _remove_chroma2x                          qam.py:17   n = 2W  */
 #define QF_DEMOD_LP 3    /* _demod_lowpass                            qam.py:18   n = 2W  */
 #define QF_PALD_LP 4     /* PalDModem._filter                         pal.py:67   n = 2W  */
+#define QF_NOTCH 5       /* comb._notch(backend, q): luma notch at fsc comb.py:18-20 n = W  (optional) */
 #define QR_UP2 0         /* resample_poly(up=2, down=1) */
 #define QR_DOWN2 1       /* resample_poly(up=1, down=2) */
 #define QP_STEP1X 0      /* carrier advance per sample at 1x rate, turns (2*carrier_phase_step/2pi, qam.py:24) */

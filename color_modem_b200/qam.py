@@ -55,6 +55,7 @@ class AbstractQamColorModem(GpuModem, utils.ConstantFrequencyCarrier):
     DEC = None
     kind = N.KIND_QAM_BANDSPLIT
     flags = 0
+    _notch_q = 0.0        # comb decoders: Q of the luma notch (comb.py:18-20); 0 = no notch
 
     def __init__(self, line_config, config, precision='fp32'):
         GpuModem.__init__(self, line_config, precision)
@@ -98,6 +99,11 @@ class AbstractQamColorModem(GpuModem, utils.ConstantFrequencyCarrier):
         d.phases[S.QP_STEP2X] = utils.turns_fixed(q.wc / 4.0)
         d.phases[S.QP_BP_SHIFT] = utils.radians_fixed(q.extract_chroma_phase_shift)
         d.phases[S.QP_HALF_LS] = utils.radians_fixed(0.5 * self.line_shift)
+        if self._notch_q:
+            import scipy.signal
+            b, a = scipy.signal.iirnotch(2.0 * fsc / self.line_config.fs, self._notch_q)        # comb.py:18-20
+            put_filter(d, S.QF_NOTCH, utils.FilterFunction(b, a, wp=0.0, btype='bandstop', shift=True), W, 1)
+            d.flags |= N.FLAG_NOTCH
 
     def _flags(self):
         return self.flags

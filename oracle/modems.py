@@ -23,7 +23,8 @@ vectorised over all rows of a frame:
     niir_hue    HueCorrectingNiirModem         (niir.py:166-202)
     protosecam  ProtoSecamModem                (protosecam.py:28-112)
     mac         MacModem                       (mac.py:15-125)
-``chroma_avg=True`` wraps the encoder in ColorAveragingModem (comb.py:130-167).
+``chroma_avg=True`` wraps the encoder in ColorAveragingModem (comb.py:130-167); ``notch=Q`` gives the comb decoders
+the luma notch of comb.py:18-20.
 """
 import collections
 import fractions
@@ -33,8 +34,8 @@ import numpy as np
 from . import dsp, presets
 from .raster import Raster
 
-ModemSpec = collections.namedtuple('ModemSpec', 'kind variant width height standard chroma_avg')
-ModemSpec.__new__.__defaults__ = (None, None, False)
+ModemSpec = collections.namedtuple('ModemSpec', 'kind variant width height standard chroma_avg notch')
+ModemSpec.__new__.__defaults__ = (None, None, False, 0.0)
 
 TWO_PI = 2.0 * np.pi
 
@@ -127,6 +128,11 @@ class _QamModem(_Base):
         fs = self.raster.fs
         self.qam = QamCore(2.0 * cfg.fsc / fs, 2.0 * cfg.bw3 / fs, 2.0 * cfg.bw20 / fs)   # qam.py:65-66
         self.line_shift = self.raster.line_shift(cfg.fsc)
+        self.notch = None
+        if getattr(spec, 'notch', 0.0):                                               # comb.py:18-20
+            import scipy.signal
+            b, a = scipy.signal.iirnotch(2.0 * cfg.fsc / fs, spec.notch)
+            self.notch = dsp.Filt(b, a, 0.0, 'bandstop', True)
 
     def start_phase(self, frame, lines):
         return self.raster.start_phase(self.cfg.fsc, frame, lines)
@@ -192,6 +198,8 @@ class NtscComb(Ntsc):
     def demodulate_planes(self, frame, comp):
         u, v = self.comb_stage_uv(frame, comp)
         y = comp - self.remod(frame, self.rows, u, v)                             # comb.py:52-53
+        if self.notch:
+            y = self.notch(y)                                                     # comb.py:54-55 (combed rows only)
         yt, _, _ = self.bandsplit(frame, self.rows[:2], comp[:2], True)           # field top: comb.py:48-49
         y[:2] = yt
         return y, u, v
@@ -207,6 +215,8 @@ class Ntsc3D(NtscComb):
         u = 0.5 * (u0 + u1)
         v = 0.5 * (v0 + v1)
         y = comp - self.remod(frame, self.rows, u, v)
+        if self.notch:
+            y = self.notch(y)                                                     # comb.py:108-109: every kept row
         return y, u, v
 
 
@@ -256,6 +266,8 @@ class PalD(PalS):
     def _pald_planes(self, frame, comp):
         u, v = self.combed_uv(frame, self.rows, _rows_prev(comp), comp)
         y = comp - self.remod(frame, self.rows, u, v)
+        if self.notch:
+            y = self.notch(y)                                                     # comb.py:54-55 (combed rows only)
         yt, ut, vt = self.bandsplit(frame, self.rows[:2], comp[:2], True)
         y[:2], u[:2], v[:2] = yt, ut, vt
         return y, u, v
@@ -304,6 +316,8 @@ class Pal3D(PalD):
         _, ut, vt = self.bandsplit(frame, self.rows[:2], comp[:2], False)
         u[:2], v[:2] = ut, vt
         y = comp - self.remod(frame, self.rows, u, v)                             # pal.py:225-226
+        if self.notch:
+            y = self.notch(y)                                                     # pal.py:227-228: every kept row
         return y, u, v
 
 

@@ -6,11 +6,12 @@ Frames are small (24 rows) with an explicit line standard so the fixtures stay a
 """
 import collections
 
-Case = collections.namedtuple('Case', 'kind variant width height standard chroma_avg frame seed content')
+Case = collections.namedtuple('Case', 'kind variant width height standard chroma_avg frame seed content notch')
+Case.__new__.__defaults__ = (0.0,)        # notch: Q of the luma notch of the comb decoders (comb.py:18-20), 0 = off
 
 
-def _c(kind, variant, std, frame, width=720, height=24, avg=False, seed=None, content='smooth'):
-    return Case(kind, variant, width, height, std, avg, frame, frame * 7 + 1 if seed is None else seed, content)
+def _c(kind, variant, std, frame, width=720, height=24, avg=False, seed=None, content='smooth', notch=0.0):
+    return Case(kind, variant, width, height, std, avg, frame, frame * 7 + 1 if seed is None else seed, content, notch)
 
 
 GOLDEN_CASES = [
@@ -57,11 +58,18 @@ GOLDEN_CASES = [
     _c('ntsc_3d', 'NTSC', 'NTSC_525', 1, width=1920),
     _c('mac', 'D2MAC_7MHZ', 'GERBER_625', 1, width=1920),
     _c('niir_hue', 'PAL', 'GERBER_625', 3, width=1920),
+    # luma notch of the comb decoders (non-default knob notch=Q, comb.py:18-20,54-55,108-109, pal.py:227-228)
+    _c('ntsc_comb', 'NTSC', 'NTSC_525', 3, notch=8.0),
+    _c('ntsc_3d', 'NTSC', 'NTSC_525', 4, notch=4.0),
+    _c('pal_d', 'PAL', 'GERBER_625', 4, notch=8.0),
+    _c('pal_3d', 'PAL', 'GERBER_625', 5, notch=2.0, content='noise'),
+    _c('pal_d', 'PAL', 'GERBER_625', 3, width=1920, notch=12.0),
 ]
 
 FLOAT_ROWS = (1, 10, 22)   # rows whose float64 composite / RGB lines are stored: field top, interior, field bottom
 
 
 def case_id(c):
-    return '%s-%s-%dx%d-%s%s-f%d-%s' % (c.kind, c.variant, c.width, c.height, c.standard,
-                                        '-avg' if c.chroma_avg else '', c.frame, c.content)
+    return '%s-%s-%dx%d-%s%s-f%d-%s%s' % (c.kind, c.variant, c.width, c.height, c.standard,
+                                          '-avg' if c.chroma_avg else '', c.frame, c.content,
+                                          '-notch%g' % c.notch if c.notch else '')

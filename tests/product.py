@@ -11,14 +11,15 @@ def make_modem(c, precision='fp32'):
     std = getattr(LineStandard, c.standard) if c.standard else None
     lc = LineConfig((c.width, c.height), std)
     k, v = c.kind, c.variant
+    notch = getattr(c, 'notch', 0.0)
     if k == 'ntsc':
         m = ntsc.NtscModem(lc, getattr(ntsc.NtscVariant, v), precision=precision)
     elif k == 'ntsc_comb':
-        m = ntsc.NtscCombModem(lc, getattr(ntsc.NtscVariant, v), precision=precision)
+        m = ntsc.NtscCombModem(lc, getattr(ntsc.NtscVariant, v), notch, precision=precision)
     elif k == 'ntsc_3d':
-        m = comb.Simple3DCombModem(ntsc.NtscCombModem(lc, getattr(ntsc.NtscVariant, v), precision=precision))
+        m = comb.Simple3DCombModem(ntsc.NtscCombModem(lc, getattr(ntsc.NtscVariant, v), precision=precision), notch)
     elif k == 'pal_3d':
-        m = pal.Pal3DModem(lc, getattr(pal.PalVariant, v), precision=precision)
+        m = pal.Pal3DModem(lc, getattr(pal.PalVariant, v), notch, precision=precision)
     elif k == 'secam':
         m = secam.SecamModem(lc, getattr(secam.SecamVariant, v), precision=precision)
     elif k == 'niir':
@@ -32,7 +33,7 @@ def make_modem(c, precision='fp32'):
     elif k == 'pal_s':
         m = pal.PalSModem(lc, getattr(pal.PalVariant, v), precision=precision)
     elif k == 'pal_d':
-        m = pal.PalDModem(lc, getattr(pal.PalVariant, v), precision=precision)
+        m = pal.PalDModem(lc, getattr(pal.PalVariant, v), notch, precision=precision)
     else:
         raise NotImplementedError(k)
     if c.chroma_avg:

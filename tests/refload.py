@@ -63,18 +63,19 @@ def load_reference():
         std = getattr(line.LineStandard, c.standard) if c.standard else None
         lc = line.LineConfig((c.width, c.height), std)
         k, v = c.kind, c.variant
+        notch = getattr(c, 'notch', 0.0)
         if k == 'ntsc':
             m = ntsc.NtscModem(lc, getattr(ntsc.NtscVariant, v))
         elif k == 'ntsc_comb':
-            m = ntsc.NtscCombModem(lc, getattr(ntsc.NtscVariant, v))
+            m = ntsc.NtscCombModem(lc, getattr(ntsc.NtscVariant, v), notch)
         elif k == 'ntsc_3d':
-            m = comb.Simple3DCombModem(ntsc.NtscCombModem(lc, getattr(ntsc.NtscVariant, v)))
+            m = comb.Simple3DCombModem(ntsc.NtscCombModem(lc, getattr(ntsc.NtscVariant, v)), notch)
         elif k == 'pal_s':
             m = pal.PalSModem(lc, getattr(pal.PalVariant, v))
         elif k == 'pal_d':
-            m = pal.PalDModem(lc, getattr(pal.PalVariant, v))
+            m = pal.PalDModem(lc, getattr(pal.PalVariant, v), notch)
         elif k == 'pal_3d':
-            m = pal.Pal3DModem(lc, getattr(pal.PalVariant, v))
+            m = pal.Pal3DModem(lc, getattr(pal.PalVariant, v), notch)
         elif k == 'secam':
             m = secam.SecamModem(lc, getattr(secam.SecamVariant, v))
         elif k == 'niir':
