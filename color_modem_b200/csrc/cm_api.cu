@@ -129,7 +129,7 @@ static void fill_params(const cm_desc &d, DevParams<T> &p, const FiltHdr *fh, co
     p.line_shift = d.line_shift_turns;
     for (int i = 0; i < CM_NPHASE; ++i) p.phases[i] = d.phases[i];
     for (int i = 0; i < CM_NSCAL; ++i) p.scalars[i] = (T)d.scalars[i];
-    for (int i = 0; i < 9; ++i) { p.enc[i] = (T)d.enc_matrix[i]; p.dec[i] = (T)d.dec_matrix[i]; }
+    for (int i = 0; i < 9; ++i) { p.enc[i] = (T)d.enc_matrix[i]; p.dec[i] = (T)d.dec_matrix[i]; p.encd[i] = d.enc_matrix[i]; }
     for (int i = 0; i < CM_NFILT; ++i) p.filt[i] = fh[i];
     // line-buffer geometry: every buffer that feeds an IIR is padded to the site's 32*L*nsuper
     auto up4 = [](int v) { return (v + 3) & ~3; };
@@ -377,10 +377,10 @@ template <typename T>
 static int run_ex(cm_modem *m, bool encode, const cm_window *win, const uint8_t *in_u8, const void *in_f,
                   uint8_t *out_u8, void *out_f, int64_t first_frame, int32_t nframes, void *stream) {
     if (!m) return fail(CM_ERR_INVALID, "null handle%s");
+    if (nframes < 0 || first_frame < 0) return fail(CM_ERR_INVALID, "bad frame range%s");
+    if (nframes == 0) return CM_OK;                    // an empty batch may come with null buffers
     if ((in_u8 == nullptr) == (in_f == nullptr)) return fail(CM_ERR_INVALID, "exactly one input buffer required%s");
     if (!out_u8 && !out_f) return fail(CM_ERR_INVALID, "no output buffer%s");
-    if (nframes < 0 || first_frame < 0) return fail(CM_ERR_INVALID, "bad frame range%s");
-    if (nframes == 0) return CM_OK;
     IoArgs<T> io;
     memset(&io, 0, sizeof(io));
     io.in_u8 = in_u8;

@@ -47,6 +47,8 @@ struct DevParams {
     T scalars[CM_NSCAL];
     T enc[9];
     T dec[9];
+    double encd[9];   // encoder matrix in float64 (NIIR: the *direction* of the chroma vector is decided in float64 with the
+                      // reference's own operation order, see cm_niir.cuh)
     FiltHdr filt[CM_NFILT];
     ResHdr res[CM_NRES];
     const T *tab;

@@ -22,6 +22,39 @@
 template <typename T>
 __device__ __forceinline__ T &poly3(T *buf, int hb, int j) { return buf[(j % 3) * hb + j / 3]; }
 
+// The NIIR encoders add their +0.1 saturation offset along the *direction* of the chroma vector (niir.py:43-48,
+// 186-197).  For grey pixels that vector is zero in exact arithmetic, and the reference's direction is whatever the
+// float64 rounding residue (~1e-17) of its matrix product points at — an O(0.1) effect on the composite decided by the
+// last bit.  To stay a drop-in on such pixels (every black, white or grey area of a real picture) the vector is
+// computed here in float64 with the reference's own operation order and no FMA contraction, from u8 / 255.0 exactly as
+// image.py:35-37 does; only the result is rounded to T.
+template <typename T>
+__device__ __forceinline__ void niir_load_rgb4_f64(const IoArgs<T> &io, size_t px, double r[4], double g[4], double b[4]) {
+    if (io.in_f) {
+        T v[12];
+#pragma unroll
+        for (int q = 0; q < 3; ++q) ld4(io.in_f + px * 3 + 4 * q, v + 4 * q);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { r[i] = (double)v[3 * i]; g[i] = (double)v[3 * i + 1]; b[i] = (double)v[3 * i + 2]; }
+    } else {
+        const uint32_t *w = reinterpret_cast<const uint32_t *>(io.in_u8 + px * 3);
+        const uint32_t ww[3] = {__ldg(w), __ldg(w + 1), __ldg(w + 2)};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int k = 3 * i;
+            r[i] = __ddiv_rn((double)((ww[k >> 2] >> (8 * (k & 3))) & 0xff), 255.0);
+            g[i] = __ddiv_rn((double)((ww[(k + 1) >> 2] >> (8 * ((k + 1) & 3))) & 0xff), 255.0);
+            b[i] = __ddiv_rn((double)((ww[(k + 2) >> 2] >> (8 * ((k + 2) & 3))) & 0xff), 255.0);
+        }
+    }
+}
+
+// niir.py:35-38: c0 * r + c1 * g + c2 * b evaluated left to right in float64 (c2 carries the sign of the reference's "-")
+__device__ __forceinline__ void niir_chroma_f64(const double *e, double r, double g, double b, double &db, double &dr) {
+    db = __dadd_rn(__dadd_rn(__dmul_rn(e[3], r), __dmul_rn(e[4], g)), __dmul_rn(e[5], b));
+    dr = __dadd_rn(__dadd_rn(__dmul_rn(e[6], r), __dmul_rn(e[7], g)), __dmul_rn(e[8], b));
+}
+
 // ------------------------------------------------------------------------------------------------------------
 // Encode.  2 warps per row.  smem: R * 3 * N1   (luma | db | dr)
 // ------------------------------------------------------------------------------------------------------------
@@ -41,47 +74,83 @@ k_niir_encode(const __grid_constant__ DevParams<T> p, const __grid_constant__ Io
         T *ys = sm + (size_t)k * 3 * N1, *bs = ys + N1, *rs_ = bs + N1;
         for (int q = threadIdx.x; q < W4; q += blockDim.x) {
             const int x = 4 * q;
-            T r[4], gg[4], b[4], y[4], db[4], dr[4];
-            load_rgb4(io, ((size_t)g.fidx * io.nrows + row) * W + x, r, gg, b);
+            const size_t px = ((size_t)g.fidx * io.nrows + row) * W + x, pxn = ((size_t)g.fidx * io.nrows + nrow) * W + x;
+            T r[4], gg[4], b[4], r2[4], g2[4], b2[4], y[4], db[4], dr[4];
+            load_rgb4(io, px, r, gg, b);
+            if (avg || hue) load_rgb4(io, pxn, r2, g2, b2);
+            bool exact[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 y[i] = p.enc[0] * r[i] + p.enc[1] * gg[i] + p.enc[2] * b[i];
-                db[i] = p.enc[3] * r[i] + p.enc[4] * gg[i] + p.enc[5] * b[i];
-                dr[i] = p.enc[6] * r[i] + p.enc[7] * gg[i] + p.enc[8] * b[i];
-            }
-            if (avg || hue) load_rgb4(io, ((size_t)g.fidx * io.nrows + nrow) * W + x, r, gg, b);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                T mag_out, vb = db[i], vr = dr[i];
+                T vb = p.enc[3] * r[i] + p.enc[4] * gg[i] + p.enc[5] * b[i];
+                T vr = p.enc[6] * r[i] + p.enc[7] * gg[i] + p.enc[8] * b[i];
+                T mag_out;
                 if (hue) {
                     // niir.py:186-197: hue of the saturation-weighted mean of this row and the next, this row's saturation
-                    const T nb = p.enc[3] * r[i] + p.enc[4] * gg[i] + p.enc[5] * b[i];
-                    const T nr = p.enc[6] * r[i] + p.enc[7] * gg[i] + p.enc[8] * b[i];
-                    const T ls = Real<T>::sqrt_(vb * vb + vr * vr), s = Real<T>::sqrt_(nb * nb + nr * nr);
-                    T div = ls + s;
+                    const T nb = p.enc[3] * r2[i] + p.enc[4] * g2[i] + p.enc[5] * b2[i];
+                    const T nr = p.enc[6] * r2[i] + p.enc[7] * g2[i] + p.enc[8] * b2[i];
+                    const T ls = Real<T>::sqrt_(vb * vb + vr * vr), sn = Real<T>::sqrt_(nb * nb + nr * nr);
+                    T div = ls + sn;
                     if (div == (T)0) div = (T)1;
-                    const T ab = (vb * ls + nb * s) / div, ar = (vr * ls + nr * s) / div;
+                    const T ab = (vb * ls + nb * sn) / div, ar = (vr * ls + nr * sn) / div;
                     mag_out = ls + (T)0.1;
                     vb = ab;
                     vr = ar;
                 } else {
                     if (avg) {
-                        const T nb = p.enc[3] * r[i] + p.enc[4] * gg[i] + p.enc[5] * b[i];
-                        const T nr = p.enc[6] * r[i] + p.enc[7] * gg[i] + p.enc[8] * b[i];
+                        const T nb = p.enc[3] * r2[i] + p.enc[4] * g2[i] + p.enc[5] * b2[i];
+                        const T nr = p.enc[6] * r2[i] + p.enc[7] * g2[i] + p.enc[8] * b2[i];
                         vb = (T)0.5 * (nb + vb);
                         vr = (T)0.5 * (nr + vr);
                     }
                     mag_out = Real<T>::sqrt_(vb * vb + vr * vr) + (T)0.1;      // niir.py:43
                 }
-                // mag_out * (sin, cos)(atan2(vb, vr));  atan2(0, 0) = 0 -> (0, mag_out)
+                // mag_out * (sin, cos)(atan2(vb, vr))
                 const T m2 = vb * vb + vr * vr;
-                if (m2 > (T)0) {
-                    const T sc = mag_out * Real<T>::rsqrt_(m2);
-                    db[i] = vb * sc;
-                    dr[i] = vr * sc;
-                } else {
-                    db[i] = (T)0;
-                    dr[i] = mag_out;
+                // The direction of a vector shorter than 1e-4 is not reliable in fp32 (and is rounding noise of the
+                // reference itself when it is ~1e-17): redo those pixels in float64 the reference's way.  The fp64 build
+                // always takes the exact path.
+                exact[i] = sizeof(T) == 8 || !(m2 >= (T)1e-8);
+                const T sc = mag_out * Real<T>::rsqrt_(m2);
+                db[i] = vb * sc;
+                dr[i] = vr * sc;
+            }
+            if (exact[0] || exact[1] || exact[2] || exact[3]) {
+                double rd[4], gd[4], bd[4], r2d[4], g2d[4], b2d[4];
+                niir_load_rgb4_f64(io, px, rd, gd, bd);
+                if (avg || hue) niir_load_rgb4_f64(io, pxn, r2d, g2d, b2d);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    if (!exact[i]) continue;
+                    double vb, vr, nb = 0.0, nr = 0.0, mag_out;
+                    niir_chroma_f64(p.encd, rd[i], gd[i], bd[i], vb, vr);
+                    if (avg || hue) niir_chroma_f64(p.encd, r2d[i], g2d[i], b2d[i], nb, nr);
+                    if (hue) {
+                        const double ls = sqrt(__dadd_rn(__dmul_rn(vb, vb), __dmul_rn(vr, vr)));
+                        const double sn = sqrt(__dadd_rn(__dmul_rn(nb, nb), __dmul_rn(nr, nr)));
+                        double div = __dadd_rn(ls, sn);
+                        if (div == 0.0) div = 1.0;
+                        const double ab = __ddiv_rn(__dadd_rn(__dmul_rn(vb, ls), __dmul_rn(nb, sn)), div);
+                        const double ar = __ddiv_rn(__dadd_rn(__dmul_rn(vr, ls), __dmul_rn(nr, sn)), div);
+                        mag_out = ls + 0.1;
+                        vb = ab;
+                        vr = ar;
+                    } else {
+                        if (avg) {                                                    // comb.py:149-150
+                            vb = __dmul_rn(0.5, __dadd_rn(nb, vb));
+                            vr = __dmul_rn(0.5, __dadd_rn(nr, vr));
+                        }
+                        mag_out = sqrt(__dadd_rn(__dmul_rn(vb, vb), __dmul_rn(vr, vr))) + 0.1;
+                    }
+                    const double m2 = vb * vb + vr * vr;
+                    if (m2 > 0.0) {
+                        const double sc = mag_out / sqrt(m2);
+                        db[i] = (T)(vb * sc);
+                        dr[i] = (T)(vr * sc);
+                    } else {                          // atan2(0, 0) = 0 -> (sin, cos) = (0, 1)
+                        db[i] = (T)0;
+                        dr[i] = (T)mag_out;
+                    }
                 }
             }
             st4(ys + x, y);

@@ -1,0 +1,119 @@
+"""Edge cases of the CUDA path (run with -m gpu): empty batches, odd and tiny heights (one row per field, fields of
+unequal length, row counts that do not divide the rows-per-CTA / rows-per-segment constants of the kernels), large
+absolute frame numbers (carrier phase wraps), unsupported widths.  Results are held to the same +-1 LSB bound against
+the float64 oracle as the golden cases."""
+import numpy as np
+import pytest
+
+import oracle
+from oracle import frame as oframe
+from color_modem_b200 import comb
+from color_modem_b200.color import ntsc, pal, secam, niir, protosecam, mac
+from color_modem_b200.line import LineConfig, LineStandard as LS
+from color_modem_b200.synth import synth_frames_u8
+
+pytestmark = pytest.mark.gpu
+
+
+def _lsb(a, b):
+    return int(np.abs(a.astype(np.int32) - b.astype(np.int32)).max())
+
+
+MAKERS = {
+    'ntsc': ('NTSC', 'NTSC_525', lambda lc: ntsc.NtscModem(lc)),
+    'ntsc_comb': ('NTSC', 'NTSC_525', lambda lc: ntsc.NtscCombModem(lc)),
+    'ntsc_3d': ('NTSC', 'NTSC_525', lambda lc: comb.Simple3DCombModem(ntsc.NtscCombModem(lc))),
+    'pal_s': ('PAL', 'GERBER_625', lambda lc: pal.PalSModem(lc)),
+    'pal_d': ('PAL', 'GERBER_625', lambda lc: pal.PalDModem(lc)),
+    'pal_3d': ('PAL', 'GERBER_625', lambda lc: pal.Pal3DModem(lc)),
+    'secam': ('SECAM', 'GERBER_625', lambda lc: secam.SecamModem(lc)),
+    'niir': ('PAL', 'GERBER_625', lambda lc: niir.NiirModem(lc)),
+    'niir_hue': ('PAL', 'GERBER_625', lambda lc: niir.HueCorrectingNiirModem(lc)),
+    'protosecam': ('SECAM_1957', 'FRENCH_819', lambda lc: protosecam.ProtoSecamModem(lc)),
+    'mac': ('D2MAC_12MHZ', 'GERBER_625', lambda lc: mac.MacModem(lc)),
+}
+
+
+def _roundtrip_vs_oracle(kind, h, w=720, frames=(0,), n=None):
+    import torch
+    variant, std, make = MAKERS[kind]
+    m = make(LineConfig((w, h), getattr(LS, std)))
+    om = oracle.build(oracle.ModemSpec(kind, variant, w, h, std))
+    first = frames[0]
+    n = n or len(frames)
+    rgb = synth_frames_u8(n, h, w, first_frame=first, seed=11)
+    comp = m.encode_frames(torch.from_numpy(rgb).cuda(), first_frame=first)
+    out = m.decode_frames(comp, first_frame=first)
+    comp, out = comp.cpu().numpy(), out.cpu().numpy()
+    for i in range(n):
+        assert _lsb(comp[i], oframe.encode_frame_u8(om, first + i, rgb[i])) <= 1, (kind, h, i)
+        assert _lsb(out[i], oframe.decode_frame_u8(om, first + i, comp[i])) <= 1, (kind, h, i)
+
+
+@pytest.mark.parametrize('h', [2, 3, 5, 7, 17, 34, 35])
+@pytest.mark.parametrize('kind', sorted(MAKERS))
+def test_odd_and_tiny_heights(kind, h, cuda_required):
+    _roundtrip_vs_oracle(kind, h, n=3)
+
+
+@pytest.mark.parametrize('kind', ['ntsc_3d', 'pal_d', 'pal_3d', 'secam', 'niir'])
+def test_large_absolute_frame_numbers(kind, cuda_required):
+    # 2^31 + 12345: beyond int32, far beyond any frame cycle of the carrier (4 frames NTSC, 8 frames PAL)
+    _roundtrip_vs_oracle(kind, 24, frames=(2147483648 + 12345,), n=2)
+
+
+def test_empty_batch(cuda_required):
+    import torch
+    m = pal.PalDModem(LineConfig((720, 24), LS.GERBER_625))
+    comp = m.encode_frames(torch.empty((0, 24, 720, 3), dtype=torch.uint8, device='cuda'))
+    assert tuple(comp.shape) == (0, 24, 720)
+    out = m.decode_frames(comp)
+    assert tuple(out.shape) == (0, 24, 720, 3)
+    assert m.encode_frames_host(np.empty((0, 24, 720, 3), np.uint8)).shape == (0, 24, 720)
+
+
+def test_batch_not_multiple_of_chunks(cuda_required):
+    """65 and 129 frames: one more than the 64-frame pass-1/pass-2 chunk of the comb decoders; 17: one more than the
+    16-frame chunk of the host entry points."""
+    import torch
+    m = comb.Simple3DCombModem(ntsc.NtscCombModem(LineConfig((720, 24), LS.NTSC_525)))
+    rgb = synth_frames_u8(129, 24, 720, first_frame=0, seed=4)
+    x = torch.from_numpy(rgb).cuda()
+    comp = m.encode_frames(x)
+    out = m.decode_frames(comp).cpu().numpy()
+    comp = comp.cpu().numpy()
+    for n in (17, 65):
+        c = m.encode_frames_host(rgb[:n], 0)
+        assert np.array_equal(c, comp[:n])
+        assert np.array_equal(m.decode_frames_host(c, 0), out[:n])
+    one = m.decode_frames(torch.from_numpy(comp[128:129]).cuda(), first_frame=128).cpu().numpy()
+    assert np.array_equal(one[0], out[128])
+
+
+def test_unsupported_width_is_a_clean_error(cuda_required):
+    import torch
+    m = pal.PalDModem(LineConfig((722, 24), LS.GERBER_625))        # not a multiple of 4
+    with pytest.raises((RuntimeError, ValueError, NotImplementedError)):
+        m.encode_frames(torch.zeros((1, 24, 722, 3), dtype=torch.uint8, device='cuda'))
+
+
+@pytest.mark.parametrize('kind', ['niir', 'niir_hue'])
+def test_niir_grey_pixels_follow_the_reference_rounding(kind, cuda_required):
+    """Grey pixels have zero chroma in exact arithmetic; the NIIR encoders nevertheless add their 0.1 saturation offset
+    along the direction of the float64 rounding residue of the reference's matrix product (niir.py:35-48).  The kernel
+    reproduces that residue (csrc/cm_niir.cuh: niir_chroma_f64), so flat grey areas, grey ramps and grey/colour edges
+    encode to the reference's bytes."""
+    import torch
+    from color_modem_b200.color import niir as pniir
+    h, w = 24, 720
+    rgb = synth_frames_u8(2, h, w, first_frame=3, seed=21)
+    rgb[:, :, 100:400, :] = rgb[:, :, 100:400, :1]                 # grey picture content (r = g = b)
+    rgb[:, 4:12, 400:600, :] = 0                                   # black
+    rgb[:, 12:20, 400:600, :] = 255                                # white
+    rgb[0, :, 600:700, :] = (np.arange(100, dtype=np.uint8) * 2)[None, :, None]   # grey ramp
+    lc = LineConfig((w, h), LS.GERBER_625)
+    m = pniir.NiirModem(lc) if kind == 'niir' else pniir.HueCorrectingNiirModem(lc)
+    om = oracle.build(oracle.ModemSpec(kind, 'PAL', w, h, 'GERBER_625'))
+    comp = m.encode_frames(torch.from_numpy(rgb).cuda(), first_frame=3).cpu().numpy()
+    for i in range(2):
+        assert _lsb(comp[i], oframe.encode_frame_u8(om, 3 + i, rgb[i])) <= 1

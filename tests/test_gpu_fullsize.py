@@ -93,32 +93,8 @@ def test_1000_frames_batch_invariance(which, cuda_required):
     assert np.array_equal(m.decode_frames_host(comp[lo:hi], lo), out[lo:hi])
     om = oracle.build(spec)
     for f in (0, 1, 500, 999):
-        ref = oframe.encode_frame_u8(om, f, rgb[f])
-        if which == 'niir_hue':
-            good = _hue_well_conditioned_rows(om, rgb[f])
-            assert good.mean() > 0.95
-            assert _lsb(comp[f][good], ref[good]) <= 1
-        else:
-            assert _lsb(comp[f], ref) <= 1
+        assert _lsb(comp[f], oframe.encode_frame_u8(om, f, rgb[f])) <= 1
         assert _lsb(out[f], oframe.decode_frame_u8(om, f, comp[f])) <= 1
-
-
-def _hue_well_conditioned_rows(om, rgb_u8, limit=1e4):
-    """HueCorrectingNiirModem takes the hue of the saturation-weighted mean of two lines' chroma vectors
-    (niir.py:187-194).  Where the two vectors cancel, the mean is ~0 and arctan2 of it is decided by the last bit of the
-    reference's own float64 rounding: the function is discontinuous there, and the encoder low-pass then spreads the
-    difference along the row.  Relative input perturbations d move the hue by d * cond with
-    cond = (sat_y^2 + sat_n^2) / |sat_y c_y + sat_n c_n|;  rows whose worst pixel has cond >= limit (fp32 epsilon x 1e4
-    x amplitude 0.6 ~ one tenth of an LSB) are excluded from the bit comparison.  On integer test pictures exact
-    cancellation does occur (a handful of rows per frame); even the fp64 build differs from the oracle there."""
-    rgb = rgb_u8 / 255.0
-    _, db, dr = om.encode_components(rgb[..., 0], rgb[..., 1], rgb[..., 2])
-    ndb, ndr = db[om.next_row], dr[om.next_row]
-    sat_y, sat_n = np.hypot(db, dr), np.hypot(ndb, ndr)
-    num = np.hypot(db * sat_y + ndb * sat_n, dr * sat_y + ndr * sat_n)
-    den = sat_y * sat_y + sat_n * sat_n
-    cond = np.where(num > 0, den / np.where(num > 0, num, 1.0), np.where(den > 0, np.inf, 0.0))
-    return cond.max(axis=1) < limit
 
 
 HD = [('ntsc_3d', 'NTSC443', 'NTSC_525',
