@@ -117,3 +117,36 @@ def test_niir_grey_pixels_follow_the_reference_rounding(kind, cuda_required):
     comp = m.encode_frames(torch.from_numpy(rgb).cuda(), first_frame=3).cpu().numpy()
     for i in range(2):
         assert _lsb(comp[i], oframe.encode_frame_u8(om, 3 + i, rgb[i])) <= 1
+
+
+def _special_frames(h, w):
+    """black, white, flat colour, 1-pixel impulses on grey, full-swing vertical stripes, hard colour edges"""
+    f = np.zeros((6, h, w, 3), np.uint8)
+    f[1] = 255
+    f[2] = (200, 40, 90)
+    f[3] = 128
+    f[3, h // 2, w // 3] = (255, 0, 0)
+    f[3, h // 3, w // 2] = (0, 0, 255)
+    f[4, :, ::2] = 255
+    f[5, :, : w // 2] = (255, 255, 0)
+    f[5, :, w // 2:] = (0, 0, 255)
+    f[5, h // 2:, :] = f[5, h // 2:, ::-1]
+    return f
+
+
+@pytest.mark.parametrize('kind', sorted(MAKERS))
+def test_flat_and_extreme_pictures(kind, cuda_required):
+    """Pictures that exercise exact zeros, clipping and full-swing transients (the level map clips to [0, 1] on both
+    sides of the path, image.py:7-8)."""
+    import torch
+    h, w = 24, 720
+    variant, std, make = MAKERS[kind]
+    m = make(LineConfig((w, h), getattr(LS, std)))
+    om = oracle.build(oracle.ModemSpec(kind, variant, w, h, std))
+    rgb = _special_frames(h, w)
+    comp = m.encode_frames(torch.from_numpy(rgb).cuda(), first_frame=2)
+    out = m.decode_frames(comp, first_frame=2)
+    comp, out = comp.cpu().numpy(), out.cpu().numpy()
+    for i in range(rgb.shape[0]):
+        assert _lsb(comp[i], oframe.encode_frame_u8(om, 2 + i, rgb[i])) <= 1, (kind, 'encode', i)
+        assert _lsb(out[i], oframe.decode_frame_u8(om, 2 + i, comp[i])) <= 1, (kind, 'decode', i)
