@@ -34,8 +34,8 @@ import numpy as np
 from . import dsp, presets
 from .raster import Raster
 
-ModemSpec = collections.namedtuple('ModemSpec', 'kind variant width height standard chroma_avg notch')
-ModemSpec.__new__.__defaults__ = (None, None, False, 0.0)
+ModemSpec = collections.namedtuple('ModemSpec', 'kind variant width height standard chroma_avg notch opt')
+ModemSpec.__new__.__defaults__ = (None, None, False, 0.0, '')
 
 TWO_PI = 2.0 * np.pi
 
@@ -699,18 +699,21 @@ class Mac(_Base):
 # =================================================================================================
 def build(spec):
     kind = spec.kind
+    opt = getattr(spec, 'opt', '') or ''      # non-default constructor knobs, see tests/cases.py
     if kind in ('ntsc', 'ntsc_comb', 'ntsc_3d'):
         cls = {'ntsc': Ntsc, 'ntsc_comb': NtscComb, 'ntsc_3d': Ntsc3D}[kind]
         return cls(spec, presets.NTSC[spec.variant or 'NTSC'])
     if kind in ('pal_s', 'pal_d', 'pal_3d'):
         cls = {'pal_s': PalS, 'pal_d': PalD, 'pal_3d': Pal3D}[kind]
+        if kind == 'pal_3d':
+            return Pal3D(spec, presets.PAL[spec.variant or 'PAL'], use_sin=(opt != 'nosin'), use_cos=(opt != 'nocos'))
         return cls(spec, presets.PAL[spec.variant or 'PAL'])
     if kind == 'secam':
-        return Secam(spec, presets.SECAM[spec.variant or 'SECAM'])
+        return Secam(spec, presets.SECAM[spec.variant or 'SECAM'], alternate_phases=(opt == 'altph'))
     if kind in ('niir', 'niir_hue'):
         return (Niir if kind == 'niir' else NiirHue)(spec, presets.PAL[spec.variant or 'PAL'])
     if kind == 'protosecam':
-        return ProtoSecam(spec, presets.PROTOSECAM[spec.variant or 'SECAM_1957'])
+        return ProtoSecam(spec, presets.PROTOSECAM[spec.variant or 'SECAM_1957'], premod_luma_filter=(opt != 'noluma'))
     if kind == 'mac':
         v = spec.variant or 'D2MAC_12MHZ'
         return Mac(spec, presets.MAC[v] if isinstance(v, str) else int(v))

@@ -6,12 +6,16 @@ Frames are small (24 rows) with an explicit line standard so the fixtures stay a
 """
 import collections
 
-Case = collections.namedtuple('Case', 'kind variant width height standard chroma_avg frame seed content notch')
-Case.__new__.__defaults__ = (0.0,)        # notch: Q of the luma notch of the comb decoders (comb.py:18-20), 0 = off
+Case = collections.namedtuple('Case', 'kind variant width height standard chroma_avg frame seed content notch opt')
+# notch: Q of the luma notch of the comb decoders (comb.py:18-20), 0 = off
+# opt:   other non-default constructor knobs: 'nosin' / 'nocos' (Pal3DModem use_sin / use_cos = False, pal.py:131),
+#        'altph' (SecamModem alternate_phases=True, secam.py:163-166), 'noluma' (ProtoSecamModem premod_luma_filter=False)
+Case.__new__.__defaults__ = (0.0, '')
 
 
-def _c(kind, variant, std, frame, width=720, height=24, avg=False, seed=None, content='smooth', notch=0.0):
-    return Case(kind, variant, width, height, std, avg, frame, frame * 7 + 1 if seed is None else seed, content, notch)
+def _c(kind, variant, std, frame, width=720, height=24, avg=False, seed=None, content='smooth', notch=0.0, opt=''):
+    return Case(kind, variant, width, height, std, avg, frame, frame * 7 + 1 if seed is None else seed, content, notch,
+                opt)
 
 
 GOLDEN_CASES = [
@@ -64,6 +68,12 @@ GOLDEN_CASES = [
     _c('pal_d', 'PAL', 'GERBER_625', 4, notch=8.0),
     _c('pal_3d', 'PAL', 'GERBER_625', 5, notch=2.0, content='noise'),
     _c('pal_d', 'PAL', 'GERBER_625', 3, width=1920, notch=12.0),
+    # other non-default knobs
+    _c('pal_3d', 'PAL', 'GERBER_625', 4, opt='nosin'),
+    _c('pal_3d', 'PAL', 'GERBER_625', 2, opt='nocos'),
+    _c('pal_3d', 'PAL_M', 'NTSC_525', 1, opt='nocos', notch=6.0),
+    _c('secam', 'SECAM', 'GERBER_625', 6, opt='altph'),
+    _c('protosecam', 'SECAM_1957', 'FRENCH_819', 3, opt='noluma'),
 ]
 
 FLOAT_ROWS = (1, 10, 22)   # rows whose float64 composite / RGB lines are stored: field top, interior, field bottom
@@ -72,4 +82,4 @@ FLOAT_ROWS = (1, 10, 22)   # rows whose float64 composite / RGB lines are stored
 def case_id(c):
     return '%s-%s-%dx%d-%s%s-f%d-%s%s' % (c.kind, c.variant, c.width, c.height, c.standard,
                                           '-avg' if c.chroma_avg else '', c.frame, c.content,
-                                          '-notch%g' % c.notch if c.notch else '')
+                                          ('-notch%g' % c.notch if c.notch else '') + ('-' + c.opt if c.opt else ''))

@@ -22,7 +22,7 @@ for c in GOLDEN_CASES:
         continue
     g = np.load(os.path.join(HERE, 'golden', case_id(c) + '.npz'))
     rgb = synth_frames_u8(1, c.height, c.width, first_frame=c.frame, seed=c.seed, kind=c.content)[0]
-    om = oracle.build(oracle.ModemSpec(c.kind, c.variant, c.width, c.height, c.standard, c.chroma_avg, c.notch))
+    om = oracle.build(oracle.ModemSpec(c.kind, c.variant, c.width, c.height, c.standard, c.chroma_avg, c.notch, c.opt))
     rgb01 = rgb / 255.0
     comp_ref = om.encode(c.frame, rgb01)
     comp_in = oframe.composite_unlevel(g['comp_u8'] / 255.0)

@@ -12,6 +12,7 @@ def make_modem(c, precision='fp32'):
     lc = LineConfig((c.width, c.height), std)
     k, v = c.kind, c.variant
     notch = getattr(c, 'notch', 0.0)
+    opt = getattr(c, 'opt', '')
     if k == 'ntsc':
         m = ntsc.NtscModem(lc, getattr(ntsc.NtscVariant, v), precision=precision)
     elif k == 'ntsc_comb':
@@ -19,15 +20,15 @@ def make_modem(c, precision='fp32'):
     elif k == 'ntsc_3d':
         m = comb.Simple3DCombModem(ntsc.NtscCombModem(lc, getattr(ntsc.NtscVariant, v), precision=precision), notch)
     elif k == 'pal_3d':
-        m = pal.Pal3DModem(lc, getattr(pal.PalVariant, v), notch, precision=precision)
+        m = pal.Pal3DModem(lc, getattr(pal.PalVariant, v), notch, use_sin=(opt != 'nosin'), use_cos=(opt != 'nocos'), precision=precision)
     elif k == 'secam':
-        m = secam.SecamModem(lc, getattr(secam.SecamVariant, v), precision=precision)
+        m = secam.SecamModem(lc, getattr(secam.SecamVariant, v), alternate_phases=(opt == 'altph'), precision=precision)
     elif k == 'niir':
         m = niir.NiirModem(lc, getattr(pal.PalVariant, v), precision=precision)
     elif k == 'niir_hue':
         m = niir.HueCorrectingNiirModem(lc, getattr(pal.PalVariant, v), precision=precision)
     elif k == 'protosecam':
-        m = protosecam.ProtoSecamModem(lc, getattr(protosecam.ProtoSecamVariant, v), precision=precision)
+        m = protosecam.ProtoSecamModem(lc, getattr(protosecam.ProtoSecamVariant, v), premod_luma_filter=(opt != 'noluma'), precision=precision)
     elif k == 'mac':
         m = mac.MacModem(lc, getattr(mac.MacVariant, v), precision=precision)
     elif k == 'pal_s':

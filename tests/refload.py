@@ -64,6 +64,7 @@ def load_reference():
         lc = line.LineConfig((c.width, c.height), std)
         k, v = c.kind, c.variant
         notch = getattr(c, 'notch', 0.0)
+        opt = getattr(c, 'opt', '')
         if k == 'ntsc':
             m = ntsc.NtscModem(lc, getattr(ntsc.NtscVariant, v))
         elif k == 'ntsc_comb':
@@ -75,15 +76,15 @@ def load_reference():
         elif k == 'pal_d':
             m = pal.PalDModem(lc, getattr(pal.PalVariant, v), notch)
         elif k == 'pal_3d':
-            m = pal.Pal3DModem(lc, getattr(pal.PalVariant, v), notch)
+            m = pal.Pal3DModem(lc, getattr(pal.PalVariant, v), notch, use_sin=(opt != 'nosin'), use_cos=(opt != 'nocos'))
         elif k == 'secam':
-            m = secam.SecamModem(lc, getattr(secam.SecamVariant, v))
+            m = secam.SecamModem(lc, getattr(secam.SecamVariant, v), alternate_phases=(opt == 'altph'))
         elif k == 'niir':
             m = niir.NiirModem(lc, getattr(pal.PalVariant, v))
         elif k == 'niir_hue':
             m = niir.HueCorrectingNiirModem(lc, getattr(pal.PalVariant, v))
         elif k == 'protosecam':
-            m = protosecam.ProtoSecamModem(lc, getattr(protosecam.ProtoSecamVariant, v))
+            m = protosecam.ProtoSecamModem(lc, getattr(protosecam.ProtoSecamVariant, v), premod_luma_filter=(opt != 'noluma'))
         elif k == 'mac':
             m = mac.MacModem(lc, getattr(mac.MacVariant, v))
         else:

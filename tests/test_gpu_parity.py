@@ -26,7 +26,7 @@ FP64_TOL = 1e-9
 def _inputs(c):
     g = np.load(os.path.join(GOLDEN_DIR, case_id(c) + '.npz'))
     rgb = synth_frames_u8(1, c.height, c.width, first_frame=c.frame, seed=c.seed, kind=c.content)[0]
-    om = oracle.build(oracle.ModemSpec(c.kind, c.variant, c.width, c.height, c.standard, c.chroma_avg, c.notch))
+    om = oracle.build(oracle.ModemSpec(c.kind, c.variant, c.width, c.height, c.standard, c.chroma_avg, c.notch, c.opt))
     return g, rgb, om
 
 

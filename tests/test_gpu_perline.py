@@ -59,7 +59,7 @@ def test_per_line_protocol(c, cuda_required):
     c = c._replace(height=h)
     rgb = synth_frames_u8(1, h, c.width, first_frame=c.frame, seed=c.seed, kind=c.content)[0]
     rgb01 = rgb / 255.0
-    om = oracle.build(oracle.ModemSpec(c.kind, c.variant, c.width, h, c.standard, c.chroma_avg, c.notch))
+    om = oracle.build(oracle.ModemSpec(c.kind, c.variant, c.width, h, c.standard, c.chroma_avg, c.notch, c.opt))
     m = make_modem(c, 'fp64')
     comp_ref = om.encode(c.frame, rgb01)
     comp = drive_modulate(m, rgb01, c.frame)

@@ -57,7 +57,7 @@ def test_descriptor_builds_and_filters_match_oracle(c):
     m = make_modem(c)
     d = m.describe()
     assert d.width == c.width and d.height == c.height
-    om = oracle.build(oracle.ModemSpec(c.kind, c.variant, c.width, c.height, c.standard, c.chroma_avg, c.notch))
+    om = oracle.build(oracle.ModemSpec(c.kind, c.variant, c.width, c.height, c.standard, c.chroma_avg, c.notch, c.opt))
     filts = [v for obj in (om, getattr(om, 'qam', None), getattr(om, 'fm', None)) if obj is not None
              for v in vars(obj).values() if isinstance(v, dsp.Filt)]
     x = np.random.default_rng(0).standard_normal(400)

@@ -19,7 +19,7 @@ def load_golden(c):
 @pytest.mark.parametrize('c', GOLDEN_CASES, ids=case_id)
 def test_oracle_matches_reference_golden(c):
     g = load_golden(c)
-    modem = oracle.build(oracle.ModemSpec(c.kind, c.variant, c.width, c.height, c.standard, c.chroma_avg, c.notch))
+    modem = oracle.build(oracle.ModemSpec(c.kind, c.variant, c.width, c.height, c.standard, c.chroma_avg, c.notch, c.opt))
     rgb = synth_frames_u8(1, c.height, c.width, first_frame=c.frame, seed=c.seed, kind=c.content)[0]
     rows = list(FLOAT_ROWS)
 

@@ -34,6 +34,6 @@ def test_full_frame_u8_identical(c):
     comp_img = driver.modulate(Image.fromarray(rgb, 'RGB'), c.frame)
     comp_ref = np.asarray(comp_img)
     out_ref = np.asarray(driver.demodulate(comp_img, c.frame))
-    modem = oracle.build(oracle.ModemSpec(c.kind, c.variant, c.width, c.height, c.standard, c.chroma_avg, c.notch))
+    modem = oracle.build(oracle.ModemSpec(c.kind, c.variant, c.width, c.height, c.standard, c.chroma_avg, c.notch, c.opt))
     assert np.array_equal(oframe.encode_frame_u8(modem, c.frame, rgb), comp_ref)
     assert np.array_equal(oframe.decode_frame_u8(modem, c.frame, comp_ref), out_ref)
