@@ -191,7 +191,7 @@ k_niir_encode(const __grid_constant__ DevParams<T> p, const __grid_constant__ Io
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// Decode.  smem: taps[128] + (R+1) rows x ( c[N1] | up[N3] | mod->pm[N3] | sat[N3] ), 3x buffers polyphase
+// Decode.  smem: scratch[128] (IIR team scratch) + (R+1) rows x ( c[N1] | up[N3] | mod->pm[N3] | sat[N3] ), 3x buffers polyphase
 // ------------------------------------------------------------------------------------------------------------
 template <typename T>
 __global__ void __launch_bounds__(192, 2)
@@ -201,7 +201,6 @@ k_niir_decode(const __grid_constant__ DevParams<T> p, const __grid_constant__ Io
     RowGroup g;
     if (!decode_group(io, g)) return;
     const int W = p.W, N1 = p.n1p, hb = p.hb3, N3 = 3 * hb, n3 = 3 * W;
-    const int warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     T *taps = sm;
     T *rows = sm + 128;
     const size_t per_row = (size_t)N1 + 3 * (size_t)N3;

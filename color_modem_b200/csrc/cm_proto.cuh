@@ -7,7 +7,7 @@
 #pragma once
 #include "cm_niir.cuh"
 
-// Encode.  2 warps per row.  smem: taps[128] + R * (luma[N1] | chroma[N1] | up[N3])
+// Encode.  2 warps per row.  smem: scratch[128] (IIR team scratch) + R * (luma[N1] | chroma[N1] | up[N3])
 template <typename T>
 __global__ void __launch_bounds__(CM_NTHREADS)
 k_proto_encode(const __grid_constant__ DevParams<T> p, const __grid_constant__ IoArgs<T> io) {
@@ -18,7 +18,6 @@ k_proto_encode(const __grid_constant__ DevParams<T> p, const __grid_constant__ I
     const int W = p.W, N1 = p.n1p, hb = p.hb3, N3 = 3 * hb, n3 = 3 * W, W4 = W >> 2;
     const int warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     const bool avg = (p.flags & 2) != 0, luma_filter = (p.flags & 256) != 0;
-    T *taps = sm;
     T *rows = sm + 128;
     const size_t per_row = 2 * (size_t)N1 + N3;
     const FirTaps<T> hup{p.firc[PR_UP3], p.fircp[PR_UP3]}, hdn{p.firc[PR_DOWN3], p.fircp[PR_DOWN3]};   // constant bank (kernel parameter)
@@ -92,7 +91,7 @@ k_proto_encode(const __grid_constant__ DevParams<T> p, const __grid_constant__ I
     }
 }
 
-// Decode.  smem: taps[128] + (R+1) rows x ( c -> X [N1] | up[N3] | chroma[N3] | luma[N3] )
+// Decode.  smem: scratch[128] (IIR team scratch) + (R+1) rows x ( c -> X [N1] | up[N3] | chroma[N3] | luma[N3] )
 template <typename T>
 __global__ void __launch_bounds__(CM_NTHREADS, 2)
 k_proto_decode(const __grid_constant__ DevParams<T> p, const __grid_constant__ IoArgs<T> io) {
@@ -101,7 +100,6 @@ k_proto_decode(const __grid_constant__ DevParams<T> p, const __grid_constant__ I
     RowGroup g;
     if (!decode_group(io, g)) return;
     const int W = p.W, N1 = p.n1p, hb = p.hb3, N3 = 3 * hb, n3 = 3 * W;
-    const int warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     T *taps = sm;
     T *rows = sm + 128;
     const size_t per_row = (size_t)N1 + 3 * (size_t)N3;

@@ -118,7 +118,7 @@ CM_INSTANTIATE(template int launch_bandsplit<float>(cm_modem *, IoArgs<float>, i
 #endif
 
 #if CM_PART(1) || CM_PART(2)
-// Two-pass decoders over independent rows (cm_qam.cuh: k_pald_rows / k_qam_rows, then k_qam_pair<MODE>).  The batch
+// Two-pass decoders over independent rows (cm_qam.cuh: k_qam_rows<PALD / STD>, then k_qam_combine<MODE>).  The batch
 // is cut into chunks of 64 frames so that the (a, b) scratch stays modest (64 frames of 720x576: 425 MB, partly
 // L2-resident between the passes).
 template <typename T, int MODE>

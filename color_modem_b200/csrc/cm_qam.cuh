@@ -41,7 +41,6 @@ k_qam_encode(const __grid_constant__ DevParams<T> p, const __grid_constant__ IoA
     RowGroup g;
     if (!decode_group(io, g)) return;
     const int W = p.W, N1 = p.n1p, W4 = W >> 2;
-    const int warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     const bool avg = (p.flags & 2) != 0;
 
     for (int k = 0; k < g.count; ++k) {
@@ -243,7 +242,7 @@ __device__ __forceinline__ void remod_store_row(const DevParams<T> &p, const IoA
 //   luma_mode 1: luma = c - remod(u, v)         (field-top rows of Pal3DModem, pal.py:191-202,225-226)
 //   luma_mode 2: luma = c                       (strip_chroma=False: the reset-branch return value of the comb
 //                                                decoders, CM_MODE_BANDSPLIT_NOSTRIP)
-// 2 warps per row.  smem: taps[128] + R * (c[N1] + 4 x [N2])
+// 2 warps per row.  smem: scratch[256] (IIR team scratch) + R * (c[N1] + 4 x [N2])
 // ------------------------------------------------------------------------------------------------------------
 template <typename T, bool TEAMS>
 __global__ void __launch_bounds__(CM_NTHREADS, 2)
@@ -253,8 +252,6 @@ k_qam_bandsplit(const __grid_constant__ DevParams<T> p, const __grid_constant__ 
     RowGroup g;
     if (!decode_group(io, g)) return;
     const int W = p.W, W2 = 2 * W, N1 = p.n1p, hb = p.hb2, N2 = 2 * hb;
-    const int warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-    T *taps = sm;
     T *rows = sm + CM_TAPS_ELEMS, *scratch = sm + 128;
     const size_t per_row = (size_t)N1 + 4 * (size_t)N2;     // c | a2 | b2 | l2 | v2
     const FirTaps<T> hup{p.firc[QR_UP2], p.fircp[QR_UP2]}, hdn{p.firc[QR_DOWN2], p.fircp[QR_DOWN2]};   // constant bank (kernel parameter)
@@ -377,7 +374,7 @@ k_qam_bandsplit(const __grid_constant__ DevParams<T> p, const __grid_constant__ 
 //   S = down2(LP(sin(ph)       * (G[k] + G[k-1])))      D = down2(LP(sin(ph + pi/2) * (G[k] - G[k-1])))
 //   u = D sin(LS/2) + S cos(LS/2);  v = D cos(LS/2) - S sin(LS/2);  v = -v on alternate lines
 //   y = c - (sin(phi) LP_pre(u) + cos(phi) LP_pre(+-v))
-// smem: taps[128] + (R+1) * (c[N1] + G[N2]) + 2R * [N2] work
+// smem: scratch[256] (IIR team scratch) + (R+1) * (c[N1] + G[N2]) + 2R * [N2] work
 // ------------------------------------------------------------------------------------------------------------
 template <typename T, bool TEAMS>
 __global__ void __launch_bounds__(CM_NTHREADS, 2)
@@ -388,9 +385,7 @@ k_pald_combed(const __grid_constant__ DevParams<T> p, const __grid_constant__ Io
     if (!decode_group(io, g)) return;
     PhaseClock pc(io.prof);
     const int W = p.W, W2 = 2 * W, N1 = p.n1p, hb = p.hb2, N2 = 2 * hb;
-    const int warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     const int R = io.rows_per_cta;
-    T *taps = sm;
     T *scratch = sm + 128;
     T *cbuf = sm + CM_TAPS_ELEMS;                          // (R+1) x N1    composite rows, index k+1
     T *gbuf = cbuf + (size_t)(R + 1) * N1;       // (R+1) x N2    G rows, index k+1
@@ -503,8 +498,8 @@ k_pald_combed(const __grid_constant__ DevParams<T> p, const __grid_constant__ Io
 //     a_k = down2(LP(sin(psi_k) G_k)),   b_k = down2(LP(cos(psi_k) G_k)),   psi_k = start_phase(k) + bp_shift - LS/2
 // (G_k = up2(down2(BP(up2 c_k))) as above) the sum / difference channels are
 //     S_k = a_k + cos(LS) a_{k-1} + sin(LS) b_{k-1},     D_k = b_k - cos(LS) b_{k-1} + sin(LS) a_{k-1}.
-// Pass 1 (k_pald_rows, all the arithmetic: 1 row per CTA of two warps, ~21 KB of shared memory, 11 CTAs per SM, no
-// halo row, no idle warps) writes (a_k, b_k) to an fp32 scratch in HBM / L2; pass 2 (k_pald_pair) combines
+// Pass 1 (k_qam_rows<PALD>, all the arithmetic: 1 row at a time per CTA of two warps, ~21 KB of shared memory, 8 CTAs per
+// SM, no halo row) writes (a_k, b_k) and their encoder-low-passed copies to an fp32 scratch; pass 2 (k_qam_combine) combines
 // neighbouring rows, rotates to (u, v), re-modulates through the encoder low-pass and stores RGB.
 // ------------------------------------------------------------------------------------------------------------
 
@@ -902,7 +897,7 @@ k_notch_rows(const __grid_constant__ DevParams<T> p, const __grid_constant__ IoA
 //         S = demod(c[k+1]-c[k-1]), D = demod(c[k+1]-2c[k]+c[k-1]) at the phase of row k,
 //         u = a_ss S.v + a_cu D.u,  v = a_ss S.u + a_cv D.v, V switch; c[k+1] := c[k] at the bottom
 //   then  y = c[k] - remod(u, v)  for all three.
-// smem: taps[128] + (R+2) * (c[N1] + B[N2]) + 2R * [N2]
+// smem: scratch[256] (IIR team scratch) + (R+2) * (c[N1] + B[N2]) + 2R * [N2]
 // ------------------------------------------------------------------------------------------------------------
 enum { COMB_NTSC2 = 0, COMB_NTSC3 = 1, COMB_PAL3 = 2 };
 
@@ -914,9 +909,7 @@ k_qam_comb(const __grid_constant__ DevParams<T> p, const __grid_constant__ IoArg
     RowGroup g;
     if (!decode_group(io, g)) return;
     const int W = p.W, W2 = 2 * W, N1 = p.n1p, hb = p.hb2, N2 = 2 * hb;
-    const int warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     const int R = io.rows_per_cta;
-    T *taps = sm;
     T *scratch = sm + 128;
     T *cbuf = sm + CM_TAPS_ELEMS;                          // (R+2) x N1    index k+1, k = -1 .. R
     T *bbuf = cbuf + (size_t)(R + 2) * N1;       // (R+2) x N2

@@ -184,10 +184,9 @@ k_secam_decode(const __grid_constant__ DevParams<T> p, const __grid_constant__ I
     RowGroup g;
     if (!decode_group(io, g)) return;
     const int W = p.W, N1 = p.n1p, hb = p.hb2, N2 = 2 * hb;
-    const int warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     const int pre = W / 40 - 1;                 // samples of flipped warm-up (secam.py:283)
     const int ncc = W + pre, ncc4 = (ncc + 3) & ~3, n2 = 2 * ncc;
-    T *taps = sm, *scratch = sm + 128;
+    T *scratch = sm + 128;
     T *rows = sm + CM_TAPS_ELEMS;
     const size_t per_row = 2 * (size_t)N1 + 3 * (size_t)N2;
     const int k_lo = 0;                          // rows are independent here: pairing with the previous row happens
