@@ -14,7 +14,7 @@ KIND_QAM_BANDSPLIT, KIND_NTSC_COMB, KIND_NTSC_3D, KIND_PAL_D, KIND_PAL_3D = 1, 2
 KIND_SECAM, KIND_NIIR, KIND_PROTOSECAM, KIND_MAC = 6, 7, 8, 9
 
 FLAG_PAL_VSWITCH, FLAG_CHROMA_AVG, FLAG_HUE_CORRECT, FLAG_NTSC_NO_COMB = 1, 2, 4, 8
-FLAG_PAL3D_SIN, FLAG_PAL3D_COS, FLAG_SECAM_BELL, FLAG_SECAM_LF, FLAG_PROTO_LUMA, FLAG_NOTCH = 16, 32, 64, 128, 256, 512
+FLAG_PAL3D_SIN, FLAG_PAL3D_COS, FLAG_SECAM_BELL, FLAG_SECAM_LF, FLAG_PROTO_LUMA, FLAG_NOTCH, FLAG_MINAVG = 16, 32, 64, 128, 256, 512, 1024
 
 FP32, FP64 = 0, 1
 

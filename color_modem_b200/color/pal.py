@@ -59,9 +59,9 @@ class Pal3DModem(PalDModem):
 
     def __init__(self, line_config, variant=PalVariant.PAL, notch=0.0, use_sin=True, use_cos=True, avg=None,
                  precision='fp32'):
-        if avg is not None:
-            raise NotImplementedError('avg= is a non-default knob that is not built (SURVEY.md §8f)')
         super(Pal3DModem, self).__init__(line_config, variant, notch, precision)
+        from .. import comb
+        self._minavg = comb._avg_mode(avg)
         lssin = numpy.sin(self.line_shift)
         lscos = numpy.cos(self.line_shift)
         if abs(lssin) < 0.1:
@@ -69,6 +69,8 @@ class Pal3DModem(PalDModem):
         if abs(lscos) > 0.9:
             use_cos = False
         self._use_sin, self._use_cos = bool(use_sin), bool(use_cos)
+        if not (self._use_sin and self._use_cos):
+            self._minavg = False                 # pal.py:213-218: a single estimate is not combined
         self.demodulation_delay = 1 if (use_sin or use_cos) else 0
         self.decoder_rows = 3 if self.demodulation_delay else 2
         self._sin_sum_factor = 0.5 / lssin if use_sin else 0.0
@@ -80,7 +82,8 @@ class Pal3DModem(PalDModem):
 
     def _fill_desc(self, d):
         super(Pal3DModem, self)._fill_desc(d)
-        both = 0.5 if (self._use_sin and self._use_cos) else 1.0      # comb.avg of the two estimates, pal.py:210-218
+        # comb.avg of the two estimates (pal.py:210-218) is folded into the factors; comb.minavg needs them separate
+        both = 0.5 if (self._use_sin and self._use_cos and not self._minavg) else 1.0
         d.scalars[S.QS_P3D_SINSUM] = both * self._sin_sum_factor
         d.scalars[S.QS_P3D_COSU] = both * self._cos_u_factor
         d.scalars[S.QS_P3D_COSV] = both * self._cos_v_factor

@@ -8,7 +8,29 @@ but that are not built raise NotImplementedError (there is no CPU fallback).
 """
 import copy
 
+import numpy
+
 from . import _native as N
+
+
+def avg(val1, val2):
+    """comb.py:9-10"""
+    return 0.5 * (val1 + val2)
+
+
+def minavg(val1, val2):
+    """comb.py:13-15: the smaller magnitude where the two estimates agree in sign, zero where they do not"""
+    sign = (1.0 - numpy.signbit(val1)) - numpy.signbit(val2)
+    return sign * numpy.minimum(numpy.abs(val1), numpy.abs(val2))
+
+
+def _avg_mode(fn):
+    """Which of the reference's two combiners `fn` is: False = mean (None or comb.avg), True = comb.minavg."""
+    if fn is None or fn is avg or getattr(fn, '__name__', '') == 'avg':
+        return False
+    if fn is minavg or getattr(fn, '__name__', '') == 'minavg':
+        return True
+    raise NotImplementedError('avg= accepts comb.avg or comb.minavg; arbitrary Python callables cannot run in the kernels')
 
 
 def _clone(backend, **changes):
@@ -41,12 +63,10 @@ class Simple3DCombModem(_Wrapper):
 
     def __init__(self, backend, notch=0.0, avg=None):
         from .color.ntsc import NtscCombModem
-        if avg is not None:
-            raise NotImplementedError('avg= is a non-default knob that is not built (SURVEY.md §8f)')
         if type(backend) is not NtscCombModem:
             raise NotImplementedError('Simple3DCombModem is built for NtscCombModem backends only')
         # the wrapper's own notch (comb.py:108-109); the backend's is never applied (it is called with strip_chroma=False)
-        impl = _clone(backend, kind=N.KIND_NTSC_3D, decoder_rows=3, _notch_q=float(notch),
+        impl = _clone(backend, kind=N.KIND_NTSC_3D, decoder_rows=3, _notch_q=float(notch), _minavg=_avg_mode(avg),
                       demodulation_delay=getattr(backend, 'demodulation_delay', 0) + 1)
         super(Simple3DCombModem, self).__init__(backend, impl)
 

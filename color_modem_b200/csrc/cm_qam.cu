@@ -148,6 +148,7 @@ int launch_rows_pair(cm_modem *m, IoArgs<T> io, cudaStream_t st) {
         if (c.in_f) c.in_f += (size_t)f0 * in_frame;
         if (c.out_u8) c.out_u8 += (size_t)f0 * out_frame;
         if (c.out_f) c.out_f += (size_t)f0 * out_frame;
+        if (c.yuv) c.yuv += (size_t)f0 * io.nrows * 3 * p.Wo;
         IoArgs<T> a = c;                      // pass 1 also covers the neighbour rows the combination reads
         a.out_begin = c.out_begin >= 2 ? c.out_begin - 2 : 0;
         int end = c.out_begin + c.out_count + (MODE >= PAIR_NTSC3 ? 2 : 0);
@@ -212,7 +213,9 @@ template <typename T, int MODE>
 int launch_comb(cm_modem *m, IoArgs<T> io, cudaStream_t st) {
     const DevParams<T> &p = params_of<T>(m);
     if (io.out_count <= 0) return CM_OK;
-    if (!getenv("CM_ONEPASS") && (128 + (size_t)p.n1p + 6 * (size_t)p.hb2) * sizeof(T) <= (size_t)m->smem_optin)
+    // (the legacy kernels below do not implement avg=minavg)
+    if ((!getenv("CM_ONEPASS") || (p.flags & CM_FLAG_MINAVG)) &&
+        (128 + (size_t)p.n1p + 6 * (size_t)p.hb2) * sizeof(T) <= (size_t)m->smem_optin)
         return launch_rows_pair<T, MODE == COMB_NTSC2 ? PAIR_NTSC2 : (MODE == COMB_NTSC3 ? PAIR_NTSC3 : PAIR_PAL3)>(m, io, st);
     auto bytes = [&](int r) {
         return (CM_TAPS_ELEMS + (size_t)(r + 2) * (p.n1p + 2 * (size_t)p.hb2) + (size_t)r * 4 * p.hb2) * sizeof(T);
@@ -243,23 +246,51 @@ CM_INSTANTIATE(CM_COMB_INST(float), CM_COMB_INST(double))
 #endif
 
 #if CM_PART(3)
-// Comb decoders with a luma notch: run the decoder with the (y, u, v) of the rows that take the notch diverted to a
-// scratch, then k_notch_rows.  2-line decoders notch the rows that have a predecessor (comb.py:48-55), the 3-line
-// decoders every row they keep (comb.py:96-109, pal.py:191-228).
+// Comb decoders with non-default knobs (luma notch, avg=minavg): run the decoder with the (y, u, v) of the rows
+// concerned diverted to a scratch, then k_finish_rows.  2-line decoders notch the rows that have a predecessor
+// (comb.py:48-55), the 3-line decoders every row they keep (comb.py:96-109, pal.py:191-228); minavg applies to the
+// combed rows of the 3-line decoders (the field tops of Pal3DModem keep their band-split chroma).
 template <typename T>
-static int qam_decode_notched(cm_modem *m, IoArgs<T> io, cudaStream_t st) {
+static int qam_decode_post(cm_modem *m, IoArgs<T> io, cudaStream_t st) {
     const DevParams<T> &p = params_of<T>(m);
     if (io.out_count <= 0) return CM_OK;
-    const bool three_line = p.kind == CM_KIND_NTSC_3D ||
-                            (p.kind == CM_KIND_PAL_3D && (p.flags & (CM_FLAG_PAL3D_SIN | CM_FLAG_PAL3D_COS)));
-    const size_t smem = (size_t)p.n1p * sizeof(T);
-    int rc = set_smem(k_notch_rows<T>, smem);
+    const bool notch = (p.flags & CM_FLAG_NOTCH) != 0;
+    const bool pal3 = p.kind == CM_KIND_PAL_3D && (p.flags & (CM_FLAG_PAL3D_SIN | CM_FLAG_PAL3D_COS));
+    const bool three_line = p.kind == CM_KIND_NTSC_3D || pal3;
+    const bool minavg = three_line && (p.flags & CM_FLAG_MINAVG) && !(p.flags & CM_FLAG_NTSC_NO_COMB);
+    const size_t smem1 = (size_t)p.n1p * sizeof(T), smem3 = 3 * smem1;
+    int rc = set_smem(k_finish_rows<T, false>, smem1);
+    if (rc) return rc;
+    rc = set_smem(k_finish_rows<T, true>, smem3);
     if (rc) return rc;
     const int chunk = io.nframes < 64 ? io.nframes : 64;
     const size_t frame_elems = (size_t)io.nrows * 3 * p.Wo;
     T *yuv = (T *)cm_ensure_aux(m, (size_t)chunk * frame_elems * sizeof(T), 1);
     if (!yuv) return CM_ERR_NOMEM;
     const size_t in_frame = (size_t)io.nrows * p.Wc, out_frame = (size_t)io.nrows * p.Wo * 3;
+    auto rows_from = [](IoArgs<T> a, int begin) {            // the rows of a at or below `begin`
+        if (a.out_begin < begin) {
+            a.out_count -= begin - a.out_begin;
+            a.out_begin = begin;
+        }
+        return a;
+    };
+    auto rows_before = [](IoArgs<T> a, int end) {
+        if (a.out_begin + a.out_count > end) a.out_count = end - a.out_begin;
+        return a;
+    };
+    auto finish = [&](const IoArgs<T> &n, bool remod) -> int {
+        if (n.out_count <= 0) return CM_OK;
+        const dim3 grid((unsigned)n.out_count, 1u, (unsigned)n.nframes);
+        {
+            LaunchTimer lt(m, CM_K_DECODE_OTHER, st);
+            if (remod) k_finish_rows<T, true><<<grid, CM_ROW_THREADS, smem3, st>>>(p, n);
+            else k_finish_rows<T, false><<<grid, CM_ROW_THREADS, smem1, st>>>(p, n);
+        }
+        cm_count_launch();
+        CUDA_TRY(cudaGetLastError());
+        return CM_OK;
+    };
     for (int f0 = 0; f0 < io.nframes; f0 += chunk) {
         IoArgs<T> c = io;
         c.nframes = io.nframes - f0 < chunk ? io.nframes - f0 : chunk;
@@ -271,18 +302,17 @@ static int qam_decode_notched(cm_modem *m, IoArgs<T> io, cudaStream_t st) {
         if (c.out_f) c.out_f += (size_t)f0 * out_frame;
         rc = qam_decode<T>(m, c, CM_MODE_DEFAULT, st);
         if (rc) return rc;
-        IoArgs<T> n = c;
-        if (!three_line && n.out_begin < 2) {
-            n.out_count -= 2 - n.out_begin;
-            n.out_begin = 2;
+        if (!three_line) {
+            rc = finish(rows_from(c, 2), false);                          // notch on the rows with a predecessor
+        } else if (!minavg) {
+            rc = finish(c, false);                                        // notch on every row
+        } else if (pal3) {
+            rc = finish(rows_from(c, 2), true);                           // combed rows: re-modulate (+ notch)
+            if (!rc && notch) rc = finish(rows_before(c, 2), false);      // field tops: notch only
+        } else {
+            rc = finish(c, true);
         }
-        if (n.out_count <= 0) continue;
-        {
-            LaunchTimer lt(m, CM_K_DECODE_OTHER, st);
-            k_notch_rows<T><<<dim3((unsigned)n.out_count, 1u, (unsigned)n.nframes), CM_ROW_THREADS, smem, st>>>(p, n);
-        }
-        cm_count_launch();
-        CUDA_TRY(cudaGetLastError());
+        if (rc) return rc;
     }
     return CM_OK;
 }
@@ -291,11 +321,14 @@ template <typename T>
 int qam_decode(cm_modem *m, IoArgs<T> io, int mode, cudaStream_t st) {
     const DevParams<T> &p = params_of<T>(m);
     if (mode == CM_MODE_BANDSPLIT_NOSTRIP) return launch_bandsplit<T>(m, io, 2, st);
-    if ((p.flags & CM_FLAG_NOTCH) && p.kind != CM_KIND_QAM_BANDSPLIT && !io.yuv) return qam_decode_notched<T>(m, io, st);
+    const bool pal3 = p.kind == CM_KIND_PAL_3D && (p.flags & (CM_FLAG_PAL3D_SIN | CM_FLAG_PAL3D_COS));
+    const bool three_line = p.kind == CM_KIND_NTSC_3D || pal3;
+    const bool post = (p.flags & CM_FLAG_NOTCH) || (three_line && (p.flags & CM_FLAG_MINAVG) && !(p.flags & CM_FLAG_NTSC_NO_COMB));
+    if (post && p.kind != CM_KIND_QAM_BANDSPLIT && !io.yuv) return qam_decode_post<T>(m, io, st);
     IoArgs<T> top, rest;
     split_top(io, top, rest);
-    if (!(p.kind == CM_KIND_PAL_3D && (p.flags & (CM_FLAG_PAL3D_SIN | CM_FLAG_PAL3D_COS))))
-        top.yuv = nullptr;                      // field tops of the 2-line decoders bypass the notch (comb.py:48-49)
+    // field tops: the 2-line decoders bypass the notch there (comb.py:48-49); Pal3DModem's take it but never minavg
+    if (!(pal3 && (p.flags & CM_FLAG_NOTCH))) top.yuv = nullptr;
     int rc;
     switch (p.kind) {
         case CM_KIND_QAM_BANDSPLIT:

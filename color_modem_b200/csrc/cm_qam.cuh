@@ -738,9 +738,20 @@ struct PairCoef {
 };
 
 // (u, v) of one sample from the (a, b) of the previous / current / next row of the field
+// comb.py:13-15: the estimate of smaller magnitude where the two agree in sign (signbit, so -0 counts as negative),
+// zero where they do not
+template <typename T>
+__device__ __forceinline__ T minavg_(T a, T b) {
+    const T sign = ((T)1 - (signbit(a) ? (T)1 : (T)0)) - (signbit(b) ? (T)1 : (T)0);
+    const T aa = Real<T>::abs_(a), ab = Real<T>::abs_(b);
+    return sign * (aa < ab ? aa : ab);
+}
+
+// mn: the two estimates of the 3-line decoders are combined by comb.minavg instead of their mean (CM_FLAG_MINAVG; the
+// host then passes the PAL factors without the 0.5 of comb.avg)
 template <typename T, int MODE>
-__device__ __forceinline__ void pair_uv(const PairCoef<T> &k, bool hp, bool hn, bool alt, T ap, T bp, T ac, T bc, T an,
-                                        T bn, T &u, T &v) {
+__device__ __forceinline__ void pair_uv(const PairCoef<T> &k, bool hp, bool hn, bool alt, bool mn, T ap, T bp, T ac, T bc,
+                                        T an, T bn, T &u, T &v) {
     if (MODE == PAIR_PALD) {
         const T s = ac + (k.cl * ap + k.sl * bp);
         const T d = bc - (k.cl * bp - k.sl * ap);
@@ -751,23 +762,33 @@ __device__ __forceinline__ void pair_uv(const PairCoef<T> &k, bool hp, bool hn, 
         u = k.f2 * ((k.ch * bc + k.sh * ac) - (k.ch * bp - k.sh * ap));
         v = -k.f2 * ((k.ch * ac - k.sh * bc) - (k.ch * ap + k.sh * bp));
     } else if (MODE == PAIR_NTSC3) {
-        T uu = hp ? k.f2 * ((k.ch * bc + k.sh * ac) - (k.ch * bp - k.sh * ap)) : (T)2 * ac;
-        T vv = hp ? -k.f2 * ((k.ch * ac - k.sh * bc) - (k.ch * ap + k.sh * bp)) : (T)2 * bc;
-        if (hn) {
-            uu += k.f2 * ((k.ch * bn + k.sh * an) - (k.ch * bc - k.sh * ac));
-            vv -= k.f2 * ((k.ch * an - k.sh * bn) - (k.ch * ac + k.sh * bc));
+        const T u0 = hp ? k.f2 * ((k.ch * bc + k.sh * ac) - (k.ch * bp - k.sh * ap)) : (T)2 * ac;
+        const T v0 = hp ? -k.f2 * ((k.ch * ac - k.sh * bc) - (k.ch * ap + k.sh * bp)) : (T)2 * bc;
+        // at the field bottom the re-fed row gives a zero line difference: (+0) * f, (+0) * (-f)   (ntsc.py:78-81)
+        const T u1 = hn ? k.f2 * ((k.ch * bn + k.sh * an) - (k.ch * bc - k.sh * ac)) : (T)0;
+        const T v1 = hn ? -k.f2 * ((k.ch * an - k.sh * bn) - (k.ch * ac + k.sh * bc)) : -(T)0;
+        if (mn) {
+            u = minavg_(u0, u1);
+            v = minavg_(v0, v1);
+        } else {
+            u = (T)0.5 * (u0 + u1);
+            v = (T)0.5 * (v0 + v1);
         }
-        u = (T)0.5 * uu;
-        v = (T)0.5 * vv;
     } else {
         const T sin_n = hn ? k.cl * an - k.sl * bn : ac, cos_n = hn ? k.cl * bn + k.sl * an : bc;
         const T sin_p = k.cl * ap + k.sl * bp, cos_p = k.cl * bp - k.sl * ap;
-        u = k.a_ss * (cos_n - cos_p) + k.a_cu * (sin_n - (T)2 * ac + sin_p);
-        v = k.a_ss * (sin_n - sin_p) + k.a_cv * (cos_n - (T)2 * bc + cos_p);
+        const T us = k.a_ss * (cos_n - cos_p), ud = k.a_cu * (sin_n - (T)2 * ac + sin_p);
+        const T vs = k.a_ss * (sin_n - sin_p), vd = k.a_cv * (cos_n - (T)2 * bc + cos_p);
+        if (mn) {
+            u = minavg_(us, ud);
+            v = minavg_(vs, vd);
+        } else {
+            u = us + ud;
+            v = vs + vd;
+        }
         v = alt ? -v : v;
     }
 }
-
 template <typename T, int MODE>
 __global__ void __launch_bounds__(128)
 k_qam_combine(const __grid_constant__ DevParams<T> p, const __grid_constant__ IoArgs<T> io) {
@@ -815,6 +836,7 @@ k_qam_combine(const __grid_constant__ DevParams<T> p, const __grid_constant__ Io
         const int line = io.y0 + row;
         const bool alt = is_alternate(p, frame, line);
         const bool neg = (p.flags & 1) && alt;
+        const bool mn = MODE >= PAIR_NTSC3 && (p.flags & CM_FLAG_MINAVG);
         T cc[4], y[4], u[4], v[4];
         const size_t cbase = ((size_t)f * io.nrows + row) * W + x;
         if (io.in_f) {
@@ -827,11 +849,13 @@ k_qam_combine(const __grid_constant__ DevParams<T> p, const __grid_constant__ Io
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             T ul, vl;
-            pair_uv<T, MODE>(kc, hp, hn, alt, P[0][i], P[1][i], C[0][i], C[1][i], Nx[0][i], Nx[1][i], u[i], v[i]);
-            pair_uv<T, MODE>(kc, hp, hn, alt, P[2][i], P[3][i], C[2][i], C[3][i], Nx[2][i], Nx[3][i], ul, vl);
+            pair_uv<T, MODE>(kc, hp, hn, alt, mn, P[0][i], P[1][i], C[0][i], C[1][i], Nx[0][i], Nx[1][i], u[i], v[i]);
+            pair_uv<T, MODE>(kc, hp, hn, alt, false, P[2][i], P[3][i], C[2][i], C[3][i], Nx[2][i], Nx[3][i], ul, vl);
             y[i] = cc[i] - (s[i] * ul + co[i] * (neg ? -vl : vl));
         }
-        store_rgb4(p, io, f, row, x, y, u, v);
+        // comb.minavg is not linear: the encoder low-pass of (u, v) cannot be taken from the pre-filtered planes, so the
+        // row goes to k_finish_rows as (composite, u, v) through io.yuv
+        store_rgb4(p, io, f, row, x, mn ? cc : y, u, v);
 #pragma unroll
         for (int j = 0; j < 4; ++j)
 #pragma unroll
@@ -846,26 +870,60 @@ k_qam_combine(const __grid_constant__ DevParams<T> p, const __grid_constant__ Io
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// Luma notch of the comb decoders (non-default knob notch=Q: comb.py:18-20, 54-55, 108-109, pal.py:227-228).  The
-// decoders above leave (y, u, v) of the rows that take the notch in io.yuv (store_rgb4); this kernel filters y along
-// the row (one biquad at fsc, zero initial state, utils.py:28-36) and finishes with the inverse matrix.  One row per
-// CTA.
+// Finishing pass of the comb decoders for the non-default knobs: rows whose (y, u, v) the decoders above diverted to
+// io.yuv (store_rgb4) are completed here, one row per CTA of two warps.
+//   REMOD (avg=comb.minavg, comb.py:13-15): the y plane holds the composite; (u, v) go through the encoder low-pass
+//         (one warp each) and y = c - remod(u, v)                                   comb.py:104-107, pal.py:225-226
+//   notch (notch=Q, CM_FLAG_NOTCH): y is filtered along the row by one biquad at fsc, zero initial state
+//                                                                 comb.py:18-20, 54-55, 108-109, pal.py:227-228
+// then the inverse matrix and the store.
 // ------------------------------------------------------------------------------------------------------------
-template <typename T>
+template <typename T, bool REMOD>
 __global__ void __launch_bounds__(CM_ROW_THREADS, 8)
-k_notch_rows(const __grid_constant__ DevParams<T> p, const __grid_constant__ IoArgs<T> io) {
+k_finish_rows(const __grid_constant__ DevParams<T> p, const __grid_constant__ IoArgs<T> io) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    T *y = reinterpret_cast<T *>(smem_raw);
+    T *y = reinterpret_cast<T *>(smem_raw);              // REMOD: + ulp[N1] | vlp[N1]
     const int W = p.Wo, N1 = p.n1p;
     const int row = io.out_begin + blockIdx.x, f = blockIdx.z;
+    const long long frame = io.first_frame + f;
     const T *src = io.yuv + ((size_t)f * io.nrows + row) * 3 * W;
+    T *ulp = y + N1, *vlp = ulp + N1;
     for (int x = 4 * threadIdx.x; x < W; x += 4 * blockDim.x) {
         T v[4];
         ld4(src + x, v);
         st4(y + x, v);
+        if (REMOD) {
+            ld4(src + W + x, v);
+            st4(ulp + x, v);
+            ld4(src + 2 * W + x, v);
+            st4(vlp + x, v);
+        }
     }
     __syncthreads();
-    if (threadIdx.x < 32) {
+    if (REMOD) {
+        const FiltHdr &fpre = p.filt[QF_PRE_LP];
+        T *buf = (threadIdx.x >> 5) ? vlp : ulp;
+        warp_fill_tail<T, 1>(buf, N1, W, N1);
+        warp_iir<T, 1>(p.tab + fpre.off, fpre, [&](int q, int, int) { return buf[q]; }, [&](int j, T x) { buf[j] = x; });
+        __syncthreads();
+        T rs, rc;
+        Real<T>::sincos_turns(p.phases[QP_STEP1X], rs, rc);
+        const int line = io.y0 + row;
+        const unsigned long long ph0 = start_phase(p, frame, line);
+        const bool neg = (p.flags & 1) && is_alternate(p, frame, line);
+        for (int x = 4 * threadIdx.x; x < W; x += 4 * blockDim.x) {
+            T cc[4], a[4], b[4], s[4], co[4];
+            ld4(y + x, cc);
+            ld4(ulp + x, a);
+            ld4(vlp + x, b);
+            carrier4(ph0 + (unsigned long long)x * p.phases[QP_STEP1X], rs, rc, s, co);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) cc[i] = cc[i] - (s[i] * a[i] + co[i] * (neg ? -b[i] : b[i]));
+            st4(y + x, cc);
+        }
+        __syncthreads();
+    }
+    if ((p.flags & CM_FLAG_NOTCH) && threadIdx.x < 32) {
         const FiltHdr &fn = p.filt[QF_NOTCH];
         warp_fill_tail<T, 1>(y, N1, W, N1);
         warp_iir<T, 1>(p.tab + fn.off, fn, [&](int q, int, int) { return y[q]; }, [&](int j, T v) { y[j] = v; });

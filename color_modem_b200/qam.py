@@ -56,6 +56,7 @@ class AbstractQamColorModem(GpuModem, utils.ConstantFrequencyCarrier):
     kind = N.KIND_QAM_BANDSPLIT
     flags = 0
     _notch_q = 0.0        # comb decoders: Q of the luma notch (comb.py:18-20); 0 = no notch
+    _minavg = False       # 3-line decoders: avg=comb.minavg (comb.py:13-15)
 
     def __init__(self, line_config, config, precision='fp32'):
         GpuModem.__init__(self, line_config, precision)
@@ -104,6 +105,8 @@ class AbstractQamColorModem(GpuModem, utils.ConstantFrequencyCarrier):
             b, a = scipy.signal.iirnotch(2.0 * fsc / self.line_config.fs, self._notch_q)        # comb.py:18-20
             put_filter(d, S.QF_NOTCH, utils.FilterFunction(b, a, wp=0.0, btype='bandstop', shift=True), W, 1)
             d.flags |= N.FLAG_NOTCH
+        if self._minavg:
+            d.flags |= N.FLAG_MINAVG
 
     def _flags(self):
         return self.flags

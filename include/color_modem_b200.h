@@ -62,7 +62,8 @@ enum cm_flags {
     CM_FLAG_SECAM_BELL = 64,   /* SECAM anti-bell filter present (secam.py:167-170)                      */
     CM_FLAG_SECAM_LF = 128,    /* SECAM LF pre-/de-emphasis present (secam.py:173-177)                   */
     CM_FLAG_PROTO_LUMA = 256,  /* ProtoSecam premod_luma_filter (protosecam.py:82-85)                    */
-    CM_FLAG_NOTCH = 512        /* comb decoders: luma notch after the chroma subtraction (comb.py:18-20,54-55) */
+    CM_FLAG_NOTCH = 512,       /* comb decoders: luma notch after the chroma subtraction (comb.py:18-20,54-55) */
+    CM_FLAG_MINAVG = 1024      /* 3-line decoders: avg=comb.minavg instead of the mean (comb.py:13-15, pal.py:146-149) */
 };
 
 enum cm_precision { CM_FP32 = 0, CM_FP64 = 1 };

@@ -51,6 +51,15 @@ def _col(v):
     return np.asarray(v)[:, None]
 
 
+def _avg(a, b):                                                                   # comb.py:9-10
+    return 0.5 * (a + b)
+
+
+def _minavg(a, b):                                                                # comb.py:13-15
+    sign = (1.0 - np.signbit(a)) - np.signbit(b)
+    return sign * np.minimum(np.abs(a), np.abs(b))
+
+
 # =================================================================================================
 # QAM core, qam.py:14-58
 # =================================================================================================
@@ -212,8 +221,9 @@ class Ntsc3D(NtscComb):
         u0, v0 = self.comb_stage_uv(frame, comp)
         # the delayed call: line number y+2, previous = row y, current = next row of the field (row y at the bottom)
         u1, v1 = self.combed_uv(frame, self.rows + 2, comp, comp[self.next_row])
-        u = 0.5 * (u0 + u1)
-        v = 0.5 * (v0 + v1)
+        avg = _minavg if getattr(self.spec, 'opt', '') == 'minavg' else _avg       # comb.py:81-84, 101-102
+        u = avg(u0, u1)
+        v = avg(v0, v1)
         y = comp - self.remod(frame, self.rows, u, v)
         if self.notch:
             y = self.notch(y)                                                     # comb.py:108-109: every kept row
@@ -305,8 +315,9 @@ class Pal3D(PalD):
         _, su, sv = self.qam.demod(start, ssig, False)
         _, du, dv = self.qam.demod(start, dsig, False)
         if self.use_sin and self.use_cos:                                         # pal.py:210-218
-            u = 0.5 * (sv * self.sin_sum + du * self.cos_u)
-            v = 0.5 * (su * self.sin_sum + dv * self.cos_v)
+            avg = _minavg if getattr(self.spec, 'opt', '') == 'minavg' else _avg   # pal.py:146-149
+            u = avg(sv * self.sin_sum, du * self.cos_u)
+            v = avg(su * self.sin_sum, dv * self.cos_v)
         elif self.use_sin:
             u, v = self.sin_sum * sv, self.sin_sum * su
         else:

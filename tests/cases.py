@@ -9,7 +9,8 @@ import collections
 Case = collections.namedtuple('Case', 'kind variant width height standard chroma_avg frame seed content notch opt')
 # notch: Q of the luma notch of the comb decoders (comb.py:18-20), 0 = off
 # opt:   other non-default constructor knobs: 'nosin' / 'nocos' (Pal3DModem use_sin / use_cos = False, pal.py:131),
-#        'altph' (SecamModem alternate_phases=True, secam.py:163-166), 'noluma' (ProtoSecamModem premod_luma_filter=False)
+#        'altph' (SecamModem alternate_phases=True, secam.py:163-166), 'noluma' (ProtoSecamModem premod_luma_filter=False),
+#        'minavg' (Simple3DCombModem / Pal3DModem avg=comb.minavg, comb.py:13-15)
 Case.__new__.__defaults__ = (0.0, '')
 
 
@@ -74,6 +75,10 @@ GOLDEN_CASES = [
     _c('pal_3d', 'PAL_M', 'NTSC_525', 1, opt='nocos', notch=6.0),
     _c('secam', 'SECAM', 'GERBER_625', 6, opt='altph'),
     _c('protosecam', 'SECAM_1957', 'FRENCH_819', 3, opt='noluma'),
+    _c('ntsc_3d', 'NTSC', 'NTSC_525', 5, opt='minavg'),
+    _c('ntsc_3d', 'NTSC443', 'NTSC_525', 6, opt='minavg', notch=5.0, content='noise'),
+    _c('pal_3d', 'PAL', 'GERBER_625', 7, opt='minavg'),
+    _c('pal_3d', 'PAL', 'GERBER_625', 0, opt='minavg', notch=3.0),
 ]
 
 FLOAT_ROWS = (1, 10, 22)   # rows whose float64 composite / RGB lines are stored: field top, interior, field bottom

@@ -18,9 +18,11 @@ def make_modem(c, precision='fp32'):
     elif k == 'ntsc_comb':
         m = ntsc.NtscCombModem(lc, getattr(ntsc.NtscVariant, v), notch, precision=precision)
     elif k == 'ntsc_3d':
-        m = comb.Simple3DCombModem(ntsc.NtscCombModem(lc, getattr(ntsc.NtscVariant, v), precision=precision), notch)
+        m = comb.Simple3DCombModem(ntsc.NtscCombModem(lc, getattr(ntsc.NtscVariant, v), precision=precision), notch,
+                                   comb.minavg if opt == 'minavg' else None)
     elif k == 'pal_3d':
-        m = pal.Pal3DModem(lc, getattr(pal.PalVariant, v), notch, use_sin=(opt != 'nosin'), use_cos=(opt != 'nocos'), precision=precision)
+        m = pal.Pal3DModem(lc, getattr(pal.PalVariant, v), notch, use_sin=(opt != 'nosin'), use_cos=(opt != 'nocos'),
+                           avg=comb.minavg if opt == 'minavg' else None, precision=precision)
     elif k == 'secam':
         m = secam.SecamModem(lc, getattr(secam.SecamVariant, v), alternate_phases=(opt == 'altph'), precision=precision)
     elif k == 'niir':

@@ -70,13 +70,15 @@ def load_reference():
         elif k == 'ntsc_comb':
             m = ntsc.NtscCombModem(lc, getattr(ntsc.NtscVariant, v), notch)
         elif k == 'ntsc_3d':
-            m = comb.Simple3DCombModem(ntsc.NtscCombModem(lc, getattr(ntsc.NtscVariant, v)), notch)
+            m = comb.Simple3DCombModem(ntsc.NtscCombModem(lc, getattr(ntsc.NtscVariant, v)), notch,
+                                       comb.minavg if opt == 'minavg' else None)
         elif k == 'pal_s':
             m = pal.PalSModem(lc, getattr(pal.PalVariant, v))
         elif k == 'pal_d':
             m = pal.PalDModem(lc, getattr(pal.PalVariant, v), notch)
         elif k == 'pal_3d':
-            m = pal.Pal3DModem(lc, getattr(pal.PalVariant, v), notch, use_sin=(opt != 'nosin'), use_cos=(opt != 'nocos'))
+            m = pal.Pal3DModem(lc, getattr(pal.PalVariant, v), notch, use_sin=(opt != 'nosin'), use_cos=(opt != 'nocos'),
+                               avg=comb.minavg if opt == 'minavg' else None)
         elif k == 'secam':
             m = secam.SecamModem(lc, getattr(secam.SecamVariant, v), alternate_phases=(opt == 'altph'))
         elif k == 'niir':
