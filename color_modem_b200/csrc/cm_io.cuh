@@ -100,17 +100,38 @@ __device__ __forceinline__ void store_comp4(const IoArgs<T> &io, size_t off, con
     }
 }
 
-// 4 decoded pixels out (inverse colour matrix, e.g. ntsc.py:36-41), float before clipping and/or u8
+template <typename T>
+__device__ __forceinline__ void store_yuv4(const DevParams<T> &p, const IoArgs<T> &io, int fidx, int row, int x0,
+                                           const T y[4], const T c1[4], const T c2[4]);
+template <typename T>
+__device__ __forceinline__ void store_rgb4_direct(const DevParams<T> &p, const IoArgs<T> &io, int fidx, int row, int x0,
+                                                  const T y[4], const T c1[4], const T c2[4]);
+
+// 4 decoded pixels out (inverse colour matrix, e.g. ntsc.py:36-41), float before clipping and/or u8; or, when io.yuv is
+// set, the planes to the finishing-pass scratch
 template <typename T>
 __device__ __forceinline__ void store_rgb4(const DevParams<T> &p, const IoArgs<T> &io, int fidx, int row, int x0,
                                            const T y[4], const T c1[4], const T c2[4]) {
     if (io.yuv) {
-        T *dst = io.yuv + ((size_t)fidx * io.nrows + row) * 3 * p.Wo + x0;
-        st4(dst, y);
-        st4(dst + p.Wo, c1);
-        st4(dst + 2 * p.Wo, c2);
+        store_yuv4(p, io, fidx, row, x0, y, c1, c2);
         return;
     }
+    store_rgb4_direct(p, io, fidx, row, x0, y, c1, c2);
+}
+
+// the planes of 4 pixels to the finishing-pass scratch yuv[frame][row][3][Wo] (comb decoders with non-default knobs)
+template <typename T>
+__device__ __forceinline__ void store_yuv4(const DevParams<T> &p, const IoArgs<T> &io, int fidx, int row, int x0,
+                                           const T y[4], const T c1[4], const T c2[4]) {
+    T *dst = io.yuv + ((size_t)fidx * io.nrows + row) * 3 * p.Wo + x0;
+    st4(dst, y);
+    st4(dst + p.Wo, c1);
+    st4(dst + 2 * p.Wo, c2);
+}
+
+template <typename T>
+__device__ __forceinline__ void store_rgb4_direct(const DevParams<T> &p, const IoArgs<T> &io, int fidx, int row, int x0,
+                                                  const T y[4], const T c1[4], const T c2[4]) {
     T v[12];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {

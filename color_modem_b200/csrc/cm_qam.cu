@@ -166,7 +166,9 @@ int launch_rows_pair(cm_modem *m, IoArgs<T> io, cudaStream_t st) {
             LaunchTimer lt(m, CM_K_DECODE_OTHER, st);
             const int segs = (((c.out_count + 1) >> 1) + CM_SEG - 1) / CM_SEG, threads = 128;
             dim3 grid((unsigned)((segs * (p.W >> 2) + threads - 1) / threads), 2u, (unsigned)c.nframes);
-            k_qam_combine<T, MODE><<<grid, threads, 0, st>>>(p, c);
+            if (!c.yuv) k_qam_combine<T, MODE, 0><<<grid, threads, 0, st>>>(p, c);
+            else if (MODE >= PAIR_NTSC3 && (p.flags & CM_FLAG_MINAVG)) k_qam_combine<T, MODE, 2><<<grid, threads, 0, st>>>(p, c);
+            else k_qam_combine<T, MODE, 1><<<grid, threads, 0, st>>>(p, c);
         }
         cm_count_launch();
         CUDA_TRY(cudaGetLastError());

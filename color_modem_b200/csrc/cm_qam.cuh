@@ -749,9 +749,9 @@ __device__ __forceinline__ T minavg_(T a, T b) {
 
 // mn: the two estimates of the 3-line decoders are combined by comb.minavg instead of their mean (CM_FLAG_MINAVG; the
 // host then passes the PAL factors without the 0.5 of comb.avg)
-template <typename T, int MODE>
-__device__ __forceinline__ void pair_uv(const PairCoef<T> &k, bool hp, bool hn, bool alt, bool mn, T ap, T bp, T ac, T bc,
-                                        T an, T bn, T &u, T &v) {
+template <typename T, int MODE, bool mn>
+__device__ __forceinline__ void pair_uv(const PairCoef<T> &k, bool hp, bool hn, bool alt, T ap, T bp, T ac, T bc, T an,
+                                        T bn, T &u, T &v) {
     if (MODE == PAIR_PALD) {
         const T s = ac + (k.cl * ap + k.sl * bp);
         const T d = bc - (k.cl * bp - k.sl * ap);
@@ -771,8 +771,8 @@ __device__ __forceinline__ void pair_uv(const PairCoef<T> &k, bool hp, bool hn, 
             u = minavg_(u0, u1);
             v = minavg_(v0, v1);
         } else {
-            u = (T)0.5 * (u0 + u1);
-            v = (T)0.5 * (v0 + v1);
+            u = (T)0.5 * (u0 + (hn ? u1 : (T)0));
+            v = (T)0.5 * (v0 + (hn ? v1 : (T)0));
         }
     } else {
         const T sin_n = hn ? k.cl * an - k.sl * bn : ac, cos_n = hn ? k.cl * bn + k.sl * an : bc;
@@ -789,7 +789,8 @@ __device__ __forceinline__ void pair_uv(const PairCoef<T> &k, bool hp, bool hn, 
         v = alt ? -v : v;
     }
 }
-template <typename T, int MODE>
+// OUT: 0 = RGB; 1 = (y, u, v) to io.yuv (luma notch follows); 2 = (composite, u, v) to io.yuv with comb.minavg
+template <typename T, int MODE, int OUT>
 __global__ void __launch_bounds__(128)
 k_qam_combine(const __grid_constant__ DevParams<T> p, const __grid_constant__ IoArgs<T> io) {
     const int W = p.W, W4 = W >> 2;
@@ -836,7 +837,7 @@ k_qam_combine(const __grid_constant__ DevParams<T> p, const __grid_constant__ Io
         const int line = io.y0 + row;
         const bool alt = is_alternate(p, frame, line);
         const bool neg = (p.flags & 1) && alt;
-        const bool mn = MODE >= PAIR_NTSC3 && (p.flags & CM_FLAG_MINAVG);
+        constexpr bool mn = OUT == 2 && MODE >= PAIR_NTSC3;
         T cc[4], y[4], u[4], v[4];
         const size_t cbase = ((size_t)f * io.nrows + row) * W + x;
         if (io.in_f) {
@@ -849,13 +850,14 @@ k_qam_combine(const __grid_constant__ DevParams<T> p, const __grid_constant__ Io
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             T ul, vl;
-            pair_uv<T, MODE>(kc, hp, hn, alt, mn, P[0][i], P[1][i], C[0][i], C[1][i], Nx[0][i], Nx[1][i], u[i], v[i]);
-            pair_uv<T, MODE>(kc, hp, hn, alt, false, P[2][i], P[3][i], C[2][i], C[3][i], Nx[2][i], Nx[3][i], ul, vl);
+            pair_uv<T, MODE, mn>(kc, hp, hn, alt, P[0][i], P[1][i], C[0][i], C[1][i], Nx[0][i], Nx[1][i], u[i], v[i]);
+            pair_uv<T, MODE, false>(kc, hp, hn, alt, P[2][i], P[3][i], C[2][i], C[3][i], Nx[2][i], Nx[3][i], ul, vl);
             y[i] = cc[i] - (s[i] * ul + co[i] * (neg ? -vl : vl));
         }
         // comb.minavg is not linear: the encoder low-pass of (u, v) cannot be taken from the pre-filtered planes, so the
         // row goes to k_finish_rows as (composite, u, v) through io.yuv
-        store_rgb4(p, io, f, row, x, mn ? cc : y, u, v);
+        if (OUT == 0) store_rgb4_direct(p, io, f, row, x, y, u, v);
+        else store_yuv4(p, io, f, row, x, mn ? cc : y, u, v);
 #pragma unroll
         for (int j = 0; j < 4; ++j)
 #pragma unroll
