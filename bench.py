@@ -392,7 +392,7 @@ def run_ours(args):
                                          if pair_ms > 0 else 0.0},
                          'kernel_share_of_step': shares,
                          'whole_chain_frac': fps / world * BYTES_PER_FRAME / 1e9 / peak,
-                         'note': 'the decode chain is bound by instruction issue and FP32 latency, not by HBM: k_qam_rows runs the FMA pipe at 51 % and DRAM at 9 % of peak (profiles/r1_v7_pald_summary.md, DESIGN.md §5)'},
+                         'note': 'the decode chain is bound by instruction issue and FP32 latency, not by HBM: k_qam_rows runs the FMA pipe at 51 % and DRAM at 9 % of peak (profiles/r1_v8_pald_summary.md, DESIGN.md §5)'},
         }
         if cpu_line is not None:
             line['cpu_baseline'] = cpu_line
