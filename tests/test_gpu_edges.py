@@ -73,8 +73,9 @@ def test_empty_batch(cuda_required):
 
 
 def test_batch_not_multiple_of_chunks(cuda_required):
-    """65 and 129 frames: one more than the 64-frame pass-1/pass-2 chunk of the comb decoders; 17: one more than the
-    16-frame chunk of the host entry points."""
+    """Ragged batches: 17 and 65 frames are one more than one / four 16-frame chunks of the host entry points; the
+    pass-1 / pass-2 chunking of the comb decoders (frames per 2 GiB of scratch) is exercised with CM_CHUNK in
+    tests/test_gpu_parity.py::test_comb_decoder_paths and below."""
     import torch
     m = comb.Simple3DCombModem(ntsc.NtscCombModem(LineConfig((720, 24), LS.NTSC_525)))
     rgb = synth_frames_u8(129, 24, 720, first_frame=0, seed=4)
@@ -88,6 +89,18 @@ def test_batch_not_multiple_of_chunks(cuda_required):
         assert np.array_equal(m.decode_frames_host(c, 0), out[:n])
     one = m.decode_frames(torch.from_numpy(comp[128:129]).cuda(), first_frame=128).cpu().numpy()
     assert np.array_equal(one[0], out[128])
+
+
+def test_decode_chunking_is_invisible(cuda_required, monkeypatch):
+    """the same 129 frames decoded with 64-, 50- and 1-frame pass-1 / pass-2 chunks"""
+    import torch
+    m = comb.Simple3DCombModem(ntsc.NtscCombModem(LineConfig((720, 24), LS.NTSC_525)))
+    rgb = synth_frames_u8(129, 24, 720, first_frame=0, seed=4)
+    comp = m.encode_frames(torch.from_numpy(rgb).cuda())
+    ref = m.decode_frames(comp).cpu().numpy()
+    for c in ('64', '50', '1'):
+        monkeypatch.setenv('CM_CHUNK', c)
+        assert np.array_equal(m.decode_frames(comp).cpu().numpy(), ref)
 
 
 def test_unsupported_width_is_a_clean_error(cuda_required):

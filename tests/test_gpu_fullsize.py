@@ -5,7 +5,7 @@ few sampled frames are compared with the oracle directly:
 
   * sharding invariance (configs[2]): a 600-frame NTSC 3-line-comb sequence encoded and decoded in one call equals,
     byte for byte, the same sequence processed as 1/2/4/8 contiguous frame ranges that are each given their absolute
-    first frame (SURVEY.md section 8e) — also across the internal 64-frame chunking of the two-pass decoders;
+    first frame (SURVEY.md section 8e);
   * batch invariance (configs[3]): 1000 frames of ColorAveraging(SECAM) / HueCorrectingNiir through the chunked host
     entry points equal the device-resident batch;
   * sampled frames (first, shard boundaries, last) against the float64 oracle: +-1 LSB;
