@@ -730,7 +730,9 @@ k_qam_bs_row(const __grid_constant__ DevParams<T> p, const __grid_constant__ IoA
 //                                the next row (nothing at the bottom, where the driver re-feeds the row, image.py:51-53)
 //   PAIR_PAL3   pal.py:198-226   sums / differences of three rows at the phase of the middle one
 enum { PAIR_PALD = 0, PAIR_NTSC2 = 1, PAIR_NTSC3 = 2, PAIR_PAL3 = 3 };
-#define CM_SEG 8
+#ifndef CM_SEG
+#define CM_SEG 8       // rows of a field per thread of the combine pass
+#endif
 
 template <typename T>
 struct PairCoef {
