@@ -65,3 +65,18 @@ def test_product_does_not_import_oracle():
             if f.endswith('.py'):
                 src = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r'^\s*(from|import)\s+oracle\b', src, re.M), f
+
+
+def test_build_stamp_follows_source_content_not_file_times(lib):
+    """build() decides staleness by the digest of the sources (file times do not survive the snapshot to the GPU box)."""
+    import __graft_entry__ as ge
+    srcs = [os.path.join(ge.CSRC, f) for f in sorted(os.listdir(ge.CSRC)) if f.endswith(('.cu', '.cuh', '.h'))]
+    srcs.append(os.path.join(ROOT, 'include', 'color_modem_b200.h'))
+    assert os.path.exists(ge.STAMP)
+    assert open(ge.STAMP).read().strip() == ge._digest(srcs)
+    newest = max(os.path.getmtime(s) for s in srcs)
+    os.utime(srcs[0], (newest + 10, newest + 10))          # a newer file time alone must not trigger a rebuild
+    try:
+        assert ge._lib_current(srcs)
+    finally:
+        os.utime(srcs[0], (newest, newest))
