@@ -6,10 +6,10 @@ Same names, fields and behaviour: ``LineStandard`` (a namedtuple with the five p
 """
 import collections
 
-_Fields = collections.namedtuple('LineStandard', ['frame_rate', 'total_lines',
-                                                  'odd_field_first_active_line', 'odd_field_last_active_line',
-                                                  'even_field_first_active_line', 'even_field_last_active_line',
-                                                  'total_width_factor'])
+_Fields = collections.namedtuple(
+    'LineStandard',
+    'frame_rate total_lines ' + ' '.join('%s_field_%s_active_line' % (f, e) for f in ('odd', 'even') for e in ('first', 'last'))
+    + ' total_width_factor')
 
 
 class LineStandard(_Fields):
@@ -41,11 +41,14 @@ class LineStandard(_Fields):
         return min(fitting, key=lambda s: s.active_lines)
 
 
-LineStandard.BAIRD_405 = LineStandard(25.0, 405, 16, 203, 218, 405, 1.2)
-LineStandard.NTSC_525 = LineStandard(30000.0 / 1001.0, 525, 21, 263, 283, 525, 858.0 / 720.0)
-LineStandard.GERBER_625 = LineStandard(25.0, 625, 336, 623, 23, 310, 1.2)
-LineStandard.FRENCH_819 = LineStandard(25.0, 819, 39, 407, 448, 816, 1.2)
-LineStandard.BELGIAN_819 = LineStandard(25.0, 819, 437, 816, 27, 406, 1.2)
+# name: frames/s, lines per frame, (first, last) active line of the odd field, of the even field, line length / active length
+for _name, (_rate, _lines, _odd, _even, _wf) in {
+        'BAIRD_405': (25.0, 405, (16, 203), (218, 405), 1.2),
+        'NTSC_525': (30000.0 / 1001.0, 525, (21, 263), (283, 525), 858.0 / 720.0),
+        'GERBER_625': (25.0, 625, (336, 623), (23, 310), 1.2),
+        'FRENCH_819': (25.0, 819, (39, 407), (448, 816), 1.2),
+        'BELGIAN_819': (25.0, 819, (437, 816), (27, 406), 1.2)}.items():
+    setattr(LineStandard, _name, LineStandard(_rate, _lines, _odd[0], _odd[1], _even[0], _even[1], _wf))
 
 
 class LineConfig(object):
