@@ -12,6 +12,7 @@ from .pal import PalVariant
 class NiirModem(GpuModem, utils.ConstantFrequencyCarrier):
     kind = N.KIND_NIIR
     decoder_rows = 2
+    has_demodulate_components = True
     # rows (luma, db, dr) over (r, g, b)  — niir.py:35-37
     ENC = (0.299, 0.587, 0.114,
            0.1472906403940887, 0.2891625615763547, -0.4364532019704434,

@@ -43,7 +43,10 @@ static void pick_chunk(int rate, int total, int &L, int &nsuper) {
     }
 }
 
-static void build_filter(const cm_filter &f, FiltHdr &h, std::vector<double> &tab) {
+void cm_build_filter_table(const cm_filter &f, FiltHdr &h, std::vector<double> &tab);
+static void build_filter(const cm_filter &f, FiltHdr &h, std::vector<double> &tab) { cm_build_filter_table(f, h, tab); }
+
+void cm_build_filter_table(const cm_filter &f, FiltHdr &h, std::vector<double> &tab) {
     int L = 0, nsuper = 0;
     pick_chunk(f.rate, f.n + f.shift, L, nsuper);
     h.nsec = f.nsec;
@@ -207,6 +210,10 @@ extern "C" int cm_create(const cm_desc *desc, int precision, cm_modem **out) {
         default:
             return fail(CM_ERR_UNSUPPORTED, "modem kind not built%s");
     }
+    if (desc->kind == CM_KIND_NTSC_3D && (desc->flags & CM_FLAG_NTSC_NO_COMB))
+        // comb.py:96-109 over ntsc.py:71-72 averages the band-split chroma of two lines there; the fused 3-line kernel
+        // does not (the Python mirror serves that composition through the composed path)
+        return fail(CM_ERR_UNSUPPORTED, "Simple3DCombModem(NtscCombModem) without a usable line comb is not a fused kind%s");
     cm_modem *m = new (std::nothrow) cm_modem();
     if (!m) return fail(CM_ERR_NOMEM, "out of host memory%s");
     m->desc = *desc;
@@ -351,8 +358,9 @@ static int dispatch_encode(cm_modem *m, IoArgs<T> io, cudaStream_t st) {
 template <typename T>
 static int dispatch_decode(cm_modem *m, IoArgs<T> io, int mode, cudaStream_t st) {
     const int kind = m->desc.kind;
-    if (mode == CM_MODE_BANDSPLIT_NOSTRIP && (kind < CM_KIND_QAM_BANDSPLIT || kind > CM_KIND_PAL_3D))
-        return fail(CM_ERR_INVALID, "CM_MODE_BANDSPLIT_NOSTRIP is only defined for the QAM family%s");
+    if (mode != CM_MODE_DEFAULT && (kind < CM_KIND_QAM_BANDSPLIT || kind > CM_KIND_PAL_3D))
+        return fail(CM_ERR_INVALID, "cm_window.mode is only defined for the QAM family%s");
+    if (mode < CM_MODE_DEFAULT || mode > CM_MODE_EXTRACT_CHROMA) return fail(CM_ERR_INVALID, "bad cm_window.mode%s");
     switch (kind) {
         case CM_KIND_QAM_BANDSPLIT:
         case CM_KIND_NTSC_COMB:
@@ -405,6 +413,7 @@ static int run_ex(cm_modem *m, bool encode, const cm_window *win, const uint8_t 
     }
     CUDA_TRY(cudaSetDevice(m->device));
     const int mode = win ? win->mode : CM_MODE_DEFAULT;
+    m->pf.phase0 = m->pd.phase0 = win ? win->phase_offset : 0ull;     // (a handle is not re-entrant)
     // gridDim.z carries the frame index: at most 65535 frames per launch
     const size_t in_w = encode ? (size_t)m->desc.width * 3 : (size_t)m->desc.comp_width;
     const size_t out_w = encode ? (size_t)m->desc.comp_width : (size_t)m->desc.out_width * 3;

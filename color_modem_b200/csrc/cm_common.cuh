@@ -43,6 +43,7 @@ struct DevParams {
     int hb2;          // elements per phase of 2x polyphase buffers (multiple of 4, >= n1p)
     int hb3;          // elements per phase of 3x polyphase buffers
     unsigned long long frame_shift, line_shift;
+    unsigned long long phase0;     // cm_window.phase_offset of the current call (explicit start phase, qam.py:28,43)
     unsigned long long phases[CM_NPHASE];
     T scalars[CM_NSCAL];
     T enc[9];
@@ -186,7 +187,7 @@ template <typename T>
 __device__ __forceinline__ unsigned long long start_phase(const DevParams<T> &p, long long frame, int line) {
     unsigned long long fr = (unsigned long long)(frame % (long long)p.frame_cycle);
     long long dl = (long long)(analog_line(p, line) - p.ref_line);
-    return fr * p.frame_shift + (unsigned long long)dl * p.line_shift;
+    return fr * p.frame_shift + (unsigned long long)dl * p.line_shift + p.phase0;
 }
 
 // Row bookkeeping of a CTA: which buffer rows it outputs.

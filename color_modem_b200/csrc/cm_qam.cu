@@ -14,6 +14,7 @@
 
 template <typename T> int launch_bandsplit(cm_modem *m, IoArgs<T> io, int luma_mode, cudaStream_t st);
 template <typename T> int launch_pald(cm_modem *m, IoArgs<T> io, cudaStream_t st);
+template <typename T> int launch_extract(cm_modem *m, IoArgs<T> io, cudaStream_t st);
 template <typename T, int MODE> int launch_comb(cm_modem *m, IoArgs<T> io, cudaStream_t st);
 template <typename T> int qam_decode(cm_modem *m, IoArgs<T> io, int mode, cudaStream_t st);
 
@@ -111,6 +112,23 @@ int launch_bandsplit(cm_modem *m, IoArgs<T> io, int luma_mode, cudaStream_t st) 
     return CM_OK;
 }
 
+template <typename T>
+int launch_extract(cm_modem *m, IoArgs<T> io, cudaStream_t st) {
+    const DevParams<T> &p = params_of<T>(m);
+    if (io.out_count <= 0) return CM_OK;
+    if (!io.out_f) return cm_fail(CM_ERR_INVALID, "CM_MODE_EXTRACT_CHROMA needs a float output buffer%s");
+    const size_t b1 = (128 + (size_t)p.n1p + 2 * (size_t)p.hb2) * sizeof(T);
+    if (b1 > (size_t)m->smem_optin) return cm_fail(CM_ERR_UNSUPPORTED, "line too wide for the extract kernel%s");
+    int rc = set_smem(k_qam_extract<T>, b1);
+    if (rc) return rc;
+    k_qam_extract<T><<<dim3((unsigned)io.out_count, 1u, (unsigned)io.nframes), CM_NTHREADS, b1, st>>>(p, io);
+    cm_count_launch();
+    CUDA_TRY(cudaGetLastError());
+    return CM_OK;
+}
+
+CM_INSTANTIATE(template int launch_extract<float>(cm_modem *, IoArgs<float>, cudaStream_t);,
+               template int launch_extract<double>(cm_modem *, IoArgs<double>, cudaStream_t);)
 CM_INSTANTIATE(template int qam_encode<float>(cm_modem *, IoArgs<float>, cudaStream_t);,
                template int qam_encode<double>(cm_modem *, IoArgs<double>, cudaStream_t);)
 CM_INSTANTIATE(template int launch_bandsplit<float>(cm_modem *, IoArgs<float>, int, cudaStream_t);,
@@ -325,6 +343,7 @@ template <typename T>
 int qam_decode(cm_modem *m, IoArgs<T> io, int mode, cudaStream_t st) {
     const DevParams<T> &p = params_of<T>(m);
     if (mode == CM_MODE_BANDSPLIT_NOSTRIP) return launch_bandsplit<T>(m, io, 2, st);
+    if (mode == CM_MODE_EXTRACT_CHROMA) return launch_extract<T>(m, io, st);
     const bool pal3 = p.kind == CM_KIND_PAL_3D && (p.flags & (CM_FLAG_PAL3D_SIN | CM_FLAG_PAL3D_COS));
     const bool three_line = p.kind == CM_KIND_NTSC_3D || pal3;
     const bool post = (p.flags & CM_FLAG_NOTCH) || (three_line && (p.flags & CM_FLAG_MINAVG) && !(p.flags & CM_FLAG_NTSC_NO_COMB));

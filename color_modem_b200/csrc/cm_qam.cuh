@@ -717,6 +717,40 @@ k_qam_bs_row(const __grid_constant__ DevParams<T> p, const __grid_constant__ IoA
     }
 }
 
+// QamColorModem.extract_chroma (qam.py:34-37) of one row per CTA: E = down2(BP(up2 c)), stored as the first output plane
+// (float output only; the L0 kit call of the drop-in boundary, not on the frame path).
+template <typename T>
+__global__ void __launch_bounds__(CM_NTHREADS)
+k_qam_extract(const __grid_constant__ DevParams<T> p, const __grid_constant__ IoArgs<T> io) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T *scratch = reinterpret_cast<T *>(smem_raw), *sm = scratch + 128;
+    const int W = p.W, W2 = 2 * W, N1 = p.n1p, hb = p.hb2, N2 = 2 * hb;
+    const int row = io.out_begin + blockIdx.x, f = blockIdx.z;
+    T *cb = sm, *g = cb + N1;
+    const FirTaps<T> hup{p.firc[QR_UP2], p.fircp[QR_UP2]}, hdn{p.firc[QR_DOWN2], p.fircp[QR_DOWN2]};
+    load_comp_row(cb, io, f, row, W);
+    __syncthreads();
+    fir_up2(g, g + hb, cb, W, hup, threadIdx.x, blockDim.x);
+    __syncthreads();
+    cta_fill_tail<T, 2>(g, (size_t)N2, 1, hb, W2, N2);
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        const FiltHdr &fb = p.filt[QF_BP2X];
+        T *ge = g, *go = g + hb;
+        warp_iir<T, 2>(p.tab + fb.off, fb, [&](int q, int ph, int) { return (ph ? go : ge)[q]; }, Poly2Out<T>{ge, go});
+    }
+    __syncthreads();
+    T *dst = io.out_f + ((size_t)f * io.nrows + row) * W * 3;
+    fir_down2(g, g + hb, W, hdn, threadIdx.x, blockDim.x, [&](int j0, const T *y) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            dst[3 * (j0 + i)] = y[i];
+            dst[3 * (j0 + i) + 1] = (T)0;
+            dst[3 * (j0 + i) + 2] = (T)0;
+        }
+    });
+}
+
 // Pass 2 (elementwise): combine the planes of neighbouring rows of a field into (u, v) and the low-passed (u, v) the
 // re-modulation needs, y = c - remod, inverse matrix, store.  A thread owns 4 consecutive samples of CM_SEG consecutive
 // rows of one field and walks down the rows keeping the previous rows' planes in registers, so every plane is read

@@ -8,6 +8,35 @@ device->host copy).  ``modulate_batch`` / ``demodulate_batch`` do the same for [
 import numpy
 
 
+def _as_bytes(array):
+    """image.py:7-8"""
+    return numpy.uint8(numpy.rint(255.0 * numpy.maximum(numpy.minimum(array, 1.0), 0.0)))
+
+
+def drive_demodulate_float(modem, composite, frame):
+    """The line loop of image.py:75-83 over ``modem.demodulate`` for compositions that exist only as the per-line
+    protocol (composed wrappers, comb.py): [H, Wc] float composite -> [H, Wo, 3] float RGB.  Every ``demodulate`` call
+    runs on the GPU; this is the slow, general path — fused compositions never come here."""
+    h = composite.shape[0]
+    delay = getattr(modem, 'demodulation_delay', 0)
+    rows = [None] * h
+    for field in range(2):
+        for y in range(field, 2 * delay, 2):
+            if y < h:
+                modem.demodulate(frame, y, composite[y])
+        for y in range(field, h, 2):
+            src = y + 2 * delay
+            while src >= h:
+                src -= 2
+            rows[y] = numpy.stack(modem.demodulate(frame, y + 2 * delay, composite[src]), axis=-1)
+    return numpy.stack(rows)
+
+
+def drive_demodulate_u8(modem, comp_u8, frame):
+    comp = ImageModem.decode_composite_level(numpy.asarray(comp_u8, dtype=numpy.uint8) / 255.0)
+    return _as_bytes(drive_demodulate_float(modem, comp, frame))
+
+
 class ImageModem(object):
     def __init__(self, modem):
         self._modem = modem

@@ -74,16 +74,22 @@ class GpuModem(object):
         self._fill_desc(d)
         return d
 
-    def _handle(self, precision=None):
+    def _handle(self, precision=None, components=False):
+        """Native handle of this composition.  ``components=True``: the same composition with identity colour matrices,
+        i.e. the carrier of ``modulate_components`` / ``demodulate_components`` (planes in, planes out)."""
         precision = precision or self.precision
-        h = self._handles.get(precision)
+        key = (precision, bool(components))
+        h = self._handles.get(key)
         if h is None:
             lib = N.load()
             _torch()
             desc = self.describe()
+            if components:
+                for i in range(9):
+                    desc.enc_matrix[i] = desc.dec_matrix[i] = 1.0 if i % 4 == 0 else 0.0
             ptr = C.c_void_p()
             N.check(lib.cm_create(C.byref(desc), N.FP32 if precision == 'fp32' else N.FP64, C.byref(ptr)))
-            h = self._handles[precision] = ptr
+            h = self._handles[key] = ptr
         return h
 
     # ---- per-kernel device timing (bench.py roofline) ------------------------------------------------------
@@ -110,11 +116,24 @@ class GpuModem(object):
             pass
 
     # ---- frame batches on the device -----------------------------------------------------------------------
+    def _check_outputs(self, src, out, out_float, tail):
+        """out / out_float are written by the kernels through raw pointers: hold them to the exact layout."""
+        torch = _torch()
+        n = src.shape[0]
+        for t, dtype in ((out, torch.uint8), (out_float, torch.float32 if self.precision == 'fp32' else torch.float64)):
+            if t is None:
+                continue
+            if (not t.is_cuda or t.device != src.device or t.dtype != dtype or tuple(t.shape) != (n,) + tuple(tail)
+                    or not t.is_contiguous()):
+                raise ValueError('output must be a contiguous CUDA %s tensor of shape [%d, %s] on %s' % (
+                    dtype, n, ', '.join(map(str, tail)), src.device))
+
     def encode_frames(self, rgb, first_frame=0, out=None, out_float=None):
         """rgb: CUDA uint8 tensor [N, H, W, 3] -> composite uint8 [N, H, Wc] (ImageModem.modulate, image.py:27-56)."""
         torch = _torch()
         self._check(rgb, torch.uint8, (self.height, self.width, 3))
         n = rgb.shape[0]
+        self._check_outputs(rgb, out, out_float, (self.height, self.composite_width))
         if out is None and out_float is None:
             out = torch.empty((n, self.height, self.composite_width), dtype=torch.uint8, device=rgb.device)
         with torch.cuda.device(rgb.device):
@@ -129,6 +148,7 @@ class GpuModem(object):
         torch = _torch()
         self._check(comp, torch.uint8, (self.height, self.composite_width))
         n = comp.shape[0]
+        self._check_outputs(comp, out, out_float, (self.height, self.output_width, 3))
         if out is None and out_float is None:
             out = torch.empty((n, self.height, self.output_width, 3), dtype=torch.uint8, device=comp.device)
         with torch.cuda.device(comp.device):
@@ -174,7 +194,7 @@ class GpuModem(object):
     def _np_dtype(self):
         return numpy.float32 if self.precision == 'fp32' else numpy.float64
 
-    def _run_window(self, encode, frame, y0, rows_in, out_row, mode=N.MODE_DEFAULT, rgb_in_u8=None):
+    def _run_window(self, encode, frame, y0, rows_in, out_row, mode=N.MODE_DEFAULT, components=False, phase=0.0):
         """rows_in: float array [nrows, Win(, 3)] -> one output row as float64."""
         torch = _torch()
         dt = self._np_dtype()
@@ -183,10 +203,11 @@ class GpuModem(object):
         wout = self.composite_width if encode else self.output_width
         shape = (nrows, wout) if encode else (nrows, wout, 3)
         tout = torch.zeros(shape, dtype=tin.dtype, device=tin.device)
-        win = N.Window(nrows, int(y0), int(out_row), 1, int(mode), 0)
+        from .utils import radians_fixed
+        win = N.Window(nrows, int(y0), int(out_row), 1, int(mode), 0, radians_fixed(phase) if phase else 0)
         fn = N.load().cm_encode_ex if encode else N.load().cm_decode_ex
-        N.check(fn(self._handle(), C.byref(win), None, tin.data_ptr(), None, tout.data_ptr(), int(frame), 1,
-                   torch.cuda.current_stream().cuda_stream))
+        N.check(fn(self._handle(components=components), C.byref(win), None, tin.data_ptr(), None, tout.data_ptr(),
+                   int(frame), 1, torch.cuda.current_stream().cuda_stream))
         return tout[out_row].double().cpu().numpy()
 
     def encode_frame_float(self, rgb01, frame=0):
@@ -210,48 +231,69 @@ class GpuModem(object):
     # ---- per-line protocol --------------------------------------------------------------------------------
     encoder_lookahead = False     # True: encoder reads the next line of the field (ColorAveraging / HueCorrecting)
     decoder_rows = 1              # 1: row itself; 2: + previous row; 3: previous, current and next (one-line delay)
+    has_demodulate_components = False     # the reference class offers demodulate_components (comb-wrappable)
 
-    def modulate(self, frame, line, r, g, b):
-        cur = numpy.stack([numpy.asarray(r, dtype=numpy.float64), numpy.asarray(g, dtype=numpy.float64),
-                           numpy.asarray(b, dtype=numpy.float64)], axis=-1)
-        if len(r) != self.width:
+    def _modulate_planes(self, frame, line, p0, p1, p2, components):
+        cur = numpy.stack([numpy.asarray(p0, dtype=numpy.float64), numpy.asarray(p1, dtype=numpy.float64),
+                           numpy.asarray(p2, dtype=numpy.float64)], axis=-1)
+        if cur.shape[0] != self.width:
             raise AssertionError('line length does not match the modem width')
         if not self.encoder_lookahead:
-            return self._run_window(True, frame, line, cur[None], 0)
+            return self._run_window(True, frame, line, cur[None], 0, components=components)
         mem = self._enc_mem
-        cont = mem is not None and mem[0] == frame and line == mem[1] + 2
-        self._enc_mem = (frame, line, cur)
+        cont = mem is not None and mem[0] == frame and line == mem[1] + 2 and mem[3] == components
+        self._enc_mem = (frame, line, cur, components)
         if not cont:      # comb.py:142-146 / niir.py:180-184: the line is paired with itself
-            return self._run_window(True, frame, line - 2, cur[None], 0)
+            return self._run_window(True, frame, line - 2, cur[None], 0, components=components)
         rows = numpy.stack([mem[2], numpy.zeros_like(cur), cur])
-        return self._run_window(True, frame, line - 2, rows, 0)
+        return self._run_window(True, frame, line - 2, rows, 0, components=components)
 
-    def demodulate(self, frame, line, composite):
+    def modulate(self, frame, line, r, g, b):
+        """qam.py:68-69, secam.py:258, niir.py:76,176, protosecam.py:71, mac.py:124, comb.py:43,92,157."""
+        return self._modulate_planes(frame, line, r, g, b, False)
+
+    def modulate_components(self, frame, line, y, c1, c2):
+        """ntsc.py:43-45, pal.py:48-52, secam.py:261, niir.py:80,179, protosecam.py:74, mac.py:42, comb.py:40,89,141:
+        the same chain entered after the colour matrix (planes in the order of the class's encode_components)."""
+        return self._modulate_planes(frame, line, y, c1, c2, True)
+
+    def _demodulate_planes(self, frame, line, composite, components):
         cur = numpy.asarray(composite, dtype=numpy.float64)
         if len(cur) != self.composite_width:
             raise AssertionError('line length does not match the modem width')
         mem = self._dec_mem
         cont = mem is not None and mem[0] == frame and line == mem[1] + 2
         zero = numpy.zeros_like(cur)
+        kw = {'components': components}
         if self.decoder_rows == 1:
-            rgb = self._run_window(False, frame, line, cur[None], 0)
-        elif self.decoder_rows == 2:
+            return cur, self._run_window(False, frame, line, cur[None], 0, **kw)
+        if self.decoder_rows == 2:
             self._dec_mem = (frame, line, cur)
             if cont:
-                rgb = self._run_window(False, frame, line - 2, numpy.stack([mem[2], zero, cur]), 2)
-            else:
-                rgb = self._run_window(False, frame, line, cur[None], 0)
-        else:
-            # one-line delay (Pal3DModem pal.py:180-234, Simple3DCombModem comb.py:96-113): the call for `line`
-            # returns row line-2, computed from rows line-4 (if any), line-2 and line.
-            if not cont:
-                self._dec_mem = (frame, line, cur, None)
-                rgb = self._run_window(False, frame, line, cur[None], 0, mode=N.MODE_BANDSPLIT_NOSTRIP)
-            else:
-                last, before = mem[2], mem[3]
-                self._dec_mem = (frame, line, cur, last)
-                if before is None:
-                    rgb = self._run_window(False, frame, line - 2, numpy.stack([last, zero, cur]), 0)
-                else:
-                    rgb = self._run_window(False, frame, line - 4, numpy.stack([before, zero, last, zero, cur]), 2)
+                return cur, self._run_window(False, frame, line - 2, numpy.stack([mem[2], zero, cur]), 2, **kw)
+            return cur, self._run_window(False, frame, line, cur[None], 0, **kw)
+        # one-line delay (Pal3DModem pal.py:180-234, Simple3DCombModem comb.py:96-113): the call for `line`
+        # returns row line-2, computed from rows line-4 (if any), line-2 and line.
+        if not cont:
+            self._dec_mem = (frame, line, cur, None)
+            return cur, self._run_window(False, frame, line, cur[None], 0, mode=N.MODE_BANDSPLIT_NOSTRIP, **kw)
+        last, before = mem[2], mem[3]
+        self._dec_mem = (frame, line, cur, last)
+        if before is None:
+            return last, self._run_window(False, frame, line - 2, numpy.stack([last, zero, cur]), 0, **kw)
+        return last, self._run_window(False, frame, line - 4, numpy.stack([before, zero, last, zero, cur]), 2, **kw)
+
+    def demodulate(self, frame, line, composite):
+        """qam.py:71-72, comb.py:67-68,121-122, secam.py:278, niir.py:95, protosecam.py:92, mac.py:77."""
+        _, rgb = self._demodulate_planes(frame, line, composite, False)
         return rgb[:, 0], rgb[:, 1], rgb[:, 2]
+
+    def demodulate_components(self, frame, line, composite, strip_chroma=True):
+        """ntsc.py:47-49, pal.py:54-59,180-234, comb.py:47-59, niir.py:98-163: (y, c1, c2) before the inverse matrix.
+        strip_chroma=False leaves the luma un-stripped: the composite of the row the call answers for (the row itself, or
+        the previous one for the decoders with a one-line delay); the chroma planes do not depend on the flag."""
+        if not self.has_demodulate_components:
+            raise AttributeError('%s has no demodulate_components (neither has the reference class)' % type(self).__name__)
+        src, yuv = self._demodulate_planes(frame, line, composite, True)
+        y = yuv[:, 0] if strip_chroma else numpy.array(src)
+        return y, yuv[:, 1], yuv[:, 2]

@@ -15,7 +15,8 @@ TWO_PI = 2.0 * numpy.pi
 
 
 class FilterFunction(object):
-    """Design record of one IIR use-site (reference utils.py:9-26).  Not callable: filtering is GPU-only."""
+    """One IIR use-site (reference utils.py:9-36): the design record the kernels are fed from, and — called — the
+    reference's delay-compensated causal filter, run on the GPU (csrc/cm_util.cu: cm_filter_rows)."""
 
     def __init__(self, b, a, wp, btype, shift):
         self._b = numpy.asarray(b, dtype=numpy.float64)
@@ -46,8 +47,31 @@ class FilterFunction(object):
         sos = sos / sos[:, 3:4]
         return numpy.ascontiguousarray(sos[:, [0, 1, 2, 4, 5]])
 
-    def __call__(self, x):
-        raise NotImplementedError('FilterFunction is a design record; filtering runs inside the CUDA kernels')
+    def __call__(self, x, precision='fp64'):
+        """utils.py:28-36 along the last axis of ``x`` (zero initial state, ``shift`` copies of the last sample appended,
+        the first ``shift`` outputs dropped).  numpy in, float64 numpy out; the recursion runs in ``precision``."""
+        import ctypes as C
+        import torch
+        from . import _native as N
+        if not torch.cuda.is_available():
+            raise N.NativeUnavailable('no CUDA device: color_modem_b200 has no CPU path')
+        x = numpy.asarray(x, dtype=numpy.float64)
+        rows = numpy.ascontiguousarray(x.reshape(-1, x.shape[-1]), dtype=numpy.float32 if precision == 'fp32' else numpy.float64)
+        if rows.shape[1] == 0 or rows.shape[0] == 0:
+            return numpy.array(x)
+        f = N.Filter()
+        sos = self.sos
+        if sos.shape[0] > N.MAX_SECTIONS:
+            raise ValueError('filter order %d exceeds the CUDA cascade limit' % (2 * sos.shape[0]))
+        f.nsec, f.shift, f.n, f.rate = sos.shape[0], self._shift, rows.shape[1], 1
+        for s_ in range(sos.shape[0]):
+            for k in range(5):
+                f.sos[s_][k] = float(sos[s_, k])
+        tin = torch.from_numpy(rows).cuda()
+        tout = torch.empty_like(tin)
+        N.check(N.load().cm_filter_rows(C.byref(f), N.FP32 if precision == 'fp32' else N.FP64, tin.data_ptr(),
+                                        tout.data_ptr(), rows.shape[0], torch.cuda.current_stream().cuda_stream))
+        return tout.double().cpu().numpy().reshape(x.shape)
 
 
 def _scipy_iirdesign(wp, ws, gpass, gstop, ftype):

@@ -14,6 +14,12 @@
  *   modem.modulate(frame, line, r, g, b)   qam.py:68-69 etc.        cm_encode_ex() on a 1..3-row window
  *   modem.demodulate(frame, line, comp)    qam.py:71-72 etc.        cm_decode_ex() on a 1..5-row window
  *                                                                    (see cm_window below)
+ *   modem.modulate_components / demodulate_components               the same two calls on a handle created with identity
+ *     ntsc.py:43-49  pal.py:48-59,180-234  comb.py:40-59             colour matrices (planes in, planes out)
+ *     niir.py:80,98  secam.py:261  protosecam.py:74  mac.py:42
+ *   QamColorModem.modulate / demodulate / extract_chroma            cm_encode_ex / cm_decode_ex with cm_window.phase_offset
+ *     qam.py:28-58                                                   (explicit start phase), CM_MODE_EXTRACT_CHROMA
+ *   FilterFunction.__call__                utils.py:28-36           cm_filter_rows()
  *
  * Conventions: every function returns 0 on success or a negative cm_status; it never throws.  All frame
  * pointers are DEVICE pointers owned by the caller (cm_*_host variants take HOST pointers and do the copies
@@ -29,7 +35,7 @@
 extern "C" {
 #endif
 
-#define CM_ABI_VERSION 1
+#define CM_ABI_VERSION 2
 
 enum cm_status {
     CM_OK = 0,
@@ -132,6 +138,9 @@ typedef struct cm_window {
     int32_t out_count;
     int32_t mode;       /* cm_window_mode; 0 for the composition's normal behaviour */
     int32_t reserved;
+    uint64_t phase_offset;  /* added to the subcarrier phase at the first sample of every row, in turns as 0.64 fixed
+                             * point.  With a descriptor whose frame / line shifts are zero this is the explicit
+                             * start_phase argument of QamColorModem.modulate / demodulate (qam.py:28,43); 0 otherwise */
 } cm_window;
 
 enum cm_window_mode {
@@ -139,7 +148,10 @@ enum cm_window_mode {
     /* decode: what backend.demodulate_components(..., strip_chroma=False) returns — band-split chroma with the
      * composite itself as luma.  This is the value the stateful comb decoders hand back from their reset branch
      * (pal.py:191-195, comb.py:97-99); ImageModem discards it, the per-line protocol exposes it. */
-    CM_MODE_BANDSPLIT_NOSTRIP = 1
+    CM_MODE_BANDSPLIT_NOSTRIP = 1,
+    /* decode, QAM family: QamColorModem.extract_chroma (qam.py:34-37), down2(BP(up2 composite)), returned in the first
+     * output plane (the other two are zero) */
+    CM_MODE_EXTRACT_CHROMA = 2
 };
 
 int cm_abi_version(void);
@@ -174,6 +186,12 @@ int cm_decode_ex(cm_modem *m, const cm_window *win, const uint8_t *comp_u8, cons
 /* Whole frames with HOST buffers: copies in, runs, copies out, synchronises. */
 int cm_encode_frames_host(cm_modem *m, const uint8_t *rgb, uint8_t *comp, int64_t first_frame, int32_t nframes);
 int cm_decode_frames_host(cm_modem *m, const uint8_t *comp, uint8_t *rgb, int64_t first_frame, int32_t nframes);
+
+/* FilterFunction.__call__ (utils.py:28-36) on `nrows` independent rows of f->n samples each: causal IIR from zero
+ * state, the input extended by f->shift copies of its last sample and the first f->shift outputs dropped.  `in` / `out`
+ * are DEVICE buffers [nrows][f->n] of the given precision (float or double); f->rate is ignored.  Synchronises the
+ * stream.  Carrier of the reference's L0 filter kit and of the luma notch of composed comb wrappers (comb.py:18-20). */
+int cm_filter_rows(const cm_filter *f, int precision, const void *in, void *out, int32_t nrows, void *stream);
 
 /* Optional per-kernel device timing (CUDA events recorded on the launch stream around every kernel launch).
  * bench.py uses it for the roofline line; it is off by default and costs nothing when off. */

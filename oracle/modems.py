@@ -23,6 +23,8 @@ vectorised over all rows of a frame:
     niir_hue    HueCorrectingNiirModem         (niir.py:166-202)
     protosecam  ProtoSecamModem                (protosecam.py:28-112)
     mac         MacModem                       (mac.py:15-125)
+    scomb+K     SimpleCombModem(K)             (comb.py:71-122)  K in ntsc, pal_s, ntsc_comb, niir, niir_hue
+    scomb3+K    Simple3DCombModem(K)           (comb.py:125-127)
 ``chroma_avg=True`` wraps the encoder in ColorAveragingModem (comb.py:130-167); ``notch=Q`` gives the comb decoders
 the luma notch of comb.py:18-20.
 """
@@ -519,6 +521,12 @@ class Niir(_Base):
 
     def demodulate_planes(self, frame, comp):
         """niir.py:98-163"""
+        return self.planes_of_calls(frame, self.rows, comp, np.maximum(self.rows - 2, 0), self.rows < 2, True)
+
+    def planes_of_calls(self, frame, lines, comp, prev_idx, top, strip):
+        """niir.py:98-163 for a list of calls: call i has line number lines[i] and composite comp[i]; its predecessor
+        (line - 2, same frame) is call prev_idx[i] unless top[i] (reset branch, niir.py:103-106)."""
+        lines = np.asarray(lines)
         n = comp.shape[-1]
         rate = self.rate
         up = dsp.resample(comp, rate, 1)
@@ -526,11 +534,10 @@ class Niir(_Base):
         sat_up = self.base_lp(0.5 * np.pi * np.abs(mod_up))
         pm_up = mod_up / sat_up
         # previous row's phase carrier; at field top a synthetic reference carrier (niir.py:103-106)
-        ones = np.ones((2, n))
-        synth = self.up_bp(dsp.resample(self._carrier_mod(frame, self.rows[:2] - 2, ones, 0.0 * ones), rate, 1))
-        last_pm = _rows_prev(pm_up)
-        last_pm[:2] = synth
-        alt = _col(self.raster.is_alternate(frame, self.rows))
+        ones = np.ones((comp.shape[0], n))
+        synth = self.up_bp(dsp.resample(self._carrier_mod(frame, lines - 2, ones, 0.0 * ones), rate, 1))
+        last_pm = np.where(_col(top), synth, pm_up[prev_idx])
+        alt = _col(self.raster.is_alternate(frame, lines))
         carrier = np.where(alt, pm_up, last_pm)                                   # niir.py:114-121
         huemod = np.where(alt, last_pm, pm_up)
         shift = np.where(alt, -self.line_shift, self.line_shift)
@@ -547,13 +554,15 @@ class Niir(_Base):
         sat = dsp.resample(sat_up, 1, rate)
         db = sat * sinphi
         dr = sat * cosphi
-        sincar = dsp.resample(carrier, 1, rate)                                   # niir.py:143-158
-        coscar = dsp.resample(alt_carrier, 1, rate)
-        psh = np.where(alt, 0.0, self.line_shift) + (np.pi - self.up_bp.phase_shift)
-        us = np.where(alt, -np.sqrt(db * db + dr * dr), db)
-        vs = np.where(alt, 0.0, dr)
-        us, vs = us * np.cos(psh) - vs * np.sin(psh), us * np.sin(psh) + vs * np.cos(psh)
-        luma = comp - (us * sincar + vs * coscar)
+        luma = comp
+        if strip:
+            sincar = dsp.resample(carrier, 1, rate)                               # niir.py:143-158
+            coscar = dsp.resample(alt_carrier, 1, rate)
+            psh = np.where(alt, 0.0, self.line_shift) + (np.pi - self.up_bp.phase_shift)
+            us = np.where(alt, -np.sqrt(db * db + dr * dr), db)
+            vs = np.where(alt, 0.0, dr)
+            us, vs = us * np.cos(psh) - vs * np.sin(psh), us * np.sin(psh) + vs * np.cos(psh)
+            luma = comp - (us * sincar + vs * coscar)
         db, dr = self._remove_offset(db, dr)                                      # niir.py:98-100
         return luma, db, dr
 
@@ -708,9 +717,120 @@ class Mac(_Base):
 
 
 # =================================================================================================
+# SimpleCombModem / Simple3DCombModem over any backend with demodulate_components, comb.py:71-127
+# =================================================================================================
+class SimpleComb(_Base):
+    """comb.py:71-122, written down for the call sequence of ImageModem (image.py:75-83): per field the backend is called
+    for rows y = field, field+2, ... with line number y (delay=False), or - one call ahead - for rows y+2 with line
+    number y+2, the last row of the field being fed a second time with the line number after it (delay=True)."""
+
+    def __init__(self, spec, inner, delay):
+        super(SimpleComb, self).__init__(spec)
+        self.inner = inner
+        self.delay = bool(delay)
+        self.avg = _minavg if 'minavg' in (getattr(spec, 'opt', '') or '') else _avg
+        self.notch = None
+        if getattr(spec, 'notch', 0.0):                                               # comb.py:18-20, 86-88
+            import scipy.signal
+            b, a = scipy.signal.iirnotch(2.0 * inner.cfg.fsc / self.raster.fs, spec.notch)
+            self.notch = dsp.Filt(b, a, 0.0, 'bandstop', True)
+        self.encode_components = inner.encode_components
+        self.decode_components = inner.decode_components
+
+    def encode(self, frame, rgb):
+        return self.inner.encode(frame, rgb)                                          # comb.py:89-93
+
+    def _calls(self, comp):
+        """(lines, rows fed, predecessor call, reset flag) of the backend calls of one frame."""
+        H = self.raster.height
+        lines, src, prev, top = list(range(H)), list(range(H)), [max(r - 2, 0) for r in range(H)], [r < 2 for r in range(H)]
+        if self.delay:
+            for f in range(min(2, H)):
+                last = H - 1 - ((H - 1 - f) % 2)          # last row of field f
+                lines.append(last + 2)
+                src.append(last)
+                prev.append(last)
+                top.append(False)
+        return np.array(lines), np.array(src), np.array(prev), np.array(top)
+
+    def _backend_uv(self, frame, comp):
+        """(u, v) of backend.demodulate_components(..., strip_chroma=False) for every call (comb.py:98,100)."""
+        lines, src, prev, top = self._calls(comp)
+        inner, c = self.inner, comp[src]
+        if isinstance(inner, NtscComb):
+            u, v = inner.combed_uv(frame, lines, c[prev], c)
+            _, ut, vt = inner.bandsplit(frame, lines[top], c[top], False)
+            u[top], v[top] = ut, vt
+            return u, v
+        if isinstance(inner, Niir):
+            _, u, v = inner.planes_of_calls(frame, lines, c, prev, top, False)
+            return u, v
+        if type(inner) in (Ntsc, PalS):
+            _, u, v = inner.bandsplit(frame, lines, c, False)
+            return u, v
+        raise NotImplementedError('oracle: SimpleCombModem over %s' % type(inner).__name__)
+
+    def _remod(self, frame, rows, u, v):
+        """backend.modulate_components(frame, line - 2 * (own_delay - modulation_delay), 0, u, v) for the rows that take
+        the averaging branch, in call order per field (comb.py:104-107)."""
+        inner = self.inner
+        if not isinstance(inner, NiirHue):
+            return inner.modulate_components(frame, rows, np.zeros_like(u), u, v)
+        # HueCorrectingNiirModem.modulate_components is stateful (niir.py:179-202): every call answers for the previous
+        # call's line, with the magnitude of the previous call's chroma and the hue of the saturation-weighted mean of
+        # the two; the first call of a field is paired with itself.  The line number passed is row + 2 and the encoder
+        # emits for line - 2 = row.
+        out = np.empty_like(u)
+        for f in range(2):
+            idx = np.nonzero(rows % 2 == f)[0]
+            if not len(idx):
+                continue
+            pidx = np.concatenate((idx[:1], idx[:-1]))
+            ldb, ldr, db, dr = u[pidx], v[pidx], u[idx], v[idx]
+            last_sat = np.sqrt(ldb * ldb + ldr * ldr)
+            sat = np.sqrt(db * db + dr * dr)
+            div = last_sat + sat
+            div[np.equal(div, 0.0)] = 1.0
+            adb = (ldb * last_sat + db * sat) / div
+            adr = (ldr * last_sat + dr * sat) / div
+            mag = last_sat + 0.1
+            hue = np.arctan2(adb, adr)
+            out[idx] = inner._mod_offset(frame, rows[idx], np.zeros_like(db), mag * np.sin(hue), mag * np.cos(hue))
+        return out
+
+    def demodulate_planes(self, frame, comp):
+        H = self.raster.height
+        cu, cv = self._backend_uv(frame, comp)
+        rows = self.rows
+        if self.delay:
+            # output row y: last = call of row y, curr = the call after it in the field (the re-fed row at the bottom)
+            nxt = np.where(rows + 2 < H, rows + 2, H + (rows % 2))
+            u, v = self.avg(cu[rows], cu[nxt]), self.avg(cv[rows], cv[nxt])
+            y = comp - self._remod(frame, rows, u, v)
+            if self.notch:
+                y = self.notch(y)
+            return y, u, v
+        prev = np.maximum(rows - 2, 0)
+        u, v = self.avg(cu[prev], cu[rows]), self.avg(cv[prev], cv[rows])
+        y = np.array(comp)
+        body = rows >= 2
+        if np.any(body):
+            yb = comp[body] - self._remod(frame, rows[body], u[body], v[body])
+            if self.notch:
+                yb = self.notch(yb)
+            y[body] = yb
+        u[:2], v[:2] = cu[:2], cv[:2]                     # comb.py:97-99: the first row of a field, luma un-stripped
+        return y, u, v
+
+
+# =================================================================================================
 def build(spec):
     kind = spec.kind
     opt = getattr(spec, 'opt', '') or ''      # non-default constructor knobs, see tests/cases.py
+    if kind.startswith('scomb+') or kind.startswith('scomb3+'):     # SimpleCombModem / Simple3DCombModem over a backend
+        head, inner_kind = kind.split('+', 1)
+        inner = build(spec._replace(kind=inner_kind, notch=0.0, opt=''))
+        return SimpleComb(spec, inner, head == 'scomb3')
     if kind in ('ntsc', 'ntsc_comb', 'ntsc_3d'):
         cls = {'ntsc': Ntsc, 'ntsc_comb': NtscComb, 'ntsc_3d': Ntsc3D}[kind]
         return cls(spec, presets.NTSC[spec.variant or 'NTSC'])

@@ -16,6 +16,9 @@ NTSC = {
     'NTSC443': Qam(4433618.75, 1.3e6, 3.6e6),
     'NTSC_N': Qam(3585937.5, 1.3e6, 3.6e6),
     'NTSC361': Qam(229.5 * 15750.0 * 1000.0 / 1001.0, 1.3e6, 3.6e6),
+    # not a preset of the reference: a subcarrier at a whole multiple of the line rate, for which NtscCombModem gives up
+    # combing (|sin(LS/2)| <= 0.05, ntsc.py:55-59,71-72); built from the reference's own NtscVariant(fsc=...) constructor
+    'NTSC_NOCOMB': Qam(227.0 * 15750.0 * 1000.0 / 1001.0, 1.3e6, 3.6e6),
 }
 
 PAL = {

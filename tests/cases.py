@@ -79,6 +79,41 @@ GOLDEN_CASES = [
     _c('ntsc_3d', 'NTSC443', 'NTSC_525', 6, opt='minavg', notch=5.0, content='noise'),
     _c('pal_3d', 'PAL', 'GERBER_625', 7, opt='minavg'),
     _c('pal_3d', 'PAL', 'GERBER_625', 0, opt='minavg', notch=3.0),
+    # every preset / standard pair of BASELINE configs[4] at 1920 samples per line (23-47 MHz sampling: the multi-warp
+    # kernels); the pairs not already covered above (SECAM_E, D2MAC_7MHZ, PAL, NTSC)
+    _c('ntsc_3d', 'NTSC_A', 'BAIRD_405', 2, width=1920),
+    _c('ntsc_3d', 'NTSC_I', 'GERBER_625', 3, width=1920),
+    _c('ntsc_3d', 'NTSC_N', 'GERBER_625', 4, width=1920),
+    _c('ntsc_3d', 'NTSC361', 'NTSC_525', 5, width=1920),
+    _c('ntsc_3d', 'NTSC443', 'NTSC_525', 6, width=1920),
+    _c('pal_d', 'PAL_M', 'NTSC_525', 1, width=1920),
+    _c('pal_d', 'PAL_N', 'GERBER_625', 2, width=1920),
+    _c('secam', 'SECAM_I', 'GERBER_625', 1, width=1920, avg=True),
+    _c('secam', 'SECAM_II', 'GERBER_625', 2, width=1920, avg=True),
+    _c('secam', 'SECAM_III', 'GERBER_625', 3, width=1920, avg=True),
+    _c('secam', 'SECAM_A', 'BAIRD_405', 4, width=1920, avg=True),
+    _c('secam', 'SECAM_M', 'NTSC_525', 5, width=1920, avg=True),
+    _c('secam', 'SECAM_N', 'GERBER_625', 6, width=1920, avg=True),
+    _c('protosecam', 'SECAM_1957', 'FRENCH_819', 2, width=1920, avg=True),
+    # the fifth line standard (line.py:46)
+    _c('pal_s', 'PAL', 'BELGIAN_819', 3),
+    _c('ntsc_comb', 'NTSC443', 'BELGIAN_819', 4, width=1920),
+    # SimpleCombModem / Simple3DCombModem over other backends (comb.py:71-127; cli.py:52 is the first one)
+    _c('scomb+niir_hue', 'PAL', 'GERBER_625', 1),
+    _c('scomb+niir', 'PAL', 'GERBER_625', 2, notch=4.0),
+    _c('scomb3+niir', 'PAL', 'GERBER_625', 3),
+    _c('scomb+pal_s', 'PAL', 'GERBER_625', 4, notch=6.0),
+    _c('scomb3+pal_s', 'PAL', 'GERBER_625', 5),
+    _c('scomb+ntsc', 'NTSC', 'NTSC_525', 6, opt='minavg'),
+    _c('scomb3+ntsc', 'NTSC', 'NTSC_525', 7, opt='minavg', notch=5.0),
+    _c('scomb+ntsc_comb', 'NTSC', 'NTSC_525', 1),
+    _c('scomb3+pal_s', 'PAL_M', 'NTSC_525', 2, width=1920),
+    # NtscCombModem where the line comb is unusable (custom subcarrier; ntsc.py:55-59,71-72), alone and under Simple3DCombModem
+    _c('ntsc_comb', 'NTSC_NOCOMB', 'NTSC_525', 2),
+    _c('ntsc_3d', 'NTSC_NOCOMB', 'NTSC_525', 3, notch=3.0),
+    # BASELINE configs[0] and configs[1] at their own size: one whole frame each
+    _c('ntsc', 'NTSC', 'NTSC_525', 0, height=480, seed=0),
+    _c('pal_d', 'PAL', 'GERBER_625', 0, height=576, seed=0),
 ]
 
 FLOAT_ROWS = (1, 10, 22)   # rows whose float64 composite / RGB lines are stored: field top, interior, field bottom

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Generate tests/golden/*.npz by running the UNMODIFIED reference (/root/reference) in this container.
 
-    python tests/golden/make_golden.py
+    python tests/golden/make_golden.py [--missing]        (--missing: only the cases without a fixture yet)
 
 For every case in tests/cases.py this imports kFYatek/color_modem read-only, installs the scipy
 ``iirdesign`` validation shim of SURVEY.md §8c (needed by NTSC / PAL-M / PAL-N presets on scipy >= 1.6,
@@ -38,7 +38,10 @@ def main():
     warnings.filterwarnings('ignore')
     ref = load_reference()
     from PIL import Image
+    only_missing = '--missing' in sys.argv
     for c in GOLDEN_CASES:
+        if only_missing and os.path.exists(os.path.join(HERE, case_id(c) + '.npz')):
+            continue
         rgb = synth_frames_u8(1, c.height, c.width, first_frame=c.frame, seed=c.seed, kind=c.content)[0]
         modem = ref.make_modem(c)
         driver = ref.image.ImageModem(modem)
@@ -50,7 +53,7 @@ def main():
             out_img = driver.demodulate(comp_img, c.frame)
         out = np.asarray(out_img)
         rgb_f = ref.rows_in_raster_order(cap, c.height, 3)
-        rows = list(FLOAT_ROWS)
+        rows = [r for r in FLOAT_ROWS if r < c.height]
         path = os.path.join(HERE, case_id(c) + '.npz')
         np.savez_compressed(path, comp_u8=comp, rgb_u8=out,
                             comp_f64=comp_f[rows, 0], rgb_f64=np.moveaxis(rgb_f[rows], 1, -1))

@@ -2,18 +2,25 @@
 from color_modem_b200.line import LineConfig, LineStandard
 
 BUILT_KINDS = {'ntsc', 'ntsc_comb', 'ntsc_3d', 'pal_s', 'pal_d', 'pal_3d', 'secam', 'niir', 'niir_hue', 'protosecam',
-               'mac'}
+               'mac', 'scomb+niir_hue', 'scomb+niir', 'scomb3+niir', 'scomb+pal_s', 'scomb3+pal_s', 'scomb+ntsc',
+               'scomb3+ntsc', 'scomb+ntsc_comb'}
 
 
 def make_modem(c, precision='fp32'):
     from color_modem_b200.color import ntsc, pal, secam, niir, protosecam, mac
     from color_modem_b200 import comb
+    if not hasattr(ntsc.NtscVariant, 'NTSC_NOCOMB'):      # see oracle/presets.py
+        ntsc.NtscVariant.NTSC_NOCOMB = ntsc.NtscVariant(fsc=227.0 * 15750.0 * 1000.0 / 1001.0)
     std = getattr(LineStandard, c.standard) if c.standard else None
     lc = LineConfig((c.width, c.height), std)
     k, v = c.kind, c.variant
     notch = getattr(c, 'notch', 0.0)
     opt = getattr(c, 'opt', '')
-    if k == 'ntsc':
+    if k.startswith('scomb'):
+        head, inner = k.split('+', 1)
+        backend = make_modem(c._replace(kind=inner, notch=0.0, opt='', chroma_avg=False), precision)
+        m = comb.SimpleCombModem(backend, notch, comb.minavg if opt == 'minavg' else None, head == 'scomb3')
+    elif k == 'ntsc':
         m = ntsc.NtscModem(lc, getattr(ntsc.NtscVariant, v), precision=precision)
     elif k == 'ntsc_comb':
         m = ntsc.NtscCombModem(lc, getattr(ntsc.NtscVariant, v), notch, precision=precision)

@@ -55,6 +55,8 @@ def load_reference():
     import color_modem.comb as comb
     from color_modem.color import ntsc, pal, secam, niir, protosecam, mac
 
+    if not hasattr(ntsc.NtscVariant, 'NTSC_NOCOMB'):      # see oracle/presets.py
+        ntsc.NtscVariant.NTSC_NOCOMB = ntsc.NtscVariant(fsc=227.0 * 15750.0 * 1000.0 / 1001.0)
     ref = _Ref()
     ref.image, ref.line, ref.comb = image, line, comb
     ref.ntsc, ref.pal, ref.secam, ref.niir, ref.protosecam, ref.mac = ntsc, pal, secam, niir, protosecam, mac
@@ -65,7 +67,11 @@ def load_reference():
         k, v = c.kind, c.variant
         notch = getattr(c, 'notch', 0.0)
         opt = getattr(c, 'opt', '')
-        if k == 'ntsc':
+        if k.startswith('scomb'):
+            head, inner = k.split('+', 1)
+            backend = make_modem(c._replace(kind=inner, notch=0.0, opt='', chroma_avg=False))
+            m = comb.SimpleCombModem(backend, notch, comb.minavg if opt == 'minavg' else None, head == 'scomb3')
+        elif k == 'ntsc':
             m = ntsc.NtscModem(lc, getattr(ntsc.NtscVariant, v))
         elif k == 'ntsc_comb':
             m = ntsc.NtscCombModem(lc, getattr(ntsc.NtscVariant, v), notch)

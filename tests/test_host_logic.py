@@ -55,14 +55,16 @@ def test_descriptor_builds_and_filters_match_oracle(c):
     """Every composition yields a descriptor on a CPU box, and its SOS cascades reproduce the oracle's (b, a)."""
     import scipy.signal
     m = make_modem(c)
+    om = oracle.build(oracle.ModemSpec(c.kind, c.variant, c.width, c.height, c.standard, c.chroma_avg, c.notch, c.opt))
+    if c.kind.startswith('scomb'):          # composed wrapper: the kernels belong to the backend
+        om = om.inner
     d = m.describe()
     assert d.width == c.width and d.height == c.height
-    om = oracle.build(oracle.ModemSpec(c.kind, c.variant, c.width, c.height, c.standard, c.chroma_avg, c.notch, c.opt))
     filts = [v for obj in (om, getattr(om, 'qam', None), getattr(om, 'fm', None)) if obj is not None
              for v in vars(obj).values() if isinstance(v, dsp.Filt)]
     x = np.random.default_rng(0).standard_normal(400)
     used = [d.filters[i] for i in range(d.nfilters) if d.filters[i].nsec > 0]
-    assert len(used) == len(filts) or c.kind in ('pal_s', 'pal_3d', 'ntsc', 'ntsc_comb', 'ntsc_3d', 'mac')
+    assert len(used) == len(filts) or c.kind.split('+')[-1] in ('pal_s', 'pal_3d', 'ntsc', 'ntsc_comb', 'ntsc_3d', 'mac')
     for f in used:
         sos = np.array([[f.sos[s][0], f.sos[s][1], f.sos[s][2], 1.0, f.sos[s][3], f.sos[s][4]] for s in range(f.nsec)])
         y = scipy.signal.sosfilt(sos, x)
