@@ -67,6 +67,22 @@ def _clone(backend, **changes):
     return m
 
 
+def _fp64_twin(modem):
+    """The same composition with float64 kernels.  Composed wrappers run every backend call through it: the path is bound
+    by launches, not arithmetic, and the NIIR backends (hue from atan2 after the saturation clamp of niir.py:61-65) are
+    discontinuous at zero chroma, where float32 rounding would decide the hue."""
+    from .modem import GpuModem
+    if isinstance(modem, GpuModem):
+        return modem if modem.precision == 'fp64' else _clone(modem, precision='fp64')
+    impl = getattr(modem, '_impl', None)
+    if impl is not None:
+        twin = object.__new__(type(modem))
+        twin.__dict__.update(modem.__dict__)
+        twin._impl = _fp64_twin(impl)
+        return twin
+    return modem          # a composed wrapper: already float64 inside
+
+
 def _gpu_impl(modem):
     """The GpuModem that does the work of `modem` (a GpuModem itself, or a fused wrapper around one); None for composed
     wrappers."""
@@ -118,6 +134,7 @@ class SimpleCombModem(_Fused):
         if not hasattr(backend, 'demodulate_components') or not getattr(backend, 'has_demodulate_components', True):
             raise AttributeError('%s has no demodulate_components: not comb-wrappable (as in the reference)'
                                  % type(backend).__name__)
+        self._exec = _fp64_twin(backend)
         self._modulation_delay = getattr(backend, 'modulation_delay', 0)
         self._demodulation_delay = getattr(backend, 'demodulation_delay', 0) + self._own_delay
         if self._notch_q:
@@ -149,7 +166,7 @@ class SimpleCombModem(_Fused):
     def demodulate_components(self, frame, line, composite, strip_chroma=True):
         if self._impl is not None:
             return self._impl.demodulate_components(frame, line, composite, strip_chroma)
-        curr = self.backend.demodulate_components(frame, line, composite, strip_chroma=False)
+        curr = self._exec.demodulate_components(frame, line, composite, strip_chroma=False)
         if frame != self._last_frame or line != self._last_line + 2:
             y, u, v = curr
         else:
@@ -158,10 +175,10 @@ class SimpleCombModem(_Fused):
             u = self._avg(last[1], curr[1])
             v = self._avg(last[2], curr[2])
             if strip_chroma:
-                y = y - self.backend.modulate_components(frame, line - 2 * (self._own_delay - self._modulation_delay),
-                                                         numpy.zeros(len(composite)), u, v)
+                y = y - self._exec.modulate_components(frame, line - 2 * (self._own_delay - self._modulation_delay),
+                                                       numpy.zeros(len(composite)), u, v)
                 if self._notch is not None:
-                    y = self._notch(y, precision=self._precision())
+                    y = self._notch(y, precision='fp64')
         self._last_frame = frame
         self._last_line = line
         self._last_demodulated = curr

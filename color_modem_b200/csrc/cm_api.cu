@@ -8,6 +8,7 @@
 
 #include "cm_host.h"
 #include "cm_iir.cuh"
+#include "cm_slots.h"
 
 static thread_local char g_err[512] = "";
 static std::atomic<long long> g_launches{0};
@@ -46,16 +47,23 @@ static void pick_chunk(int rate, int total, int &L, int &nsuper) {
 void cm_build_filter_table(const cm_filter &f, FiltHdr &h, std::vector<double> &tab);
 static void build_filter(const cm_filter &f, FiltHdr &h, std::vector<double> &tab) { cm_build_filter_table(f, h, tab); }
 
+static void build_filter_L(const cm_filter &f, FiltHdr &h, std::vector<double> &tab, int L, int nsuper, int lanes);
+
 void cm_build_filter_table(const cm_filter &f, FiltHdr &h, std::vector<double> &tab) {
     int L = 0, nsuper = 0;
     pick_chunk(f.rate, f.n + f.shift, L, nsuper);
+    build_filter_L(f, h, tab, L, nsuper, 32);
+}
+
+// lanes: chunks per super-chunk (32 for one warp; 32 * team size for the packed team path, where nsuper == 1)
+static void build_filter_L(const cm_filter &f, FiltHdr &h, std::vector<double> &tab, int L, int nsuper, int lanes) {
     h.nsec = f.nsec;
     h.shift = f.shift;
     h.n = f.n;
     h.L = L;
     h.nsuper = nsuper;
     h.rate = f.rate;
-    h.npad = 32 * L * nsuper;
+    h.npad = lanes * L * nsuper;
     h.off = (int)tab.size();
     for (int s = 0; s < f.nsec; ++s) {
         const double *c = f.sos[s];
@@ -85,6 +93,22 @@ void cm_build_filter_table(const cm_filter &f, FiltHdr &h, std::vector<double> &
             mat_mul(M, M, Q);
             memcpy(M, Q, sizeof(M));
         }
+        {   // DF-I tables of the packed multi-warp path (team_iir_pk): (A^L)^t per lane, (A^L)^32 per warp
+            double Ml[4] = {1.0, 0.0, 0.0, 1.0};
+            for (int i = 0; i < L; ++i) {
+                double Q[4];
+                mat_mul(A, Ml, Q);
+                memcpy(Ml, Q, sizeof(Ml));
+            }
+            double Pw[4] = {1.0, 0.0, 0.0, 1.0};
+            for (int t = 0; t < 32; ++t) {
+                for (int i = 0; i < 4; ++i) sec[CM_SEC_D_LANE + 4 * t + i] = Pw[i];
+                double Q[4];
+                mat_mul(Ml, Pw, Q);
+                memcpy(Pw, Q, sizeof(Pw));
+            }
+            for (int i = 0; i < 4; ++i) sec[CM_SEC_D_M32 + i] = Pw[i];
+        }
         // DF-II-T tables of the multi-warp path: state (s1, s2), one step = [[-a1, 1], [-a2, 0]]
         const double At[4] = {-c[3], 1.0, -c[4], 0.0};
         double Mt[4] = {1.0, 0.0, 0.0, 1.0};
@@ -113,6 +137,50 @@ void cm_build_filter_table(const cm_filter &f, FiltHdr &h, std::vector<double> &
     }
 }
 
+// Geometry of k_qam_rows2 (cm_qam.cuh: RowL<1..3>) for this line length: the first one whose teams cover the three IIR
+// use-sites with the chunk lengths compiled for it; fills the QF_ROW_* headers and section tables.  0: none fits.
+static int plan_row_kernel(const cm_desc &d, FiltHdr *fh, std::vector<double> &tab) {
+    if (d.kind < CM_KIND_NTSC_COMB || d.kind > CM_KIND_PAL_3D) return 0;
+    const bool pald = d.kind == CM_KIND_PAL_D ||
+                      (d.kind == CM_KIND_PAL_3D && !(d.flags & (CM_FLAG_PAL3D_SIN | CM_FLAG_PAL3D_COS)));
+    const cm_filter &fbp = d.filters[QF_BP2X], &flp = d.filters[pald ? QF_PALD_LP : QF_DEMOD_LP], &fpre = d.filters[QF_PRE_LP];
+    if (!fbp.nsec || !flp.nsec || !fpre.nsec) return 0;
+    static const int nws[3] = {2, 4, 4};            // RowL<1..3> of cm_qam.cuh
+    static const int lbp[3] = {24, 24, 32}, lpa[3] = {46, 46, 62}, lpb[3] = {50, 50, 64}, lpre[3] = {23, 23, 31};
+    for (int k = 0; k < 3; ++k) {
+        const int nw = nws[k], th = nw / 2;
+        if (fbp.n + fbp.shift > 32 * nw * lbp[k]) continue;
+        if (fpre.n + fpre.shift > 32 * th * lpre[k]) continue;
+        int ll = 0;
+        if (flp.n + flp.shift <= 32 * th * lpa[k]) ll = lpa[k];
+        else if (flp.n + flp.shift <= 32 * th * lpb[k]) ll = lpb[k];
+        if (!ll) continue;
+        build_filter_L(fbp, fh[6], tab, lbp[k], 1, 32 * nw);
+        build_filter_L(flp, fh[7], tab, ll, 1, 32 * th);
+        build_filter_L(fpre, fh[8], tab, lpre[k], 1, 32 * th);
+        return k + 1;
+    }
+    return 0;
+}
+
+// Row-independent carrier of k_qam_rows2: sin / cos of (j * step) for the 2x sample index j, tail replicated, in the
+// load order of LoadPoly2Carrier: [task][i / 2][chunk][i & 1] with j = chunk * L + i.
+static void build_carrier_table(const cm_desc &d, const FiltHdr &fl, int th, std::vector<double> &out) {
+    const int L = fl.L, nchunks = 32 * th;
+    out.assign((size_t)2 * fl.npad, 0.0);
+    const unsigned long long step = d.phases[QP_STEP2X];
+    for (int chunk = 0; chunk < nchunks; ++chunk)
+        for (int i = 0; i < L; ++i) {
+            int j = chunk * L + i;
+            if (j > fl.n - 1) j = fl.n - 1;
+            const unsigned long long ph = (unsigned long long)j * step;                // wraps mod one turn
+            const double turns = (double)(long long)ph * 5.421010862427522170e-20;     // 2^-64: [-0.5, 0.5)
+            const size_t at = 2 * ((size_t)(i >> 1) * nchunks + chunk) + (i & 1);
+            out[at] = sin(6.283185307179586476925 * turns);
+            out[(size_t)fl.npad + at] = cos(6.283185307179586476925 * turns);
+        }
+}
+
 template <typename T>
 static void fill_params(const cm_desc &d, DevParams<T> &p, const FiltHdr *fh, const ResHdr *rh, const void *tab,
                         const void *taps) {
@@ -133,6 +201,12 @@ static void fill_params(const cm_desc &d, DevParams<T> &p, const FiltHdr *fh, co
     for (int i = 0; i < CM_NPHASE; ++i) p.phases[i] = d.phases[i];
     for (int i = 0; i < CM_NSCAL; ++i) p.scalars[i] = (T)d.scalars[i];
     for (int i = 0; i < 9; ++i) { p.enc[i] = (T)d.enc_matrix[i]; p.dec[i] = (T)d.dec_matrix[i]; p.encd[i] = d.enc_matrix[i]; }
+    p.ident_enc = p.ident_dec = 1;
+    for (int i = 0; i < 9; ++i) {
+        const double id = (i % 4 == 0) ? 1.0 : 0.0;
+        if (d.enc_matrix[i] != id) p.ident_enc = 0;
+        if (d.dec_matrix[i] != id) p.ident_dec = 0;
+    }
     for (int i = 0; i < CM_NFILT; ++i) p.filt[i] = fh[i];
     // line-buffer geometry: every buffer that feeds an IIR is padded to the site's 32*L*nsuper
     auto up4 = [](int v) { return (v + 3) & ~3; };
@@ -251,15 +325,24 @@ extern "C" int cm_create(const cm_desc *desc, int precision, cm_modem **out) {
         rh[i].off = (int)taps.size();
         taps.insert(taps.end(), r.taps, r.taps + r.ntaps);
     }
+    const int row_geo = plan_row_kernel(*desc, fh, tab);
+    std::vector<double> ctab;
+    if (row_geo) build_carrier_table(*desc, fh[7], row_geo == 1 ? 1 : 2, ctab);
     int rc;
     if (precision == CM_FP32) {
         rc = upload<float>(tab, &m->d_tab);
         if (rc == CM_OK) rc = upload<float>(taps, &m->d_taps);
+        if (rc == CM_OK) rc = upload<float>(ctab, &m->d_ctab);
         fill_params<float>(*desc, m->pf, fh, rh, m->d_tab, m->d_taps);
+        m->pf.ctab = (const float *)m->d_ctab;
+        m->pf.row_geo = row_geo;
     } else {
         rc = upload<double>(tab, &m->d_tab);
         if (rc == CM_OK) rc = upload<double>(taps, &m->d_taps);
+        if (rc == CM_OK) rc = upload<double>(ctab, &m->d_ctab);
         fill_params<double>(*desc, m->pd, fh, rh, m->d_tab, m->d_taps);
+        m->pd.ctab = (const double *)m->d_ctab;
+        m->pd.row_geo = row_geo;
     }
     if (rc != CM_OK) { cm_destroy(m); return rc; }
     *out = m;
@@ -270,6 +353,7 @@ extern "C" void cm_destroy(cm_modem *m) {
     if (!m) return;
     cudaFree(m->d_tab);
     cudaFree(m->d_taps);
+    cudaFree(m->d_ctab);
     for (int i = 0; i < cm_modem::kHostStreams; ++i) {
         cudaFree(m->d_in[i]);
         cudaFree(m->d_out[i]);

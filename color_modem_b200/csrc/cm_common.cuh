@@ -37,6 +37,8 @@ struct ResHdr {
 template <typename T>
 struct DevParams {
     int kind, flags;
+    int ident_enc, ident_dec;   // the colour matrix is the identity (component-level handles): planes pass through untouched,
+                                // so that signed zeros survive (numpy.arctan2 of niir.py:45,64 tells -0.0 from +0.0)
     int W, H, Wc, Wo;
     int digital_shift, odd_first, even_first, ref_line, frame_cycle;
     int n1p;          // padded length of 1x line buffers (multiple of 4, >= every 1x IIR site's npad)
@@ -54,6 +56,8 @@ struct DevParams {
     ResHdr res[CM_NRES];
     const T *tab;
     const T *taps;
+    const T *ctab;    // k_qam_rows2: row-independent carrier table [sin | cos][npad of the QF_ROW_LP site] (cm_api.cu)
+    int row_geo;      // k_qam_rows2: geometry 1..3 (cm_qam.cuh: RowL); 0 = the row kernel does not serve this line length
     // dense taps of resampler slots 0 and 1 (the x2 / x3 half-band pair of every family except MAC), zero-filled:
     // read with compile-time indices they become constant-bank operands of the FIR FMAs (FFMA R, R, c[0][..], R
     // issues at full rate; with the tap in a third register the sm_100 register file caps FFMA at ~0.7 / clk,

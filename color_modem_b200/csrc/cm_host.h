@@ -28,6 +28,7 @@ struct cm_modem {
     DevParams<double> pd;
     void *d_tab = nullptr;
     void *d_taps = nullptr;
+    void *d_ctab = nullptr;
     bool timing = false;
     unsigned long long *phase_prof = nullptr;
     // pairing scratch of the line-sequential decoders (grown on demand); one per host-path stream (+ slot 0 for

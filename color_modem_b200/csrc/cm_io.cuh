@@ -139,6 +139,10 @@ __device__ __forceinline__ void store_rgb4_direct(const DevParams<T> &p, const I
         v[3 * i + 1] = p.dec[3] * y[i] + p.dec[4] * c1[i] + p.dec[5] * c2[i];
         v[3 * i + 2] = p.dec[6] * y[i] + p.dec[7] * c1[i] + p.dec[8] * c2[i];
     }
+    if (p.ident_dec) {          // demodulate_components: the planes themselves (a product with 0 would eat the sign of -0.0)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { v[3 * i] = y[i]; v[3 * i + 1] = c1[i]; v[3 * i + 2] = c2[i]; }
+    }
     const size_t o = (((size_t)fidx * io.nrows + row) * p.Wo + x0) * 3;
     if (io.out_f) {
 #pragma unroll

@@ -84,11 +84,13 @@ k_niir_encode(const __grid_constant__ DevParams<T> p, const __grid_constant__ Io
                 y[i] = p.enc[0] * r[i] + p.enc[1] * gg[i] + p.enc[2] * b[i];
                 T vb = p.enc[3] * r[i] + p.enc[4] * gg[i] + p.enc[5] * b[i];
                 T vr = p.enc[6] * r[i] + p.enc[7] * gg[i] + p.enc[8] * b[i];
+                if (p.ident_enc) { y[i] = r[i]; vb = gg[i]; vr = b[i]; }       // modulate_components: planes as given
                 T mag_out;
                 if (hue) {
                     // niir.py:186-197: hue of the saturation-weighted mean of this row and the next, this row's saturation
-                    const T nb = p.enc[3] * r2[i] + p.enc[4] * g2[i] + p.enc[5] * b2[i];
-                    const T nr = p.enc[6] * r2[i] + p.enc[7] * g2[i] + p.enc[8] * b2[i];
+                    T nb = p.enc[3] * r2[i] + p.enc[4] * g2[i] + p.enc[5] * b2[i];
+                    T nr = p.enc[6] * r2[i] + p.enc[7] * g2[i] + p.enc[8] * b2[i];
+                    if (p.ident_enc) { nb = g2[i]; nr = b2[i]; }
                     const T ls = Real<T>::sqrt_(vb * vb + vr * vr), sn = Real<T>::sqrt_(nb * nb + nr * nr);
                     T div = ls + sn;
                     if (div == (T)0) div = (T)1;
@@ -98,8 +100,9 @@ k_niir_encode(const __grid_constant__ DevParams<T> p, const __grid_constant__ Io
                     vr = ar;
                 } else {
                     if (avg) {
-                        const T nb = p.enc[3] * r2[i] + p.enc[4] * g2[i] + p.enc[5] * b2[i];
-                        const T nr = p.enc[6] * r2[i] + p.enc[7] * g2[i] + p.enc[8] * b2[i];
+                        T nb = p.enc[3] * r2[i] + p.enc[4] * g2[i] + p.enc[5] * b2[i];
+                        T nr = p.enc[6] * r2[i] + p.enc[7] * g2[i] + p.enc[8] * b2[i];
+                        if (p.ident_enc) { nb = g2[i]; nr = b2[i]; }
                         vb = (T)0.5 * (nb + vb);
                         vr = (T)0.5 * (nr + vr);
                     }
@@ -125,6 +128,11 @@ k_niir_encode(const __grid_constant__ DevParams<T> p, const __grid_constant__ Io
                     double vb, vr, nb = 0.0, nr = 0.0, mag_out;
                     niir_chroma_f64(p.encd, rd[i], gd[i], bd[i], vb, vr);
                     if (avg || hue) niir_chroma_f64(p.encd, r2d[i], g2d[i], b2d[i], nb, nr);
+                    if (p.ident_enc) {
+                        vb = gd[i];
+                        vr = bd[i];
+                        if (avg || hue) { nb = g2d[i]; nr = b2d[i]; }
+                    }
                     if (hue) {
                         const double ls = sqrt(__dadd_rn(__dmul_rn(vb, vb), __dmul_rn(vr, vr)));
                         const double sn = sqrt(__dadd_rn(__dmul_rn(nb, nb), __dmul_rn(nr, nr)));
@@ -147,9 +155,12 @@ k_niir_encode(const __grid_constant__ DevParams<T> p, const __grid_constant__ Io
                         const double sc = mag_out / sqrt(m2);
                         db[i] = (T)(vb * sc);
                         dr[i] = (T)(vr * sc);
-                    } else {                          // atan2(0, 0) = 0 -> (sin, cos) = (0, 1)
-                        db[i] = (T)0;
+                    } else if (!signbit(vr)) {        // atan2(+-0, +0) = +-0 -> (sin, cos) = (+-0, 1)
+                        db[i] = (T)(mag_out * copysign(0.0, vb));
                         dr[i] = (T)mag_out;
+                    } else {                          // atan2(+-0, -0) = +-pi -> (sin, cos) = (+-1.2e-16, -1), as numpy has it
+                        db[i] = (T)(mag_out * copysign(1.2246467991473532e-16, vb));
+                        dr[i] = (T)(-mag_out);
                     }
                 }
             }

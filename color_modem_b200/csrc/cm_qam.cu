@@ -145,8 +145,14 @@ int launch_rows_pair(cm_modem *m, IoArgs<T> io, cudaStream_t st) {
     const size_t b1 = (128 + (size_t)p.n1p + 6 * (size_t)p.hb2) * sizeof(T);
     if (b1 > (size_t)m->smem_optin) return cm_fail(CM_ERR_UNSUPPORTED, "line too wide for the row kernels%s");
     const bool teams = needs_teams(p);
-    auto pass1 = teams ? k_qam_rows<T, MODE == PAIR_PALD, true> : k_qam_rows<T, MODE == PAIR_PALD, false>;
-    const int threads1 = teams ? row_threads(p) : CM_ROW_THREADS;
+    constexpr bool kPald = MODE == PAIR_PALD;
+    void (*pass1)(const DevParams<T>, const IoArgs<T>) = teams ? k_qam_rows<T, kPald, true> : k_qam_rows<T, kPald, false>;
+    int threads1 = teams ? row_threads(p) : CM_ROW_THREADS;
+    static const bool rows_v1 = getenv("CM_ROWS_V1") != nullptr;          // A/B aid: the first-generation row kernel
+    if (p.row_geo && !rows_v1) {
+        pass1 = p.row_geo == 1 ? k_qam_rows2<T, kPald, 1> : (p.row_geo == 2 ? k_qam_rows2<T, kPald, 2> : k_qam_rows2<T, kPald, 3>);
+        threads1 = p.row_geo == 1 ? 64 : 128;
+    }
     int rc = set_smem(pass1, b1);
     if (rc) return rc;
     // frames per pass-1 / pass-2 launch pair: as many as a 2 GiB scratch holds (720x576: 6.6 MB per frame -> 323 frames;

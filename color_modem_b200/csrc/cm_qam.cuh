@@ -644,6 +644,119 @@ k_qam_rows(const __grid_constant__ DevParams<T> p, const __grid_constant__ IoArg
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// Pass 1, second generation (k_qam_rows2): the same planes as k_qam_rows, with
+//   * every IIR stage run by ALL warps of the CTA: the single band-pass task by a team of NW warps, the task pairs
+//     (sin || cos low-pass, alpha || beta pre-low-pass) by two teams of NW / 2 warps — no warp idles at a barrier while
+//     another one filters (15 % of the warp-stall samples of k_qam_rows), and 1920-sample lines get the packed f32x2
+//     recursion that the older multi-warp path (team_iir_L, scalar DF-II-T) lacked;
+//   * the demodulating carrier taken from a row-independent table: sin / cos(2 pi j step) for the 2x sample index j, laid
+//     out for coalesced loads, tail replicated (DevParams::ctab).  The row's own phase psi is applied afterwards, as a
+//     rotation of the decimated pair:  a = cos(psi) a' + sin(psi) b',  b = cos(psi) b' - sin(psi) a'  (low-pass and
+//     decimation are linear) — 4 operations per output sample instead of a rotating carrier with an end-of-line
+//     predicate per 2x sample and channel (13 % of the instructions of k_qam_rows).
+// Geometry GEO (warps per CTA, chunk lengths per lane; chosen by the host, cm_api.cu: plan_row_kernel):
+//   1: 2 warps, lines up to ~760 samples;  2: 4 warps, up to ~1520;  3: 4 warps with long chunks, up to ~1970 (1920-wide
+//   rasters).  Short chunks on more warps lose: the per-chunk cost of a section (warp scan, team fold, barrier) is fixed,
+//   8 warps x 16 samples measured 98 us per 1080p frame against 65 of the first-generation kernel.
+// ------------------------------------------------------------------------------------------------------------
+template <int GEO> struct RowL;
+template <> struct RowL<1> { static constexpr int NW = 2, BP = 24, LPA = 46, LPB = 50, PRE = 23; };
+template <> struct RowL<2> { static constexpr int NW = 4, BP = 24, LPA = 46, LPB = 50, PRE = 23; };
+template <> struct RowL<3> { static constexpr int NW = 4, BP = 32, LPA = 62, LPB = 64, PRE = 31; };
+
+#define QF_ROW_BP 6      // DevParams::filt slots of the row kernel's use-sites (same filters as QF_BP2X, QF_DEMOD_LP or
+#define QF_ROW_LP 7      // QF_PALD_LP, QF_PRE_LP; chunk lengths and tables for its team geometry, built in cm_api.cu)
+#define QF_ROW_PRE 8
+
+template <typename T, bool PALD, int GEO>
+__global__ void __launch_bounds__(32 * RowL<GEO>::NW, sizeof(T) == 8 ? 1 : 16 / RowL<GEO>::NW)
+k_qam_rows2(const __grid_constant__ DevParams<T> p, const __grid_constant__ IoArgs<T> io) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T *scratch = reinterpret_cast<T *>(smem_raw), *sm = scratch + 128;      // [0, 128): team exchange
+    typedef RowL<GEO> RL;
+    constexpr int NW = RL::NW;
+    constexpr int TH = NW / 2;                                              // warps per team of a task pair
+    const int W = p.W, W2 = 2 * W, N1 = p.n1p, hb = p.hb2, N2 = 2 * hb;
+    const int f = blockIdx.z, end = io.out_begin + io.out_count;
+    const int warp = threadIdx.x >> 5;
+    const int task = warp / TH, wr = warp - task * TH;
+    T *cb = sm, *g = cb + N1, *wa = g + N2, *wb = wa + N2;
+    const FirTaps<T> hup{p.firc[QR_UP2], p.fircp[QR_UP2]}, hdn{p.firc[QR_DOWN2], p.fircp[QR_DOWN2]};
+    const FiltHdr &fb = p.filt[QF_ROW_BP], &fl = p.filt[QF_ROW_LP], &fpre = p.filt[QF_ROW_PRE];
+    const long long frame = io.first_frame + f;
+    const bool pre = io.in_u8 != nullptr && W <= 4 * RowPrefetch::kMaxQuads * (int)blockDim.x;
+    RowPrefetch pf;
+    int row = io.out_begin + blockIdx.x;
+    if (pre && row < end) pf.fetch(io, f, row, W);
+    for (; row < end; row += gridDim.x) {
+        if (pre) pf.stage(cb, W);
+        else load_comp_row(cb, io, f, row, W);
+        __syncthreads();
+        if (pre && row + (int)gridDim.x < end) pf.fetch(io, f, row + gridDim.x, W);
+        T *__restrict__ dst = io.aux + ((size_t)f * io.nrows + row) * 4 * W;
+        fir_up2(g, g + hb, cb, W, hup, threadIdx.x, blockDim.x);
+        __syncthreads();
+        // band-pass in place, all warps
+        warp_fill_tail<T, 2>(g, hb, W2, fb.npad);                   // every warp writes the same values
+        team_iir_pk<T, 2, RL::BP, NW>(p.tab + fb.off, fb, LoadPoly2<T, RL::BP>{g, g + hb}, Poly2Out<T>{g, g + hb}, warp, 1,
+                                      scratch);
+        __syncthreads();
+        if (PALD) {
+            fir_down2(g, g + hb, W, hdn, threadIdx.x, blockDim.x, [&](int j0, const T *y) { st4(cb + j0, y); });
+            __syncthreads();
+            fir_up2(g, g + hb, cb, W, hup, threadIdx.x, blockDim.x);
+            __syncthreads();
+        }
+        {   // a' = LP(sin(theta) X) by team 0, b' = LP(cos(theta) X) by team 1
+            warp_fill_tail<T, 2>(g, hb, W2, fl.npad);
+            T *de = task ? wb : wa;
+            const T *ct = p.ctab + (size_t)task * fl.npad;
+            if (fl.L == RL::LPA)
+                team_iir_pk<T, 2, RL::LPA, TH>(p.tab + fl.off, fl, LoadPoly2Carrier<T, RL::LPA>{g, g + hb, ct, 32 * TH},
+                                               Poly2Out<T>{de, de + hb}, wr, 2 + task, scratch + 32 + 32 * task);
+            else
+                team_iir_pk<T, 2, RL::LPB, TH>(p.tab + fl.off, fl, LoadPoly2Carrier<T, RL::LPB>{g, g + hb, ct, 32 * TH},
+                                               Poly2Out<T>{de, de + hb}, wr, 2 + task, scratch + 32 + 32 * task);
+        }
+        __syncthreads();
+        {   // decimate, rotate to the row's own phase, keep (a, b) for the pre-low-pass
+            T sphi, cphi;
+            Real<T>::sincos_turns(start_phase(p, frame, io.y0 + row) + p.phases[QP_BP_SHIFT] -
+                                      (PALD ? p.phases[QP_HALF_LS] : 0ull), sphi, cphi);
+            T *sa = cb, *sb = g;
+            fir_down2_pair(wa, wa + hb, wb, wb + hb, W, hdn, threadIdx.x, blockDim.x, [&](int j0, const T *a0, const T *b0) {
+                T a[4], b[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    a[i] = Real<T>::fma_(cphi, a0[i], sphi * b0[i]);
+                    b[i] = Real<T>::fma_(cphi, b0[i], -(sphi * a0[i]));
+                }
+                st4(dst + j0, a);
+                st4(dst + W + j0, b);
+                st4(sa + j0, a);
+                st4(sb + j0, b);
+            });
+        }
+        __syncthreads();
+        {   // alpha = LPpre(a) by team 0, beta = LPpre(b) by team 1
+            T *src = task ? g : cb, *out = task ? wb : wa;
+            warp_fill_tail<T, 1>(src, N1, W, fpre.npad);
+            team_iir_pk<T, 1, RL::PRE, TH>(p.tab + fpre.off, fpre, LoadLinear<T, RL::PRE>{src}, [&](int j, T x) { out[j] = x; },
+                                           wr, 2 + task, scratch + 32 + 32 * task);
+        }
+        __syncthreads();
+        for (int x = 4 * threadIdx.x; x < W; x += 4 * blockDim.x) {
+            T v[4];
+            ld4(wa + x, v);
+            st4(dst + 2 * W + x, v);
+            ld4(wb + x, v);
+            st4(dst + 3 * W + x, v);
+        }
+        __syncthreads();
+    }
+}
+
 // Band-split decode (qam.py:43-58 with strip_chroma=True: NtscModem, PalSModem) of one row per CTA of two warps:
 // the two IIR stages are pairs of independent tasks (band-pass || band-stop, then the u || v low-pass), so both warps
 // are busy in every phase; 26.5 KB of shared memory, 8 CTAs per SM.

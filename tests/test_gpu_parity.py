@@ -8,6 +8,7 @@ import os
 import numpy as np
 import pytest
 
+import conditioning
 import oracle
 from oracle import frame as oframe
 from cases import GOLDEN_CASES, case_id
@@ -50,12 +51,18 @@ def test_u8_frames_against_reference_golden(c, cuda_required):
     assert np.array_equal(m.decode_frames_host(g['comp_u8'][None], c.frame)[0], out)
 
 
-# Ill-conditioned decoders: NIIR divides by the demodulated envelope and by |(sin, cos)| (niir.py:112,132-134).
-# At 36 MHz sampling a 1e-7 relative perturbation of the *float64 reference's own input* already moves isolated
-# output samples by 7e-5 (condition number ~700, measured on the oracle), so fp32 cannot hold
-# 1e-4 at those samples.  There the bound is: 99.9 % of samples within 1e-4, every sample within 1e-2, and the
-# 8-bit frames still within +-1 LSB (test_u8_frames_against_reference_golden).
-ILL_CONDITIONED_FP32 = {('niir', 1920), ('niir_hue', 1920)}
+# Ill-conditioned samples.  The non-linear decoders divide by a demodulated amplitude (FM discriminator: |I - jQ|^2,
+# secam.py:143-148; NIIR: envelope and |(sin, cos)|, niir.py:112,132-134); where it passes near zero the float64
+# reference's own output moves by more than 1e-4 under a float32-level noise floor on its input.  tests/conditioning.py
+# measures that per sample on the oracle; a sample may exceed 1e-4 only by 4x what the reference itself moves, on at
+# most 0.1 % of the samples (measured: none for any QAM / MAC / proto-SECAM case and for SECAM at 720 samples per line;
+# 22 samples of SECAM_N and 126 of NIIR at 1920 samples per line), and the 8-bit frames stay within +-1 LSB everywhere
+# (test_u8_frames_against_reference_golden).
+#
+# NIIR at 1920 samples per line (36 MHz sampling, 3x oversampled = 108 MHz) keeps the bound of round 1 on top of that:
+# its float32 errors also appear at samples the input-noise probe does not flag (the envelope division acts on
+# intermediate signals at the 3x rate); 99.9 % of the samples within 1e-4, every sample within 1e-2.
+NIIR_WIDE_FP32 = {('niir', 1920), ('niir_hue', 1920)}
 
 
 def _make_or_skip(c, precision, fn):
@@ -81,8 +88,11 @@ def test_float_planes_against_oracle(c, precision, tol, cuda_required):
     out_ref = om.decode(c.frame, comp_in)
     out = _make_or_skip(c, precision, lambda: m.decode_frame_float(comp_in, c.frame))
     err = np.abs(out - out_ref)
-    if precision == 'fp32' and (c.kind, c.width) in ILL_CONDITIONED_FP32:
+    if precision == 'fp32' and (c.kind, c.width) in NIIR_WIDE_FP32:
         assert np.quantile(err, 0.999) <= tol and err.max() <= 1e-2
+    elif precision == 'fp32':
+        bound = conditioning.fp32_bound(lambda x: om.decode(c.frame, x), comp_in, out_ref, tol)
+        assert (err <= bound).all(), 'max excess %.2e at %s' % ((err - bound).max(), np.unravel_index((err - bound).argmax(), err.shape))
     else:
         assert err.max() <= tol
 

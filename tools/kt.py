@@ -1,6 +1,6 @@
 """Tuning aid: per-kernel device time (CUDA events inside the library) of one modem's encode->decode.
 
-    python tools/kt.py [pald|ntsc3d|ntsc|pals|pal3d|secam|niir|proto|mac] [frames]
+    python tools/kt.py [pald|ntsc3d|ntsc|pals|pal3d|secam|niir|proto|mac|mac7|pald1080|ntsc3d1080|secam1080|proto1080|mac1080] [frames]
 """
 import os
 import sys
@@ -21,7 +21,14 @@ make = {'pald': lambda: pal.PalDModem(lc6), 'pals': lambda: pal.PalSModem(lc6), 
         'ntsc3d': lambda: comb.Simple3DCombModem(ntsc.NtscCombModem(lc5)),
         'secam': lambda: comb.ColorAveragingModem(secam.SecamModem(lc6)), 'niir': lambda: niir.HueCorrectingNiirModem(lc6),
         'proto': lambda: comb.ColorAveragingModem(protosecam.ProtoSecamModem(LineConfig((720, 576), LS.FRENCH_819))),
-        'mac': lambda: comb.ColorAveragingModem(mac.MacModem(lc6))}[which]
+        'mac': lambda: comb.ColorAveragingModem(mac.MacModem(lc6)),
+        'mac7': lambda: mac.MacModem(lc6, mac.MacVariant.D2MAC_7MHZ),
+        # 1920x1080 (BASELINE configs[4]; explicit line standards)
+        'pald1080': lambda: pal.PalDModem(LineConfig((1920, 1080), LS.GERBER_625), pal.PalVariant.PAL_N),
+        'ntsc3d1080': lambda: comb.Simple3DCombModem(ntsc.NtscCombModem(LineConfig((1920, 1080), LS.NTSC_525), ntsc.NtscVariant.NTSC443)),
+        'secam1080': lambda: comb.ColorAveragingModem(secam.SecamModem(LineConfig((1920, 1080), LS.GERBER_625), secam.SecamVariant.SECAM_III)),
+        'proto1080': lambda: comb.ColorAveragingModem(protosecam.ProtoSecamModem(LineConfig((1920, 1080), LS.FRENCH_819))),
+        'mac1080': lambda: mac.MacModem(LineConfig((1920, 1080), LS.GERBER_625), mac.MacVariant.D2MAC_7MHZ)}[which]
 m = make()
 h, w = m.height, m.width
 rgb = torch.from_numpy(synth_frames_u8(8, h, w)).repeat(F // 8, 1, 1, 1).contiguous().cuda()
