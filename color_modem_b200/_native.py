@@ -7,7 +7,7 @@ modem raises NativeUnavailable.
 import ctypes as C
 import os
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 MAX_SECTIONS, MAX_FILTERS, MAX_SCALARS, MAX_RESAMPLERS, MAX_TAPS = 6, 10, 48, 6, 1024
 
 KIND_QAM_BANDSPLIT, KIND_NTSC_COMB, KIND_NTSC_3D, KIND_PAL_D, KIND_PAL_3D = 1, 2, 3, 4, 5
@@ -60,7 +60,7 @@ MODE_DEFAULT, MODE_BANDSPLIT_NOSTRIP, MODE_EXTRACT_CHROMA = 0, 1, 2
 
 EXPORTS = ['cm_abi_version', 'cm_sizeof_desc', 'cm_last_error', 'cm_device_info', 'cm_create', 'cm_destroy', 'cm_encode_frames',
            'cm_decode_frames', 'cm_encode_ex', 'cm_decode_ex', 'cm_encode_frames_host', 'cm_decode_frames_host',
-           'cm_filter_rows', 'cm_launch_count', 'cm_timing_enable', 'cm_timing_reset', 'cm_timing_read', 'cm_phase_profile']
+           'cm_filter_rows', 'cm_transcode_frames_host', 'cm_measure_fma_peak', 'cm_launch_count', 'cm_timing_enable', 'cm_timing_reset', 'cm_timing_read', 'cm_phase_profile']
 
 K_ENCODE, K_BANDSPLIT, K_PALD, K_COMB, K_DECODE_OTHER = 0, 1, 2, 3, 4
 
@@ -92,6 +92,8 @@ def load():
     lib.cm_decode_ex.argtypes = [vp, C.POINTER(Window), vp, vp, vp, vp, i64, i32, vp]
     lib.cm_encode_frames_host.argtypes = [vp, vp, vp, i64, i32]
     lib.cm_decode_frames_host.argtypes = [vp, vp, vp, i64, i32]
+    lib.cm_transcode_frames_host.argtypes = [vp, vp, vp, vp, i64, i32]
+    lib.cm_measure_fma_peak.argtypes = [C.POINTER(C.c_double)]
     lib.cm_filter_rows.argtypes = [C.POINTER(Filter), C.c_int, vp, vp, i32, vp]
     lib.cm_launch_count.restype = C.c_int64
     lib.cm_timing_enable.argtypes = [vp, C.c_int]

@@ -208,6 +208,13 @@ class SimpleCombModem(_Fused):
             return out
         return res
 
+    def transcode_frames_host(self, rgb, first_frame=0, out=None, comp_out=None, want_composite=True):
+        if self._impl is not None:
+            return self._impl.transcode_frames_host(rgb, first_frame, out=out, comp_out=comp_out,
+                                                    want_composite=want_composite)
+        comp = self.encode_frames_host(rgb, first_frame, out=comp_out)
+        return (comp if want_composite or comp_out is not None else None), self.decode_frames_host(comp, first_frame, out=out)
+
     def decode_frames(self, comp, first_frame=0, out=None, out_float=None):
         if self._impl is not None:
             return self._impl.decode_frames(comp, first_frame, out=out, out_float=out_float)

@@ -146,7 +146,7 @@ static int plan_row_kernel(const cm_desc &d, FiltHdr *fh, std::vector<double> &t
     const cm_filter &fbp = d.filters[QF_BP2X], &flp = d.filters[pald ? QF_PALD_LP : QF_DEMOD_LP], &fpre = d.filters[QF_PRE_LP];
     if (!fbp.nsec || !flp.nsec || !fpre.nsec) return 0;
     static const int nws[3] = {2, 4, 4};            // RowL<1..3> of cm_qam.cuh
-    static const int lbp[3] = {24, 24, 32}, lpa[3] = {46, 46, 62}, lpb[3] = {50, 50, 64}, lpre[3] = {23, 23, 31};
+    static const int lbp[3] = {26, 26, 34}, lpa[3] = {46, 46, 62}, lpb[3] = {50, 50, 66}, lpre[3] = {23, 23, 31};
     for (int k = 0; k < 3; ++k) {
         const int nw = nws[k], th = nw / 2;
         if (fbp.n + fbp.shift > 32 * nw * lbp[k]) continue;
@@ -292,6 +292,22 @@ extern "C" int cm_create(const cm_desc *desc, int precision, cm_modem **out) {
     if (!m) return fail(CM_ERR_NOMEM, "out of host memory%s");
     m->desc = *desc;
     m->precision = precision;
+    {   // tuning knobs: the environment is read here, once per handle (cm_host.h: cm_tune)
+        auto env_int = [](const char *name, int dflt) {
+            const char *e = getenv(name);
+            if (!e) return dflt;
+            const int v = atoi(e);
+            return v > 0 ? v : dflt;
+        };
+        m->tune.onepass = getenv("CM_ONEPASS") != nullptr;
+        m->tune.rows_v1 = getenv("CM_ROWS_V1") != nullptr;
+        m->tune.rpc = env_int("CM_RPC", m->tune.rpc);
+        m->tune.chunk = env_int("CM_CHUNK", m->tune.chunk);
+        m->tune.host_chunk = env_int("CM_HOST_CHUNK", m->tune.host_chunk);
+        m->tune.rows_max = env_int("CM_ROWS_MAX", m->tune.rows_max);
+        m->tune.min_warps = env_int("CM_MIN_WARPS", m->tune.min_warps);
+        if (const char *e = getenv("CM_OVERLAP")) m->tune.overlap = atoi(e);
+    }
     cudaError_t e = cudaGetDevice(&m->device);
     if (e != cudaSuccess) { delete m; return fail(CM_ERR_CUDA, "cudaGetDevice: %s", cudaGetErrorString(e)); }
     cudaDeviceGetAttribute(&m->sm_count, cudaDevAttrMultiProcessorCount, m->device);
@@ -354,12 +370,18 @@ extern "C" void cm_destroy(cm_modem *m) {
     cudaFree(m->d_tab);
     cudaFree(m->d_taps);
     cudaFree(m->d_ctab);
+    if (m->s2) cudaStreamDestroy(m->s2);
+    for (int i = 0; i < 2; ++i) {
+        if (m->ev_p1[i]) cudaEventDestroy(m->ev_p1[i]);
+        if (m->ev_p2[i]) cudaEventDestroy(m->ev_p2[i]);
+    }
     for (int i = 0; i < cm_modem::kHostStreams; ++i) {
         cudaFree(m->d_in[i]);
         cudaFree(m->d_out[i]);
+        cudaFree(m->d_mid[i]);
         if (m->hs[i]) cudaStreamDestroy(m->hs[i]);
     }
-    for (int i = 0; i < 8; ++i) cudaFree(m->d_aux[i]);
+    for (int i = 0; i < 12; ++i) cudaFree(m->d_aux[i]);
     cm_timing_reset(m);
     delete m;
 }
@@ -554,55 +576,77 @@ static int ensure(void **buf, size_t *cap, size_t need) {
     return CM_OK;
 }
 
-// Host-buffer path shared by encode and decode: chunked, triple-buffered over three streams.  With pinned host
-// memory the H2D copy of the next chunk, the kernels of the current one and the D2H copy of the previous one run
+// Host-buffer path shared by encode, decode and encode->decode: chunked, triple-buffered over three streams.  With pinned
+// host memory the H2D copy of the next chunk, the kernels of the current one and the D2H copy of the previous one run
 // concurrently (two copy engines + SMs); with pageable memory it is still correct, just serialised by the driver.
-static int run_host(cm_modem *m, bool encode, const uint8_t *in, uint8_t *out, size_t in_frame, size_t out_frame,
-                    int64_t first_frame, int32_t nframes) {
+// what: 0 encode (in = RGB, out = composite), 1 decode (in = composite, out = RGB), 2 encode -> decode with the composite
+// staying in device memory (in = RGB, out = RGB, mid = composite copy-out or null).
+static int run_host(cm_modem *m, int what, const uint8_t *in, uint8_t *out, uint8_t *mid, size_t in_frame, size_t out_frame,
+                    size_t mid_frame, int64_t first_frame, int32_t nframes) {
     if (!m || !in || !out) return fail(CM_ERR_INVALID, "null argument%s");
     if (nframes < 0) return fail(CM_ERR_INVALID, "bad frame count%s");
     if (nframes == 0) return CM_OK;
     CUDA_TRY(cudaSetDevice(m->device));
-    int chunk = 16;
-    if (const char *e = getenv("CM_HOST_CHUNK")) {
-        int v = atoi(e);
-        if (v >= 1) chunk = v;
-    }
+    int chunk = m->tune.host_chunk;
     if (chunk > nframes) chunk = nframes;
     for (int s = 0; s < cm_modem::kHostStreams; ++s) {
         if (!m->hs[s]) CUDA_TRY(cudaStreamCreateWithFlags(&m->hs[s], cudaStreamNonBlocking));
         int rc = ensure(&m->d_in[s], &m->in_cap[s], (size_t)chunk * in_frame);
         if (!rc) rc = ensure(&m->d_out[s], &m->out_cap[s], (size_t)chunk * out_frame);
+        if (!rc && what == 2) rc = ensure(&m->d_mid[s], &m->mid_cap[s], (size_t)chunk * mid_frame);
         if (rc) return rc;
     }
     int rc = CM_OK;
-    for (int f = 0, i = 0; f < nframes && rc == CM_OK; f += chunk, ++i) {
+    cudaError_t ce = cudaSuccess;
+    for (int f = 0, i = 0; f < nframes && rc == CM_OK && ce == cudaSuccess; f += chunk, ++i) {
         const int s = i % cm_modem::kHostStreams;
         const int n = nframes - f < chunk ? nframes - f : chunk;
         cudaStream_t st = m->hs[s];
-        CUDA_TRY(cudaMemcpyAsync(m->d_in[s], in + (size_t)f * in_frame, (size_t)n * in_frame, cudaMemcpyHostToDevice, st));
+        ce = cudaMemcpyAsync(m->d_in[s], in + (size_t)f * in_frame, (size_t)n * in_frame, cudaMemcpyHostToDevice, st);
+        if (ce != cudaSuccess) break;
         m->aux_slot = 1 + s;
-        rc = encode ? cm_encode_frames(m, (const uint8_t *)m->d_in[s], (uint8_t *)m->d_out[s], first_frame + f, n, st)
-                    : cm_decode_frames(m, (const uint8_t *)m->d_in[s], (uint8_t *)m->d_out[s], first_frame + f, n, st);
+        const uint8_t *din = (const uint8_t *)m->d_in[s];
+        uint8_t *dout = (uint8_t *)m->d_out[s], *dmid = (uint8_t *)m->d_mid[s];
+        if (what == 0) rc = cm_encode_frames(m, din, dout, first_frame + f, n, st);
+        else if (what == 1) rc = cm_decode_frames(m, din, dout, first_frame + f, n, st);
+        else {
+            rc = cm_encode_frames(m, din, dmid, first_frame + f, n, st);
+            if (rc == CM_OK && mid)
+                ce = cudaMemcpyAsync(mid + (size_t)f * mid_frame, dmid, (size_t)n * mid_frame, cudaMemcpyDeviceToHost, st);
+            if (rc == CM_OK) rc = cm_decode_frames(m, dmid, dout, first_frame + f, n, st);
+        }
         m->aux_slot = 0;
-        if (rc == CM_OK)
-            CUDA_TRY(cudaMemcpyAsync(out + (size_t)f * out_frame, m->d_out[s], (size_t)n * out_frame,
-                                     cudaMemcpyDeviceToHost, st));
+        if (rc == CM_OK && ce == cudaSuccess)
+            ce = cudaMemcpyAsync(out + (size_t)f * out_frame, dout, (size_t)n * out_frame, cudaMemcpyDeviceToHost, st);
     }
-    for (int s = 0; s < cm_modem::kHostStreams; ++s) CUDA_TRY(cudaStreamSynchronize(m->hs[s]));
-    return rc;
+    // also on failure: no copy into the caller's memory may still be in flight when this returns
+    for (int s = 0; s < cm_modem::kHostStreams; ++s) {
+        const cudaError_t e2 = cudaStreamSynchronize(m->hs[s]);
+        if (ce == cudaSuccess) ce = e2;
+    }
+    if (rc != CM_OK) return rc;
+    if (ce != cudaSuccess) return fail(CM_ERR_CUDA, "host path: %s", cudaGetErrorString(ce));
+    return CM_OK;
 }
 
 extern "C" int cm_encode_frames_host(cm_modem *m, const uint8_t *rgb, uint8_t *comp, int64_t first_frame,
                                      int32_t nframes) {
     if (!m) return fail(CM_ERR_INVALID, "null handle%s");
-    return run_host(m, true, rgb, comp, (size_t)m->desc.height * m->desc.width * 3,
-                    (size_t)m->desc.height * m->desc.comp_width, first_frame, nframes);
+    return run_host(m, 0, rgb, comp, nullptr, (size_t)m->desc.height * m->desc.width * 3,
+                    (size_t)m->desc.height * m->desc.comp_width, 0, first_frame, nframes);
 }
 
 extern "C" int cm_decode_frames_host(cm_modem *m, const uint8_t *comp, uint8_t *rgb, int64_t first_frame,
                                      int32_t nframes) {
     if (!m) return fail(CM_ERR_INVALID, "null handle%s");
-    return run_host(m, false, comp, rgb, (size_t)m->desc.height * m->desc.comp_width,
-                    (size_t)m->desc.height * m->desc.out_width * 3, first_frame, nframes);
+    return run_host(m, 1, comp, rgb, nullptr, (size_t)m->desc.height * m->desc.comp_width,
+                    (size_t)m->desc.height * m->desc.out_width * 3, 0, first_frame, nframes);
+}
+
+extern "C" int cm_transcode_frames_host(cm_modem *m, const uint8_t *rgb_in, uint8_t *comp_out, uint8_t *rgb_out,
+                                        int64_t first_frame, int32_t nframes) {
+    if (!m) return fail(CM_ERR_INVALID, "null handle%s");
+    return run_host(m, 2, rgb_in, rgb_out, comp_out, (size_t)m->desc.height * m->desc.width * 3,
+                    (size_t)m->desc.height * m->desc.out_width * 3, (size_t)m->desc.height * m->desc.comp_width, first_frame,
+                    nframes);
 }

@@ -18,8 +18,23 @@ void cm_count_launch();
         if (_e != cudaSuccess) return cm_fail(CM_ERR_CUDA, #expr ": %s", cudaGetErrorString(_e)); \
     } while (0)
 
+// Tuning knobs of a handle.  Read ONCE, in cm_create, from the environment (CM_ONEPASS, CM_ROWS_V1, CM_RPC, CM_CHUNK,
+// CM_HOST_CHUNK, CM_ROWS_MAX, CM_MIN_WARPS, CM_OVERLAP: A/B aids of tools/ab.py and of the alternative-path parity tests) — no launch
+// path calls getenv.
+struct cm_tune {
+    bool onepass = false;      // legacy multi-row halo kernels instead of the two-pass row kernels
+    bool rows_v1 = false;      // first-generation pass-1 kernel (k_qam_rows)
+    int rpc = 2;               // rows a CTA of the row kernels walks through (the next one prefetched)
+    int chunk = 0;             // frames per pass-1 / pass-2 launch pair (0: as many as a 2 GiB scratch holds)
+    int host_chunk = 16;       // frames per host<->device chunk of the *_host entry points
+    int rows_max = 0;          // upper bound of rows per CTA of the multi-row kernels (0: none)
+    int min_warps = 2;         // fewest warps per CTA of the multi-row kernels
+    int overlap = 0;           // pass 2 of chunk i on a second stream under pass 1 of chunk i + 1 (measured: no gain)
+};
+
 struct cm_modem {
     cm_desc desc;
+    cm_tune tune;
     int precision;
     int device;
     int sm_count;
@@ -33,9 +48,13 @@ struct cm_modem {
     unsigned long long *phase_prof = nullptr;
     // pairing scratch of the line-sequential decoders (grown on demand); one per host-path stream (+ slot 0 for
     // caller-provided streams: a handle must not be used from two streams at once)
-    void *d_aux[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // [which * 4 + slot]
-    size_t aux_cap[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    void *d_aux[12] = {};   // [which * 4 + slot]
+    size_t aux_cap[12] = {};
     int aux_slot = 0;
+    // two-pass decoders, device-resident calls: pass 2 (HBM-bound) of chunk i runs on s2 under pass 1 (issue-bound) of
+    // chunk i + 1; ev_p1[b] = planes of buffer b written, ev_p2[b] = planes of buffer b consumed
+    cudaStream_t s2 = nullptr;
+    cudaEvent_t ev_p1[2] = {nullptr, nullptr}, ev_p2[2] = {nullptr, nullptr};
     struct Ev { cudaEvent_t a, b; int id; };
     std::vector<Ev> events;
     // *_host entry points: the batch is cut into chunks that ping-pong over CM_HOST_STREAMS streams so that the
@@ -43,7 +62,8 @@ struct cm_modem {
     static const int kHostStreams = 3;
     cudaStream_t hs[kHostStreams] = {nullptr, nullptr, nullptr};
     void *d_in[kHostStreams] = {nullptr, nullptr, nullptr}, *d_out[kHostStreams] = {nullptr, nullptr, nullptr};
-    size_t in_cap[kHostStreams] = {0, 0, 0}, out_cap[kHostStreams] = {0, 0, 0};
+    void *d_mid[kHostStreams] = {nullptr, nullptr, nullptr};      // cm_transcode_frames_host: the composite between the two halves
+    size_t in_cap[kHostStreams] = {0, 0, 0}, out_cap[kHostStreams] = {0, 0, 0}, mid_cap[kHostStreams] = {0, 0, 0};
 };
 
 struct LaunchTimer {
@@ -78,13 +98,10 @@ static int set_smem(K kernel, size_t bytes) {
 }
 
 // Largest R in [1, rmax] whose shared-memory footprint fits `budget`; 0 if even R = 1 does not fit.
-// CM_ROWS_MAX (environment, tuning aid) lowers rmax.
+// cm_tune::rows_max lowers rmax.
 template <class F>
-static int pick_rows(int rmax, size_t budget, F bytes_for) {
-    if (const char *e = getenv("CM_ROWS_MAX")) {
-        int v = atoi(e);
-        if (v >= 1 && v < rmax) rmax = v;
-    }
+static int pick_rows(const cm_modem *m, int rmax, size_t budget, F bytes_for) {
+    if (m->tune.rows_max >= 1 && m->tune.rows_max < rmax) rmax = m->tune.rows_max;
     for (int r = rmax; r >= 1; --r)
         if (bytes_for(r) <= budget) return r;
     return 0;
@@ -93,9 +110,8 @@ static int pick_rows(int rmax, size_t budget, F bytes_for) {
 // Threads per CTA for `tasks` concurrent warp-level IIR tasks: one warp per task, at least two.  Small CTAs win on
 // B200 for these kernels (measured sweep of rows per CTA x warps): many independent CTAs per SM
 // in different phases overlap better than a few large ones that synchronise 8 warps at every phase boundary.
-static inline int cta_threads(int tasks) {
-    int minw = 2;
-    if (const char *e = getenv("CM_MIN_WARPS")) minw = atoi(e) > 0 ? atoi(e) : minw;     // tuning aid
+static inline int cta_threads(const cm_modem *m, int tasks) {
+    const int minw = m->tune.min_warps;
     int warps = tasks < minw ? minw : tasks;
     if (warps > CM_NWARPS) warps = CM_NWARPS;
     return 32 * warps;
@@ -128,7 +144,7 @@ static void split_top(const IoArgs<T> &io, IoArgs<T> &top, IoArgs<T> &rest) {
 }
 
 // Grow-only device scratch of a handle (stream-ordered use only).
-// which = 0: pass-1 -> pass-2 planes; 1: (y, u, v) rows waiting for the luma notch
+// which = 0: pass-1 -> pass-2 planes; 1: (y, u, v) rows waiting for the luma notch; 2: second planes buffer (overlap)
 void *cm_ensure_aux(cm_modem *m, size_t bytes, int which = 0);   // nullptr on failure (cm_last_error set)
 
 // Explicit instantiation of the float / double variants; the build may compile a unit once per type

@@ -15,7 +15,7 @@ int mac_encode(cm_modem *m, IoArgs<T> io, cudaStream_t st) {
     if (p.Wc > 1080) return cm_fail(CM_ERR_UNSUPPORTED, "MAC widths above 1080 are not built%s");
     const int tl = mac_taps_len(m);
     auto bytes = [&](int r) { return ((size_t)tl + (size_t)r * (2 * (size_t)p.W + 720 + 360 + 1080)) * sizeof(T); };
-    int R = pick_rows(2, (size_t)m->smem_optin / 2, bytes);
+    int R = pick_rows(m, 2, (size_t)m->smem_optin / 2, bytes);
     if (!R) return cm_fail(CM_ERR_UNSUPPORTED, "line too wide for the MAC encode kernel%s");
     set_groups(io, R);
     int rc = set_smem(k_mac_encode<T>, bytes(R));
@@ -38,7 +38,7 @@ int mac_decode(cm_modem *m, IoArgs<T> io, cudaStream_t st) {
     auto bytes = [&](int r) {
         return ((size_t)tl + (size_t)(r + 1) * ((size_t)p.Wc + 1080 + 720 + 360 + 720)) * sizeof(T);
     };
-    int R = pick_rows(2, (size_t)m->smem_optin / 2, bytes);
+    int R = pick_rows(m, 2, (size_t)m->smem_optin / 2, bytes);
     if (!R) return cm_fail(CM_ERR_UNSUPPORTED, "line too wide for the MAC decode kernel%s");
     set_groups(io, R);
     int rc = set_smem(k_mac_decode<T>, bytes(R));

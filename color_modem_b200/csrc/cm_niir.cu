@@ -7,14 +7,14 @@ template <typename T, class K, class F>
 static int launch_rows(cm_modem *m, IoArgs<T> io, cudaStream_t st, K kernel, F bytes, int rmax, int warps_per_row,
                        int extra_rows, int timer_id, const char *what) {
     if (io.out_count <= 0) return CM_OK;
-    int R = pick_rows(rmax, (size_t)m->smem_optin / 2, bytes);
-    if (!R) R = pick_rows(1, (size_t)m->smem_optin, bytes);
+    int R = pick_rows(m, rmax, (size_t)m->smem_optin / 2, bytes);
+    if (!R) R = pick_rows(m, 1, (size_t)m->smem_optin, bytes);
     if (!R) return cm_fail(CM_ERR_UNSUPPORTED, "line too wide for the %s kernel", what);
     set_groups(io, R);
     int rc = set_smem(kernel, bytes(R));
     if (rc) return rc;
     dim3 grid = cm_grid(io);
-    int threads = cta_threads(warps_per_row * (R + extra_rows));
+    int threads = cta_threads(m, warps_per_row * (R + extra_rows));
     {
         LaunchTimer lt(m, timer_id, st);
         kernel<<<grid, threads, bytes(R), st>>>(params_of<T>(m), io);

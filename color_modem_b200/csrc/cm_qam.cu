@@ -42,14 +42,13 @@ int qam_encode(cm_modem *m, IoArgs<T> io, cudaStream_t st) {
     const DevParams<T> &p = params_of<T>(m);
     if (io.out_count <= 0) return CM_OK;
     auto bytes = [&](int r) { return (128 + (size_t)r * 3 * p.n1p) * sizeof(T); };
-    int R = pick_rows(1, (size_t)m->smem_optin / 2, bytes);     // one row, two warps (u and v low-pass): 1.84 vs 2.64 us/frame
+    int R = pick_rows(m, 1, (size_t)m->smem_optin / 2, bytes);     // one row, two warps (u and v low-pass): 1.84 vs 2.64 us/frame
     if (!R) return cm_fail(CM_ERR_UNSUPPORTED, "line too wide for the encode kernel%s");
     const bool teams = needs_teams(p);
-    if (!teams && io.in_u8 && p.W <= 768 && !getenv("CM_ONEPASS")) {        // one row at a time, next row prefetched
+    if (!teams && io.in_u8 && p.W <= 768 && !m->tune.onepass) {        // one row at a time, next row prefetched
         int rc1 = set_smem(k_qam_encode_row<T>, bytes(1));
         if (rc1) return rc1;
-        int rpc = 2;
-        if (const char *e = getenv("CM_RPC")) rpc = atoi(e) > 0 ? atoi(e) : rpc;      // tuning aid
+        const int rpc = m->tune.rpc;
         const int nf = (io.out_count + 1) >> 1;
         {
             LaunchTimer lt(m, CM_K_ENCODE, st);
@@ -66,7 +65,7 @@ int qam_encode(cm_modem *m, IoArgs<T> io, cudaStream_t st) {
     {
         LaunchTimer lt(m, CM_K_ENCODE, st);
         if (teams) k_qam_encode<T, true><<<grid, CM_NTHREADS, bytes(R), st>>>(p, io);
-        else k_qam_encode<T, false><<<grid, cta_threads(2 * R), bytes(R), st>>>(p, io);
+        else k_qam_encode<T, false><<<grid, cta_threads(m, 2 * R), bytes(R), st>>>(p, io);
     }
     cm_count_launch();
     CUDA_TRY(cudaGetLastError());
@@ -78,11 +77,11 @@ int launch_bandsplit(cm_modem *m, IoArgs<T> io, int luma_mode, cudaStream_t st) 
     const DevParams<T> &p = params_of<T>(m);
     if (io.out_count <= 0) return CM_OK;
     auto bytes = [&](int r) { return (CM_TAPS_ELEMS + (size_t)r * (p.n1p + 8 * (size_t)p.hb2)) * sizeof(T); };
-    int R = pick_rows(4, (size_t)m->smem_optin / 2, bytes);
-    if (!R) R = pick_rows(1, (size_t)m->smem_optin, bytes);
+    int R = pick_rows(m, 4, (size_t)m->smem_optin / 2, bytes);
+    if (!R) R = pick_rows(m, 1, (size_t)m->smem_optin, bytes);
     if (!R) return cm_fail(CM_ERR_UNSUPPORTED, "line too wide for the band-split kernel%s");
     const bool teams = needs_teams(p);
-    if (luma_mode == 0 && !getenv("CM_ONEPASS")) {       // one row per CTA: two IIR tasks, one warp (team) each
+    if (luma_mode == 0 && !m->tune.onepass) {       // one row per CTA: two IIR tasks, one warp (team) each
         const size_t b1 = (128 + (size_t)p.n1p + 8 * (size_t)p.hb2) * sizeof(T);
         if (b1 <= (size_t)m->smem_optin) {
             int rc1 = teams ? set_smem(k_qam_bs_row<T, true>, b1) : set_smem(k_qam_bs_row<T, false>, b1);
@@ -105,7 +104,7 @@ int launch_bandsplit(cm_modem *m, IoArgs<T> io, int luma_mode, cudaStream_t st) 
     {
         LaunchTimer lt(m, CM_K_BANDSPLIT, st);
         if (teams) k_qam_bandsplit<T, true><<<grid, CM_NTHREADS, bytes(R), st>>>(p, io, luma_mode);
-        else k_qam_bandsplit<T, false><<<grid, cta_threads(2 * R), bytes(R), st>>>(p, io, luma_mode);
+        else k_qam_bandsplit<T, false><<<grid, cta_threads(m, 2 * R), bytes(R), st>>>(p, io, luma_mode);
     }
     cm_count_launch();
     CUDA_TRY(cudaGetLastError());
@@ -142,34 +141,64 @@ template <typename T, int MODE>
 int launch_rows_pair(cm_modem *m, IoArgs<T> io, cudaStream_t st) {
     const DevParams<T> &p = params_of<T>(m);
     if (io.out_count <= 0) return CM_OK;
-    const size_t b1 = (128 + (size_t)p.n1p + 6 * (size_t)p.hb2) * sizeof(T);
-    if (b1 > (size_t)m->smem_optin) return cm_fail(CM_ERR_UNSUPPORTED, "line too wide for the row kernels%s");
+    size_t b1 = (128 + (size_t)p.n1p + 6 * (size_t)p.hb2) * sizeof(T);
     const bool teams = needs_teams(p);
     constexpr bool kPald = MODE == PAIR_PALD;
     void (*pass1)(const DevParams<T>, const IoArgs<T>) = teams ? k_qam_rows<T, kPald, true> : k_qam_rows<T, kPald, false>;
     int threads1 = teams ? row_threads(p) : CM_ROW_THREADS;
-    static const bool rows_v1 = getenv("CM_ROWS_V1") != nullptr;          // A/B aid: the first-generation row kernel
-    if (p.row_geo && !rows_v1) {
+    if (p.row_geo && !m->tune.rows_v1) {
         pass1 = p.row_geo == 1 ? k_qam_rows2<T, kPald, 1> : (p.row_geo == 2 ? k_qam_rows2<T, kPald, 2> : k_qam_rows2<T, kPald, 3>);
         threads1 = p.row_geo == 1 ? 64 : 128;
+        b1 = (128 + 2 * (size_t)p.n1p + 4 * (size_t)p.hb2) * sizeof(T);
     }
+    if (b1 > (size_t)m->smem_optin) return cm_fail(CM_ERR_UNSUPPORTED, "line too wide for the row kernels%s");
     int rc = set_smem(pass1, b1);
     if (rc) return rc;
-    // frames per pass-1 / pass-2 launch pair: as many as a 2 GiB scratch holds (720x576: 6.6 MB per frame -> 323 frames;
-    // 1920x1080: 33 MB -> 64).  Measured on 256 PAL-D frames: 32 per launch 81.7 k, 64: 86.5 k, 128: 88.8 k, 256: 89.9 k frames/s
+    // Frames per pass-1 / pass-2 launch pair.  Pass 1 is bound by instruction issue, pass 2 by HBM: with the batch cut into
+    // chunks, pass 2 of chunk i runs on a second (high-priority) stream while pass 1 of chunk i + 1 runs on the caller's,
+    // the planes double-buffered (cm_tune::overlap; device-resident calls only — the host entry points already pipeline
+    // their chunks over three streams).  Without overlap a chunk is as large as a 2 GiB scratch allows (720x576: 6.6 MB
+    // per frame -> 323 frames; 1920x1080: 33 MB -> 64): measured on 256 PAL-D frames, serial, 32 per launch 81.7 k,
+    // 64: 86.5 k, 128: 88.8 k, 256: 89.9 k frames/s.
     const size_t frame_elems = (size_t)io.nrows * 4 * p.W;
     int kChunk = (int)(((size_t)2 << 30) / (frame_elems * sizeof(T)));
     if (kChunk < 16) kChunk = 16;
-    if (const char *e = getenv("CM_CHUNK")) kChunk = atoi(e) > 0 ? atoi(e) : kChunk;     // tuning aid
+    bool overlap = m->tune.overlap && m->aux_slot == 0;
+    if (overlap) {
+        // chunks of ~1/4 of the batch, at least 32 frames of 720x576 worth of rows: enough CTAs per launch to fill the chip
+        int c = (io.nframes + 3) / 4;
+        const int min_frames = (int)((32ull * 576 * 720 + (size_t)io.nrows * p.W - 1) / ((size_t)io.nrows * p.W));
+        if (c < min_frames) c = min_frames;
+        if (c < kChunk) kChunk = c;
+    }
+    if (m->tune.chunk > 0) kChunk = m->tune.chunk;
     const int chunk = io.nframes < kChunk ? io.nframes : kChunk;
-    T *aux = (T *)cm_ensure_aux(m, (size_t)chunk * frame_elems * sizeof(T));
-    if (!aux) return CM_ERR_NOMEM;
+    if (chunk >= io.nframes) overlap = false;
+    T *aux[2];
+    aux[0] = (T *)cm_ensure_aux(m, (size_t)chunk * frame_elems * sizeof(T));
+    if (!aux[0]) return CM_ERR_NOMEM;
+    aux[1] = aux[0];
+    if (overlap) {
+        aux[1] = (T *)cm_ensure_aux(m, (size_t)chunk * frame_elems * sizeof(T), 2);
+        if (!aux[1]) return CM_ERR_NOMEM;
+        if (!m->s2) {
+            int lo = 0, hi = 0;
+            CUDA_TRY(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+            CUDA_TRY(cudaStreamCreateWithPriority(&m->s2, cudaStreamNonBlocking, hi));
+            for (int i = 0; i < 2; ++i) {
+                CUDA_TRY(cudaEventCreateWithFlags(&m->ev_p1[i], cudaEventDisableTiming));
+                CUDA_TRY(cudaEventCreateWithFlags(&m->ev_p2[i], cudaEventDisableTiming));
+            }
+        }
+    }
     const size_t in_frame = (size_t)io.nrows * p.Wc, out_frame = (size_t)io.nrows * p.Wo * 3;
-    for (int f0 = 0; f0 < io.nframes; f0 += chunk) {
+    int nchunks = 0;
+    for (int f0 = 0; f0 < io.nframes; f0 += chunk, ++nchunks) {
+        const int buf = nchunks & 1;
         IoArgs<T> c = io;
         c.nframes = io.nframes - f0 < chunk ? io.nframes - f0 : chunk;
         c.first_frame = io.first_frame + f0;
-        c.aux = aux;
+        c.aux = aux[buf];
         if (c.in_u8) c.in_u8 += (size_t)f0 * in_frame;
         if (c.in_f) c.in_f += (size_t)f0 * in_frame;
         if (c.out_u8) c.out_u8 += (size_t)f0 * out_frame;
@@ -180,24 +209,35 @@ int launch_rows_pair(cm_modem *m, IoArgs<T> io, cudaStream_t st) {
         int end = c.out_begin + c.out_count + (MODE >= PAIR_NTSC3 ? 2 : 0);
         if (end > c.nrows) end = c.nrows;
         a.out_count = end - a.out_begin;
+        if (overlap && nchunks >= 2) CUDA_TRY(cudaStreamWaitEvent(st, m->ev_p2[buf], 0));     // buffer free again
         {
             LaunchTimer lt(m, MODE == PAIR_PALD ? CM_K_PALD : CM_K_COMB, st);
-            int rpc = 2;     // rows per CTA: the next row is prefetched while one is filtered (1: 7.97, 2: 7.67, 4: 8.15 us/frame)
-            if (const char *e = getenv("CM_RPC")) rpc = atoi(e) > 0 ? atoi(e) : rpc;      // tuning aid
+            const int rpc = m->tune.rpc;     // rows per CTA: the next row is prefetched while one is filtered (1: 7.97, 2: 7.67, 4: 8.15 us/frame)
             pass1<<<dim3((unsigned)((a.out_count + rpc - 1) / rpc), 1u, (unsigned)c.nframes), threads1, b1, st>>>(p, a);
         }
         cm_count_launch();
         CUDA_TRY(cudaGetLastError());
+        cudaStream_t st2 = st;
+        if (overlap) {
+            CUDA_TRY(cudaEventRecord(m->ev_p1[buf], st));
+            CUDA_TRY(cudaStreamWaitEvent(m->s2, m->ev_p1[buf], 0));
+            st2 = m->s2;
+        }
         {
-            LaunchTimer lt(m, CM_K_DECODE_OTHER, st);
+            LaunchTimer lt(m, CM_K_DECODE_OTHER, st2);
             const int segs = (((c.out_count + 1) >> 1) + CM_SEG - 1) / CM_SEG, threads = 128;
             dim3 grid((unsigned)((segs * (p.W >> 2) + threads - 1) / threads), 2u, (unsigned)c.nframes);
-            if (!c.yuv) k_qam_combine<T, MODE, 0><<<grid, threads, 0, st>>>(p, c);
-            else if (MODE >= PAIR_NTSC3 && (p.flags & CM_FLAG_MINAVG)) k_qam_combine<T, MODE, 2><<<grid, threads, 0, st>>>(p, c);
-            else k_qam_combine<T, MODE, 1><<<grid, threads, 0, st>>>(p, c);
+            if (!c.yuv) k_qam_combine<T, MODE, 0><<<grid, threads, 0, st2>>>(p, c);
+            else if (MODE >= PAIR_NTSC3 && (p.flags & CM_FLAG_MINAVG)) k_qam_combine<T, MODE, 2><<<grid, threads, 0, st2>>>(p, c);
+            else k_qam_combine<T, MODE, 1><<<grid, threads, 0, st2>>>(p, c);
         }
         cm_count_launch();
         CUDA_TRY(cudaGetLastError());
+        if (overlap) CUDA_TRY(cudaEventRecord(m->ev_p2[buf], m->s2));
+    }
+    if (overlap) {          // everything this call produced is ordered before whatever the caller queues next on `st`
+        CUDA_TRY(cudaStreamWaitEvent(st, m->ev_p2[(nchunks - 1) & 1], 0));
+        if (nchunks >= 2) CUDA_TRY(cudaStreamWaitEvent(st, m->ev_p2[nchunks & 1], 0));
     }
     return CM_OK;
 }
@@ -208,14 +248,14 @@ template <typename T>
 int launch_pald(cm_modem *m, IoArgs<T> io, cudaStream_t st) {
     const DevParams<T> &p = params_of<T>(m);
     if (io.out_count <= 0) return CM_OK;
-    if (!io.prof && !getenv("CM_ONEPASS") &&
+    if (!io.prof && !m->tune.onepass &&
         (128 + (size_t)p.n1p + 6 * (size_t)p.hb2) * sizeof(T) <= (size_t)m->smem_optin)
         return launch_rows_pair<T, PAIR_PALD>(m, io, st);
     auto bytes = [&](int r) {
         return (CM_TAPS_ELEMS + (size_t)(r + 1) * (p.n1p + 2 * (size_t)p.hb2) + (size_t)r * 4 * p.hb2) * sizeof(T);
     };
-    int R = pick_rows(4, (size_t)m->smem_optin / 2, bytes);
-    if (!R) R = pick_rows(2, (size_t)m->smem_optin, bytes);
+    int R = pick_rows(m, 4, (size_t)m->smem_optin / 2, bytes);
+    if (!R) R = pick_rows(m, 2, (size_t)m->smem_optin, bytes);
     if (!R) return cm_fail(CM_ERR_UNSUPPORTED, "line too wide for the PAL-D kernel%s");
     const bool teams = needs_teams(p);
     set_groups(io, R);
@@ -225,7 +265,7 @@ int launch_pald(cm_modem *m, IoArgs<T> io, cudaStream_t st) {
     {
         LaunchTimer lt(m, CM_K_PALD, st);
         if (teams) k_pald_combed<T, true><<<grid, CM_NTHREADS, bytes(R), st>>>(p, io);
-        else k_pald_combed<T, false><<<grid, cta_threads(2 * R), bytes(R), st>>>(p, io);
+        else k_pald_combed<T, false><<<grid, cta_threads(m, 2 * R), bytes(R), st>>>(p, io);
     }
     cm_count_launch();
     CUDA_TRY(cudaGetLastError());
@@ -242,14 +282,14 @@ int launch_comb(cm_modem *m, IoArgs<T> io, cudaStream_t st) {
     const DevParams<T> &p = params_of<T>(m);
     if (io.out_count <= 0) return CM_OK;
     // (the legacy kernels below do not implement avg=minavg)
-    if ((!getenv("CM_ONEPASS") || (p.flags & CM_FLAG_MINAVG)) &&
+    if ((!m->tune.onepass || (p.flags & CM_FLAG_MINAVG)) &&
         (128 + (size_t)p.n1p + 6 * (size_t)p.hb2) * sizeof(T) <= (size_t)m->smem_optin)
         return launch_rows_pair<T, MODE == COMB_NTSC2 ? PAIR_NTSC2 : (MODE == COMB_NTSC3 ? PAIR_NTSC3 : PAIR_PAL3)>(m, io, st);
     auto bytes = [&](int r) {
         return (CM_TAPS_ELEMS + (size_t)(r + 2) * (p.n1p + 2 * (size_t)p.hb2) + (size_t)r * 4 * p.hb2) * sizeof(T);
     };
-    int R = pick_rows(4, (size_t)m->smem_optin / 2, bytes);
-    if (!R) R = pick_rows(2, (size_t)m->smem_optin, bytes);
+    int R = pick_rows(m, 4, (size_t)m->smem_optin / 2, bytes);
+    if (!R) R = pick_rows(m, 2, (size_t)m->smem_optin, bytes);
     if (!R) return cm_fail(CM_ERR_UNSUPPORTED, "line too wide for the comb kernel%s");
     const bool teams = needs_teams(p);
     set_groups(io, R);
@@ -259,7 +299,7 @@ int launch_comb(cm_modem *m, IoArgs<T> io, cudaStream_t st) {
     {
         LaunchTimer lt(m, CM_K_COMB, st);
         if (teams) k_qam_comb<T, MODE, true><<<grid, CM_NTHREADS, bytes(R), st>>>(p, io);
-        else k_qam_comb<T, MODE, false><<<grid, cta_threads(2 * R), bytes(R), st>>>(p, io);
+        else k_qam_comb<T, MODE, false><<<grid, cta_threads(m, 2 * R), bytes(R), st>>>(p, io);
     }
     cm_count_launch();
     CUDA_TRY(cudaGetLastError());

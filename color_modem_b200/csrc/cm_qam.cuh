@@ -661,9 +661,11 @@ k_qam_rows(const __grid_constant__ DevParams<T> p, const __grid_constant__ IoArg
 //   8 warps x 16 samples measured 98 us per 1080p frame against 65 of the first-generation kernel.
 // ------------------------------------------------------------------------------------------------------------
 template <int GEO> struct RowL;
-template <> struct RowL<1> { static constexpr int NW = 2, BP = 24, LPA = 46, LPB = 50, PRE = 23; };
-template <> struct RowL<2> { static constexpr int NW = 4, BP = 24, LPA = 46, LPB = 50, PRE = 23; };
-template <> struct RowL<3> { static constexpr int NW = 4, BP = 32, LPA = 62, LPB = 64, PRE = 31; };
+// (every L / RATE is odd: lane t starts at element t * L / RATE of its polyphase plane, an odd stride keeps the 32 lanes of
+// a load or store on 32 different banks; 24 and 32 measured 17 M and 74 M bank conflicts per 64 / 16 frames)
+template <> struct RowL<1> { static constexpr int NW = 2, BP = 26, LPA = 46, LPB = 50, PRE = 23; };
+template <> struct RowL<2> { static constexpr int NW = 4, BP = 26, LPA = 46, LPB = 50, PRE = 23; };
+template <> struct RowL<3> { static constexpr int NW = 4, BP = 34, LPA = 62, LPB = 66, PRE = 31; };
 
 #define QF_ROW_BP 6      // DevParams::filt slots of the row kernel's use-sites (same filters as QF_BP2X, QF_DEMOD_LP or
 #define QF_ROW_LP 7      // QF_PALD_LP, QF_PRE_LP; chunk lengths and tables for its team geometry, built in cm_api.cu)
@@ -681,7 +683,9 @@ k_qam_rows2(const __grid_constant__ DevParams<T> p, const __grid_constant__ IoAr
     const int f = blockIdx.z, end = io.out_begin + io.out_count;
     const int warp = threadIdx.x >> 5;
     const int task = warp / TH, wr = warp - task * TH;
-    T *cb = sm, *g = cb + N1, *wa = g + N2, *wb = wa + N2;
+    // cb | sb: 1x rows; g | wb: 2x rows.  The sin-channel low-pass writes over its own input (wa == g: both teams load
+    // their chunks, the CTA synchronises, then they filter and store), which keeps 1920-sample rows at 4 CTAs per SM
+    T *cb = sm, *sb = cb + N1, *g = sb + N1, *wa = g, *wb = g + N2;
     const FirTaps<T> hup{p.firc[QR_UP2], p.fircp[QR_UP2]}, hdn{p.firc[QR_DOWN2], p.fircp[QR_DOWN2]};
     const FiltHdr &fb = p.filt[QF_ROW_BP], &fl = p.filt[QF_ROW_LP], &fpre = p.filt[QF_ROW_PRE];
     const long long frame = io.first_frame + f;
@@ -713,18 +717,18 @@ k_qam_rows2(const __grid_constant__ DevParams<T> p, const __grid_constant__ IoAr
             T *de = task ? wb : wa;
             const T *ct = p.ctab + (size_t)task * fl.npad;
             if (fl.L == RL::LPA)
-                team_iir_pk<T, 2, RL::LPA, TH>(p.tab + fl.off, fl, LoadPoly2Carrier<T, RL::LPA>{g, g + hb, ct, 32 * TH},
-                                               Poly2Out<T>{de, de + hb}, wr, 2 + task, scratch + 32 + 32 * task);
+                team_iir_pk<T, 2, RL::LPA, TH, true>(p.tab + fl.off, fl, LoadPoly2Carrier<T, RL::LPA>{g, g + hb, ct, 32 * TH},
+                                                     Poly2Out<T>{de, de + hb}, wr, 2 + task, scratch + 32 + 32 * task);
             else
-                team_iir_pk<T, 2, RL::LPB, TH>(p.tab + fl.off, fl, LoadPoly2Carrier<T, RL::LPB>{g, g + hb, ct, 32 * TH},
-                                               Poly2Out<T>{de, de + hb}, wr, 2 + task, scratch + 32 + 32 * task);
+                team_iir_pk<T, 2, RL::LPB, TH, true>(p.tab + fl.off, fl, LoadPoly2Carrier<T, RL::LPB>{g, g + hb, ct, 32 * TH},
+                                                     Poly2Out<T>{de, de + hb}, wr, 2 + task, scratch + 32 + 32 * task);
         }
         __syncthreads();
         {   // decimate, rotate to the row's own phase, keep (a, b) for the pre-low-pass
             T sphi, cphi;
             Real<T>::sincos_turns(start_phase(p, frame, io.y0 + row) + p.phases[QP_BP_SHIFT] -
                                       (PALD ? p.phases[QP_HALF_LS] : 0ull), sphi, cphi);
-            T *sa = cb, *sb = g;
+            T *sa = cb;
             fir_down2_pair(wa, wa + hb, wb, wb + hb, W, hdn, threadIdx.x, blockDim.x, [&](int j0, const T *a0, const T *b0) {
                 T a[4], b[4];
 #pragma unroll
@@ -740,7 +744,7 @@ k_qam_rows2(const __grid_constant__ DevParams<T> p, const __grid_constant__ IoAr
         }
         __syncthreads();
         {   // alpha = LPpre(a) by team 0, beta = LPpre(b) by team 1
-            T *src = task ? g : cb, *out = task ? wb : wa;
+            T *src = task ? sb : cb, *out = task ? wb : wa;
             warp_fill_tail<T, 1>(src, N1, W, fpre.npad);
             team_iir_pk<T, 1, RL::PRE, TH>(p.tab + fpre.off, fpre, LoadLinear<T, RL::PRE>{src}, [&](int j, T x) { out[j] = x; },
                                            wr, 2 + task, scratch + 32 + 32 * task);

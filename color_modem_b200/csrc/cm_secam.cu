@@ -7,7 +7,7 @@ int secam_encode(cm_modem *m, IoArgs<T> io, cudaStream_t st) {
     const DevParams<T> &p = params_of<T>(m);
     if (io.out_count <= 0) return CM_OK;
     auto bytes = [&](int r) { return (size_t)r * 2 * p.n1p * sizeof(T); };
-    int R = pick_rows(2, (size_t)m->smem_optin / 2, bytes);
+    int R = pick_rows(m, 2, (size_t)m->smem_optin / 2, bytes);
     if (!R) return cm_fail(CM_ERR_UNSUPPORTED, "line too wide for the SECAM encode kernel%s");
     set_groups(io, R);
     int rc = set_smem(k_secam_encode<T>, bytes(R));
@@ -15,7 +15,7 @@ int secam_encode(cm_modem *m, IoArgs<T> io, cudaStream_t st) {
     dim3 grid = cm_grid(io);
     {
         LaunchTimer lt(m, CM_K_ENCODE, st);
-        k_secam_encode<T><<<grid, cta_threads(R), bytes(R), st>>>(p, io);
+        k_secam_encode<T><<<grid, cta_threads(m, R), bytes(R), st>>>(p, io);
     }
     cm_count_launch();
     CUDA_TRY(cudaGetLastError());
@@ -35,8 +35,8 @@ int secam_decode(cm_modem *m, IoArgs<T> io, cudaStream_t st) {
     a.out_begin = io.out_begin >= 2 ? io.out_begin - 2 : 0;
     a.out_count = io.out_begin + io.out_count - a.out_begin;
     auto bytes = [&](int r) { return (CM_TAPS_ELEMS + (size_t)r * (2 * (size_t)p.n1p + 6 * (size_t)p.hb2)) * sizeof(T); };
-    int R = pick_rows(2, (size_t)m->smem_optin / 2, bytes);
-    if (!R) R = pick_rows(1, (size_t)m->smem_optin, bytes);
+    int R = pick_rows(m, 2, (size_t)m->smem_optin / 2, bytes);
+    if (!R) R = pick_rows(m, 1, (size_t)m->smem_optin, bytes);
     if (!R) return cm_fail(CM_ERR_UNSUPPORTED, "line too wide for the SECAM decode kernel%s");
     set_groups(a, R);
     bool teams = false;
@@ -46,7 +46,7 @@ int secam_decode(cm_modem *m, IoArgs<T> io, cudaStream_t st) {
     {
         LaunchTimer lt(m, CM_K_DECODE_OTHER, st);
         if (teams) k_secam_decode<T, true><<<cm_grid(a), CM_NTHREADS, bytes(R), st>>>(p, a);
-        else k_secam_decode<T, false><<<cm_grid(a), cta_threads(2 * R), bytes(R), st>>>(p, a);
+        else k_secam_decode<T, false><<<cm_grid(a), cta_threads(m, 2 * R), bytes(R), st>>>(p, a);
     }
     cm_count_launch();
     CUDA_TRY(cudaGetLastError());

@@ -55,3 +55,54 @@ extern "C" int cm_filter_rows(const cm_filter *f, int precision, const void *in,
     return precision == CM_FP32 ? filter_rows<float>(f, in, out, nrows, (cudaStream_t)stream)
                                 : filter_rows<double>(f, in, out, nrows, (cudaStream_t)stream);
 }
+
+// ------------------------------------------------------------------------------------------------------------
+// Measured FP32 multiply-add peak of the device: the denominator of bench.py's `roofline_fma`.  Eight independent packed
+// chains per thread, the multiplier and addend uniform (constant-bank) operands, 8 x 256-thread CTAs per SM — the form in
+// which sm_100 issues FFMA2 at full rate (tools/ubench/fma_forms.cu).
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_fma_peak(float *out, float a, float b, int iters) {
+    float2 x[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) x[i] = make_float2(threadIdx.x * 0.001f + i, threadIdx.x * 0.002f - i);
+    const float2 A = make_float2(a, a), B = make_float2(b, b);
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) x[i] = __ffma2_rn(x[i], A, B);
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += x[i].x + x[i].y;
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+extern "C" int cm_measure_fma_peak(double *tfma_per_s) {
+    if (!tfma_per_s) return cm_fail(CM_ERR_INVALID, "null argument%s");
+    int dev = 0, sms = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const int ctas = sms * 8, iters = 20000;
+    float *out = nullptr;
+    CUDA_TRY(cudaMalloc(&out, (size_t)ctas * 256 * sizeof(float)));
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    float best = 0.f;
+    cudaError_t e = cudaSuccess;
+    for (int rep = 0; rep < 4 && e == cudaSuccess; ++rep) {
+        cudaEventRecord(e0);
+        k_fma_peak<<<ctas, 256>>>(out, 0.999f, 0.001f, iters);
+        cudaEventRecord(e1);
+        e = cudaEventSynchronize(e1);
+        float ms = 0.f;
+        if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, e0, e1);
+        if (rep && ms > 0.f && (best == 0.f || ms < best)) best = ms;          // rep 0 warms up
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(out);
+    if (e != cudaSuccess) return cm_fail(CM_ERR_CUDA, "cm_measure_fma_peak: %s", cudaGetErrorString(e));
+    *tfma_per_s = (double)ctas * 256 * 16.0 * iters / (best * 1e-3) / 1e12;
+    return CM_OK;
+}

@@ -55,6 +55,12 @@ class ImageModem(object):
     def demodulate_batch(self, comp_u8, first_frame=0, out=None):
         return self._modem.decode_frames_host(comp_u8, first_frame, out=out)
 
+    def transcode_batch(self, rgb_u8, first_frame=0, out=None, comp_out=None, want_composite=True):
+        """modulate_batch then demodulate_batch of the result in one native call: the composite is handed over in device
+        memory (and copied out too unless ``want_composite`` is false).  Returns (composite or None, rgb)."""
+        return self._modem.transcode_frames_host(rgb_u8, first_frame, out=out, comp_out=comp_out,
+                                                 want_composite=want_composite)
+
     def modulate(self, img, frame=0):
         from PIL import Image
         if img.mode != 'RGB':

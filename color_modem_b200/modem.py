@@ -190,6 +190,20 @@ class GpuModem(object):
                                                int(comp.shape[0])))
         return out
 
+    def transcode_frames_host(self, rgb, first_frame=0, out=None, comp_out=None, want_composite=True):
+        """encode_frames_host followed by decode_frames_host of its result (what the reference's cli.py:62-65 does), the
+        composite staying in device memory between the two.  Returns (composite or None, rgb)."""
+        rgb = numpy.ascontiguousarray(rgb, dtype=numpy.uint8)
+        if rgb.shape[1:] != (self.height, self.width, 3):
+            raise ValueError('expected uint8 [N, %d, %d, 3]' % (self.height, self.width))
+        out = self._host_out(out, (rgb.shape[0], self.height, self.output_width, 3))
+        if want_composite or comp_out is not None:
+            comp_out = self._host_out(comp_out, (rgb.shape[0], self.height, self.composite_width))
+        N.check(N.load().cm_transcode_frames_host(self._handle(), rgb.ctypes.data,
+                                                  comp_out.ctypes.data if comp_out is not None else None,
+                                                  out.ctypes.data, int(first_frame), int(rgb.shape[0])))
+        return comp_out, out
+
     # ---- float frames (parity tests: composite before the level map / RGB before clipping) -------------------
     def _np_dtype(self):
         return numpy.float32 if self.precision == 'fp32' else numpy.float64

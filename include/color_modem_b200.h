@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define CM_ABI_VERSION 2
+#define CM_ABI_VERSION 3
 
 enum cm_status {
     CM_OK = 0,
@@ -187,6 +187,13 @@ int cm_decode_ex(cm_modem *m, const cm_window *win, const uint8_t *comp_u8, cons
 int cm_encode_frames_host(cm_modem *m, const uint8_t *rgb, uint8_t *comp, int64_t first_frame, int32_t nframes);
 int cm_decode_frames_host(cm_modem *m, const uint8_t *comp, uint8_t *rgb, int64_t first_frame, int32_t nframes);
 
+/* ImageModem.modulate followed by ImageModem.demodulate of the result (the sequence of the reference's cli.py:62-65) in
+ * one call with HOST buffers: rgb_in [n][H][W][3] -> rgb_out [n][H][Wo][3].  The composite stays in device memory between
+ * the two halves; it is copied out to comp_out [n][H][Wc] as well unless comp_out is NULL.  Same bytes as the two calls
+ * above, one host->device trip less. */
+int cm_transcode_frames_host(cm_modem *m, const uint8_t *rgb_in, uint8_t *comp_out, uint8_t *rgb_out, int64_t first_frame,
+                             int32_t nframes);
+
 /* FilterFunction.__call__ (utils.py:28-36) on `nrows` independent rows of f->n samples each: causal IIR from zero
  * state, the input extended by f->shift copies of its last sample and the first f->shift outputs dropped.  `in` / `out`
  * are DEVICE buffers [nrows][f->n] of the given precision (float or double); f->rate is ignored.  Synchronises the
@@ -211,6 +218,10 @@ int cm_timing_read(cm_modem *m, int id, double *total_ms, int64_t *launches);
 /* Tuning aid: when `device_counters` (>= 32 zeroed uint64 on the device) is non-NULL, instrumented kernels add the
  * cycles thread 0 of every CTA spends between consecutive barriers to counters[phase].  NULL switches it off. */
 int cm_phase_profile(cm_modem *m, void *device_counters);
+
+/* Measured FP32 multiply-add peak of the current device in 1e12 multiply-adds per second (packed FFMA2 with uniform
+ * operands, every SM full): the denominator of bench.py's roofline_fma.  Takes ~20 ms. */
+int cm_measure_fma_peak(double *tfma_per_s);
 
 /* Number of kernel launches issued by this library in the calling process (bench.py's gpu_launches). */
 int64_t cm_launch_count(void);
