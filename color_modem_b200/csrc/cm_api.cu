@@ -139,6 +139,21 @@ static void build_filter_L(const cm_filter &f, FiltHdr &h, std::vector<double> &
 
 // Geometry of k_qam_rows2 (cm_qam.cuh: RowL<1..3>) for this line length: the first one whose teams cover the three IIR
 // use-sites with the chunk lengths compiled for it; fills the QF_ROW_* headers and section tables.  0: none fits.
+// Geometry of k_qam_encode_row2 (cm_qam.cuh) for this line length: 1 = 2 warps / 23 samples per lane, 2 = 4 warps / 23,
+// 3 = 4 warps / 31; fills the QF_ENC_PRE header.  0: none fits (the multi-row encoder serves the line).
+static int plan_encode_kernel(const cm_desc &d, FiltHdr *fh, std::vector<double> &tab) {
+    if (d.kind < CM_KIND_QAM_BANDSPLIT || d.kind > CM_KIND_PAL_3D) return 0;
+    const cm_filter &fpre = d.filters[QF_PRE_LP];
+    if (!fpre.nsec) return 0;
+    static const int th[3] = {1, 2, 2}, lpre[3] = {23, 23, 31}, wmax[3] = {768, 1536, 2048};
+    for (int k = 0; k < 3; ++k) {
+        if (d.width > wmax[k] || fpre.n + fpre.shift > 32 * th[k] * lpre[k]) continue;
+        build_filter_L(fpre, fh[9], tab, lpre[k], 1, 32 * th[k]);
+        return k + 1;
+    }
+    return 0;
+}
+
 static int plan_row_kernel(const cm_desc &d, FiltHdr *fh, std::vector<double> &tab) {
     if (d.kind < CM_KIND_NTSC_COMB || d.kind > CM_KIND_PAL_3D) return 0;
     const bool pald = d.kind == CM_KIND_PAL_D ||
@@ -163,12 +178,36 @@ static int plan_row_kernel(const cm_desc &d, FiltHdr *fh, std::vector<double> &t
     return 0;
 }
 
-// Row-independent carrier of k_qam_rows2: sin / cos of (j * step) for the 2x sample index j, tail replicated, in the
-// load order of LoadPoly2Carrier: [task][i / 2][chunk][i & 1] with j = chunk * L + i.
-static void build_carrier_table(const cm_desc &d, const FiltHdr &fl, int th, std::vector<double> &out) {
+// Geometry of k_secam_decode2 (cm_secam.cuh: SecGeo) for this line length: 1 = 2 warps, 3 = 4 warps; fills the SF_ROW_*
+// headers and section tables.  0: none fits (the multi-row kernel serves the line).
+static int plan_secam_kernel(const cm_desc &d, FiltHdr *fh, std::vector<double> &tab) {
+    if (d.kind != CM_KIND_SECAM) return 0;
+    static const int geo[2] = {1, 3}, th[2] = {1, 2}, l1[2] = {25, 33}, l2[2] = {50, 66}, iter[2] = {12, 16};
+    static const int src[5] = {SF_LUMA_BS, SF_CHROMA_BP, SF_ANTI_BELL, SF_FM_LP, SF_DE_EMPH};
+    const int ncc4 = (d.width + d.width / 40 - 1 + 3) & ~3;
+    for (int k = 0; k < 2; ++k) {
+        bool ok = ncc4 <= 32 * 2 * th[k] * iter[k] && d.width <= 16 * 32 * 2 * th[k];
+        for (int i = 0; i < 5 && ok; ++i) {
+            const cm_filter &f = d.filters[src[i]];
+            if (!f.nsec) continue;
+            const int cap = 32 * th[k] * (f.rate == 2 ? l2[k] : l1[k]);
+            if (f.rate > 2 || f.n + f.shift > cap) ok = false;
+        }
+        if (!ok || !d.filters[SF_LUMA_BS].nsec || !d.filters[SF_CHROMA_BP].nsec || !d.filters[SF_FM_LP].nsec) continue;
+        for (int i = 0; i < 5; ++i) {
+            const cm_filter &f = d.filters[src[i]];
+            if (f.nsec) build_filter_L(f, fh[7 + i], tab, f.rate == 2 ? l2[k] : l1[k], 1, 32 * th[k]);
+        }
+        return geo[k];
+    }
+    return 0;
+}
+
+// Row-independent carrier of k_qam_rows2 / k_secam_decode2: sin / cos of (j * step) for the 2x sample index j, tail
+// replicated, in the load order of LoadPoly2Carrier: [task][i / 2][chunk][i & 1] with j = chunk * L + i.
+static void build_carrier_table(unsigned long long step, const FiltHdr &fl, int th, std::vector<double> &out) {
     const int L = fl.L, nchunks = 32 * th;
     out.assign((size_t)2 * fl.npad, 0.0);
-    const unsigned long long step = d.phases[QP_STEP2X];
     for (int chunk = 0; chunk < nchunks; ++chunk)
         for (int i = 0; i < L; ++i) {
             int j = chunk * L + i;
@@ -179,6 +218,41 @@ static void build_carrier_table(const cm_desc &d, const FiltHdr &fl, int th, std
             out[at] = sin(6.283185307179586476925 * turns);
             out[(size_t)fl.npad + at] = cos(6.283185307179586476925 * turns);
         }
+}
+
+// Aligned polyphase form of a rational resampler (PolyHdr, cm_common.cuh).  scipy.signal.resample_poly / upfirdn
+// (SURVEY.md section 8 a9): y[j] = sum_i h[c - i up] x[i], c = half + j down, taps 0 .. 2 half, zeros outside the line.
+// For j = up m + r:  c = up (m down) + (half + r down), so the lowest line index is m down + lo_r with
+// lo_r = ceil((r down - half) / up) and the tap that meets it is t_r = half + r down - lo_r up  (2 half - up < t_r <= 2 half).
+// Window of group m: starts at s = (m down + lo_0 + FP) & ~3; phase r begins d_r = a + lo_r - lo_0 samples into it.
+static bool build_poly(const cm_resampler &rs, PolyHdr &ph, std::vector<double> &tab) {
+    memset(&ph, 0, sizeof(ph));
+    if (rs.ntaps == 0 || rs.up > 4) return false;
+    auto ceil_div = [](int a, int b) { return a >= 0 ? (a + b - 1) / b : -((-a) / b); };
+    int K = 0, lo[4] = {0, 0, 0, 0}, t_r[4] = {0, 0, 0, 0};
+    for (int r = 0; r < rs.up; ++r) {
+        lo[r] = ceil_div(r * rs.down - rs.half, rs.up);
+        t_r[r] = rs.half + r * rs.down - lo[r] * rs.up;
+        const int k = t_r[r] / rs.up + 1 + (lo[r] - lo[0]);        // reach of phase r inside the window (a = 0)
+        if (k > K) K = k;
+    }
+    ph.up = rs.up;
+    ph.down = rs.down;
+    ph.lo0 = lo[0];
+    ph.KU = (K + 3 + 7) & ~7;
+    ph.stride = ph.KU;
+    if (((ph.stride >> 2) & 1) == 0) ph.stride += 4;          // stride / 4 odd: rows read together sit on distinct banks
+    ph.FP = (-lo[0] + 3) & ~3;
+    if (ph.FP < 0) ph.FP = 0;
+    ph.off = (int)tab.size();
+    tab.resize(tab.size() + (size_t)4 * rs.up * ph.stride, 0.0);
+    for (int a = 0; a < 4; ++a)
+        for (int r = 0; r < rs.up; ++r)
+            for (int q = 0; q < ph.KU; ++q) {
+                const int t = t_r[r] + (a + lo[r] - lo[0] - q) * rs.up;
+                if (t >= 0 && t <= 2 * rs.half) tab[(size_t)ph.off + (size_t)(a * rs.up + r) * ph.stride + q] = rs.taps[t];
+            }
+    return true;
 }
 
 template <typename T>
@@ -341,24 +415,58 @@ extern "C" int cm_create(const cm_desc *desc, int precision, cm_modem **out) {
         rh[i].off = (int)taps.size();
         taps.insert(taps.end(), r.taps, r.taps + r.ntaps);
     }
+    std::vector<double> ptab;
+    PolyHdr poly[CM_NRES];
+    memset(poly, 0, sizeof(poly));
+    int mac_fp = 0, mac_bp = 0;
+    if (desc->kind == CM_KIND_MAC)
+        for (int i = 0; i < desc->nresamplers && i < CM_NRES; ++i)
+            if (build_poly(desc->resamplers[i], poly[i], ptab)) {
+                if (poly[i].FP > mac_fp) mac_fp = poly[i].FP;
+                if (poly[i].KU > mac_bp) mac_bp = poly[i].KU;
+            }
+    mac_fp = (mac_fp + 31) & ~31;          // one front pad for every resampler, a whole number of 32-element skew blocks
+    int mac_skew = 0;
+    for (int i = 0; i < CM_NRES; ++i)
+        if (poly[i].up && poly[i].down % 8 == 0) mac_skew = -1;
+    for (int i = 0; i < CM_NRES; ++i)
+        if (poly[i].up) { poly[i].FP = mac_fp; poly[i].skew = mac_skew; }
+    ptab.resize((ptab.size() + 3) & ~(size_t)3, 0.0);
     const int row_geo = plan_row_kernel(*desc, fh, tab);
+    const int enc_geo = plan_encode_kernel(*desc, fh, tab);
     std::vector<double> ctab;
-    if (row_geo) build_carrier_table(*desc, fh[7], row_geo == 1 ? 1 : 2, ctab);
+    if (row_geo) build_carrier_table(desc->phases[QP_STEP2X], fh[7], row_geo == 1 ? 1 : 2, ctab);
+    const int sec_geo = plan_secam_kernel(*desc, fh, tab);
+    if (sec_geo) build_carrier_table(desc->phases[SP_FM_STEP2X], fh[10], sec_geo == 1 ? 1 : 2, ctab);
     int rc;
     if (precision == CM_FP32) {
         rc = upload<float>(tab, &m->d_tab);
         if (rc == CM_OK) rc = upload<float>(taps, &m->d_taps);
         if (rc == CM_OK) rc = upload<float>(ctab, &m->d_ctab);
+        if (rc == CM_OK) rc = upload<float>(ptab, &m->d_ptab);
         fill_params<float>(*desc, m->pf, fh, rh, m->d_tab, m->d_taps);
+        m->pf.ptab = (const float *)m->d_ptab;
+        memcpy(m->pf.poly, poly, sizeof(poly));
+        m->pf.mac_fp = mac_fp;
+        m->pf.mac_skew = mac_skew;
+        m->pf.mac_bp = mac_bp;
         m->pf.ctab = (const float *)m->d_ctab;
-        m->pf.row_geo = row_geo;
+        m->pf.row_geo = row_geo ? row_geo : sec_geo;
+        m->pf.enc_geo = enc_geo;
     } else {
         rc = upload<double>(tab, &m->d_tab);
         if (rc == CM_OK) rc = upload<double>(taps, &m->d_taps);
         if (rc == CM_OK) rc = upload<double>(ctab, &m->d_ctab);
+        if (rc == CM_OK) rc = upload<double>(ptab, &m->d_ptab);
         fill_params<double>(*desc, m->pd, fh, rh, m->d_tab, m->d_taps);
+        m->pd.ptab = (const double *)m->d_ptab;
+        memcpy(m->pd.poly, poly, sizeof(poly));
+        m->pd.mac_fp = mac_fp;
+        m->pd.mac_skew = mac_skew;
+        m->pd.mac_bp = mac_bp;
         m->pd.ctab = (const double *)m->d_ctab;
-        m->pd.row_geo = row_geo;
+        m->pd.row_geo = row_geo ? row_geo : sec_geo;
+        m->pd.enc_geo = enc_geo;
     }
     if (rc != CM_OK) { cm_destroy(m); return rc; }
     *out = m;
@@ -370,6 +478,7 @@ extern "C" void cm_destroy(cm_modem *m) {
     cudaFree(m->d_tab);
     cudaFree(m->d_taps);
     cudaFree(m->d_ctab);
+    cudaFree(m->d_ptab);
     if (m->s2) cudaStreamDestroy(m->s2);
     for (int i = 0; i < 2; ++i) {
         if (m->ev_p1[i]) cudaEventDestroy(m->ev_p1[i]);

@@ -15,7 +15,7 @@
 #define CM_NWARPS 8
 #define CM_NTHREADS (CM_NWARPS * 32)
 #define CM_MAXSEC 6
-#define CM_NFILT 10
+#define CM_NFILT 12
 #define CM_NRES 6
 #define CM_NSCAL 48
 #define CM_NPHASE 16
@@ -32,6 +32,15 @@ struct ResHdr {
     int up, down, half, ntaps;
     int off;                                 // offset (in elements) into DevParams::taps
     int _pad[3];
+};
+
+// Rational resampler (MAC) in aligned polyphase form, built by the host (cm_api.cu: build_poly).  The `up` outputs
+// j = up m + r (r = 0 .. up-1) of one group m read overlapping stretches of the line, so one thread computes the whole
+// group from ONE window of KU samples x[s .. s + KU), s = (m down + lo0 + FP) & ~3, of a zero-padded line (FP zeros in
+// front, KU behind), against the taps G[((a * up) + r) * stride + q], a = (m down + lo0 + FP) & 3.  up <= 4.
+struct PolyHdr {
+    int up, down, KU, stride, FP, off;       // off: offset (elements) of G in DevParams::ptab; up == 0: not built
+    int lo0, skew;                            // skew: mask of poly_skew (cm_fir.cuh), the same for every resampler of a handle
 };
 
 template <typename T>
@@ -56,8 +65,14 @@ struct DevParams {
     ResHdr res[CM_NRES];
     const T *tab;
     const T *taps;
+    const T *ptab;    // MAC: polyphase tap tables of the resamplers (PolyHdr::off)
+    PolyHdr poly[CM_NRES];
+    int mac_skew;         // mask of poly_skew: -1 when some resampler steps by a multiple of 8 samples, else 0
+    int mac_fp, mac_bp;   // zero padding (elements, multiples of 4) in front of / behind every line a resampler reads
     const T *ctab;    // k_qam_rows2: row-independent carrier table [sin | cos][npad of the QF_ROW_LP site] (cm_api.cu)
-    int row_geo;      // k_qam_rows2: geometry 1..3 (cm_qam.cuh: RowL); 0 = the row kernel does not serve this line length
+    int enc_geo;      // k_qam_encode_row2: geometry 1..3 (cm_api.cu: plan_encode_kernel); 0 = not served
+    int row_geo;      // k_qam_rows2: geometry 1..3 (cm_qam.cuh: RowL) / k_secam_decode2: 1 or 3 (cm_secam.cuh: SecGeo);
+                      // 0 = the row kernel does not serve this line length
     // dense taps of resampler slots 0 and 1 (the x2 / x3 half-band pair of every family except MAC), zero-filled:
     // read with compile-time indices they become constant-bank operands of the FIR FMAs (FFMA R, R, c[0][..], R
     // issues at full rate; with the tap in a third register the sm_100 register file caps FFMA at ~0.7 / clk,

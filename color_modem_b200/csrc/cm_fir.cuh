@@ -335,8 +335,8 @@ __device__ __forceinline__ void down3_quad_prod(const Down3Taps<T> &tp, const T 
 }
 
 // General rational resampler (MAC: 3/8, 3/16, 2/3, 3/2, ...).  x[0..n) -> n_out outputs.
-template <typename T, class Post>
-__device__ __forceinline__ void fir_general(const T *__restrict__ x, int n, int n_out, const ResHdr rh,
+template <typename T, class Load, class Post>
+__device__ __forceinline__ void fir_general(Load x, int n, int n_out, const ResHdr rh,
                                             const T *__restrict__ h, int tid, int nthr, Post post) {
     for (int j = tid; j < n_out; j += nthr) {
         const int c = rh.half + j * rh.down;
@@ -345,7 +345,64 @@ __device__ __forceinline__ void fir_general(const T *__restrict__ x, int n, int 
         int lo_num = c - 2 * rh.half;
         int i_lo = lo_num <= 0 ? 0 : (lo_num + rh.up - 1) / rh.up;
         T acc = (T)0;
-        for (int i = i_lo; i <= i_hi; ++i) acc = Real<T>::fma_(h[c - i * rh.up], x[i], acc);
+        for (int i = i_lo; i <= i_hi; ++i) acc = Real<T>::fma_(h[c - i * rh.up], x(i), acc);
         post(j, acc);
     }
+}
+
+// Rational resampler in aligned polyphase form (PolyHdr, cm_common.cuh): one thread per output GROUP (the UP outputs
+// j = UP m + r), one 128-bit load of the line per four samples shared by the UP phases, the taps of each phase read with
+// 128-bit loads that are broadcasts whenever `down` is a multiple of 4, UP independent accumulators.  Shared-memory
+// bandwidth, not arithmetic, binds this loop: one output per thread (every sample loaded once per output) ran at 2.8
+// TFMA/s.  `xpad` points at the element of the FRONT PAD that is FP samples ahead of the line (a multiple of 32 elements
+// from the start of the skewed segment, so the skew is the same function for every resampler): xpad[skew(FP + i)] = x[i],
+// zeros outside [0, n).
+// Skewed line layout of the resampler inputs: element i of the padded line lives at i + 4 (i / 32) — one 16-byte chunk
+// of slack per 128 bytes.  The lanes of a warp start their windows `down` samples apart (8 or 16 for the MAC ratios):
+// unskewed, their 128-bit loads fall on 2 or 4 bank groups only (4-way conflicts measured as the bound of the loop).
+// (mask: all ones with the skew, zero without — lines whose resamplers step by 2 or 3 samples need none)
+__device__ __forceinline__ int poly_skew(int i, int mask) { return i + (((i >> 5) << 2) & mask); }
+
+template <typename T, int UP, bool SKEW, class Post>
+__device__ __forceinline__ void fir_poly_up(const T *__restrict__ xpad, int n_out, const PolyHdr &ph, const T *__restrict__ G,
+                                            int tid, int nthr, Post post) {
+    const int ngroups = (n_out + UP - 1) / UP;
+    for (int m = tid; m < ngroups; m += nthr) {
+        const int idx = m * ph.down + ph.lo0 + ph.FP;
+        const int a = idx & 3, s0 = idx - a;
+        const T *__restrict__ g = G + (size_t)(a * UP) * ph.stride;
+        T acc[UP];
+#pragma unroll
+        for (int r = 0; r < UP; ++r) acc[r] = (T)0;
+        for (int q = 0; q < ph.KU; q += 4) {
+            T xv[4];
+            ld4(xpad + (SKEW ? poly_skew(s0 + q, -1) : s0 + q), xv);
+#pragma unroll
+            for (int r = 0; r < UP; ++r) {
+                T gv[4];
+                ld4(g + r * ph.stride + q, gv);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) acc[r] = Real<T>::fma_(gv[i], xv[i], acc[r]);
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < UP; ++r)
+            if (UP * m + r < n_out) post(UP * m + r, acc[r]);
+    }
+}
+
+template <typename T, class Post>
+__device__ __forceinline__ void fir_poly(const T *__restrict__ xpad, int n_out, const PolyHdr &ph, const T *__restrict__ G,
+                                         int tid, int nthr, Post post) {
+    if (ph.skew) {          // the skew only occurs with the 3/8 and 3/16 families (down a multiple of 8)
+        if (ph.up == 3) fir_poly_up<T, 3, true>(xpad, n_out, ph, G, tid, nthr, post);
+        else if (ph.up == 2) fir_poly_up<T, 2, true>(xpad, n_out, ph, G, tid, nthr, post);
+        else if (ph.up == 1) fir_poly_up<T, 1, true>(xpad, n_out, ph, G, tid, nthr, post);
+        else fir_poly_up<T, 4, true>(xpad, n_out, ph, G, tid, nthr, post);
+        return;
+    }
+    if (ph.up == 1) fir_poly_up<T, 1, false>(xpad, n_out, ph, G, tid, nthr, post);
+    else if (ph.up == 2) fir_poly_up<T, 2, false>(xpad, n_out, ph, G, tid, nthr, post);
+    else if (ph.up == 3) fir_poly_up<T, 3, false>(xpad, n_out, ph, G, tid, nthr, post);
+    else fir_poly_up<T, 4, false>(xpad, n_out, ph, G, tid, nthr, post);
 }

@@ -44,6 +44,7 @@ struct cm_modem {
     void *d_tab = nullptr;
     void *d_taps = nullptr;
     void *d_ctab = nullptr;
+    void *d_ptab = nullptr;
     bool timing = false;
     unsigned long long *phase_prof = nullptr;
     // pairing scratch of the line-sequential decoders (grown on demand); one per host-path stream (+ slot 0 for

@@ -187,3 +187,32 @@ __global__ void __launch_bounds__(256) k_pair_rows_store(const __grid_constant__
         else store_rgb4(p, io, f, row, 4 * q, y, a, b);
     }
 }
+
+// u8 composite row held in registers between its (early) global load and its staging into shared memory: the DRAM
+// latency of the row a CTA works on next is hidden behind the row it is working on now.
+struct RowPrefetch {
+    static constexpr int kMaxQuads = 4;          // 4 pixels per quad: rows of up to 16 * blockDim samples
+    uint32_t w[kMaxQuads];
+    template <typename T>
+    __device__ __forceinline__ void fetch(const IoArgs<T> &io, int f, int row, int Wc) {
+        const uint8_t *src = io.in_u8 + ((size_t)f * io.nrows + row) * Wc;
+#pragma unroll
+        for (int q = 0; q < kMaxQuads; ++q) {
+            const int x = 4 * (threadIdx.x + q * blockDim.x);
+            if (x < Wc) w[q] = __ldg(reinterpret_cast<const uint32_t *>(src + x));
+        }
+    }
+    template <typename T>
+    __device__ __forceinline__ void stage(T *dst, int Wc) const {
+#pragma unroll
+        for (int q = 0; q < kMaxQuads; ++q) {
+            const int x = 4 * (threadIdx.x + q * blockDim.x);
+            if (x < Wc) {
+                T v[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) v[i] = ((T)5 * Real<T>::from_u8((w[q] >> (8 * i)) & 0xff) - (T)1) * (T)(1.0 / 3.0);
+                st4(dst + x, v);
+            }
+        }
+    }
+};

@@ -2,9 +2,12 @@
 #include "cm_host.h"
 #include "cm_mac.cuh"
 
-static int mac_taps_len(const cm_modem *m) {
+// elements of the polyphase tables (DevParams::ptab) that the kernels stage in shared memory
+template <typename T>
+static int mac_taps_len(const DevParams<T> &p) {
     int total = 0;
-    for (int r = 0; r < m->desc.nresamplers; ++r) total += m->desc.resamplers[r].ntaps;
+    for (int r = 0; r < CM_NRES; ++r)
+        if (p.poly[r].up) total = p.poly[r].off + 4 * p.poly[r].up * p.poly[r].stride;
     return (total + 3) & ~3;
 }
 
@@ -13,8 +16,9 @@ int mac_encode(cm_modem *m, IoArgs<T> io, cudaStream_t st) {
     const DevParams<T> &p = params_of<T>(m);
     if (io.out_count <= 0) return CM_OK;
     if (p.Wc > 1080) return cm_fail(CM_ERR_UNSUPPORTED, "MAC widths above 1080 are not built%s");
-    const int tl = mac_taps_len(m);
-    auto bytes = [&](int r) { return ((size_t)tl + (size_t)r * (2 * (size_t)p.W + 720 + 360 + 1080)) * sizeof(T); };
+    const int tl = mac_taps_len(p);
+    auto seg = [&](int n) { const int e = p.mac_fp + ((n + 3) & ~3) + p.mac_bp; return (size_t)(e + (((e >> 5) << 2) & p.mac_skew) + 4); };
+    auto bytes = [&](int r) { return ((size_t)tl + (size_t)r * (2 * seg(p.W) + 720 + 360 + seg(1080) + 1080)) * sizeof(T); };
     int R = pick_rows(m, 2, (size_t)m->smem_optin / 2, bytes);
     if (!R) return cm_fail(CM_ERR_UNSUPPORTED, "line too wide for the MAC encode kernel%s");
     set_groups(io, R);
@@ -34,9 +38,10 @@ template <typename T>
 int mac_decode(cm_modem *m, IoArgs<T> io, cudaStream_t st) {
     const DevParams<T> &p = params_of<T>(m);
     if (io.out_count <= 0) return CM_OK;
-    const int tl = mac_taps_len(m);
+    const int tl = mac_taps_len(p);
     auto bytes = [&](int r) {
-        return ((size_t)tl + (size_t)(r + 1) * ((size_t)p.Wc + 1080 + 720 + 360 + 720)) * sizeof(T);
+        const int e = p.mac_fp + ((p.Wc + 3) & ~3) + p.mac_bp;
+        return ((size_t)tl + (size_t)(r + 1) * ((size_t)(e + (((e >> 5) << 2) & p.mac_skew) + 4) + 1080 + 720 + 360 + 720)) * sizeof(T);
     };
     int R = pick_rows(m, 2, (size_t)m->smem_optin / 2, bytes);
     if (!R) return cm_fail(CM_ERR_UNSUPPORTED, "line too wide for the MAC decode kernel%s");

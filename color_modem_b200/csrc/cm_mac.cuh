@@ -7,19 +7,38 @@
 #include "cm_io.cuh"
 #include "cm_slots.h"
 
-// dst[0..n_out) = resample(src[0..n_in)) with resampler slot r (identity when the ratio is 1)
+// Shared-memory line that a resampler reads: [FP zeros | n samples (rounded up to 4) | BP zeros]  (cm_fir.cuh: fir_poly)
+// in the skewed layout of cm_fir.cuh (poly_skew): sample i of the line lives at seg[poly_skew(FP + i, p.mac_skew)]
 template <typename T>
-__device__ __forceinline__ void mac_fit(const DevParams<T> &p, const T *taps, int r, const T *src, int n_in, T *dst,
+__device__ __forceinline__ int mac_seg(const DevParams<T> &p, int n) {
+    return poly_skew(p.mac_fp + ((n + 3) & ~3) + p.mac_bp, p.mac_skew) + 4;
+}
+
+template <typename T>
+__device__ __forceinline__ void mac_zero_pads(const DevParams<T> &p, T *seg, int n) {
+    const int n4 = (n + 3) & ~3;
+    for (int i = threadIdx.x; i < p.mac_fp; i += blockDim.x) seg[poly_skew(i, p.mac_skew)] = (T)0;
+    for (int i = n + threadIdx.x; i < n4 + p.mac_bp; i += blockDim.x) seg[poly_skew(p.mac_fp + i, p.mac_skew)] = (T)0;
+}
+
+// dst[0..n_out) = resample(src line of n_in samples, `seg` = its padded segment) with resampler slot r (identity when the
+// ratio is 1).  tabs: the polyphase tables staged in shared memory.
+template <typename T>
+__device__ __forceinline__ void mac_fit(const DevParams<T> &p, const T *tabs, int r, const T *seg, int n_in, T *dst,
                                         int n_out, T add) {
     const ResHdr rh = p.res[r];
+    const int fp = p.mac_fp;
     if (rh.ntaps == 0) {
-        for (int j = threadIdx.x; j < n_out; j += blockDim.x) dst[j] = src[j] + add;
-    } else {
-        fir_general(src, n_in, n_out, rh, taps + rh.off, threadIdx.x, blockDim.x, [&](int j, T v) { dst[j] = v + add; });
+        for (int j = threadIdx.x; j < n_out; j += blockDim.x) dst[j] = seg[poly_skew(fp + j, p.mac_skew)] + add;
+    } else if (p.poly[r].up) {
+        fir_poly(seg, n_out, p.poly[r], tabs + p.poly[r].off, threadIdx.x, blockDim.x, [&](int j, T v) { dst[j] = v + add; });
+    } else {        // ratios with up > 4 (odd composite widths): one output per thread straight from the dense taps
+        fir_general<T>([&](int i) { return seg[poly_skew(fp + i, p.mac_skew)]; }, n_in, n_out, rh, p.taps + rh.off, threadIdx.x,
+                       blockDim.x, [&](int j, T v) { dst[j] = v + add; });
     }
 }
 
-// Encode.  smem: taps + R * ( luma[W] | chroma[W] | luma720 | ch360 | line1080 )
+// Encode.  smem: tables + R * ( luma seg(W) | chroma seg(W) | luma720 | ch360 | line seg(1080) | out[1080] )
 template <typename T>
 __global__ void __launch_bounds__(CM_NTHREADS)
 k_mac_encode(const __grid_constant__ DevParams<T> p, const __grid_constant__ IoArgs<T> io, int taps_len) {
@@ -31,13 +50,17 @@ k_mac_encode(const __grid_constant__ DevParams<T> p, const __grid_constant__ IoA
     const bool avg = (p.flags & 2) != 0;
     T *taps = sm;
     T *rows = sm + taps_len;
-    const size_t per_row = 2 * (size_t)W + 720 + 360 + 1080;
-    for (int i = threadIdx.x; i < taps_len; i += blockDim.x) taps[i] = p.taps[i];
+    const int segW = mac_seg(p, W), seg1080 = mac_seg(p, 1080);
+    const size_t per_row = 2 * (size_t)segW + 720 + 360 + seg1080 + 1080;
+    for (int i = threadIdx.x; i < taps_len; i += blockDim.x) taps[i] = p.ptab[i];
     for (int k = 0; k < g.count; ++k) {
         const int row = g.r0 + 2 * k;
         const int nrow = (row + 2 < io.nrows) ? row + 2 : row;
         const int ci = is_alternate(p, g.frame, io.y0 + row) ? 6 : 3;      // D'B on alternate lines, else D'R
-        T *ys = rows + k * per_row, *cs = ys + W;
+        T *yseg = rows + k * per_row, *cseg = yseg + segW;
+        mac_zero_pads(p, yseg, W);
+        mac_zero_pads(p, cseg, W);
+        mac_zero_pads(p, cseg + segW + 720 + 360, 1080);
         for (int q = threadIdx.x; q < W4; q += blockDim.x) {
             const int x = 4 * q;
             T r[4], gg[4], b[4], y[4], c[4];
@@ -53,20 +76,20 @@ k_mac_encode(const __grid_constant__ DevParams<T> p, const __grid_constant__ IoA
                 for (int i = 0; i < 4; ++i)
                     c[i] = (T)0.5 * ((p.enc[ci] * r[i] + p.enc[ci + 1] * gg[i] + p.enc[ci + 2] * b[i]) + c[i]);
             }
-            st4(ys + x, y);
-            st4(cs + x, c);
+            st4(yseg + poly_skew(p.mac_fp + x, p.mac_skew), y);
+            st4(cseg + poly_skew(p.mac_fp + x, p.mac_skew), c);
         }
     }
     __syncthreads();
     for (int k = 0; k < g.count; ++k) {
-        T *ys = rows + k * per_row, *cs = ys + W, *l720 = cs + W, *c360 = l720 + 720;
-        mac_fit(p, taps, MR_LUMA_IN, ys, W, l720, 720, (T)0);
-        mac_fit(p, taps, MR_CHROMA_IN, cs, W, c360, 360, (T)0.5);          // mac.py:57 chroma += 0.5
+        T *yseg = rows + k * per_row, *cseg = yseg + segW, *l720 = cseg + segW, *c360 = l720 + 720;
+        mac_fit(p, taps, MR_LUMA_IN, yseg, W, l720, 720, (T)0);
+        mac_fit(p, taps, MR_CHROMA_IN, cseg, W, c360, 360, (T)0.5);         // mac.py:57 chroma += 0.5
     }
     __syncthreads();
     for (int k = 0; k < g.count; ++k) {                                    // mac.py:58-69
-        const T *l = rows + k * per_row + 2 * W, *c = l + 720;
-        T *o = rows + k * per_row + 2 * W + 1080;
+        const T *l = rows + k * per_row + 2 * segW, *c = l + 720;
+        T *oseg = rows + k * per_row + 2 * segW + 1080;
         for (int i = threadIdx.x; i < 1080; i += blockDim.x) {
             T v = (T)0.5;
             if (i == 15) v = (T)0.4375 + (T)0.125 * c[2];
@@ -80,21 +103,19 @@ k_mac_encode(const __grid_constant__ DevParams<T> p, const __grid_constant__ IoA
             else if (i == 1071) v = (T)0.0625 + (T)0.875 * l[710];
             else if (i == 1072) v = (T)0.25 + (T)0.5 * l[711];
             else if (i == 1073) v = (T)0.4375 + (T)0.125 * l[712];
-            o[i] = v;
+            oseg[poly_skew(p.mac_fp + i, p.mac_skew)] = v;
         }
     }
     __syncthreads();
     for (int k = 0; k < g.count; ++k) {
-        const T *o = rows + k * per_row + 2 * W + 1080;
-        T *dst = rows + k * per_row;                                      // luma / chroma rows are dead: Wc <= 2W? use luma720 area
-        (void)dst;
-        T *outrow = rows + k * per_row + 2 * W;                           // luma720|ch360 region (1080 elements) reused
-        mac_fit(p, taps, MR_OUT, o, 1080, outrow, Wc, (T)0);
+        const T *oseg = rows + k * per_row + 2 * segW + 1080;
+        T *outrow = rows + k * per_row + 2 * segW + 1080 + seg1080;
+        mac_fit(p, taps, MR_OUT, oseg, 1080, outrow, Wc, (T)0);
     }
     __syncthreads();
     for (int k = 0; k < g.count; ++k) {
         const int row = g.r0 + 2 * k;
-        const T *outrow = rows + k * per_row + 2 * W;
+        const T *outrow = rows + k * per_row + 2 * segW + 1080 + seg1080;
         for (int q = threadIdx.x; q < (Wc >> 2); q += blockDim.x) {
             T o[4];
             ld4(outrow + 4 * q, o);
@@ -103,7 +124,7 @@ k_mac_encode(const __grid_constant__ DevParams<T> p, const __grid_constant__ IoA
     }
 }
 
-// Decode.  smem: taps + (R+1) rows x ( comp[Wc4] | c1080 | luma720 | ch360 | XE[360] | XO[360] )
+// Decode.  smem: tables + (R+1) rows x ( comp seg(Wc) | c1080 | luma720 | ch360 | XE[360] | XO[360] )
 template <typename T>
 __global__ void __launch_bounds__(CM_NTHREADS)
 k_mac_decode(const __grid_constant__ DevParams<T> p, const __grid_constant__ IoArgs<T> io, int taps_len) {
@@ -114,18 +135,34 @@ k_mac_decode(const __grid_constant__ DevParams<T> p, const __grid_constant__ IoA
     const int Wc = p.Wc;
     T *taps = sm;
     T *rows = sm + taps_len;
-    const size_t per_row = (size_t)Wc + 1080 + 720 + 360 + 720;
+    const int segC = mac_seg(p, Wc);
+    const size_t per_row = (size_t)segC + 1080 + 720 + 360 + 720;
     const bool has_prev0 = g.r0 >= 2;
     const int k_lo = has_prev0 ? -1 : 0;
     auto rowp = [&](int k) { return rows + (size_t)(k - k_lo) * per_row; };
-    for (int i = threadIdx.x; i < taps_len; i += blockDim.x) taps[i] = p.taps[i];
-    for (int k = k_lo; k < g.count; ++k) load_comp_row(rowp(k), io, g.fidx, g.r0 + 2 * k, Wc);
+    for (int i = threadIdx.x; i < taps_len; i += blockDim.x) taps[i] = p.ptab[i];
+    for (int k = k_lo; k < g.count; ++k) {
+        mac_zero_pads(p, rowp(k), Wc);
+        T *cseg = rowp(k);
+        const size_t base = ((size_t)g.fidx * io.nrows + g.r0 + 2 * k) * Wc;
+        for (int x = 4 * threadIdx.x; x < Wc; x += 4 * blockDim.x) {       // load_comp_row into the skewed segment
+            T v[4];
+            if (io.in_f) {
+                ld4(io.in_f + base + x, v);
+            } else {
+                const uint32_t w = __ldg(reinterpret_cast<const uint32_t *>(io.in_u8 + base + x));
+#pragma unroll
+                for (int i = 0; i < 4; ++i) v[i] = ((T)5 * Real<T>::from_u8((w >> (8 * i)) & 0xff) - (T)1) * (T)(1.0 / 3.0);
+            }
+            st4(cseg + poly_skew(p.mac_fp + x, p.mac_skew), v);
+        }
+    }
     __syncthreads();
-    for (int k = k_lo; k < g.count; ++k) mac_fit(p, taps, MR_COMP_IN, rowp(k), Wc, rowp(k) + Wc, 1080, (T)0);
+    for (int k = k_lo; k < g.count; ++k) mac_fit(p, taps, MR_COMP_IN, rowp(k), Wc, rowp(k) + segC, 1080, (T)0);
     __syncthreads();
     for (int k = k_lo; k < g.count; ++k) {                                 // mac.py:86-109
-        const T *c = rowp(k) + Wc;
-        T *l = rowp(k) + Wc + 1080, *ch = l + 720;
+        const T *c = rowp(k) + segC;
+        T *l = rowp(k) + segC + 1080, *ch = l + 720;
         for (int i = threadIdx.x; i < 720 + 360; i += blockDim.x) {
             if (i < 720) {
                 const T ch355 = c[368];                                     // chroma[355] = composite[368]
@@ -161,9 +198,9 @@ k_mac_decode(const __grid_constant__ DevParams<T> p, const __grid_constant__ IoA
         }
     }
     __syncthreads();
-    const FirTaps<T> hup{taps + p.res[MR_UP2].off, nullptr};
+    const FirTaps<T> hup{p.taps + p.res[MR_UP2].off, nullptr};
     for (int k = k_lo; k < g.count; ++k) {
-        T *ch = rowp(k) + Wc + 1080 + 720, *xe = ch + 360, *xo = xe + 360;
+        T *ch = rowp(k) + segC + 1080 + 720, *xe = ch + 360, *xo = xe + 360;
         fir_up2(xe, xo, ch, 360, hup, threadIdx.x, blockDim.x);
     }
     __syncthreads();
@@ -171,8 +208,8 @@ k_mac_decode(const __grid_constant__ DevParams<T> p, const __grid_constant__ IoA
         const int row = g.r0 + 2 * k;
         const bool alt = is_alternate(p, g.frame, io.y0 + row);
         const bool hp = (k > 0) || has_prev0;
-        const T *l = rowp(k) + Wc + 1080, *xe = l + 720 + 360, *xo = xe + 360;
-        const T *pe = hp ? rowp(k - 1) + Wc + 1080 + 720 + 360 : nullptr, *po = hp ? pe + 360 : nullptr;
+        const T *l = rowp(k) + segC + 1080, *xe = l + 720 + 360, *xo = xe + 360;
+        const T *pe = hp ? rowp(k - 1) + segC + 1080 + 720 + 360 : nullptr, *po = hp ? pe + 360 : nullptr;
         for (int q = threadIdx.x; q < 180; q += blockDim.x) {
             T y[4], a[4], b[4];
             ld4(l + 4 * q, y);

@@ -45,6 +45,21 @@ int qam_encode(cm_modem *m, IoArgs<T> io, cudaStream_t st) {
     int R = pick_rows(m, 1, (size_t)m->smem_optin / 2, bytes);     // one row, two warps (u and v low-pass): 1.84 vs 2.64 us/frame
     if (!R) return cm_fail(CM_ERR_UNSUPPORTED, "line too wide for the encode kernel%s");
     const bool teams = needs_teams(p);
+    if (io.in_u8 && p.enc_geo && !m->tune.onepass && !m->tune.rows_v1) {     // second-generation row encoder
+        void (*kern)(const DevParams<T>, const IoArgs<T>) =
+            p.enc_geo == 1 ? k_qam_encode_row2<T, 1> : (p.enc_geo == 2 ? k_qam_encode_row2<T, 2> : k_qam_encode_row2<T, 3>);
+        int rc1 = set_smem(kern, bytes(1));
+        if (rc1) return rc1;
+        const int rpc = m->tune.rpc;
+        const int nf = (io.out_count + 1) >> 1;
+        {
+            LaunchTimer lt(m, CM_K_ENCODE, st);
+            kern<<<dim3((unsigned)((nf + rpc - 1) / rpc), 2u, (unsigned)io.nframes), p.enc_geo == 1 ? 64 : 128, bytes(1), st>>>(p, io);
+        }
+        cm_count_launch();
+        CUDA_TRY(cudaGetLastError());
+        return CM_OK;
+    }
     if (!teams && io.in_u8 && p.W <= 768 && !m->tune.onepass) {        // one row at a time, next row prefetched
         int rc1 = set_smem(k_qam_encode_row<T>, bytes(1));
         if (rc1) return rc1;

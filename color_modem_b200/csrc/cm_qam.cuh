@@ -211,6 +211,122 @@ k_qam_encode_row(const __grid_constant__ DevParams<T> p, const __grid_constant__
     }
 }
 
+// Encoder for u8 frames, second generation: the same chain as k_qam_encode_row for lines of up to 2048 samples.  The two
+// chroma low-passes are run by two teams of NW / 2 warps as packed DF-I recursions (team_iir_pk); KQ pixel quads per
+// thread (RGB words of the next row, and of its field neighbour for the ColorAveraging front end, prefetched in registers).
+//   GEO 1: 2 warps, 3 quads (<= 768 samples);  2: 4 warps, 3 quads (<= 1536);  3: 4 warps, 4 quads, longer chunks (<= 2048)
+#define QF_ENC_PRE 9     // DevParams::filt slot of this kernel's low-pass site (cm_api.cu: plan_encode_kernel)
+template <int GEO> struct EncGeo;
+template <> struct EncGeo<1> { static constexpr int NW = 2, KQ = 3, PRE = 23; };
+template <> struct EncGeo<2> { static constexpr int NW = 4, KQ = 3, PRE = 23; };
+template <> struct EncGeo<3> { static constexpr int NW = 4, KQ = 4, PRE = 31; };
+
+template <typename T, int GEO>
+__global__ void __launch_bounds__(32 * EncGeo<GEO>::NW, sizeof(T) == 8 ? 1 : 16 / EncGeo<GEO>::NW)
+k_qam_encode_row2(const __grid_constant__ DevParams<T> p, const __grid_constant__ IoArgs<T> io) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T *scratch = reinterpret_cast<T *>(smem_raw), *sm = scratch + 128;
+    typedef EncGeo<GEO> EG;
+    constexpr int kQ = EG::KQ, NT = 32 * EG::NW, TH = EG::NW / 2;
+    const int W = p.W, N1 = p.n1p, W4 = W >> 2;
+    const int warp = threadIdx.x >> 5, task = warp / TH, wr = warp - task * TH;
+    const bool avg = (p.flags & 2) != 0;
+    const int field = blockIdx.y, f = blockIdx.z;
+    const long long frame = io.first_frame + f;
+    const int first = io.out_begin + field, nout = (io.out_count - field + 1) >> 1;
+    const FiltHdr &fpre = p.filt[QF_ENC_PRE];
+    T *ys = sm, *us = ys + N1, *vs = us + N1;
+    uint32_t wc[kQ][3], wn[kQ][3];
+    auto fetch = [&](int row) {
+        const int nrow = (row + 2 < io.nrows) ? row + 2 : row;
+        const uint32_t *a = reinterpret_cast<const uint32_t *>(io.in_u8 + ((size_t)f * io.nrows + row) * W * 3);
+        const uint32_t *b = reinterpret_cast<const uint32_t *>(io.in_u8 + ((size_t)f * io.nrows + nrow) * W * 3);
+#pragma unroll
+        for (int j = 0; j < kQ; ++j) {
+            const int q = threadIdx.x + j * NT;
+            if (q < W4) {
+#pragma unroll
+                for (int i = 0; i < 3; ++i) {
+                    wc[j][i] = __ldg(a + 3 * q + i);
+                    if (avg) wn[j][i] = __ldg(b + 3 * q + i);
+                }
+            }
+        }
+    };
+    auto unpack = [&](const uint32_t *w, T *r, T *g, T *b) {
+        unsigned char bytes[12];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            bytes[i] = (w[0] >> (8 * i)) & 0xff;
+            bytes[4 + i] = (w[1] >> (8 * i)) & 0xff;
+            bytes[8 + i] = (w[2] >> (8 * i)) & 0xff;
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            r[i] = Real<T>::from_u8(bytes[3 * i]);
+            g[i] = Real<T>::from_u8(bytes[3 * i + 1]);
+            b[i] = Real<T>::from_u8(bytes[3 * i + 2]);
+        }
+    };
+    T rs, rc;
+    Real<T>::sincos_turns(p.phases[QP_STEP1X], rs, rc);
+    int k = blockIdx.x;
+    if (k < nout) fetch(first + 2 * k);
+    for (; k < nout; k += gridDim.x) {
+        const int row = first + 2 * k, line = io.y0 + row;
+#pragma unroll
+        for (int j = 0; j < kQ; ++j) {
+            const int q = threadIdx.x + j * NT;
+            if (q < W4) {
+                T r[4], gg[4], b[4], y[4], u[4], v[4];
+                unpack(wc[j], r, gg, b);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    y[i] = p.enc[0] * r[i] + p.enc[1] * gg[i] + p.enc[2] * b[i];
+                    u[i] = p.enc[3] * r[i] + p.enc[4] * gg[i] + p.enc[5] * b[i];
+                    v[i] = p.enc[6] * r[i] + p.enc[7] * gg[i] + p.enc[8] * b[i];
+                }
+                if (avg) {
+                    unpack(wn[j], r, gg, b);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const T un = p.enc[3] * r[i] + p.enc[4] * gg[i] + p.enc[5] * b[i];
+                        const T vn = p.enc[6] * r[i] + p.enc[7] * gg[i] + p.enc[8] * b[i];
+                        u[i] = (T)0.5 * (un + u[i]);
+                        v[i] = (T)0.5 * (vn + v[i]);
+                    }
+                }
+                st4(ys + 4 * q, y);
+                st4(us + 4 * q, u);
+                st4(vs + 4 * q, v);
+            }
+        }
+        __syncthreads();
+        if (k + (int)gridDim.x < nout) fetch(first + 2 * (k + gridDim.x));       // in flight during the filtering
+        {
+            T *buf = task ? vs : us;
+            warp_fill_tail<T, 1>(buf, N1, W, fpre.npad);          // every warp of the team writes the same values
+            team_iir_pk<T, 1, EG::PRE, TH>(p.tab + fpre.off, fpre, LoadLinear<T, EG::PRE>{buf}, [&](int j, T x) { buf[j] = x; },
+                                           wr, 2 + task, scratch + 32 * task);
+        }
+        __syncthreads();
+        const unsigned long long ph0 = start_phase(p, frame, line);
+        const bool neg = (p.flags & 1) && is_alternate(p, frame, line);
+        for (int q = threadIdx.x; q < W4; q += NT) {
+            const int x = 4 * q;
+            T y[4], u[4], v[4], s[4], c[4], o[4];
+            ld4(ys + x, y);
+            ld4(us + x, u);
+            ld4(vs + x, v);
+            carrier4(ph0 + (unsigned long long)x * p.phases[QP_STEP1X], rs, rc, s, c);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) o[i] = y[i] + (s[i] * u[i] + c[i] * (neg ? -v[i] : v[i]));
+            store_comp4(io, ((size_t)f * io.nrows + row) * p.Wc + x, o);
+        }
+        __syncthreads();
+    }
+}
+
 // Re-modulation of (u, v) through the encoder and subtraction from the composite, then colour matrix + store:
 //   y = c - (sin(phi) u_lp + cos(phi) (+-v_lp))            comb.py:52-53, pal.py:225-226
 template <typename T>
@@ -590,35 +706,6 @@ __device__ __forceinline__ void row_planes(const DevParams<T> &p, const IoArgs<T
     rows_epilogue<T, TEAMS>(p, dst, scratch, cb, g, wa, wb);
     __syncthreads();
 }
-
-// u8 composite row held in registers between its (early) global load and its staging into shared memory: the DRAM
-// latency of the row a CTA works on next is hidden behind the row it is working on now.
-struct RowPrefetch {
-    static constexpr int kMaxQuads = 4;          // 4 pixels per quad: rows of up to 16 * blockDim samples
-    uint32_t w[kMaxQuads];
-    template <typename T>
-    __device__ __forceinline__ void fetch(const IoArgs<T> &io, int f, int row, int Wc) {
-        const uint8_t *src = io.in_u8 + ((size_t)f * io.nrows + row) * Wc;
-#pragma unroll
-        for (int q = 0; q < kMaxQuads; ++q) {
-            const int x = 4 * (threadIdx.x + q * blockDim.x);
-            if (x < Wc) w[q] = __ldg(reinterpret_cast<const uint32_t *>(src + x));
-        }
-    }
-    template <typename T>
-    __device__ __forceinline__ void stage(T *dst, int Wc) const {
-#pragma unroll
-        for (int q = 0; q < kMaxQuads; ++q) {
-            const int x = 4 * (threadIdx.x + q * blockDim.x);
-            if (x < Wc) {
-                T v[4];
-#pragma unroll
-                for (int i = 0; i < 4; ++i) v[i] = ((T)5 * Real<T>::from_u8((w[q] >> (8 * i)) & 0xff) - (T)1) * (T)(1.0 / 3.0);
-                st4(dst + x, v);
-            }
-        }
-    }
-};
 
 // Pass 1 of the two-pass decoders: a CTA works through rows blockIdx.x, blockIdx.x + gridDim.x, ... of one frame (one at
 // a time; the next one is prefetched), planes to aux[frame][row][4][W].

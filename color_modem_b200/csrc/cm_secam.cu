@@ -26,38 +26,69 @@ template <typename T>
 int secam_decode(cm_modem *m, IoArgs<T> io, cudaStream_t st) {
     const DevParams<T> &p = params_of<T>(m);
     if (io.out_count <= 0) return CM_OK;
-    // pass 1 (heavy): (luma, X) per row for the output rows and the two rows above them
-    const size_t aux_bytes = (size_t)io.nframes * io.nrows * 2 * p.Wo * sizeof(T);
-    io.aux = (T *)cm_ensure_aux(m, aux_bytes);
-    if (!io.aux) return CM_ERR_NOMEM;
-    int rc;
-    IoArgs<T> a = io;
-    a.out_begin = io.out_begin >= 2 ? io.out_begin - 2 : 0;
-    a.out_count = io.out_begin + io.out_count - a.out_begin;
+    // pass 1 (heavy): (luma, X) per row for the output rows and the two rows above them, into a pairing scratch of
+    // 2 * Wo elements per row; the batch is cut so that the scratch stays within 2 GiB
+    const size_t frame_elems = (size_t)io.nrows * 2 * p.Wo;
+    int chunk = (int)(((size_t)2 << 30) / (frame_elems * sizeof(T)));
+    if (chunk < 1) chunk = 1;
+    if (m->tune.chunk > 0) chunk = m->tune.chunk;
+    if (chunk > io.nframes) chunk = io.nframes;
+    T *aux = (T *)cm_ensure_aux(m, (size_t)chunk * frame_elems * sizeof(T));
+    if (!aux) return CM_ERR_NOMEM;
+    const bool rows2 = p.row_geo && !m->tune.rows_v1 && !m->tune.onepass;
     auto bytes = [&](int r) { return (CM_TAPS_ELEMS + (size_t)r * (2 * (size_t)p.n1p + 6 * (size_t)p.hb2)) * sizeof(T); };
-    int R = pick_rows(m, 2, (size_t)m->smem_optin / 2, bytes);
-    if (!R) R = pick_rows(m, 1, (size_t)m->smem_optin, bytes);
-    if (!R) return cm_fail(CM_ERR_UNSUPPORTED, "line too wide for the SECAM decode kernel%s");
-    set_groups(a, R);
+    const size_t b2 = (128 + 2 * (size_t)p.n1p + 4 * (size_t)p.hb2) * sizeof(T);
+    void (*row_kernel)(const DevParams<T>, const IoArgs<T>) = p.row_geo == 1 ? k_secam_decode2<T, 1> : k_secam_decode2<T, 3>;
+    int R = 0, rc;
     bool teams = false;
-    for (int i = 0; i < CM_NFILT; ++i) teams = teams || (p.filt[i].nsec && p.filt[i].nsuper > 1);
-    rc = teams ? set_smem(k_secam_decode<T, true>, bytes(R)) : set_smem(k_secam_decode<T, false>, bytes(R));
-    if (rc) return rc;
-    {
-        LaunchTimer lt(m, CM_K_DECODE_OTHER, st);
-        if (teams) k_secam_decode<T, true><<<cm_grid(a), CM_NTHREADS, bytes(R), st>>>(p, a);
-        else k_secam_decode<T, false><<<cm_grid(a), cta_threads(m, 2 * R), bytes(R), st>>>(p, a);
+    if (rows2) {
+        if (b2 > (size_t)m->smem_optin) return cm_fail(CM_ERR_UNSUPPORTED, "line too wide for the SECAM decode kernel%s");
+        rc = set_smem(row_kernel, b2);
+        if (rc) return rc;
+    } else {
+        R = pick_rows(m, 2, (size_t)m->smem_optin / 2, bytes);
+        if (!R) R = pick_rows(m, 1, (size_t)m->smem_optin, bytes);
+        if (!R) return cm_fail(CM_ERR_UNSUPPORTED, "line too wide for the SECAM decode kernel%s");
+        for (int i = 0; i < 7; ++i) teams = teams || (p.filt[i].nsec && p.filt[i].nsuper > 1);
+        rc = teams ? set_smem(k_secam_decode<T, true>, bytes(R)) : set_smem(k_secam_decode<T, false>, bytes(R));
+        if (rc) return rc;
     }
-    cm_count_launch();
-    CUDA_TRY(cudaGetLastError());
-    // pass 2 (light): pair rows y / y-2, inverse matrix, store
-    {
-        LaunchTimer lt(m, CM_K_DECODE_OTHER, st);
-        dim3 grid(1u, (unsigned)io.out_count, (unsigned)io.nframes);
-        k_pair_rows_store<T><<<grid, 192, 0, st>>>(p, io);
+    const size_t in_frame = (size_t)io.nrows * p.Wc, out_frame = (size_t)io.nrows * p.Wo * 3;
+    for (int f0 = 0; f0 < io.nframes; f0 += chunk) {
+        IoArgs<T> c = io;
+        c.nframes = io.nframes - f0 < chunk ? io.nframes - f0 : chunk;
+        c.first_frame = io.first_frame + f0;
+        c.aux = aux;
+        if (c.in_u8) c.in_u8 += (size_t)f0 * in_frame;
+        if (c.in_f) c.in_f += (size_t)f0 * in_frame;
+        if (c.out_u8) c.out_u8 += (size_t)f0 * out_frame;
+        if (c.out_f) c.out_f += (size_t)f0 * out_frame;
+        IoArgs<T> a = c;
+        a.out_begin = c.out_begin >= 2 ? c.out_begin - 2 : 0;
+        a.out_count = c.out_begin + c.out_count - a.out_begin;
+        {
+            LaunchTimer lt(m, CM_K_DECODE_OTHER, st);
+            if (rows2) {
+                const int rpc = m->tune.rpc;
+                row_kernel<<<dim3((unsigned)((a.out_count + rpc - 1) / rpc), 1u, (unsigned)c.nframes), p.row_geo == 1 ? 64 : 128,
+                             b2, st>>>(p, a);
+            } else {
+                set_groups(a, R);
+                if (teams) k_secam_decode<T, true><<<cm_grid(a), CM_NTHREADS, bytes(R), st>>>(p, a);
+                else k_secam_decode<T, false><<<cm_grid(a), cta_threads(m, 2 * R), bytes(R), st>>>(p, a);
+            }
+        }
+        cm_count_launch();
+        CUDA_TRY(cudaGetLastError());
+        // pass 2 (light): pair rows y / y-2, inverse matrix, store
+        {
+            LaunchTimer lt(m, CM_K_DECODE_OTHER, st);
+            dim3 grid(1u, (unsigned)c.out_count, (unsigned)c.nframes);
+            k_pair_rows_store<T><<<grid, 192, 0, st>>>(p, c);
+        }
+        cm_count_launch();
+        CUDA_TRY(cudaGetLastError());
     }
-    cm_count_launch();
-    CUDA_TRY(cudaGetLastError());
     return CM_OK;
 }
 

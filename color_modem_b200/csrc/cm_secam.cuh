@@ -336,3 +336,157 @@ k_secam_decode(const __grid_constant__ DevParams<T> p, const __grid_constant__ I
         }
     }
 }
+
+// ------------------------------------------------------------------------------------------------------------
+// Decode, second generation (k_secam_decode2): the same chain, one row at a time per CTA of 2 (lines up to ~750 samples)
+// or 4 warps (up to ~2000), every recursion a packed DF-I team (cm_iir.cuh: team_iir_pk):
+//   A  luma band-stop (team 0) || chroma band-pass (team 1), each in place
+//   B  anti-bell (team 1)
+//   C  up2 of the chroma
+//   D  I = LP(cos x) (team 0, over its own input) || Q = LP(sin x) (team 1); the mixing carrier starts at phase 0 on every
+//      line (secam.py:137), so it comes from a row-independent table (DevParams::ctab) instead of a rotating carrier
+//   E  discriminator (results held in registers across one barrier, then stored over I), down2, clip, scale -> X
+//   F  de-emphasis (team 1)
+// (luma, X) of the row go to the pairing scratch; k_pair_rows_store finishes.  smem: scratch[128] | c[N1] | cc[N1] | u2[N2] | q2[N2]
+// ------------------------------------------------------------------------------------------------------------
+#define SF_ROW_BS 7          // DevParams::filt slots of this kernel's use-sites (cm_api.cu: plan_secam_kernel)
+#define SF_ROW_BP 8
+#define SF_ROW_BELL 9
+#define SF_ROW_FMLP 10
+#define SF_ROW_DEEMPH 11
+template <int GEO> struct SecGeo;
+template <> struct SecGeo<1> { static constexpr int NW = 2, L1 = 25, L2 = 50, ITER = 12; };
+template <> struct SecGeo<3> { static constexpr int NW = 4, L1 = 33, L2 = 66, ITER = 16; };
+
+template <typename T, int GEO>
+__global__ void __launch_bounds__(32 * SecGeo<GEO>::NW, sizeof(T) == 8 ? 1 : 16 / SecGeo<GEO>::NW)
+k_secam_decode2(const __grid_constant__ DevParams<T> p, const __grid_constant__ IoArgs<T> io) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T *scratch = reinterpret_cast<T *>(smem_raw), *sm = scratch + 128;
+    typedef SecGeo<GEO> SG;
+    constexpr int NW = SG::NW, TH = NW / 2, NT = 32 * NW;
+    const int W = p.W, N1 = p.n1p, hb = p.hb2, N2 = 2 * hb;
+    const int pre = W / 40 - 1;                 // samples of flipped warm-up (secam.py:283)
+    const int ncc = W + pre, ncc4 = (ncc + 3) & ~3, n2 = 2 * ncc;
+    const int f = blockIdx.z, end = io.out_begin + io.out_count;
+    const int warp = threadIdx.x >> 5, task = warp / TH, wr = warp - task * TH;
+    T *c = sm, *cc = c + N1, *u2 = cc + N1, *q2 = u2 + N2;
+    const FirTaps<T> hup{p.firc[SR_UP2], p.fircp[SR_UP2]}, hdn{p.firc[SR_DOWN2], p.fircp[SR_DOWN2]};
+    const FiltHdr &fbs = p.filt[SF_ROW_BS], &fbp = p.filt[SF_ROW_BP], &fbell = p.filt[SF_ROW_BELL],
+                  &flp = p.filt[SF_ROW_FMLP], &fde = p.filt[SF_ROW_DEEMPH];
+    const long long frame = io.first_frame + f;
+    const bool pref = io.in_u8 != nullptr && W <= 4 * RowPrefetch::kMaxQuads * NT;
+    RowPrefetch pf;
+    int row = io.out_begin + blockIdx.x;
+    if (pref && row < end) pf.fetch(io, f, row, W);
+    for (; row < end; row += gridDim.x) {
+        if (pref) pf.stage(c, W);
+        else load_comp_row(c, io, f, row, W);
+        __syncthreads();
+        if (pref && row + (int)gridDim.x < end) pf.fetch(io, f, row + gridDim.x, W);
+        for (int i = threadIdx.x; i < fbp.npad; i += NT) {          // warm-up prefix + composite + replicated tail
+            T v;
+            if (i < pre) v = c[pre - i];                     // flip(composite[1 : W/40])
+            else if (i < ncc) v = c[i - pre];
+            else v = c[W - 1];
+            cc[i] = v;
+        }
+        __syncthreads();
+        if (task == 0) {                                     // A: luma band-stop, in place
+            warp_fill_tail<T, 1>(c, N1, W, fbs.npad);
+            team_iir_pk<T, 1, SG::L1, TH>(p.tab + fbs.off, fbs, LoadLinear<T, SG::L1>{c}, [&](int j, T v) { c[j] = v; }, wr, 2,
+                                          scratch);
+        } else {                                             //    chroma band-pass, in place
+            team_iir_pk<T, 1, SG::L1, TH>(p.tab + fbp.off, fbp, LoadLinear<T, SG::L1>{cc}, [&](int j, T v) { cc[j] = v; }, wr,
+                                          3, scratch + 32);
+        }
+        __syncthreads();
+        if (p.flags & 64) {                                  // B: anti-bell
+            if (task == 1) {
+                warp_fill_tail<T, 1>(cc, N1, ncc, fbell.npad);
+                team_iir_pk<T, 1, SG::L1, TH>(p.tab + fbell.off, fbell, LoadLinear<T, SG::L1>{cc}, [&](int j, T v) { cc[j] = v; },
+                                              wr, 3, scratch + 32);
+            }
+            __syncthreads();
+        }
+        for (int i = ncc + threadIdx.x; i < ncc4; i += NT) cc[i] = (T)0;       // zero pad for the resampler
+        __syncthreads();
+        fir_up2(u2, u2 + hb, cc, ncc4, hup, threadIdx.x, NT);                 // C
+        __syncthreads();
+        {                                                    // D: I (cos, team 0) || Q (sin, team 1)
+            warp_fill_tail<T, 2>(u2, hb, n2, flp.npad);      // every warp writes the same values
+            T *de = task ? q2 : u2;
+            const T *ct = p.ctab + (task ? 0 : (size_t)flp.npad);
+            team_iir_pk<T, 2, SG::L2, TH, true>(p.tab + flp.off, flp, LoadPoly2Carrier<T, SG::L2>{u2, u2 + hb, ct, 32 * TH},
+                                                Poly2Out<T>{de, de + hb}, wr, 2 + task, scratch + 32 * task);
+        }
+        __syncthreads();
+        {   // E: wrapped phase step of z = I - jQ between consecutive 2x samples, first step 0 (secam.py:143-148)
+            const T fc = p.scalars[SS_FM_FC];
+            const T *ie = u2, *io_ = ie + hb, *qe = q2, *qo = qe + hb;
+            T fev[SG::ITER], fod[SG::ITER];
+#pragma unroll
+            for (int k = 0; k < SG::ITER; ++k) {
+                const int m = threadIdx.x + k * NT;
+                T f_even = (T)0, f_odd = (T)0;
+                if (m < ncc) {
+                    const T i0 = ie[m], q0 = qe[m], i1 = io_[m], q1 = qo[m];
+                    f_odd = fc + (T)0.63661977236758134308 * Real<T>::atan2_(i1 * q0 - q1 * i0, i1 * i0 + q1 * q0);
+                    if (m > 0) {
+                        const T ip = io_[m - 1], qp = qo[m - 1];
+                        f_even = fc + (T)0.63661977236758134308 * Real<T>::atan2_(i0 * qp - q0 * ip, i0 * ip + q0 * qp);
+                    } else {
+                        f_even = fc;
+                    }
+                }
+                fev[k] = f_even;
+                fod[k] = f_odd;
+            }
+            __syncthreads();
+#pragma unroll
+            for (int k = 0; k < SG::ITER; ++k) {
+                const int m = threadIdx.x + k * NT;
+                if (m < ncc4) {
+                    u2[m] = fev[k];
+                    u2[hb + m] = fod[k];
+                }
+            }
+        }
+        __syncthreads();
+        {   // down2, keep the last W samples, clip, scale to the colour-difference signal -> X in the cc buffer
+            const bool alt = is_alternate(p, frame, io.y0 + row);
+            const T fsc = alt ? p.scalars[SS_FSC_DB] : p.scalars[SS_FSC_DR];
+            const T inv_dev = (T)1 / (alt ? p.scalars[SS_FDEV_DB] : p.scalars[SS_FDEV_DR]);
+            const T lo = p.scalars[SS_F_LO], hi = p.scalars[SS_F_HI];
+            fir_down2(u2, u2 + hb, ncc4, hdn, threadIdx.x, NT, [&](int j0, const T *y) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int j = j0 + i - pre;
+                    if (j >= 0 && j < W) {
+                        T fr = y[i];
+                        fr = fr < lo ? lo : (fr > hi ? hi : fr);
+                        cc[j] = (fr - fsc) * inv_dev;
+                    }
+                }
+            });
+        }
+        __syncthreads();
+        if (p.flags & 128) {                                 // F: de-emphasis
+            if (task == 1) {
+                warp_fill_tail<T, 1>(cc, N1, W, fde.npad);
+                team_iir_pk<T, 1, SG::L1, TH>(p.tab + fde.off, fde, LoadLinear<T, SG::L1>{cc}, [&](int j, T v) { cc[j] = v; }, wr,
+                                              3, scratch + 32);
+            }
+            __syncthreads();
+        }
+        T *dst = io.aux + ((size_t)f * io.nrows + row) * 2 * W;
+        for (int q = threadIdx.x; q < (W >> 2); q += NT) {
+            T y[4], a[4];
+            ld4(c + 4 * q, y);
+            ld4(cc + 4 * q, a);
+            st4(dst + 4 * q, y);
+            st4(dst + W + 4 * q, a);
+        }
+        __syncthreads();
+    }
+}
