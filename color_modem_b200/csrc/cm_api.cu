@@ -198,6 +198,30 @@ static int plan_secam_kernel(const cm_desc &d, FiltHdr *fh, std::vector<double> 
             const cm_filter &f = d.filters[src[i]];
             if (f.nsec) build_filter_L(f, fh[7 + i], tab, f.rate == 2 ? l2[k] : l1[k], 1, 32 * th[k]);
         }
+        // the row encoder (k_secam_encode_row2): chroma low-pass and LF pre-emphasis sites, same team geometry
+        const cm_filter &fp = d.filters[SF_PRE_LP], &fe = d.filters[SF_PRE_EMPH];
+        const int lf[2] = {12, 16};
+        if (fp.nsec && fp.n + fp.shift <= 32 * th[k] * l1[k] && (!fe.nsec || fe.n + fe.shift <= 32 * th[k] * l1[k]) &&
+            d.width <= 32 * 2 * th[k] * lf[k]) {
+            build_filter_L(fp, fh[12], tab, l1[k], 1, 32 * th[k]);
+            if (fe.nsec) build_filter_L(fe, fh[13], tab, l1[k], 1, 32 * th[k]);
+        }
+        return geo[k];
+    }
+    return 0;
+}
+
+// Geometry of k_niir_decode2 (cm_niir.cuh: NiirGeo): 1 = 2 warps x 39 samples per lane, 3 = 4 warps x 51; fills NF_ROW_*.
+static int plan_niir_kernel(const cm_desc &d, FiltHdr *fh, std::vector<double> &tab) {
+    if (d.kind != CM_KIND_NIIR) return 0;
+    const cm_filter &fbp = d.filters[NF_UP_BP], &flp = d.filters[NF_BASE_LP];
+    if (!fbp.nsec || !flp.nsec || fbp.rate != 3 || flp.rate != 3) return 0;
+    static const int geo[2] = {1, 3}, nw[2] = {2, 4}, l3[2] = {39, 51};
+    for (int k = 0; k < 2; ++k) {
+        const int cap = 32 * nw[k] * l3[k];
+        if (fbp.n + fbp.shift > cap || flp.n + flp.shift > cap) continue;
+        build_filter_L(fbp, fh[4], tab, l3[k], 1, 32 * nw[k]);
+        build_filter_L(flp, fh[5], tab, l3[k], 1, 32 * nw[k]);
         return geo[k];
     }
     return 0;
@@ -438,6 +462,7 @@ extern "C" int cm_create(const cm_desc *desc, int precision, cm_modem **out) {
     if (row_geo) build_carrier_table(desc->phases[QP_STEP2X], fh[7], row_geo == 1 ? 1 : 2, ctab);
     const int sec_geo = plan_secam_kernel(*desc, fh, tab);
     if (sec_geo) build_carrier_table(desc->phases[SP_FM_STEP2X], fh[10], sec_geo == 1 ? 1 : 2, ctab);
+    const int niir_geo = plan_niir_kernel(*desc, fh, tab);
     int rc;
     if (precision == CM_FP32) {
         rc = upload<float>(tab, &m->d_tab);
@@ -451,7 +476,7 @@ extern "C" int cm_create(const cm_desc *desc, int precision, cm_modem **out) {
         m->pf.mac_skew = mac_skew;
         m->pf.mac_bp = mac_bp;
         m->pf.ctab = (const float *)m->d_ctab;
-        m->pf.row_geo = row_geo ? row_geo : sec_geo;
+        m->pf.row_geo = row_geo ? row_geo : (sec_geo ? sec_geo : niir_geo);
         m->pf.enc_geo = enc_geo;
     } else {
         rc = upload<double>(tab, &m->d_tab);
@@ -465,7 +490,7 @@ extern "C" int cm_create(const cm_desc *desc, int precision, cm_modem **out) {
         m->pd.mac_skew = mac_skew;
         m->pd.mac_bp = mac_bp;
         m->pd.ctab = (const double *)m->d_ctab;
-        m->pd.row_geo = row_geo ? row_geo : sec_geo;
+        m->pd.row_geo = row_geo ? row_geo : (sec_geo ? sec_geo : niir_geo);
         m->pd.enc_geo = enc_geo;
     }
     if (rc != CM_OK) { cm_destroy(m); return rc; }

@@ -15,7 +15,7 @@
 #define CM_NWARPS 8
 #define CM_NTHREADS (CM_NWARPS * 32)
 #define CM_MAXSEC 6
-#define CM_NFILT 12
+#define CM_NFILT 14
 #define CM_NRES 6
 #define CM_NSCAL 48
 #define CM_NPHASE 16

@@ -22,12 +22,13 @@ int mac_encode(cm_modem *m, IoArgs<T> io, cudaStream_t st) {
     int R = pick_rows(m, 2, (size_t)m->smem_optin / 2, bytes);
     if (!R) return cm_fail(CM_ERR_UNSUPPORTED, "line too wide for the MAC encode kernel%s");
     set_groups(io, R);
-    int rc = set_smem(k_mac_encode<T>, bytes(R));
+    void (*kern)(const DevParams<T>, const IoArgs<T>, int) = p.mac_skew ? k_mac_encode<T, -1> : k_mac_encode<T, 0>;
+    int rc = set_smem(kern, bytes(R));
     if (rc) return rc;
     dim3 grid = cm_grid(io);
     {
         LaunchTimer lt(m, CM_K_ENCODE, st);
-        k_mac_encode<T><<<grid, CM_NTHREADS, bytes(R), st>>>(p, io, tl);
+        kern<<<grid, CM_NTHREADS, bytes(R), st>>>(p, io, tl);
     }
     cm_count_launch();
     CUDA_TRY(cudaGetLastError());
@@ -46,12 +47,13 @@ int mac_decode(cm_modem *m, IoArgs<T> io, cudaStream_t st) {
     int R = pick_rows(m, 2, (size_t)m->smem_optin / 2, bytes);
     if (!R) return cm_fail(CM_ERR_UNSUPPORTED, "line too wide for the MAC decode kernel%s");
     set_groups(io, R);
-    int rc = set_smem(k_mac_decode<T>, bytes(R));
+    void (*kern)(const DevParams<T>, const IoArgs<T>, int) = p.mac_skew ? k_mac_decode<T, -1> : k_mac_decode<T, 0>;
+    int rc = set_smem(kern, bytes(R));
     if (rc) return rc;
     dim3 grid = cm_grid(io);
     {
         LaunchTimer lt(m, CM_K_DECODE_OTHER, st);
-        k_mac_decode<T><<<grid, CM_NTHREADS, bytes(R), st>>>(p, io, tl);
+        kern<<<grid, CM_NTHREADS, bytes(R), st>>>(p, io, tl);
     }
     cm_count_launch();
     CUDA_TRY(cudaGetLastError());

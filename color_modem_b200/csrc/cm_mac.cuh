@@ -8,38 +8,39 @@
 #include "cm_slots.h"
 
 // Shared-memory line that a resampler reads: [FP zeros | n samples (rounded up to 4) | BP zeros]  (cm_fir.cuh: fir_poly)
-// in the skewed layout of cm_fir.cuh (poly_skew): sample i of the line lives at seg[poly_skew(FP + i, p.mac_skew)]
-template <typename T>
+// in the skewed layout of cm_fir.cuh (poly_skew): sample i of the line lives at seg[poly_skew(FP + i, MSK)]
+// (MSK: the skew mask as a compile-time constant — the kernels are instantiated with and without the skew)
+template <typename T, int MSK>
 __device__ __forceinline__ int mac_seg(const DevParams<T> &p, int n) {
-    return poly_skew(p.mac_fp + ((n + 3) & ~3) + p.mac_bp, p.mac_skew) + 4;
+    return poly_skew(p.mac_fp + ((n + 3) & ~3) + p.mac_bp, MSK) + 4;
 }
 
-template <typename T>
+template <typename T, int MSK>
 __device__ __forceinline__ void mac_zero_pads(const DevParams<T> &p, T *seg, int n) {
     const int n4 = (n + 3) & ~3;
-    for (int i = threadIdx.x; i < p.mac_fp; i += blockDim.x) seg[poly_skew(i, p.mac_skew)] = (T)0;
-    for (int i = n + threadIdx.x; i < n4 + p.mac_bp; i += blockDim.x) seg[poly_skew(p.mac_fp + i, p.mac_skew)] = (T)0;
+    for (int i = threadIdx.x; i < p.mac_fp; i += blockDim.x) seg[poly_skew(i, MSK)] = (T)0;
+    for (int i = n + threadIdx.x; i < n4 + p.mac_bp; i += blockDim.x) seg[poly_skew(p.mac_fp + i, MSK)] = (T)0;
 }
 
 // dst[0..n_out) = resample(src line of n_in samples, `seg` = its padded segment) with resampler slot r (identity when the
 // ratio is 1).  tabs: the polyphase tables staged in shared memory.
-template <typename T>
+template <typename T, int MSK>
 __device__ __forceinline__ void mac_fit(const DevParams<T> &p, const T *tabs, int r, const T *seg, int n_in, T *dst,
                                         int n_out, T add) {
     const ResHdr rh = p.res[r];
     const int fp = p.mac_fp;
     if (rh.ntaps == 0) {
-        for (int j = threadIdx.x; j < n_out; j += blockDim.x) dst[j] = seg[poly_skew(fp + j, p.mac_skew)] + add;
+        for (int j = threadIdx.x; j < n_out; j += blockDim.x) dst[j] = seg[poly_skew(fp + j, MSK)] + add;
     } else if (p.poly[r].up) {
         fir_poly(seg, n_out, p.poly[r], tabs + p.poly[r].off, threadIdx.x, blockDim.x, [&](int j, T v) { dst[j] = v + add; });
     } else {        // ratios with up > 4 (odd composite widths): one output per thread straight from the dense taps
-        fir_general<T>([&](int i) { return seg[poly_skew(fp + i, p.mac_skew)]; }, n_in, n_out, rh, p.taps + rh.off, threadIdx.x,
+        fir_general<T>([&](int i) { return seg[poly_skew(fp + i, MSK)]; }, n_in, n_out, rh, p.taps + rh.off, threadIdx.x,
                        blockDim.x, [&](int j, T v) { dst[j] = v + add; });
     }
 }
 
 // Encode.  smem: tables + R * ( luma seg(W) | chroma seg(W) | luma720 | ch360 | line seg(1080) | out[1080] )
-template <typename T>
+template <typename T, int MSK>
 __global__ void __launch_bounds__(CM_NTHREADS)
 k_mac_encode(const __grid_constant__ DevParams<T> p, const __grid_constant__ IoArgs<T> io, int taps_len) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -50,7 +51,7 @@ k_mac_encode(const __grid_constant__ DevParams<T> p, const __grid_constant__ IoA
     const bool avg = (p.flags & 2) != 0;
     T *taps = sm;
     T *rows = sm + taps_len;
-    const int segW = mac_seg(p, W), seg1080 = mac_seg(p, 1080);
+    const int segW = mac_seg<T, MSK>(p, W), seg1080 = mac_seg<T, MSK>(p, 1080);
     const size_t per_row = 2 * (size_t)segW + 720 + 360 + seg1080 + 1080;
     for (int i = threadIdx.x; i < taps_len; i += blockDim.x) taps[i] = p.ptab[i];
     for (int k = 0; k < g.count; ++k) {
@@ -58,9 +59,9 @@ k_mac_encode(const __grid_constant__ DevParams<T> p, const __grid_constant__ IoA
         const int nrow = (row + 2 < io.nrows) ? row + 2 : row;
         const int ci = is_alternate(p, g.frame, io.y0 + row) ? 6 : 3;      // D'B on alternate lines, else D'R
         T *yseg = rows + k * per_row, *cseg = yseg + segW;
-        mac_zero_pads(p, yseg, W);
-        mac_zero_pads(p, cseg, W);
-        mac_zero_pads(p, cseg + segW + 720 + 360, 1080);
+        mac_zero_pads<T, MSK>(p, yseg, W);
+        mac_zero_pads<T, MSK>(p, cseg, W);
+        mac_zero_pads<T, MSK>(p, cseg + segW + 720 + 360, 1080);
         for (int q = threadIdx.x; q < W4; q += blockDim.x) {
             const int x = 4 * q;
             T r[4], gg[4], b[4], y[4], c[4];
@@ -76,15 +77,15 @@ k_mac_encode(const __grid_constant__ DevParams<T> p, const __grid_constant__ IoA
                 for (int i = 0; i < 4; ++i)
                     c[i] = (T)0.5 * ((p.enc[ci] * r[i] + p.enc[ci + 1] * gg[i] + p.enc[ci + 2] * b[i]) + c[i]);
             }
-            st4(yseg + poly_skew(p.mac_fp + x, p.mac_skew), y);
-            st4(cseg + poly_skew(p.mac_fp + x, p.mac_skew), c);
+            st4(yseg + poly_skew(p.mac_fp + x, MSK), y);
+            st4(cseg + poly_skew(p.mac_fp + x, MSK), c);
         }
     }
     __syncthreads();
     for (int k = 0; k < g.count; ++k) {
         T *yseg = rows + k * per_row, *cseg = yseg + segW, *l720 = cseg + segW, *c360 = l720 + 720;
-        mac_fit(p, taps, MR_LUMA_IN, yseg, W, l720, 720, (T)0);
-        mac_fit(p, taps, MR_CHROMA_IN, cseg, W, c360, 360, (T)0.5);         // mac.py:57 chroma += 0.5
+        mac_fit<T, MSK>(p, taps, MR_LUMA_IN, yseg, W, l720, 720, (T)0);
+        mac_fit<T, MSK>(p, taps, MR_CHROMA_IN, cseg, W, c360, 360, (T)0.5);         // mac.py:57 chroma += 0.5
     }
     __syncthreads();
     for (int k = 0; k < g.count; ++k) {                                    // mac.py:58-69
@@ -103,14 +104,14 @@ k_mac_encode(const __grid_constant__ DevParams<T> p, const __grid_constant__ IoA
             else if (i == 1071) v = (T)0.0625 + (T)0.875 * l[710];
             else if (i == 1072) v = (T)0.25 + (T)0.5 * l[711];
             else if (i == 1073) v = (T)0.4375 + (T)0.125 * l[712];
-            oseg[poly_skew(p.mac_fp + i, p.mac_skew)] = v;
+            oseg[poly_skew(p.mac_fp + i, MSK)] = v;
         }
     }
     __syncthreads();
     for (int k = 0; k < g.count; ++k) {
         const T *oseg = rows + k * per_row + 2 * segW + 1080;
         T *outrow = rows + k * per_row + 2 * segW + 1080 + seg1080;
-        mac_fit(p, taps, MR_OUT, oseg, 1080, outrow, Wc, (T)0);
+        mac_fit<T, MSK>(p, taps, MR_OUT, oseg, 1080, outrow, Wc, (T)0);
     }
     __syncthreads();
     for (int k = 0; k < g.count; ++k) {
@@ -125,7 +126,7 @@ k_mac_encode(const __grid_constant__ DevParams<T> p, const __grid_constant__ IoA
 }
 
 // Decode.  smem: tables + (R+1) rows x ( comp seg(Wc) | c1080 | luma720 | ch360 | XE[360] | XO[360] )
-template <typename T>
+template <typename T, int MSK>
 __global__ void __launch_bounds__(CM_NTHREADS)
 k_mac_decode(const __grid_constant__ DevParams<T> p, const __grid_constant__ IoArgs<T> io, int taps_len) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -135,14 +136,14 @@ k_mac_decode(const __grid_constant__ DevParams<T> p, const __grid_constant__ IoA
     const int Wc = p.Wc;
     T *taps = sm;
     T *rows = sm + taps_len;
-    const int segC = mac_seg(p, Wc);
+    const int segC = mac_seg<T, MSK>(p, Wc);
     const size_t per_row = (size_t)segC + 1080 + 720 + 360 + 720;
     const bool has_prev0 = g.r0 >= 2;
     const int k_lo = has_prev0 ? -1 : 0;
     auto rowp = [&](int k) { return rows + (size_t)(k - k_lo) * per_row; };
     for (int i = threadIdx.x; i < taps_len; i += blockDim.x) taps[i] = p.ptab[i];
     for (int k = k_lo; k < g.count; ++k) {
-        mac_zero_pads(p, rowp(k), Wc);
+        mac_zero_pads<T, MSK>(p, rowp(k), Wc);
         T *cseg = rowp(k);
         const size_t base = ((size_t)g.fidx * io.nrows + g.r0 + 2 * k) * Wc;
         for (int x = 4 * threadIdx.x; x < Wc; x += 4 * blockDim.x) {       // load_comp_row into the skewed segment
@@ -154,11 +155,11 @@ k_mac_decode(const __grid_constant__ DevParams<T> p, const __grid_constant__ IoA
 #pragma unroll
                 for (int i = 0; i < 4; ++i) v[i] = ((T)5 * Real<T>::from_u8((w >> (8 * i)) & 0xff) - (T)1) * (T)(1.0 / 3.0);
             }
-            st4(cseg + poly_skew(p.mac_fp + x, p.mac_skew), v);
+            st4(cseg + poly_skew(p.mac_fp + x, MSK), v);
         }
     }
     __syncthreads();
-    for (int k = k_lo; k < g.count; ++k) mac_fit(p, taps, MR_COMP_IN, rowp(k), Wc, rowp(k) + segC, 1080, (T)0);
+    for (int k = k_lo; k < g.count; ++k) mac_fit<T, MSK>(p, taps, MR_COMP_IN, rowp(k), Wc, rowp(k) + segC, 1080, (T)0);
     __syncthreads();
     for (int k = k_lo; k < g.count; ++k) {                                 // mac.py:86-109
         const T *c = rowp(k) + segC;

@@ -34,6 +34,29 @@ int niir_encode(cm_modem *m, IoArgs<T> io, cudaStream_t st) {
 template <typename T>
 int niir_decode(cm_modem *m, IoArgs<T> io, cudaStream_t st) {
     const DevParams<T> &p = params_of<T>(m);
+    if (p.row_geo && !m->tune.rows_v1 && !m->tune.onepass) {           // strips of rows, one at a time (k_niir_decode2)
+        if (io.out_count <= 0) return CM_OK;
+        const size_t b2 = (128 + 2 * (size_t)p.n1p + 9 * (size_t)p.hb3) * sizeof(T);
+        if (b2 <= (size_t)m->smem_optin) {
+            void (*kern)(const DevParams<T>, const IoArgs<T>) = p.row_geo == 1 ? k_niir_decode2<T, 1> : k_niir_decode2<T, 3>;
+            int rc = set_smem(kern, b2);
+            if (rc) return rc;
+            // rows per strip: the row before a strip is recomputed, so long strips are cheaper — as long as the grid
+            // still fills the chip (6 CTAs per SM)
+            const long long rows_total = (long long)io.out_count * io.nframes;
+            int R = (int)(rows_total / (6LL * m->sm_count));
+            R = R < 2 ? 2 : (R > 12 ? 12 : R);
+            if (m->tune.rows_max > 0) R = m->tune.rows_max;
+            set_groups(io, R);
+            {
+                LaunchTimer lt(m, CM_K_DECODE_OTHER, st);
+                kern<<<cm_grid(io), p.row_geo == 1 ? 64 : 128, b2, st>>>(p, io);
+            }
+            cm_count_launch();
+            CUDA_TRY(cudaGetLastError());
+            return CM_OK;
+        }
+    }
     auto bytes = [&](int r) { return (128 + (size_t)(r + 1) * (p.n1p + 9 * (size_t)p.hb3)) * sizeof(T); };
     return launch_rows<T>(m, io, st, k_niir_decode<T>, bytes, 2, 2, 1, CM_K_DECODE_OTHER, "NIIR decode");
 }

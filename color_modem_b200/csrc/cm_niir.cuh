@@ -344,3 +344,150 @@ k_niir_decode(const __grid_constant__ DevParams<T> p, const __grid_constant__ Io
         }
     }
 }
+
+// ------------------------------------------------------------------------------------------------------------
+// Decode, second generation (k_niir_decode2).  A CTA of 2 (lines up to ~800 samples) or 4 warps (up to ~2100) walks a STRIP
+// of consecutive rows of one field, one row at a time, keeping the normalised carrier of the row before in shared memory:
+// the previous row is recomputed once per strip instead of once per two rows, every recursion is a packed DF-I team of all
+// the warps (team_iir_pk), and the 3x buffers that live only within a row are shared:
+//   c[N1] | sat[N1] | A[N3] | pm[2][N3]         A: up3(c) -> envelope at 3x -> derivative of the reference carrier
+// (2 N1 + 3 N3 elements: 36 KB at 720 samples; the float64 build of 1920-sample lines fits one CTA per SM).
+// Per row: up3, band-pass (3 sections), pi/2 |.| -> low-pass = envelope, carrier = band-passed / envelope, sat = down3(envelope),
+// then the products with the neighbour row's carrier and its derivative, 4 more down3, hue / luma arithmetic, store.
+// ------------------------------------------------------------------------------------------------------------
+#define NF_ROW_BP 4          // DevParams::filt slots of this kernel's use-sites (cm_api.cu: plan_niir_kernel)
+#define NF_ROW_LP 5
+template <int GEO> struct NiirGeo;
+template <> struct NiirGeo<1> { static constexpr int NW = 2, L3 = 39; };
+template <> struct NiirGeo<3> { static constexpr int NW = 4, L3 = 51; };
+
+template <typename T, int GEO>
+__global__ void __launch_bounds__(32 * NiirGeo<GEO>::NW, sizeof(T) == 8 ? 1 : 12 / NiirGeo<GEO>::NW)
+k_niir_decode2(const __grid_constant__ DevParams<T> p, const __grid_constant__ IoArgs<T> io) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T *scratch = reinterpret_cast<T *>(smem_raw), *sm = scratch + 128;
+    typedef NiirGeo<GEO> NG;
+    constexpr int NW = NG::NW, NT = 32 * NW, L3 = NG::L3;
+    const int W = p.W, N1 = p.n1p, hb = p.hb3, N3 = 3 * hb, n3 = 3 * W;
+    const int warp = threadIdx.x >> 5;
+    const int field = blockIdx.y, f = blockIdx.z;
+    const long long frame = io.first_frame + f;
+    const int first = io.out_begin + field, nout = (io.out_count - field + 1) >> 1;      // rows first, first + 2, ...
+    const int R = io.rows_per_cta;
+    const int k0 = blockIdx.x * R, k1 = min(k0 + R, nout);
+    if (k0 >= nout) return;
+    T *c = sm, *sat = c + N1, *A = sat + N1, *pm0 = A + N3;
+    const FirTaps<T> hup{p.firc[NR_UP3], p.fircp[NR_UP3]}, hdn{p.firc[NR_DOWN3], p.fircp[NR_DOWN3]};
+    const Down3Taps<T> tp(hdn);
+    const FiltHdr &fbp = p.filt[NF_ROW_BP], &flp = p.filt[NF_ROW_LP];
+    const T inv_step3 = p.scalars[NS_INV_STEP3] * (T)0.5;
+    T ls_s, ls_c;
+    Real<T>::sincos_turns(p.phases[NP_LINE_SHIFT], ls_s, ls_c);
+
+    // stage 1 of one row into carrier slot `pm`: normalise = false keeps the band-passed signal itself
+    auto carrier_of = [&](T *pm, bool normalise) {
+        fir_up3(A, A + hb, A + 2 * hb, c, W, hup, threadIdx.x, NT);
+        __syncthreads();
+        warp_fill_tail<T, 3>(A, hb, n3, fbp.npad);                  // every warp writes the same values
+        team_iir_pk<T, 3, L3, NW>(p.tab + fbp.off, fbp, LoadPoly3<T, L3, false>{A, hb}, Poly3Out<T>{pm, hb}, warp, 1, scratch);
+        __syncthreads();
+        if (!normalise) return;
+        warp_fill_tail<T, 3>(pm, hb, n3, flp.npad);
+        team_iir_pk<T, 3, L3, NW>(p.tab + flp.off, flp, LoadPoly3<T, L3, true>{pm, hb}, Poly3Out<T>{A, hb}, warp, 1, scratch);
+        __syncthreads();
+        for (int q = 4 * threadIdx.x; q < W; q += 4 * NT) {          // saturation at 1x; carrier = band-passed / envelope
+            T y[4];
+            down3_quad(tp, A, A + hb, A + 2 * hb, W, q, y);
+            st4(sat + q, y);
+#pragma unroll
+            for (int ph = 0; ph < 3; ++ph) {
+                T a[4], b[4];
+                ld4(pm + ph * hb + q, a);
+                ld4(A + ph * hb + q, b);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) a[i] = a[i] / b[i];
+                st4(pm + ph * hb + q, a);
+            }
+        }
+        __syncthreads();
+    };
+
+    // the row before the strip: a real row, or the synthetic reference carrier at the top of the field (niir.py:103-106)
+    {
+        const int row = first + 2 * k0 - 2;
+        if (row >= 0) {
+            load_comp_row(c, io, f, row, W);
+            __syncthreads();
+            carrier_of(pm0 + (size_t)((k0 + 1) & 1) * N3, true);
+        } else {
+            const int line = io.y0 + row;
+            const unsigned long long ph0 = start_phase(p, frame, line);
+            const T sgn = is_alternate(p, frame, line) ? (T)-1 : (T)1;
+            for (int x = threadIdx.x; x < W; x += NT) {
+                T s, co;
+                Real<T>::sincos_turns(ph0 + (unsigned long long)x * p.phases[NP_STEP1X], s, co);
+                c[x] = sgn * s;
+            }
+            __syncthreads();
+            carrier_of(pm0 + (size_t)((k0 + 1) & 1) * N3, false);
+        }
+    }
+    for (int k = k0; k < k1; ++k) {
+        const int row = first + 2 * k, line = io.y0 + row;
+        T *pm = pm0 + (size_t)(k & 1) * N3;
+        const T *last = pm0 + (size_t)((k + 1) & 1) * N3;
+        load_comp_row(c, io, f, row, W);
+        __syncthreads();
+        carrier_of(pm, true);
+        const bool alt = is_alternate(p, frame, line);
+        const T *carrier = alt ? pm : last, *huemod = alt ? last : pm;
+        {   // derivative of the reference carrier (niir.py:123-125) into A (the envelope is dead)
+            const T *c0 = carrier, *c1 = carrier + hb, *c2 = carrier + 2 * hb;
+            for (int m = threadIdx.x; m < W; m += NT) {
+                A[m] = m > 0 ? (c1[m] - c2[m - 1]) * inv_step3 : (T)0;                 // j = 3m
+                A[hb + m] = (c2[m] - c0[m]) * inv_step3;                               // j = 3m + 1
+                A[2 * hb + m] = m + 1 < W ? (c0[m + 1] - c1[m]) * inv_step3 : (T)0;    // j = 3m + 2
+            }
+        }
+        __syncthreads();
+        const T sh_s = alt ? -ls_s : ls_s, sh_c = ls_c;                           // niir.py:114-121,136-137
+        T rot_s, rot_c;                                                           // niir.py:146-156
+        Real<T>::sincos_turns(p.phases[NP_LUMA_ROT] + (alt ? 0ull : p.phases[NP_LINE_SHIFT]), rot_s, rot_c);
+        for (int q = threadIdx.x; q < (W >> 2); q += NT) {
+            const int j0 = 4 * q;
+            T sinphi[4], cosphi[4], sv[4], sincar[4], coscar[4], y[4], ob[4], orr[4], cc[4];
+            down3_quad_prod(tp, huemod, carrier, hb, W, j0, sinphi);
+            down3_quad_prod(tp, huemod, (const T *)A, hb, W, j0, cosphi);
+            down3_quad(tp, carrier, carrier + hb, carrier + 2 * hb, W, j0, sincar);
+            down3_quad(tp, (const T *)A, (const T *)A + hb, (const T *)A + 2 * hb, W, j0, coscar);
+            ld4(sat + j0, sv);
+            ld4(c + j0, cc);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const T norm = Real<T>::sqrt_(cosphi[i] * cosphi[i] + sinphi[i] * sinphi[i]);
+                const T cp0 = cosphi[i] / norm, sp0 = sinphi[i] / norm;
+                const T sp = -cp0 * sh_s - sp0 * sh_c, cp = sp0 * sh_s - cp0 * sh_c;
+                T db = sv[i] * sp, dr = sv[i] * cp;
+                const T us0 = alt ? -Real<T>::sqrt_(db * db + dr * dr) : db, vs0 = alt ? (T)0 : dr;
+                const T us = us0 * rot_c - vs0 * rot_s, vs = us0 * rot_s + vs0 * rot_c;
+                y[i] = cc[i] - (us * sincar[i] + vs * coscar[i]);
+                const T m2 = db * db + dr * dr;                                   // niir.py:61-65
+                if (m2 > (T)0) {
+                    const T mag = Real<T>::sqrt_(m2);
+                    T ns = mag - (T)0.1;
+                    ns = ns > (T)0 ? ns : (T)0;
+                    const T sc = ns / mag;
+                    db *= sc;
+                    dr *= sc;
+                } else {
+                    db = (T)0;
+                    dr = (T)0;
+                }
+                ob[i] = db;
+                orr[i] = dr;
+            }
+            store_rgb4(p, io, f, row, j0, y, ob, orr);
+        }
+        __syncthreads();
+    }
+}

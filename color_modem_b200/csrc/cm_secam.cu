@@ -7,6 +7,20 @@ int secam_encode(cm_modem *m, IoArgs<T> io, cudaStream_t st) {
     const DevParams<T> &p = params_of<T>(m);
     if (io.out_count <= 0) return CM_OK;
     auto bytes = [&](int r) { return (size_t)r * 2 * p.n1p * sizeof(T); };
+    if (io.in_u8 && p.row_geo && p.filt[SF_ENC_PRE].nsec && !m->tune.rows_v1 && !m->tune.onepass) {
+        void (*kern)(const DevParams<T>, const IoArgs<T>) = p.row_geo == 1 ? k_secam_encode_row2<T, 1> : k_secam_encode_row2<T, 3>;
+        const size_t b2 = (128 + 2 * (size_t)p.n1p) * sizeof(T);
+        int rc2 = set_smem(kern, b2);
+        if (rc2) return rc2;
+        const int rpc = m->tune.rpc, nf = (io.out_count + 1) >> 1;
+        {
+            LaunchTimer lt(m, CM_K_ENCODE, st);
+            kern<<<dim3((unsigned)((nf + rpc - 1) / rpc), 2u, (unsigned)io.nframes), p.row_geo == 1 ? 64 : 128, b2, st>>>(p, io);
+        }
+        cm_count_launch();
+        CUDA_TRY(cudaGetLastError());
+        return CM_OK;
+    }
     int R = pick_rows(m, 2, (size_t)m->smem_optin / 2, bytes);
     if (!R) return cm_fail(CM_ERR_UNSUPPORTED, "line too wide for the SECAM encode kernel%s");
     set_groups(io, R);

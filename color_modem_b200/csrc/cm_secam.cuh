@@ -490,3 +490,180 @@ k_secam_decode2(const __grid_constant__ DevParams<T> p, const __grid_constant__ 
         __syncthreads();
     }
 }
+
+// ------------------------------------------------------------------------------------------------------------
+// Encode, second generation (k_secam_encode_row2): one row at a time per CTA of 2 (lines up to 768 samples) or 4 warps (up to
+// 2048), the RGB words of the next row (and of its field neighbour for the ColorAveraging front end) prefetched in
+// registers.  The chroma low-pass (+ LF pre-emphasis) is a short recursion run by the first team; the FM synthesis — the
+// expensive part: bell gain, running phase, sin / cos per sample — is spread over ALL lanes of the CTA, LF samples per
+// lane, with the integer phase prefix sum carried across the warps through shared memory.  The bell gain
+//   G = m0 (1 + j kn F) / (1 + j kd F),  F = f/f0 - f0/f     becomes, with a = f/f0 and b = a^2 - 1 (F = b / a),
+//   G = m0 (a + j kn b)(a - j kd b) / (a^2 + kd^2 b^2):      one reciprocal per sample instead of two divisions.
+// ------------------------------------------------------------------------------------------------------------
+#define SF_ENC_PRE 12        // DevParams::filt slots (cm_api.cu: plan_secam_kernel)
+#define SF_ENC_EMPH 13
+template <int GEO> struct SecEncGeo;
+template <> struct SecEncGeo<1> { static constexpr int NW = 2, KQ = 3, L1 = 25, LF = 12; };
+template <> struct SecEncGeo<3> { static constexpr int NW = 4, KQ = 4, L1 = 33, LF = 16; };
+
+template <typename T> struct FastRcp;
+template <> struct FastRcp<float> { static __device__ __forceinline__ float rcp(float x) { return __frcp_rn(x); } };
+template <> struct FastRcp<double> { static __device__ __forceinline__ double rcp(double x) { return 1.0 / x; } };
+
+template <typename T>
+__device__ __forceinline__ void secam_bell2(T f, T inv_f0, T m0, T kn, T kd, T &re, T &im) {
+    const T a = f * inv_f0, b = a * a - (T)1;
+    const T kb = kd * b;
+    const T g = m0 * FastRcp<T>::rcp(a * a + kb * kb);
+    re = g * (a * a + kn * b * kb);
+    im = g * (kn - kd) * a * b;
+}
+
+template <typename T, int GEO>
+__global__ void __launch_bounds__(32 * SecEncGeo<GEO>::NW, sizeof(T) == 8 ? 1 : 16 / SecEncGeo<GEO>::NW)
+k_secam_encode_row2(const __grid_constant__ DevParams<T> p, const __grid_constant__ IoArgs<T> io) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T *scratch = reinterpret_cast<T *>(smem_raw), *sm = scratch + 128;
+    typedef SecEncGeo<GEO> EG;
+    constexpr int kQ = EG::KQ, NW = EG::NW, NT = 32 * NW, TH = NW / 2, LF = EG::LF;
+    unsigned long long *wsum = reinterpret_cast<unsigned long long *>(scratch + 64);        // [NW] warp totals of the phase scan
+    const int W = p.W, N1 = p.n1p, W4 = W >> 2;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const bool avg = (p.flags & 2) != 0;
+    const int field = blockIdx.y, f = blockIdx.z;
+    const long long frame = io.first_frame + f;
+    const int first = io.out_begin + field, nout = (io.out_count - field + 1) >> 1;
+    const FiltHdr &fpre = p.filt[SF_ENC_PRE], &femph = p.filt[SF_ENC_EMPH];
+    T *ys = sm, *cs = ys + N1;
+    uint32_t wc[kQ][3], wn[kQ][3];
+    auto fetch = [&](int row) {
+        const int nrow = (row + 2 < io.nrows) ? row + 2 : row;
+        const uint32_t *a = reinterpret_cast<const uint32_t *>(io.in_u8 + ((size_t)f * io.nrows + row) * W * 3);
+        const uint32_t *b = reinterpret_cast<const uint32_t *>(io.in_u8 + ((size_t)f * io.nrows + nrow) * W * 3);
+#pragma unroll
+        for (int j = 0; j < kQ; ++j) {
+            const int q = threadIdx.x + j * NT;
+            if (q < W4) {
+#pragma unroll
+                for (int i = 0; i < 3; ++i) {
+                    wc[j][i] = __ldg(a + 3 * q + i);
+                    if (avg) wn[j][i] = __ldg(b + 3 * q + i);
+                }
+            }
+        }
+    };
+    auto unpack = [&](const uint32_t *w, T *r, T *g, T *b) {
+        unsigned char bytes[12];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            bytes[i] = (w[0] >> (8 * i)) & 0xff;
+            bytes[4 + i] = (w[1] >> (8 * i)) & 0xff;
+            bytes[8 + i] = (w[2] >> (8 * i)) & 0xff;
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            r[i] = Real<T>::from_u8(bytes[3 * i]);
+            g[i] = Real<T>::from_u8(bytes[3 * i + 1]);
+            b[i] = Real<T>::from_u8(bytes[3 * i + 2]);
+        }
+    };
+    const T f0 = p.scalars[SS_BELL_F0], inv_f0 = (T)1 / f0;
+    const T m0 = p.scalars[SS_M0], kn = p.scalars[SS_KN], kd = p.scalars[SS_KD];
+    int k = blockIdx.x;
+    if (k < nout) fetch(first + 2 * k);
+    for (; k < nout; k += gridDim.x) {
+        const int row = first + 2 * k, line = io.y0 + row;
+        const bool alt = is_alternate(p, frame, line);
+        const int ci = alt ? 6 : 3;                         // D'B (row 2 of the matrix) on alternate lines, else D'R
+#pragma unroll
+        for (int j = 0; j < kQ; ++j) {
+            const int q = threadIdx.x + j * NT;
+            if (q < W4) {
+                T r[4], gg[4], b[4], y[4], c[4];
+                unpack(wc[j], r, gg, b);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    y[i] = p.enc[0] * r[i] + p.enc[1] * gg[i] + p.enc[2] * b[i];
+                    c[i] = p.enc[ci] * r[i] + p.enc[ci + 1] * gg[i] + p.enc[ci + 2] * b[i];
+                }
+                if (avg) {
+                    unpack(wn[j], r, gg, b);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        c[i] = (T)0.5 * ((p.enc[ci] * r[i] + p.enc[ci + 1] * gg[i] + p.enc[ci + 2] * b[i]) + c[i]);
+                }
+                st4(ys + 4 * q, y);
+                st4(cs + 4 * q, c);
+            }
+        }
+        __syncthreads();
+        if (k + (int)gridDim.x < nout) fetch(first + 2 * (k + gridDim.x));       // in flight during the rest of the row
+        if (warp < TH) {                                     // chroma low-pass (+ LF pre-emphasis): the first team
+            warp_fill_tail<T, 1>(cs, N1, W, fpre.npad);
+            team_iir_pk<T, 1, EG::L1, TH>(p.tab + fpre.off, fpre, LoadLinear<T, EG::L1>{cs}, [&](int j, T v) { cs[j] = v; }, warp, 2,
+                                          scratch);
+            if (p.flags & 128) {
+                if (TH > 1) team_barrier(3, 32 * TH);        // all stores of the team before the tail fill
+                else __syncwarp();
+                warp_fill_tail<T, 1>(cs, N1, W, femph.npad);
+                team_iir_pk<T, 1, EG::L1, TH>(p.tab + femph.off, femph, LoadLinear<T, EG::L1>{cs}, [&](int j, T v) { cs[j] = v; },
+                                              warp, 2, scratch);
+            }
+        }
+        __syncthreads();
+        {   // FM synthesis (secam.py:240-246): phase[j] = start - angle(G[0]) + sum_{i=1..j} pi f[i], 0.64 fixed-point turns
+            const T fsc = alt ? p.scalars[SS_FSC_DB] : p.scalars[SS_FSC_DR];
+            const T fdev = alt ? p.scalars[SS_FDEV_DB] : p.scalars[SS_FDEV_DR];
+            const T dlo = p.scalars[SS_F_LO] - fsc, dhi = p.scalars[SS_F_HI] - fsc;
+            const unsigned long long centre = alt ? p.phases[SP_FSC_DB_HALF] : p.phases[SP_FSC_DR_HALF];
+            unsigned long long run = secam_phase_inverted(p, frame, line) ? 0x8000000000000000ull : 0ull;
+            {
+                T d0 = fdev * cs[0];
+                d0 = d0 < dlo ? dlo : (d0 > dhi ? dhi : d0);
+                T re, im;
+                secam_bell2(fsc + d0, inv_f0, m0, kn, kd, re, im);
+                run -= (unsigned long long)Fix64<T>::half_turns(Real<T>::atan2_(im, re) * (T)0.31830988618379067154);
+            }
+            const int base = threadIdx.x * LF;
+            T d[LF];
+            unsigned long long acc[LF];
+            unsigned long long sum = 0;
+#pragma unroll
+            for (int i = 0; i < LF; ++i) {
+                const int j = base + i;
+                T dev = fdev * cs[j < W ? j : W - 1];
+                dev = dev < dlo ? dlo : (dev > dhi ? dhi : dev);
+                d[i] = dev;
+                if (j > 0 && j < W) sum += centre + (unsigned long long)Fix64<T>::half_turns(dev);
+                acc[i] = sum;
+            }
+            unsigned long long incl = sum;                                    // inclusive scan of the lane totals
+#pragma unroll
+            for (int s = 0; s < 5; ++s) {
+                const unsigned long long v = __shfl_up_sync(0xffffffffu, incl, 1 << s);
+                if (lane >= (1 << s)) incl += v;
+            }
+            if (lane == 31) wsum[warp] = incl;
+            __syncthreads();
+            unsigned long long before = run + incl - sum;
+            for (int w = 0; w < warp; ++w) before += wsum[w];
+#pragma unroll
+            for (int i = 0; i < LF; ++i) {
+                const int j = base + i;
+                if (j < W) {
+                    T re, im, s, co;
+                    secam_bell2(fsc + d[i], inv_f0, m0, kn, kd, re, im);
+                    Real<T>::sincos_turns(before + acc[i], s, co);
+                    ys[j] += re * co - im * s;
+                }
+            }
+        }
+        __syncthreads();
+        for (int q = threadIdx.x; q < W4; q += NT) {
+            T o[4];
+            ld4(ys + 4 * q, o);
+            store_comp4(io, ((size_t)f * io.nrows + row) * p.Wc + 4 * q, o);
+        }
+        __syncthreads();
+    }
+}

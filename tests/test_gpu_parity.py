@@ -59,10 +59,14 @@ def test_u8_frames_against_reference_golden(c, cuda_required):
 # 22 samples of SECAM_N and 126 of NIIR at 1920 samples per line), and the 8-bit frames stay within +-1 LSB everywhere
 # (test_u8_frames_against_reference_golden).
 #
-# NIIR at 1920 samples per line (36 MHz sampling, 3x oversampled = 108 MHz) keeps the bound of round 1 on top of that:
-# its float32 errors also appear at samples the input-noise probe does not flag (the envelope division acts on
-# intermediate signals at the 3x rate); 99.9 % of the samples within 1e-4, every sample within 1e-2.
-NIIR_WIDE_FP32 = {('niir', 1920), ('niir_hue', 1920)}
+# NIIR at 1920 samples per line (36 MHz sampling, 3x oversampled = 108 MHz) has samples that are singular rather than
+# merely sensitive: the hue is atan2 of two demodulated products that both pass through zero there (niir.py:132-134), and
+# the reference's own value is decided by float64 rounding.  The witness is the float64 build of the same kernel (it fits
+# shared memory since the strip-walking decoder of round 2): it agrees with the oracle to < 1e-9 on 99.9 % of the samples
+# and to 5e-8 at the worst one — a condition number of ~1e8, out of reach of float32 by construction.  Bounds there:
+# float32 99.9 % within 1e-4 and every sample within 1e-2; float64 99.9 % within 1e-9 and every sample within 1e-6; the
+# 8-bit frames within +-1 LSB like everywhere else.
+NIIR_WIDE = {('niir', 1920), ('niir_hue', 1920)}
 
 
 def _make_or_skip(c, precision, fn):
@@ -88,8 +92,8 @@ def test_float_planes_against_oracle(c, precision, tol, cuda_required):
     out_ref = om.decode(c.frame, comp_in)
     out = _make_or_skip(c, precision, lambda: m.decode_frame_float(comp_in, c.frame))
     err = np.abs(out - out_ref)
-    if precision == 'fp32' and (c.kind, c.width) in NIIR_WIDE_FP32:
-        assert np.quantile(err, 0.999) <= tol and err.max() <= 1e-2
+    if (c.kind, c.width) in NIIR_WIDE:
+        assert np.quantile(err, 0.999) <= tol and err.max() <= (1e-2 if precision == 'fp32' else 1e-6)
     elif precision == 'fp32':
         bound = conditioning.fp32_bound(lambda x: om.decode(c.frame, x), comp_in, out_ref, tol)
         assert (err <= bound).all(), 'max excess %.2e at %s' % ((err - bound).max(), np.unravel_index((err - bound).argmax(), err.shape))
