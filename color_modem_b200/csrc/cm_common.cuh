@@ -133,6 +133,14 @@ template <> struct Real<float> {
         float x = (float)(int)(unsigned)(ph >> 32) * 4.656612873077393e-10f;   // 2^-31
         sincospif(x, &s, &c);
     }
+    // the same from the hardware approximations (MUFU.SIN / MUFU.COS, absolute error < 5e-7 on [-pi, pi]): for carriers
+    // that are evaluated per sample or per pixel quad and multiply a chroma amplitude well below 1 (encoders; the
+    // parity bound is 1e-4); sincospif costs ~28 instructions, this 5
+    static __device__ __forceinline__ void sincos_turns_fast(unsigned long long ph, float &s, float &c) {
+        const float x = (float)(int)(unsigned)(ph >> 32) * 1.4629180792671596e-09f;   // 2 pi * 2^-32: radians in [-pi, pi)
+        s = __sinf(x);
+        c = __cosf(x);
+    }
     static __device__ __forceinline__ float from_u8(unsigned v) { return (float)v * (1.0f / 255.0f); }
     static __device__ __forceinline__ float rsqrt_(float x) { return rsqrtf(x); }
     static __device__ __forceinline__ float sqrt_(float x) { return sqrtf(x); }
@@ -167,6 +175,7 @@ template <> struct Real<double> {
         double x = (double)(long long)ph * 1.084202172485504434e-19;           // 2^-63 => half-turns in [-1, 1)
         sincospi(x, &s, &c);
     }
+    static __device__ __forceinline__ void sincos_turns_fast(unsigned long long ph, double &s, double &c) { sincos_turns(ph, s, c); }
     static __device__ __forceinline__ double from_u8(unsigned v) { return (double)v / 255.0; }
     static __device__ __forceinline__ double rsqrt_(double x) { return 1.0 / sqrt(x); }
     static __device__ __forceinline__ double sqrt_(double x) { return sqrt(x); }
@@ -174,6 +183,12 @@ template <> struct Real<double> {
     static __device__ __forceinline__ double atan2_(double y, double x) { return atan2(y, x); }
     static __device__ __forceinline__ double fma_(double a, double b, double c) { return fma(a, b, c); }
 };
+
+// 1 / x: float32 takes the hardware approximation (MUFU.RCP, ~1 ulp) instead of the IEEE division sequence; the float64
+// verification build divides.
+template <typename T> struct FastRcp;
+template <> struct FastRcp<float> { static __device__ __forceinline__ float rcp(float x) { return __fdividef(1.0f, x); } };
+template <> struct FastRcp<double> { static __device__ __forceinline__ double rcp(double x) { return 1.0 / x; } };
 
 // uint8(rint(255 * clip(v, 0, 1)))  — reference image.py:7-8 (numpy.rint = round-half-even = cvt.rni)
 template <typename T>

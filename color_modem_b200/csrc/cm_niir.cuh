@@ -384,14 +384,33 @@ k_niir_decode2(const __grid_constant__ DevParams<T> p, const __grid_constant__ I
     T ls_s, ls_c;
     Real<T>::sincos_turns(p.phases[NP_LINE_SHIFT], ls_s, ls_c);
 
-    // stage 1 of one row into carrier slot `pm`: normalise = false keeps the band-passed signal itself
-    auto carrier_of = [&](T *pm, bool normalise) {
+    // k = k0 - 1 is the row before the strip: a real row, or the synthetic reference carrier at the top of the field
+    // (niir.py:103-106: sin(phi) on normal lines, -sin(phi) on alternate ones, band-passed but NOT normalised).  It only
+    // leaves its carrier behind.  One copy of the per-row code serves both cases (the unrolled recursions and the five
+    // decimators are ~60 KB of instructions; three inlined copies cost 18 % of the issue slots in instruction fetch).
+    for (int k = k0 - 1; k < k1; ++k) {
+        const int row = first + 2 * k, line = io.y0 + row;
+        T *pm = pm0 + (size_t)(k & 1) * N3;
+        const T *last = pm0 + (size_t)((k + 1) & 1) * N3;
+        const bool synthetic = row < 0;
+        if (!synthetic) {
+            load_comp_row(c, io, f, row, W);
+        } else {
+            const unsigned long long ph0 = start_phase(p, frame, line);
+            const T sgn = is_alternate(p, frame, line) ? (T)-1 : (T)1;
+            for (int x = threadIdx.x; x < W; x += NT) {
+                T s, co;
+                Real<T>::sincos_turns(ph0 + (unsigned long long)x * p.phases[NP_STEP1X], s, co);
+                c[x] = sgn * s;
+            }
+        }
+        __syncthreads();
         fir_up3(A, A + hb, A + 2 * hb, c, W, hup, threadIdx.x, NT);
         __syncthreads();
         warp_fill_tail<T, 3>(A, hb, n3, fbp.npad);                  // every warp writes the same values
         team_iir_pk<T, 3, L3, NW>(p.tab + fbp.off, fbp, LoadPoly3<T, L3, false>{A, hb}, Poly3Out<T>{pm, hb}, warp, 1, scratch);
         __syncthreads();
-        if (!normalise) return;
+        if (synthetic) continue;
         warp_fill_tail<T, 3>(pm, hb, n3, flp.npad);
         team_iir_pk<T, 3, L3, NW>(p.tab + flp.off, flp, LoadPoly3<T, L3, true>{pm, hb}, Poly3Out<T>{A, hb}, warp, 1, scratch);
         __syncthreads();
@@ -405,40 +424,12 @@ k_niir_decode2(const __grid_constant__ DevParams<T> p, const __grid_constant__ I
                 ld4(pm + ph * hb + q, a);
                 ld4(A + ph * hb + q, b);
 #pragma unroll
-                for (int i = 0; i < 4; ++i) a[i] = a[i] / b[i];
+                for (int i = 0; i < 4; ++i) a[i] = a[i] * FastRcp<T>::rcp(b[i]);
                 st4(pm + ph * hb + q, a);
             }
         }
         __syncthreads();
-    };
-
-    // the row before the strip: a real row, or the synthetic reference carrier at the top of the field (niir.py:103-106)
-    {
-        const int row = first + 2 * k0 - 2;
-        if (row >= 0) {
-            load_comp_row(c, io, f, row, W);
-            __syncthreads();
-            carrier_of(pm0 + (size_t)((k0 + 1) & 1) * N3, true);
-        } else {
-            const int line = io.y0 + row;
-            const unsigned long long ph0 = start_phase(p, frame, line);
-            const T sgn = is_alternate(p, frame, line) ? (T)-1 : (T)1;
-            for (int x = threadIdx.x; x < W; x += NT) {
-                T s, co;
-                Real<T>::sincos_turns(ph0 + (unsigned long long)x * p.phases[NP_STEP1X], s, co);
-                c[x] = sgn * s;
-            }
-            __syncthreads();
-            carrier_of(pm0 + (size_t)((k0 + 1) & 1) * N3, false);
-        }
-    }
-    for (int k = k0; k < k1; ++k) {
-        const int row = first + 2 * k, line = io.y0 + row;
-        T *pm = pm0 + (size_t)(k & 1) * N3;
-        const T *last = pm0 + (size_t)((k + 1) & 1) * N3;
-        load_comp_row(c, io, f, row, W);
-        __syncthreads();
-        carrier_of(pm, true);
+        if (k < k0) continue;
         const bool alt = is_alternate(p, frame, line);
         const T *carrier = alt ? pm : last, *huemod = alt ? last : pm;
         {   // derivative of the reference carrier (niir.py:123-125) into A (the envelope is dead)
@@ -464,19 +455,19 @@ k_niir_decode2(const __grid_constant__ DevParams<T> p, const __grid_constant__ I
             ld4(c + j0, cc);
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                const T norm = Real<T>::sqrt_(cosphi[i] * cosphi[i] + sinphi[i] * sinphi[i]);
-                const T cp0 = cosphi[i] / norm, sp0 = sinphi[i] / norm;
+                const T inv_norm = Real<T>::rsqrt_(cosphi[i] * cosphi[i] + sinphi[i] * sinphi[i]);
+                const T cp0 = cosphi[i] * inv_norm, sp0 = sinphi[i] * inv_norm;
                 const T sp = -cp0 * sh_s - sp0 * sh_c, cp = sp0 * sh_s - cp0 * sh_c;
                 T db = sv[i] * sp, dr = sv[i] * cp;
-                const T us0 = alt ? -Real<T>::sqrt_(db * db + dr * dr) : db, vs0 = alt ? (T)0 : dr;
+                const T m2 = db * db + dr * dr;
+                const T inv_mag = Real<T>::rsqrt_(m2), mag = m2 * inv_mag;      // (only used where m2 > 0)
+                const T us0 = alt ? (m2 > (T)0 ? -mag : (T)0) : db, vs0 = alt ? (T)0 : dr;
                 const T us = us0 * rot_c - vs0 * rot_s, vs = us0 * rot_s + vs0 * rot_c;
                 y[i] = cc[i] - (us * sincar[i] + vs * coscar[i]);
-                const T m2 = db * db + dr * dr;                                   // niir.py:61-65
-                if (m2 > (T)0) {
-                    const T mag = Real<T>::sqrt_(m2);
+                if (m2 > (T)0) {                                                  // niir.py:61-65
                     T ns = mag - (T)0.1;
                     ns = ns > (T)0 ? ns : (T)0;
-                    const T sc = ns / mag;
+                    const T sc = ns * inv_mag;
                     db *= sc;
                     dr *= sc;
                 } else {

@@ -29,6 +29,17 @@ __device__ __forceinline__ void carrier4(unsigned long long ph_x0, T rs, T rc, T
     }
 }
 
+// the same with the seed from the hardware sin / cos approximation (Real<T>::sincos_turns_fast): the u8 row encoders
+template <typename T>
+__device__ __forceinline__ void carrier4_fast(unsigned long long ph_x0, T rs, T rc, T s[4], T c[4]) {
+    Real<T>::sincos_turns_fast(ph_x0, s[0], c[0]);
+#pragma unroll
+    for (int i = 1; i < 4; ++i) {
+        s[i] = Real<T>::fma_(s[i - 1], rc, c[i - 1] * rs);
+        c[i] = Real<T>::fma_(c[i - 1], rc, -(s[i - 1] * rs));
+    }
+}
+
 // ------------------------------------------------------------------------------------------------------------
 // Encode: RGB -> Y + sin(phi) LP(U) + cos(phi) LP(+-V)          qam.py:20-32, ntsc.py:27-45, pal.py:32-52
 // optional ColorAveragingModem front end (comb.py:141-152).     smem: R * 3 * N1
@@ -318,7 +329,7 @@ k_qam_encode_row2(const __grid_constant__ DevParams<T> p, const __grid_constant_
             ld4(ys + x, y);
             ld4(us + x, u);
             ld4(vs + x, v);
-            carrier4(ph0 + (unsigned long long)x * p.phases[QP_STEP1X], rs, rc, s, c);
+            carrier4_fast(ph0 + (unsigned long long)x * p.phases[QP_STEP1X], rs, rc, s, c);
 #pragma unroll
             for (int i = 0; i < 4; ++i) o[i] = y[i] + (s[i] * u[i] + c[i] * (neg ? -v[i] : v[i]));
             store_comp4(io, ((size_t)f * io.nrows + row) * p.Wc + x, o);

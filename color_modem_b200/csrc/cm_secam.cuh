@@ -503,12 +503,9 @@ k_secam_decode2(const __grid_constant__ DevParams<T> p, const __grid_constant__ 
 #define SF_ENC_PRE 12        // DevParams::filt slots (cm_api.cu: plan_secam_kernel)
 #define SF_ENC_EMPH 13
 template <int GEO> struct SecEncGeo;
-template <> struct SecEncGeo<1> { static constexpr int NW = 2, KQ = 3, L1 = 25, LF = 12; };
-template <> struct SecEncGeo<3> { static constexpr int NW = 4, KQ = 4, L1 = 33, LF = 16; };
+template <> struct SecEncGeo<1> { static constexpr int NW = 2, KQ = 3, L1 = 13, LF = 12; };
+template <> struct SecEncGeo<3> { static constexpr int NW = 4, KQ = 4, L1 = 17, LF = 16; };
 
-template <typename T> struct FastRcp;
-template <> struct FastRcp<float> { static __device__ __forceinline__ float rcp(float x) { return __frcp_rn(x); } };
-template <> struct FastRcp<double> { static __device__ __forceinline__ double rcp(double x) { return 1.0 / x; } };
 
 template <typename T>
 __device__ __forceinline__ void secam_bell2(T f, T inv_f0, T m0, T kn, T kd, T &re, T &im) {
@@ -525,7 +522,7 @@ k_secam_encode_row2(const __grid_constant__ DevParams<T> p, const __grid_constan
     extern __shared__ __align__(16) unsigned char smem_raw[];
     T *scratch = reinterpret_cast<T *>(smem_raw), *sm = scratch + 128;
     typedef SecEncGeo<GEO> EG;
-    constexpr int kQ = EG::KQ, NW = EG::NW, NT = 32 * NW, TH = NW / 2, LF = EG::LF;
+    constexpr int kQ = EG::KQ, NW = EG::NW, NT = 32 * NW, LF = EG::LF;
     unsigned long long *wsum = reinterpret_cast<unsigned long long *>(scratch + 64);        // [NW] warp totals of the phase scan
     const int W = p.W, N1 = p.n1p, W4 = W >> 2;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -598,19 +595,17 @@ k_secam_encode_row2(const __grid_constant__ DevParams<T> p, const __grid_constan
         }
         __syncthreads();
         if (k + (int)gridDim.x < nout) fetch(first + 2 * (k + gridDim.x));       // in flight during the rest of the row
-        if (warp < TH) {                                     // chroma low-pass (+ LF pre-emphasis): the first team
-            warp_fill_tail<T, 1>(cs, N1, W, fpre.npad);
-            team_iir_pk<T, 1, EG::L1, TH>(p.tab + fpre.off, fpre, LoadLinear<T, EG::L1>{cs}, [&](int j, T v) { cs[j] = v; }, warp, 2,
-                                          scratch);
-            if (p.flags & 128) {
-                if (TH > 1) team_barrier(3, 32 * TH);        // all stores of the team before the tail fill
-                else __syncwarp();
-                warp_fill_tail<T, 1>(cs, N1, W, femph.npad);
-                team_iir_pk<T, 1, EG::L1, TH>(p.tab + femph.off, femph, LoadLinear<T, EG::L1>{cs}, [&](int j, T v) { cs[j] = v; },
-                                              warp, 2, scratch);
-            }
-        }
+        // chroma low-pass (+ LF pre-emphasis): one short task, run by all the warps as one team
+        warp_fill_tail<T, 1>(cs, N1, W, fpre.npad);
+        team_iir_pk<T, 1, EG::L1, NW>(p.tab + fpre.off, fpre, LoadLinear<T, EG::L1>{cs}, [&](int j, T v) { cs[j] = v; }, warp, 2,
+                                      scratch);
         __syncthreads();
+        if (p.flags & 128) {
+            warp_fill_tail<T, 1>(cs, N1, W, femph.npad);
+            team_iir_pk<T, 1, EG::L1, NW>(p.tab + femph.off, femph, LoadLinear<T, EG::L1>{cs}, [&](int j, T v) { cs[j] = v; }, warp,
+                                          2, scratch);
+            __syncthreads();
+        }
         {   // FM synthesis (secam.py:240-246): phase[j] = start - angle(G[0]) + sum_{i=1..j} pi f[i], 0.64 fixed-point turns
             const T fsc = alt ? p.scalars[SS_FSC_DB] : p.scalars[SS_FSC_DR];
             const T fdev = alt ? p.scalars[SS_FDEV_DB] : p.scalars[SS_FDEV_DR];
@@ -653,7 +648,7 @@ k_secam_encode_row2(const __grid_constant__ DevParams<T> p, const __grid_constan
                 if (j < W) {
                     T re, im, s, co;
                     secam_bell2(fsc + d[i], inv_f0, m0, kn, kd, re, im);
-                    Real<T>::sincos_turns(before + acc[i], s, co);
+                    Real<T>::sincos_turns_fast(before + acc[i], s, co);
                     ys[j] += re * co - im * s;
                 }
             }
