@@ -227,6 +227,27 @@ static int plan_niir_kernel(const cm_desc &d, FiltHdr *fh, std::vector<double> &
     return 0;
 }
 
+// Geometry of k_proto_decode2 / k_proto_encode_row2 (cm_proto.cuh: ProtoGeo): 1 = 4 warps, 3 = 8 warps; fills PF_ROW_* / PF_ENC_PRE.
+static int plan_proto_kernel(const cm_desc &d, FiltHdr *fh, std::vector<double> &tab) {
+    if (d.kind != CM_KIND_PROTOSECAM) return 0;
+    const cm_filter &fbp = d.filters[PF_BP_UP], &fbs = d.filters[PF_BS_UP], &fpost = d.filters[PF_POST_LP],
+                    &fpre = d.filters[PF_PRE_LP];
+    if (!fbp.nsec || !fbs.nsec || !fpost.nsec || !fpre.nsec) return 0;
+    static const int geo[2] = {1, 3}, th[2] = {2, 4}, l3[2] = {39, 51}, l1[2] = {13, 17};
+    for (int k = 0; k < 2; ++k) {
+        const int cap3 = 32 * th[k] * l3[k], cap1 = 32 * th[k] * l1[k];
+        if (fbp.n + fbp.shift > cap3 || fbs.n + fbs.shift > cap3 || fpost.n + fpost.shift > cap3 || fpre.n + fpre.shift > cap1 ||
+            d.width > 16 * 32 * 2 * th[k] / 2)
+            continue;
+        build_filter_L(fbp, fh[4], tab, l3[k], 1, 32 * th[k]);
+        build_filter_L(fbs, fh[5], tab, l3[k], 1, 32 * th[k]);
+        build_filter_L(fpost, fh[6], tab, l3[k], 1, 32 * th[k]);
+        build_filter_L(fpre, fh[7], tab, l1[k], 1, 32 * th[k]);
+        return geo[k];
+    }
+    return 0;
+}
+
 // Row-independent carrier of k_qam_rows2 / k_secam_decode2: sin / cos of (j * step) for the 2x sample index j, tail
 // replicated, in the load order of LoadPoly2Carrier: [task][i / 2][chunk][i & 1] with j = chunk * L + i.
 static void build_carrier_table(unsigned long long step, const FiltHdr &fl, int th, std::vector<double> &out) {
@@ -462,7 +483,8 @@ extern "C" int cm_create(const cm_desc *desc, int precision, cm_modem **out) {
     if (row_geo) build_carrier_table(desc->phases[QP_STEP2X], fh[7], row_geo == 1 ? 1 : 2, ctab);
     const int sec_geo = plan_secam_kernel(*desc, fh, tab);
     if (sec_geo) build_carrier_table(desc->phases[SP_FM_STEP2X], fh[10], sec_geo == 1 ? 1 : 2, ctab);
-    const int niir_geo = plan_niir_kernel(*desc, fh, tab);
+    int niir_geo = plan_niir_kernel(*desc, fh, tab);
+    if (!niir_geo) niir_geo = plan_proto_kernel(*desc, fh, tab);
     int rc;
     if (precision == CM_FP32) {
         rc = upload<float>(tab, &m->d_tab);

@@ -216,3 +216,25 @@ struct RowPrefetch {
         }
     }
 };
+
+// sin/cos of the subcarrier at 4 consecutive 1x samples starting at x0 (exact seed + 3 rotations)
+template <typename T>
+__device__ __forceinline__ void carrier4(unsigned long long ph_x0, T rs, T rc, T s[4], T c[4]) {
+    Real<T>::sincos_turns(ph_x0, s[0], c[0]);
+#pragma unroll
+    for (int i = 1; i < 4; ++i) {
+        s[i] = Real<T>::fma_(s[i - 1], rc, c[i - 1] * rs);
+        c[i] = Real<T>::fma_(c[i - 1], rc, -(s[i - 1] * rs));
+    }
+}
+
+// the same with the seed from the hardware sin / cos approximation (Real<T>::sincos_turns_fast): the u8 row encoders
+template <typename T>
+__device__ __forceinline__ void carrier4_fast(unsigned long long ph_x0, T rs, T rc, T s[4], T c[4]) {
+    Real<T>::sincos_turns_fast(ph_x0, s[0], c[0]);
+#pragma unroll
+    for (int i = 1; i < 4; ++i) {
+        s[i] = Real<T>::fma_(s[i - 1], rc, c[i - 1] * rs);
+        c[i] = Real<T>::fma_(c[i - 1], rc, -(s[i - 1] * rs));
+    }
+}

@@ -64,6 +64,23 @@ int niir_decode(cm_modem *m, IoArgs<T> io, cudaStream_t st) {
 template <typename T>
 int proto_encode(cm_modem *m, IoArgs<T> io, cudaStream_t st) {
     const DevParams<T> &p = params_of<T>(m);
+    if (io.in_u8 && p.row_geo && !m->tune.rows_v1 && !m->tune.onepass) {
+        if (io.out_count <= 0) return CM_OK;
+        void (*kern)(const DevParams<T>, const IoArgs<T>) = p.row_geo == 1 ? k_proto_encode_row2<T, 1> : k_proto_encode_row2<T, 3>;
+        const size_t b2 = (128 + 2 * (size_t)p.n1p + 3 * (size_t)p.hb3) * sizeof(T);
+        if (b2 <= (size_t)m->smem_optin) {
+            int rc = set_smem(kern, b2);
+            if (rc) return rc;
+            const int rpc = m->tune.rpc, nf = (io.out_count + 1) >> 1;
+            {
+                LaunchTimer lt(m, CM_K_ENCODE, st);
+                kern<<<dim3((unsigned)((nf + rpc - 1) / rpc), 2u, (unsigned)io.nframes), p.row_geo == 1 ? 128 : 256, b2, st>>>(p, io);
+            }
+            cm_count_launch();
+            CUDA_TRY(cudaGetLastError());
+            return CM_OK;
+        }
+    }
     auto bytes = [&](int r) { return (128 + (size_t)r * (2 * (size_t)p.n1p + 3 * (size_t)p.hb3)) * sizeof(T); };
     return launch_rows<T>(m, io, st, k_proto_encode<T>, bytes, 1, 2, 0, CM_K_ENCODE, "proto-SECAM encode");
 }
@@ -72,24 +89,58 @@ template <typename T>
 int proto_decode(cm_modem *m, IoArgs<T> io, cudaStream_t st) {
     const DevParams<T> &p = params_of<T>(m);
     if (io.out_count <= 0) return CM_OK;
-    // pass 1 (heavy): (luma, X) per row for the output rows and the two rows above them
-    io.aux = (T *)cm_ensure_aux(m, (size_t)io.nframes * io.nrows * 2 * p.Wo * sizeof(T));
-    if (!io.aux) return CM_ERR_NOMEM;
-    IoArgs<T> a = io;
-    a.out_begin = io.out_begin >= 2 ? io.out_begin - 2 : 0;
-    a.out_count = io.out_begin + io.out_count - a.out_begin;
-    auto bytes = [&](int r) { return (128 + (size_t)r * (p.n1p + 9 * (size_t)p.hb3)) * sizeof(T); };
-    // two tasks per row (chroma, luma), each run by a team of up to four warps
-    int rc = launch_rows<T>(m, a, st, k_proto_decode<T>, bytes, 2, 4, 0, CM_K_DECODE_OTHER, "proto-SECAM decode");
-    if (rc) return rc;
-    // pass 2 (light): pair rows y / y-2, inverse matrix, store
-    {
-        LaunchTimer lt(m, CM_K_DECODE_OTHER, st);
-        dim3 grid(1u, (unsigned)io.out_count, (unsigned)io.nframes);
-        k_pair_rows_store<T><<<grid, 192, 0, st>>>(p, io);
+    // pass 1 (heavy): (luma, X) per row for the output rows and the two rows above them, into a pairing scratch of
+    // 2 * Wo elements per row; the batch is cut so that the scratch stays within 2 GiB
+    const size_t frame_elems = (size_t)io.nrows * 2 * p.Wo;
+    int chunk = (int)(((size_t)2 << 30) / (frame_elems * sizeof(T)));
+    if (chunk < 1) chunk = 1;
+    if (m->tune.chunk > 0) chunk = m->tune.chunk;
+    if (chunk > io.nframes) chunk = io.nframes;
+    T *aux = (T *)cm_ensure_aux(m, (size_t)chunk * frame_elems * sizeof(T));
+    if (!aux) return CM_ERR_NOMEM;
+    const size_t b2 = (128 + (size_t)p.n1p + 6 * (size_t)p.hb3) * sizeof(T);
+    const bool rows2 = p.row_geo && !m->tune.rows_v1 && !m->tune.onepass && b2 <= (size_t)m->smem_optin;
+    void (*kern)(const DevParams<T>, const IoArgs<T>) = p.row_geo == 1 ? k_proto_decode2<T, 1> : k_proto_decode2<T, 3>;
+    if (rows2) {
+        int rc = set_smem(kern, b2);
+        if (rc) return rc;
     }
-    cm_count_launch();
-    CUDA_TRY(cudaGetLastError());
+    auto bytes = [&](int r) { return (128 + (size_t)r * (p.n1p + 9 * (size_t)p.hb3)) * sizeof(T); };
+    const size_t in_frame = (size_t)io.nrows * p.Wc, out_frame = (size_t)io.nrows * p.Wo * 3;
+    for (int f0 = 0; f0 < io.nframes; f0 += chunk) {
+        IoArgs<T> c = io;
+        c.nframes = io.nframes - f0 < chunk ? io.nframes - f0 : chunk;
+        c.first_frame = io.first_frame + f0;
+        c.aux = aux;
+        if (c.in_u8) c.in_u8 += (size_t)f0 * in_frame;
+        if (c.in_f) c.in_f += (size_t)f0 * in_frame;
+        if (c.out_u8) c.out_u8 += (size_t)f0 * out_frame;
+        if (c.out_f) c.out_f += (size_t)f0 * out_frame;
+        IoArgs<T> a = c;
+        a.out_begin = c.out_begin >= 2 ? c.out_begin - 2 : 0;
+        a.out_count = c.out_begin + c.out_count - a.out_begin;
+        if (rows2) {
+            const int rpc = m->tune.rpc;
+            {
+                LaunchTimer lt(m, CM_K_DECODE_OTHER, st);
+                kern<<<dim3((unsigned)((a.out_count + rpc - 1) / rpc), 1u, (unsigned)c.nframes), p.row_geo == 1 ? 128 : 256, b2, st>>>(p, a);
+            }
+            cm_count_launch();
+            CUDA_TRY(cudaGetLastError());
+        } else {
+            // two tasks per row (chroma, luma), each run by a team of up to four warps
+            int rc = launch_rows<T>(m, a, st, k_proto_decode<T>, bytes, 2, 4, 0, CM_K_DECODE_OTHER, "proto-SECAM decode");
+            if (rc) return rc;
+        }
+        // pass 2 (light): pair rows y / y-2, inverse matrix, store
+        {
+            LaunchTimer lt(m, CM_K_DECODE_OTHER, st);
+            dim3 grid(1u, (unsigned)c.out_count, (unsigned)c.nframes);
+            k_pair_rows_store<T><<<grid, 192, 0, st>>>(p, c);
+        }
+        cm_count_launch();
+        CUDA_TRY(cudaGetLastError());
+    }
     return CM_OK;
 }
 

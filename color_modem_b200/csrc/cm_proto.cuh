@@ -168,3 +168,179 @@ k_proto_decode(const __grid_constant__ DevParams<T> p, const __grid_constant__ I
         }
     }
 }
+
+// ------------------------------------------------------------------------------------------------------------
+// Second generation: one row at a time per CTA of 4 (lines up to ~800 samples) or 8 warps (up to ~2100), two teams of
+// NW / 2 warps, packed DF-I recursions at the 3x rate (team_iir_pk), the next composite / RGB row prefetched.
+//   decode  up3 -> chroma band-pass (team 0, u -> b) || luma band-stop (team 1, in place) -> rectifier + low-pass (team 0, in
+//           place) -> down3 of both -> (luma, X) to the pairing scratch (k_pair_rows_store finishes).  smem: c[N1] | u[N3] | b[N3]
+//   encode  luma band-stop at 3x (team 0) || chroma low-pass at 1x (team 1) -> down3, carrier, level map
+// ------------------------------------------------------------------------------------------------------------
+#define PF_ROW_BP 4          // DevParams::filt slots of these kernels' use-sites (cm_api.cu: plan_proto_kernel)
+#define PF_ROW_BS 5
+#define PF_ROW_POST 6
+#define PF_ENC_PRE 7
+template <int GEO> struct ProtoGeo;
+template <> struct ProtoGeo<1> { static constexpr int NW = 4, L3 = 39, L1 = 13, KQ = 2; };
+template <> struct ProtoGeo<3> { static constexpr int NW = 8, L3 = 51, L1 = 17, KQ = 2; };
+
+template <typename T, int GEO>
+__global__ void __launch_bounds__(32 * ProtoGeo<GEO>::NW, sizeof(T) == 8 ? 1 : 16 / ProtoGeo<GEO>::NW)
+k_proto_decode2(const __grid_constant__ DevParams<T> p, const __grid_constant__ IoArgs<T> io) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T *scratch = reinterpret_cast<T *>(smem_raw), *sm = scratch + 128;
+    typedef ProtoGeo<GEO> PG;
+    constexpr int NW = PG::NW, TH = NW / 2, NT = 32 * NW, L3 = PG::L3;
+    const int W = p.W, N1 = p.n1p, hb = p.hb3, N3 = 3 * hb, n3 = 3 * W;
+    const int f = blockIdx.z, end = io.out_begin + io.out_count;
+    const int warp = threadIdx.x >> 5, task = warp / TH, wr = warp - task * TH;
+    T *c = sm, *u = c + N1, *b = u + N3;
+    const FirTaps<T> hup{p.firc[PR_UP3], p.fircp[PR_UP3]}, hdn{p.firc[PR_DOWN3], p.fircp[PR_DOWN3]};
+    const Down3Taps<T> tp(hdn);
+    const FiltHdr &fbp = p.filt[PF_ROW_BP], &fbs = p.filt[PF_ROW_BS], &fpost = p.filt[PF_ROW_POST];
+    const bool pref = io.in_u8 != nullptr && W <= 4 * RowPrefetch::kMaxQuads * NT;
+    RowPrefetch pf;
+    int row = io.out_begin + blockIdx.x;
+    if (pref && row < end) pf.fetch(io, f, row, W);
+    for (; row < end; row += gridDim.x) {
+        if (pref) pf.stage(c, W);
+        else load_comp_row(c, io, f, row, W);
+        __syncthreads();
+        if (pref && row + (int)gridDim.x < end) pf.fetch(io, f, row + gridDim.x, W);
+        fir_up3(u, u + hb, u + 2 * hb, c, W, hup, threadIdx.x, NT);
+        __syncthreads();
+        warp_fill_tail<T, 3>(u, hb, n3, fbp.npad > fbs.npad ? fbp.npad : fbs.npad);       // every warp writes the same values
+        if (task == 0)
+            team_iir_pk<T, 3, L3, TH, true>(p.tab + fbp.off, fbp, LoadPoly3<T, L3, false>{u, hb}, Poly3Out<T>{b, hb}, wr, 2, scratch);
+        else
+            team_iir_pk<T, 3, L3, TH, true>(p.tab + fbs.off, fbs, LoadPoly3<T, L3, false>{u, hb}, Poly3Out<T>{u, hb}, wr, 3,
+                                            scratch + 32);
+        __syncthreads();
+        if (task == 0) {                                         // rectifier + low-pass, in place (the team's own barrier
+            warp_fill_tail<T, 3>(b, hb, n3, fpost.npad);         // separates its loads from its stores)
+            team_iir_pk<T, 3, L3, TH>(p.tab + fpost.off, fpost, LoadPoly3<T, L3, true>{b, hb}, Poly3Out<T>{b, hb}, wr, 2, scratch);
+        }
+        __syncthreads();
+        T *dst = io.aux + ((size_t)f * io.nrows + row) * 2 * W;
+        for (int q = threadIdx.x; q < (W >> 2); q += NT) {       // luma = down3(band-stopped), X = 8 down3(envelope) - 1
+            T y[4], x[4];
+            down3_quad(tp, u, u + hb, u + 2 * hb, W, 4 * q, y);
+            down3_quad(tp, b, b + hb, b + 2 * hb, W, 4 * q, x);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) x[i] = (T)8 * x[i] - (T)1;
+            st4(dst + 4 * q, y);
+            st4(dst + W + 4 * q, x);
+        }
+        __syncthreads();
+    }
+}
+
+template <typename T, int GEO>
+__global__ void __launch_bounds__(32 * ProtoGeo<GEO>::NW, sizeof(T) == 8 ? 1 : 16 / ProtoGeo<GEO>::NW)
+k_proto_encode_row2(const __grid_constant__ DevParams<T> p, const __grid_constant__ IoArgs<T> io) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T *scratch = reinterpret_cast<T *>(smem_raw), *sm = scratch + 128;
+    typedef ProtoGeo<GEO> PG;
+    constexpr int NW = PG::NW, TH = NW / 2, NT = 32 * NW, L3 = PG::L3, L1 = PG::L1, kQ = PG::KQ;
+    const int W = p.W, N1 = p.n1p, hb = p.hb3, N3 = 3 * hb, n3 = 3 * W, W4 = W >> 2;
+    const int warp = threadIdx.x >> 5, task = warp / TH, wr = warp - task * TH;
+    const bool avg = (p.flags & 2) != 0, luma_filter = (p.flags & 256) != 0;
+    const int field = blockIdx.y, f = blockIdx.z;
+    const long long frame = io.first_frame + f;
+    const int first = io.out_begin + field, nout = (io.out_count - field + 1) >> 1;
+    const FiltHdr &fpre = p.filt[PF_ENC_PRE], &fbs = p.filt[PF_ROW_BS];
+    const FirTaps<T> hup{p.firc[PR_UP3], p.fircp[PR_UP3]}, hdn{p.firc[PR_DOWN3], p.fircp[PR_DOWN3]};
+    const Down3Taps<T> tp(hdn);
+    T *ys = sm, *cs = ys + N1, *u = cs + N1;
+    (void)N3;
+    uint32_t wc[kQ][3], wn[kQ][3];
+    auto fetch = [&](int row) {
+        const int nrow = (row + 2 < io.nrows) ? row + 2 : row;
+        const uint32_t *a = reinterpret_cast<const uint32_t *>(io.in_u8 + ((size_t)f * io.nrows + row) * W * 3);
+        const uint32_t *b = reinterpret_cast<const uint32_t *>(io.in_u8 + ((size_t)f * io.nrows + nrow) * W * 3);
+#pragma unroll
+        for (int j = 0; j < kQ; ++j) {
+            const int q = threadIdx.x + j * NT;
+            if (q < W4) {
+#pragma unroll
+                for (int i = 0; i < 3; ++i) {
+                    wc[j][i] = __ldg(a + 3 * q + i);
+                    if (avg) wn[j][i] = __ldg(b + 3 * q + i);
+                }
+            }
+        }
+    };
+    auto unpack = [&](const uint32_t *w, T *r, T *g, T *b) {
+        unsigned char bytes[12];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            bytes[i] = (w[0] >> (8 * i)) & 0xff;
+            bytes[4 + i] = (w[1] >> (8 * i)) & 0xff;
+            bytes[8 + i] = (w[2] >> (8 * i)) & 0xff;
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            r[i] = Real<T>::from_u8(bytes[3 * i]);
+            g[i] = Real<T>::from_u8(bytes[3 * i + 1]);
+            b[i] = Real<T>::from_u8(bytes[3 * i + 2]);
+        }
+    };
+    T rs, rc;
+    Real<T>::sincos_turns(p.phases[PP_STEP1X], rs, rc);
+    int k = blockIdx.x;
+    if (k < nout) fetch(first + 2 * k);
+    for (; k < nout; k += gridDim.x) {
+        const int row = first + 2 * k, line = io.y0 + row;
+        const int ci = is_alternate(p, frame, line) ? 6 : 3;      // D'B on alternate lines, else D'R
+#pragma unroll
+        for (int j = 0; j < kQ; ++j) {
+            const int q = threadIdx.x + j * NT;
+            if (q < W4) {
+                T r[4], gg[4], b[4], y[4], c[4];
+                unpack(wc[j], r, gg, b);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    y[i] = p.enc[0] * r[i] + p.enc[1] * gg[i] + p.enc[2] * b[i];
+                    c[i] = p.enc[ci] * r[i] + p.enc[ci + 1] * gg[i] + p.enc[ci + 2] * b[i];
+                }
+                if (avg) {
+                    unpack(wn[j], r, gg, b);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        c[i] = (T)0.5 * ((p.enc[ci] * r[i] + p.enc[ci + 1] * gg[i] + p.enc[ci + 2] * b[i]) + c[i]);
+                }
+                st4(ys + 4 * q, y);
+                st4(cs + 4 * q, c);
+            }
+        }
+        __syncthreads();
+        if (k + (int)gridDim.x < nout) fetch(first + 2 * (k + gridDim.x));
+        if (luma_filter) {
+            fir_up3(u, u + hb, u + 2 * hb, ys, W, hup, threadIdx.x, NT);
+            __syncthreads();
+        }
+        if (task == 0) {
+            if (luma_filter) {                                   // luma band-stop at 3x, in place
+                warp_fill_tail<T, 3>(u, hb, n3, fbs.npad);
+                team_iir_pk<T, 3, L3, TH>(p.tab + fbs.off, fbs, LoadPoly3<T, L3, false>{u, hb}, Poly3Out<T>{u, hb}, wr, 2, scratch);
+            }
+        } else {                                                 // chroma low-pass at 1x, in place
+            warp_fill_tail<T, 1>(cs, N1, W, fpre.npad);
+            team_iir_pk<T, 1, L1, TH>(p.tab + fpre.off, fpre, LoadLinear<T, L1>{cs}, [&](int j, T v) { cs[j] = v; }, wr, 3,
+                                      scratch + 32);
+        }
+        __syncthreads();
+        const unsigned long long ph0 = start_phase(p, frame, line);
+        for (int q = threadIdx.x; q < W4; q += NT) {
+            T o[4], luma[4], ch[4], s[4], c[4];
+            if (luma_filter) down3_quad(tp, u, u + hb, u + 2 * hb, W, 4 * q, luma);
+            else ld4(ys + 4 * q, luma);
+            ld4(cs + 4 * q, ch);
+            carrier4_fast(ph0 + (unsigned long long)(4 * q) * p.phases[PP_STEP1X], rs, rc, s, c);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) o[i] = luma[i] + c[i] * ((T)0.125 * ((T)1 + ch[i]));
+            store_comp4(io, ((size_t)f * io.nrows + row) * p.Wc + 4 * q, o);
+        }
+        __syncthreads();
+    }
+}
