@@ -86,20 +86,21 @@ def _cpu_init(workload):
 
 
 def _cpu_range(rng):
-    """encode->decode of the contiguous frame range [lo, hi) on one core; the frames are synthesised first (untimed:
-    the GPU arm's inputs are resident before its timed region too).  Returns the seconds of the encode->decode loop."""
+    """encode->decode of the contiguous frame range [lo, hi) on one core.  Synthesising a frame is not timed (the GPU
+    arm's inputs are resident before its timed region too).  Returns the seconds spent in encode->decode."""
     from oracle import frame as oframe
     from color_modem_b200.synth import synth_frames_u8
     lo, hi = rng
     hh, ww = _worker['size']
-    rgb = synth_frames_u8(hi - lo, hh, ww, first_frame=lo, seed=0)
-    acc = 0
-    t0 = time.perf_counter()
-    for i in range(hi - lo):
-        comp = oframe.encode_frame_u8(_worker['modem'], lo + i, rgb[i])
-        out = oframe.decode_frame_u8(_worker['modem'], lo + i, comp)
+    acc, busy = 0, 0.0
+    for i in range(lo, hi):
+        rgb = synth_frames_u8(1, hh, ww, first_frame=i, seed=0)[0]       # (one frame at a time: the generator's int64
+        t0 = time.perf_counter()                                        #  temporaries are 100 bytes per pixel)
+        comp = oframe.encode_frame_u8(_worker['modem'], i, rgb)
+        out = oframe.decode_frame_u8(_worker['modem'], i, comp)
+        busy += time.perf_counter() - t0
         acc += int(out[0, 0, 0])
-    return time.perf_counter() - t0, acc
+    return busy, acc
 
 
 def host_cores():

@@ -526,6 +526,7 @@ extern "C" void cm_destroy(cm_modem *m) {
     cudaFree(m->d_taps);
     cudaFree(m->d_ctab);
     cudaFree(m->d_ptab);
+    if (m->last_use) cudaEventDestroy(m->last_use);
     if (m->s2) cudaStreamDestroy(m->s2);
     for (int i = 0; i < 2; ++i) {
         if (m->ev_p1[i]) cudaEventDestroy(m->ev_p1[i]);
@@ -676,6 +677,18 @@ static int run_ex(cm_modem *m, bool encode, const cm_window *win, const uint8_t 
     CUDA_TRY(cudaSetDevice(m->device));
     const int mode = win ? win->mode : CM_MODE_DEFAULT;
     m->pf.phase0 = m->pd.phase0 = win ? win->phase_offset : 0ull;     // (a handle is not re-entrant)
+    bool guard = m->aux_slot == 0;                // (the host entry points use their own scratch slot per stream)
+    if (guard) {                                  // (a stream that is being captured into a CUDA graph is left alone)
+        cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+        if (cudaStreamIsCapturing((cudaStream_t)stream, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) {
+            cudaGetLastError();
+            guard = false;
+        }
+    }
+    if (guard) {
+        if (!m->last_use) CUDA_TRY(cudaEventCreateWithFlags(&m->last_use, cudaEventDisableTiming));
+        if (m->used && m->last_stream != (cudaStream_t)stream) CUDA_TRY(cudaStreamWaitEvent((cudaStream_t)stream, m->last_use, 0));
+    }
     // gridDim.z carries the frame index: at most 65535 frames per launch
     const size_t in_w = encode ? (size_t)m->desc.width * 3 : (size_t)m->desc.comp_width;
     const size_t out_w = encode ? (size_t)m->desc.comp_width : (size_t)m->desc.out_width * 3;
@@ -691,6 +704,11 @@ static int run_ex(cm_modem *m, bool encode, const cm_window *win, const uint8_t 
         int rc = encode ? dispatch_encode<T>(m, part, (cudaStream_t)stream)
                         : dispatch_decode<T>(m, part, mode, (cudaStream_t)stream);
         if (rc) return rc;
+    }
+    if (guard) {
+        CUDA_TRY(cudaEventRecord(m->last_use, (cudaStream_t)stream));
+        m->last_stream = (cudaStream_t)stream;
+        m->used = true;
     }
     return CM_OK;
 }

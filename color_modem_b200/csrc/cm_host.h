@@ -54,6 +54,11 @@ struct cm_modem {
     int aux_slot = 0;
     // two-pass decoders, device-resident calls: pass 2 (HBM-bound) of chunk i runs on s2 under pass 1 (issue-bound) of
     // chunk i + 1; ev_p1[b] = planes of buffer b written, ev_p2[b] = planes of buffer b consumed
+    // a handle's scratch is shared by its device-resident calls: a call on another stream than the previous one first
+    // waits for that one (event recorded after every call), so consecutive calls never race on the scratch
+    cudaStream_t last_stream = nullptr;
+    cudaEvent_t last_use = nullptr;
+    bool used = false;
     cudaStream_t s2 = nullptr;
     cudaEvent_t ev_p1[2] = {nullptr, nullptr}, ev_p2[2] = {nullptr, nullptr};
     struct Ev { cudaEvent_t a, b; int id; };

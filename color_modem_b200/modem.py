@@ -33,6 +33,10 @@ class GpuModem(object):
             raise ValueError("precision must be 'fp32' or 'fp64'")
         self.line_config = line_config
         self.precision = precision
+        if line_config.size[0] % 4:
+            # the kernels move four samples per 32-bit / 128-bit access (include/color_modem_b200.h: cm_create)
+            raise NotImplementedError('line widths must be multiples of 4 samples (got %d): the reference accepts any '
+                                      'width, this implementation does not' % line_config.size[0])
         self._handles = {}
         self._enc_mem = None      # per-line protocol memories
         self._dec_mem = None

@@ -99,15 +99,32 @@ def test_decode_chunking_is_invisible(cuda_required, monkeypatch):
     comp = m.encode_frames(torch.from_numpy(rgb).cuda())
     ref = m.decode_frames(comp).cpu().numpy()
     for c in ('64', '50', '1'):
-        monkeypatch.setenv('CM_CHUNK', c)
-        assert np.array_equal(m.decode_frames(comp).cpu().numpy(), ref)
+        monkeypatch.setenv('CM_CHUNK', c)          # tuning knobs are read once per handle: a fresh modem per setting
+        m2 = comb.Simple3DCombModem(ntsc.NtscCombModem(LineConfig((720, 24), LS.NTSC_525)))
+        assert np.array_equal(m2.decode_frames(comp).cpu().numpy(), ref)
+    # line-sequential decoders cut their pairing scratch the same way
+    s1 = comb.ColorAveragingModem(secam.SecamModem(LineConfig((720, 24), LS.GERBER_625)))
+    monkeypatch.delenv('CM_CHUNK')
+    sref = comb.ColorAveragingModem(secam.SecamModem(LineConfig((720, 24), LS.GERBER_625)))
+    c24 = sref.encode_frames(torch.from_numpy(rgb[:23]).cuda())
+    want = sref.decode_frames(c24).cpu().numpy()
+    monkeypatch.setenv('CM_CHUNK', '5')
+    s1 = comb.ColorAveragingModem(secam.SecamModem(LineConfig((720, 24), LS.GERBER_625)))
+    assert np.array_equal(s1.decode_frames(c24).cpu().numpy(), want)
 
 
 def test_unsupported_width_is_a_clean_error(cuda_required):
-    import torch
-    m = pal.PalDModem(LineConfig((722, 24), LS.GERBER_625))        # not a multiple of 4
-    with pytest.raises((RuntimeError, ValueError, NotImplementedError)):
-        m.encode_frames(torch.zeros((1, 24, 722, 3), dtype=torch.uint8, device='cuda'))
+    """Line widths must be multiples of 4 samples (the reference accepts any): refused when the modem is constructed,
+    and by cm_create for callers of the C ABI."""
+    import ctypes as C
+    from color_modem_b200 import _native as N
+    with pytest.raises(NotImplementedError):
+        pal.PalDModem(LineConfig((722, 24), LS.GERBER_625))
+    d = pal.PalDModem(LineConfig((720, 24), LS.GERBER_625)).describe()
+    d.width = d.comp_width = d.out_width = 722
+    ptr = C.c_void_p()
+    assert N.load().cm_create(C.byref(d), N.FP32, C.byref(ptr)) != 0
+    assert b'multiples of 4' in N.load().cm_last_error()
 
 
 @pytest.mark.parametrize('kind', ['niir', 'niir_hue'])
