@@ -57,7 +57,7 @@ def parse():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--workload', default='pald576', choices=['pald576', 'ntsc3d600', 'sweep1080'])
     ap.add_argument('--cpu-frames', type=int, default=0, help='frames per worker in the CPU sample (0 = 8)')
-    ap.add_argument('--e2e-frames', type=int, default=256, help='frames per host batch of the end-to-end measurement')
+    ap.add_argument('--e2e-frames', type=int, default=512, help='frames per host batch of the end-to-end measurement')
     ap.add_argument('--e2e-seconds', type=float, default=1.5, help='target length of each end-to-end timed region')
     ap.add_argument('--no-extras', action='store_true', help='skip the short runs of the other BASELINE configs')
     ap.add_argument('--no-cpu', action='store_true', help='skip the CPU baseline beside the GPU number')

@@ -24,7 +24,7 @@ void cm_count_launch();
 struct cm_tune {
     bool onepass = false;      // legacy multi-row halo kernels instead of the two-pass row kernels
     bool rows_v1 = false;      // first-generation pass-1 kernel (k_qam_rows)
-    int rpc = 2;               // rows a CTA of the row kernels walks through (the next one prefetched)
+    int rpc = 0;               // rows a CTA of the row kernels walks through (the next one prefetched); 0 = cm_rows_per_cta decides
     int chunk = 0;             // frames per pass-1 / pass-2 launch pair (0: as many as a 2 GiB scratch holds)
     int host_chunk = 16;       // frames per host<->device chunk of the *_host entry points
     int rows_max = 0;          // upper bound of rows per CTA of the multi-row kernels (0: none)
@@ -92,6 +92,13 @@ struct LaunchTimer {
         }
     }
 };
+
+// Rows per CTA of the one-row-at-a-time kernels: 2 for throughput (the next row's global load overlaps the current row),
+// 1 when the launch is small (a single frame: twice the CTAs, half the latency — tools/latency.py).
+static inline int cm_rows_per_cta(const cm_modem *m, long long rows_in_launch) {
+    if (m->tune.rpc > 0) return m->tune.rpc;
+    return rows_in_launch < 8LL * m->sm_count * 2 ? 1 : 2;
+}
 
 template <typename T> inline const DevParams<T> &params_of(const cm_modem *m);
 template <> inline const DevParams<float> &params_of<float>(const cm_modem *m) { return m->pf; }

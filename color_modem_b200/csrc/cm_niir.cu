@@ -71,7 +71,7 @@ int proto_encode(cm_modem *m, IoArgs<T> io, cudaStream_t st) {
         if (b2 <= (size_t)m->smem_optin) {
             int rc = set_smem(kern, b2);
             if (rc) return rc;
-            const int rpc = m->tune.rpc, nf = (io.out_count + 1) >> 1;
+            const int rpc = cm_rows_per_cta(m, (long long)io.out_count * io.nframes), nf = (io.out_count + 1) >> 1;
             {
                 LaunchTimer lt(m, CM_K_ENCODE, st);
                 kern<<<dim3((unsigned)((nf + rpc - 1) / rpc), 2u, (unsigned)io.nframes), p.row_geo == 1 ? 128 : 256, b2, st>>>(p, io);
@@ -120,7 +120,7 @@ int proto_decode(cm_modem *m, IoArgs<T> io, cudaStream_t st) {
         a.out_begin = c.out_begin >= 2 ? c.out_begin - 2 : 0;
         a.out_count = c.out_begin + c.out_count - a.out_begin;
         if (rows2) {
-            const int rpc = m->tune.rpc;
+            const int rpc = cm_rows_per_cta(m, (long long)a.out_count * c.nframes);
             {
                 LaunchTimer lt(m, CM_K_DECODE_OTHER, st);
                 kern<<<dim3((unsigned)((a.out_count + rpc - 1) / rpc), 1u, (unsigned)c.nframes), p.row_geo == 1 ? 128 : 256, b2, st>>>(p, a);

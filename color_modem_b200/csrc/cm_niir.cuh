@@ -407,11 +407,11 @@ k_niir_decode2(const __grid_constant__ DevParams<T> p, const __grid_constant__ I
         __syncthreads();
         fir_up3(A, A + hb, A + 2 * hb, c, W, hup, threadIdx.x, NT);
         __syncthreads();
-        warp_fill_tail<T, 3>(A, hb, n3, fbp.npad);                  // every warp writes the same values
+        warp_fill_tail<T, 3>(A, hb, n3, iir_tail_end(fbp));         // every warp writes the same values
         team_iir_pk<T, 3, L3, NW>(p.tab + fbp.off, fbp, LoadPoly3<T, L3, false>{A, hb}, Poly3Out<T>{pm, hb}, warp, 1, scratch);
         __syncthreads();
         if (synthetic) continue;
-        warp_fill_tail<T, 3>(pm, hb, n3, flp.npad);
+        warp_fill_tail<T, 3>(pm, hb, n3, iir_tail_end(flp));
         team_iir_pk<T, 3, L3, NW>(p.tab + flp.off, flp, LoadPoly3<T, L3, true>{pm, hb}, Poly3Out<T>{A, hb}, warp, 1, scratch);
         __syncthreads();
         for (int q = 4 * threadIdx.x; q < W; q += 4 * NT) {          // saturation at 1x; carrier = band-passed / envelope

@@ -209,7 +209,7 @@ k_proto_decode2(const __grid_constant__ DevParams<T> p, const __grid_constant__ 
         if (pref && row + (int)gridDim.x < end) pf.fetch(io, f, row + gridDim.x, W);
         fir_up3(u, u + hb, u + 2 * hb, c, W, hup, threadIdx.x, NT);
         __syncthreads();
-        warp_fill_tail<T, 3>(u, hb, n3, fbp.npad > fbs.npad ? fbp.npad : fbs.npad);       // every warp writes the same values
+        warp_fill_tail<T, 3>(u, hb, n3, max(iir_tail_end(fbp), iir_tail_end(fbs)));       // every warp writes the same values
         if (task == 0)
             team_iir_pk<T, 3, L3, TH, true>(p.tab + fbp.off, fbp, LoadPoly3<T, L3, false>{u, hb}, Poly3Out<T>{b, hb}, wr, 2, scratch);
         else
@@ -217,7 +217,7 @@ k_proto_decode2(const __grid_constant__ DevParams<T> p, const __grid_constant__ 
                                             scratch + 32);
         __syncthreads();
         if (task == 0) {                                         // rectifier + low-pass, in place (the team's own barrier
-            warp_fill_tail<T, 3>(b, hb, n3, fpost.npad);         // separates its loads from its stores)
+            warp_fill_tail<T, 3>(b, hb, n3, iir_tail_end(fpost));  // separates its loads from its stores)
             team_iir_pk<T, 3, L3, TH>(p.tab + fpost.off, fpost, LoadPoly3<T, L3, true>{b, hb}, Poly3Out<T>{b, hb}, wr, 2, scratch);
         }
         __syncthreads();
@@ -321,11 +321,11 @@ k_proto_encode_row2(const __grid_constant__ DevParams<T> p, const __grid_constan
         }
         if (task == 0) {
             if (luma_filter) {                                   // luma band-stop at 3x, in place
-                warp_fill_tail<T, 3>(u, hb, n3, fbs.npad);
+                warp_fill_tail<T, 3>(u, hb, n3, iir_tail_end(fbs));
                 team_iir_pk<T, 3, L3, TH>(p.tab + fbs.off, fbs, LoadPoly3<T, L3, false>{u, hb}, Poly3Out<T>{u, hb}, wr, 2, scratch);
             }
         } else {                                                 // chroma low-pass at 1x, in place
-            warp_fill_tail<T, 1>(cs, N1, W, fpre.npad);
+            warp_fill_tail<T, 1>(cs, N1, W, iir_tail_end(fpre));
             team_iir_pk<T, 1, L1, TH>(p.tab + fpre.off, fpre, LoadLinear<T, L1>{cs}, [&](int j, T v) { cs[j] = v; }, wr, 3,
                                       scratch + 32);
         }

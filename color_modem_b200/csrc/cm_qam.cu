@@ -50,7 +50,7 @@ int qam_encode(cm_modem *m, IoArgs<T> io, cudaStream_t st) {
             p.enc_geo == 1 ? k_qam_encode_row2<T, 1> : (p.enc_geo == 2 ? k_qam_encode_row2<T, 2> : k_qam_encode_row2<T, 3>);
         int rc1 = set_smem(kern, bytes(1));
         if (rc1) return rc1;
-        const int rpc = m->tune.rpc;
+        const int rpc = cm_rows_per_cta(m, (long long)io.out_count * io.nframes);
         const int nf = (io.out_count + 1) >> 1;
         {
             LaunchTimer lt(m, CM_K_ENCODE, st);
@@ -63,7 +63,7 @@ int qam_encode(cm_modem *m, IoArgs<T> io, cudaStream_t st) {
     if (!teams && io.in_u8 && p.W <= 768 && !m->tune.onepass) {        // one row at a time, next row prefetched
         int rc1 = set_smem(k_qam_encode_row<T>, bytes(1));
         if (rc1) return rc1;
-        const int rpc = m->tune.rpc;
+        const int rpc = cm_rows_per_cta(m, (long long)io.out_count * io.nframes);
         const int nf = (io.out_count + 1) >> 1;
         {
             LaunchTimer lt(m, CM_K_ENCODE, st);
@@ -227,7 +227,7 @@ int launch_rows_pair(cm_modem *m, IoArgs<T> io, cudaStream_t st) {
         if (overlap && nchunks >= 2) CUDA_TRY(cudaStreamWaitEvent(st, m->ev_p2[buf], 0));     // buffer free again
         {
             LaunchTimer lt(m, MODE == PAIR_PALD ? CM_K_PALD : CM_K_COMB, st);
-            const int rpc = m->tune.rpc;     // rows per CTA: the next row is prefetched while one is filtered (1: 7.97, 2: 7.67, 4: 8.15 us/frame)
+            const int rpc = cm_rows_per_cta(m, (long long)a.out_count * c.nframes);     // rows per CTA: the next row is prefetched while one is filtered (1: 7.97, 2: 7.67, 4: 8.15 us/frame)
             pass1<<<dim3((unsigned)((a.out_count + rpc - 1) / rpc), 1u, (unsigned)c.nframes), threads1, b1, st>>>(p, a);
         }
         cm_count_launch();

@@ -294,7 +294,7 @@ k_qam_encode_row2(const __grid_constant__ DevParams<T> p, const __grid_constant_
         if (k + (int)gridDim.x < nout) fetch(first + 2 * (k + gridDim.x));       // in flight during the filtering
         {
             T *buf = task ? vs : us;
-            warp_fill_tail<T, 1>(buf, N1, W, fpre.npad);          // every warp of the team writes the same values
+            warp_fill_tail<T, 1>(buf, N1, W, iir_tail_end(fpre));  // every warp of the team writes the same values
             team_iir_pk<T, 1, EG::PRE, TH>(p.tab + fpre.off, fpre, LoadLinear<T, EG::PRE>{buf}, [&](int j, T x) { buf[j] = x; },
                                            wr, 2 + task, scratch + 32 * task);
         }
@@ -778,7 +778,7 @@ k_qam_rows2(const __grid_constant__ DevParams<T> p, const __grid_constant__ IoAr
         fir_up2(g, g + hb, cb, W, hup, threadIdx.x, blockDim.x);
         __syncthreads();
         // band-pass in place, all warps
-        warp_fill_tail<T, 2>(g, hb, W2, fb.npad);                   // every warp writes the same values
+        warp_fill_tail<T, 2>(g, hb, W2, iir_tail_end(fb));          // every warp writes the same values
         team_iir_pk<T, 2, RL::BP, NW>(p.tab + fb.off, fb, LoadPoly2<T, RL::BP>{g, g + hb}, Poly2Out<T>{g, g + hb}, warp, 1,
                                       scratch);
         __syncthreads();
@@ -789,7 +789,7 @@ k_qam_rows2(const __grid_constant__ DevParams<T> p, const __grid_constant__ IoAr
             __syncthreads();
         }
         {   // a' = LP(sin(theta) X) by team 0, b' = LP(cos(theta) X) by team 1
-            warp_fill_tail<T, 2>(g, hb, W2, fl.npad);
+            warp_fill_tail<T, 2>(g, hb, W2, iir_tail_end(fl));
             T *de = task ? wb : wa;
             const T *ct = p.ctab + (size_t)task * fl.npad;
             if (fl.L == RL::LPA)
@@ -821,7 +821,7 @@ k_qam_rows2(const __grid_constant__ DevParams<T> p, const __grid_constant__ IoAr
         __syncthreads();
         {   // alpha = LPpre(a) by team 0, beta = LPpre(b) by team 1
             T *src = task ? sb : cb, *out = task ? wb : wa;
-            warp_fill_tail<T, 1>(src, N1, W, fpre.npad);
+            warp_fill_tail<T, 1>(src, N1, W, iir_tail_end(fpre));
             team_iir_pk<T, 1, RL::PRE, TH>(p.tab + fpre.off, fpre, LoadLinear<T, RL::PRE>{src}, [&](int j, T x) { out[j] = x; },
                                            wr, 2 + task, scratch + 32 + 32 * task);
         }

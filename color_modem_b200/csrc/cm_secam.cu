@@ -12,7 +12,7 @@ int secam_encode(cm_modem *m, IoArgs<T> io, cudaStream_t st) {
         const size_t b2 = (128 + 2 * (size_t)p.n1p) * sizeof(T);
         int rc2 = set_smem(kern, b2);
         if (rc2) return rc2;
-        const int rpc = m->tune.rpc, nf = (io.out_count + 1) >> 1;
+        const int rpc = cm_rows_per_cta(m, (long long)io.out_count * io.nframes), nf = (io.out_count + 1) >> 1;
         {
             LaunchTimer lt(m, CM_K_ENCODE, st);
             kern<<<dim3((unsigned)((nf + rpc - 1) / rpc), 2u, (unsigned)io.nframes), p.row_geo == 1 ? 64 : 128, b2, st>>>(p, io);
@@ -83,7 +83,7 @@ int secam_decode(cm_modem *m, IoArgs<T> io, cudaStream_t st) {
         {
             LaunchTimer lt(m, CM_K_DECODE_OTHER, st);
             if (rows2) {
-                const int rpc = m->tune.rpc;
+                const int rpc = cm_rows_per_cta(m, (long long)a.out_count * c.nframes);
                 row_kernel<<<dim3((unsigned)((a.out_count + rpc - 1) / rpc), 1u, (unsigned)c.nframes), p.row_geo == 1 ? 64 : 128,
                              b2, st>>>(p, a);
             } else {

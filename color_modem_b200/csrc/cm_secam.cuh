@@ -384,7 +384,7 @@ k_secam_decode2(const __grid_constant__ DevParams<T> p, const __grid_constant__ 
         else load_comp_row(c, io, f, row, W);
         __syncthreads();
         if (pref && row + (int)gridDim.x < end) pf.fetch(io, f, row + gridDim.x, W);
-        for (int i = threadIdx.x; i < fbp.npad; i += NT) {          // warm-up prefix + composite + replicated tail
+        for (int i = threadIdx.x; i < iir_tail_end(fbp); i += NT) {   // warm-up prefix + composite + replicated tail
             T v;
             if (i < pre) v = c[pre - i];                     // flip(composite[1 : W/40])
             else if (i < ncc) v = c[i - pre];
@@ -393,7 +393,7 @@ k_secam_decode2(const __grid_constant__ DevParams<T> p, const __grid_constant__ 
         }
         __syncthreads();
         if (task == 0) {                                     // A: luma band-stop, in place
-            warp_fill_tail<T, 1>(c, N1, W, fbs.npad);
+            warp_fill_tail<T, 1>(c, N1, W, iir_tail_end(fbs));
             team_iir_pk<T, 1, SG::L1, TH>(p.tab + fbs.off, fbs, LoadLinear<T, SG::L1>{c}, [&](int j, T v) { c[j] = v; }, wr, 2,
                                           scratch);
         } else {                                             //    chroma band-pass, in place
@@ -403,7 +403,7 @@ k_secam_decode2(const __grid_constant__ DevParams<T> p, const __grid_constant__ 
         __syncthreads();
         if (p.flags & 64) {                                  // B: anti-bell
             if (task == 1) {
-                warp_fill_tail<T, 1>(cc, N1, ncc, fbell.npad);
+                warp_fill_tail<T, 1>(cc, N1, ncc, iir_tail_end(fbell));
                 team_iir_pk<T, 1, SG::L1, TH>(p.tab + fbell.off, fbell, LoadLinear<T, SG::L1>{cc}, [&](int j, T v) { cc[j] = v; },
                                               wr, 3, scratch + 32);
             }
@@ -414,7 +414,7 @@ k_secam_decode2(const __grid_constant__ DevParams<T> p, const __grid_constant__ 
         fir_up2(u2, u2 + hb, cc, ncc4, hup, threadIdx.x, NT);                 // C
         __syncthreads();
         {                                                    // D: I (cos, team 0) || Q (sin, team 1)
-            warp_fill_tail<T, 2>(u2, hb, n2, flp.npad);      // every warp writes the same values
+            warp_fill_tail<T, 2>(u2, hb, n2, iir_tail_end(flp)); // every warp writes the same values
             T *de = task ? q2 : u2;
             const T *ct = p.ctab + (task ? 0 : (size_t)flp.npad);
             team_iir_pk<T, 2, SG::L2, TH, true>(p.tab + flp.off, flp, LoadPoly2Carrier<T, SG::L2>{u2, u2 + hb, ct, 32 * TH},
@@ -473,7 +473,7 @@ k_secam_decode2(const __grid_constant__ DevParams<T> p, const __grid_constant__ 
         __syncthreads();
         if (p.flags & 128) {                                 // F: de-emphasis
             if (task == 1) {
-                warp_fill_tail<T, 1>(cc, N1, W, fde.npad);
+                warp_fill_tail<T, 1>(cc, N1, W, iir_tail_end(fde));
                 team_iir_pk<T, 1, SG::L1, TH>(p.tab + fde.off, fde, LoadLinear<T, SG::L1>{cc}, [&](int j, T v) { cc[j] = v; }, wr,
                                               3, scratch + 32);
             }
@@ -596,12 +596,12 @@ k_secam_encode_row2(const __grid_constant__ DevParams<T> p, const __grid_constan
         __syncthreads();
         if (k + (int)gridDim.x < nout) fetch(first + 2 * (k + gridDim.x));       // in flight during the rest of the row
         // chroma low-pass (+ LF pre-emphasis): one short task, run by all the warps as one team
-        warp_fill_tail<T, 1>(cs, N1, W, fpre.npad);
+        warp_fill_tail<T, 1>(cs, N1, W, iir_tail_end(fpre));
         team_iir_pk<T, 1, EG::L1, NW>(p.tab + fpre.off, fpre, LoadLinear<T, EG::L1>{cs}, [&](int j, T v) { cs[j] = v; }, warp, 2,
                                       scratch);
         __syncthreads();
         if (p.flags & 128) {
-            warp_fill_tail<T, 1>(cs, N1, W, femph.npad);
+            warp_fill_tail<T, 1>(cs, N1, W, iir_tail_end(femph));
             team_iir_pk<T, 1, EG::L1, NW>(p.tab + femph.off, femph, LoadLinear<T, EG::L1>{cs}, [&](int j, T v) { cs[j] = v; }, warp,
                                           2, scratch);
             __syncthreads();

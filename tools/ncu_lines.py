@@ -42,6 +42,12 @@ def main():
     raw = subprocess.run(['ncu', '-i', rep, '--page', 'source', '--print-source', 'sass', '--csv'], capture_output=True,
                          text=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
+    # a report may hold several kernels: take the first section whose kernel name matches (demangled name of `pat`'s stem)
+    stem = re.sub(r'I[A-Za-z0-9_]*$', '', pat)
+    starts = [i for i, r in enumerate(rows) if r and r[0] == 'Kernel Name']
+    pick = next((i for i in starts if stem in rows[i][1].replace(' ', '')), starts[0])
+    end = next((i for i in starts if i > pick), len(rows))
+    rows = rows[pick:end]
     hdr = rows[1]
     ai, ci, ni = hdr.index('Address'), hdr.index('Instructions Executed'), hdr.index('# Samples')
     base = None
