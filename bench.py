@@ -434,7 +434,7 @@ def run_pald(args, D, cpu_line):
     launches = (N.launch_count() - launches0) * args.steps // (args.steps + warmup)
     clocks = sampler.stop(t_begin, t_end) if D.rank == 0 else None
 
-    # ---- per-kernel device time (CUDA events around every launch), as run (pass 2 overlapped with pass 1) -------------
+    # ---- per-kernel device time (CUDA events around every launch), as run -----------------------------------------------
     modem.timing(True)
     D.barrier()
     ksteps = 3
@@ -445,7 +445,7 @@ def run_pald(args, D, cpu_line):
             (('encode', N.K_ENCODE), ('bandsplit_top_rows', N.K_BANDSPLIT), ('pald_rows', N.K_PALD),
              ('combine', N.K_DECODE_OTHER))}
     modem.timing(False)
-    # the same on a handle without the overlap: every kernel alone on the chip
+    # the same on a handle with the optional pass-1 / pass-2 overlap forced off: every kernel alone on the chip
     os.environ['CM_OVERLAP'] = '0'
     serial = make()
     serial._handle()
@@ -547,8 +547,8 @@ def run_pald(args, D, cpu_line):
                          'peak_source': peak_src,
                          'algorithmic_bytes_per_launch': fpl * DECODE_BYTES_PER_FRAME,
                          'frames_per_launch': fpl, 'avg_launch_ms': rows_ms,
-                         'timing': 'CUDA events on the launch stream around every launch, %d steps right after the timed '
-                                   'region; pass 2 of the previous chunk runs concurrently on a second stream' % ksteps,
+                         'timing': 'CUDA events on the launch stream around every launch of the kernel, over %d steps run '
+                                   'right after the timed region (same buffers, same launches)' % ksteps,
                          'alone_on_the_chip': {'avg_launch_ms': rows_serial_ms, 'frames_per_launch': fpl_serial,
                                                'achieved': achieved_serial, 'frac': achieved_serial / peak},
                          'kernel_ms_per_step': ksum, 'kernel_ms_per_step_serial': ksum_serial,
@@ -556,7 +556,7 @@ def run_pald(args, D, cpu_line):
                                                          for k, v in ksum_serial.items()},
                          'whole_chain_frac': fps / D.world * BYTES_PER_FRAME / 1e9 / peak,
                          'note': 'the decode chain is bound by instruction issue and the FP32 pipe, not by HBM: see '
-                                 'roofline_fma and profiles/r2_rows2_pald_summary.md'},
+                                 'roofline_fma and profiles/r2_pald_summary.md'},
             'roofline_fma': {'bound': 'fp32 multiply-add', 'peak': tfma, 'unit': 'TFMA/s',
                              'peak_source': 'measured live (cm_measure_fma_peak: packed FFMA2, uniform operands, all SMs)',
                              'mac_per_pixel': MAC_PER_PIXEL['pald576'],
