@@ -160,6 +160,9 @@ int cm_sizeof_desc(void);
 const char *cm_last_error(void);
 int cm_device_info(int *sm_count, int *cc_major, int *cc_minor);
 
+/* Line widths (width, comp_width, out_width) must be multiples of 4 samples and frame pointers 4-byte aligned: the kernels
+ * move four samples per 32-bit / 96-bit / 128-bit access.  (The reference accepts any width: image.py:27-84.)  The tuning
+ * knobs of a handle are read from the environment here, once. */
 int cm_create(const cm_desc *desc, int precision, cm_modem **out);
 void cm_destroy(cm_modem *m);
 
