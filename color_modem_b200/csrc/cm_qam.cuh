@@ -747,8 +747,11 @@ template <> struct RowL<3> { static constexpr int NW = 4, BP = 34, LPA = 62, LPB
 #define QF_ROW_LP 7      // QF_PALD_LP, QF_PRE_LP; chunk lengths and tables for its team geometry, built in cm_api.cu)
 #define QF_ROW_PRE 8
 
+#ifndef CM_ROWS2_MINB
+#define CM_ROWS2_MINB 8        // CTAs per SM of the 2-warp geometry (128 registers per thread); 9 / 10 are A/B variants
+#endif
 template <typename T, bool PALD, int GEO>
-__global__ void __launch_bounds__(32 * RowL<GEO>::NW, sizeof(T) == 8 ? 1 : 16 / RowL<GEO>::NW)
+__global__ void __launch_bounds__(32 * RowL<GEO>::NW, sizeof(T) == 8 ? 1 : (RowL<GEO>::NW == 2 ? CM_ROWS2_MINB : 4))
 k_qam_rows2(const __grid_constant__ DevParams<T> p, const __grid_constant__ IoArgs<T> io) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     T *scratch = reinterpret_cast<T *>(smem_raw), *sm = scratch + 128;      // [0, 128): team exchange
@@ -1019,8 +1022,11 @@ __device__ __forceinline__ void pair_uv(const PairCoef<T> &k, bool hp, bool hn, 
     }
 }
 // OUT: 0 = RGB; 1 = (y, u, v) to io.yuv (luma notch follows); 2 = (composite, u, v) to io.yuv with comb.minavg
+#ifndef CM_COMBINE_MINB
+#define CM_COMBINE_MINB 1      // CTAs per SM the compiler must leave room for (tools/variants.sh: register-budget A/B)
+#endif
 template <typename T, int MODE, int OUT>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, sizeof(T) == 4 ? CM_COMBINE_MINB : 1)
 k_qam_combine(const __grid_constant__ DevParams<T> p, const __grid_constant__ IoArgs<T> io) {
     const int W = p.W, W4 = W >> 2;
     const int field = blockIdx.y, f = blockIdx.z;

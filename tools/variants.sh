@@ -10,6 +10,7 @@ while [ $# -ge 2 ]; do
   d=build/variants/$name; mkdir -p $d
   (
     nvcc $FLAGS $defs -c -o $d/api.o color_modem_b200/csrc/cm_api.cu &
+    nvcc $FLAGS $defs -c -o $d/util.o color_modem_b200/csrc/cm_util.cu &
     for t in F32 F64; do
       for f in mac niir secam; do nvcc $FLAGS $defs -DCM_INST_$t -c -o $d/${f}_$t.o color_modem_b200/csrc/cm_$f.cu & done
       for part in 0 1 2; do nvcc $FLAGS $defs -DCM_INST_$t -DCM_QAM_PART=$part -c -o $d/qam_${part}_$t.o color_modem_b200/csrc/cm_qam.cu & done
