@@ -155,6 +155,23 @@ static int plan_encode_kernel(const cm_desc &d, FiltHdr *fh, std::vector<double>
 }
 
 static int plan_row_kernel(const cm_desc &d, FiltHdr *fh, std::vector<double> &tab) {
+    if (d.kind == CM_KIND_QAM_BANDSPLIT) {           // k_qam_bs_row2: one chunk length for its three 2x use-sites
+        const cm_filter &fbp = d.filters[QF_BP2X], &fbs = d.filters[QF_BS2X], &flp = d.filters[QF_DEMOD_LP];
+        if (!fbp.nsec || !fbs.nsec || !flp.nsec) return 0;
+        static const int th[3] = {1, 2, 2}, la[3] = {46, 46, 62}, lb[3] = {50, 50, 66};
+        int need = fbp.n + fbp.shift;
+        if (fbs.n + fbs.shift > need) need = fbs.n + fbs.shift;
+        if (flp.n + flp.shift > need) need = flp.n + flp.shift;
+        for (int k = 0; k < 3; ++k) {
+            const int ll = need <= 32 * th[k] * la[k] ? la[k] : (need <= 32 * th[k] * lb[k] ? lb[k] : 0);
+            if (!ll) continue;
+            build_filter_L(fbp, fh[6], tab, ll, 1, 32 * th[k]);
+            build_filter_L(flp, fh[7], tab, ll, 1, 32 * th[k]);
+            build_filter_L(fbs, fh[8], tab, ll, 1, 32 * th[k]);
+            return k + 1;
+        }
+        return 0;
+    }
     if (d.kind < CM_KIND_NTSC_COMB || d.kind > CM_KIND_PAL_3D) return 0;
     const bool pald = d.kind == CM_KIND_PAL_D ||
                       (d.kind == CM_KIND_PAL_3D && !(d.flags & (CM_FLAG_PAL3D_SIN | CM_FLAG_PAL3D_COS)));

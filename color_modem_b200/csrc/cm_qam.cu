@@ -96,6 +96,23 @@ int launch_bandsplit(cm_modem *m, IoArgs<T> io, int luma_mode, cudaStream_t st) 
     if (!R) R = pick_rows(m, 1, (size_t)m->smem_optin, bytes);
     if (!R) return cm_fail(CM_ERR_UNSUPPORTED, "line too wide for the band-split kernel%s");
     const bool teams = needs_teams(p);
+    if (luma_mode == 0 && p.kind == CM_KIND_QAM_BANDSPLIT && p.row_geo && !m->tune.onepass && !m->tune.rows_v1) {
+        const size_t b2 = (128 + (size_t)p.n1p + 6 * (size_t)p.hb2) * sizeof(T);
+        if (b2 <= (size_t)m->smem_optin) {
+            void (*kern)(const DevParams<T>, const IoArgs<T>) =
+                p.row_geo == 1 ? k_qam_bs_row2<T, 1> : (p.row_geo == 2 ? k_qam_bs_row2<T, 2> : k_qam_bs_row2<T, 3>);
+            int rc2 = set_smem(kern, b2);
+            if (rc2) return rc2;
+            const int rpc = cm_rows_per_cta(m, (long long)io.out_count * io.nframes);
+            {
+                LaunchTimer lt(m, CM_K_BANDSPLIT, st);
+                kern<<<dim3((unsigned)((io.out_count + rpc - 1) / rpc), 1u, (unsigned)io.nframes), p.row_geo == 1 ? 64 : 128, b2, st>>>(p, io);
+            }
+            cm_count_launch();
+            CUDA_TRY(cudaGetLastError());
+            return CM_OK;
+        }
+    }
     if (luma_mode == 0 && !m->tune.onepass) {       // one row per CTA: two IIR tasks, one warp (team) each
         const size_t b1 = (128 + (size_t)p.n1p + 8 * (size_t)p.hb2) * sizeof(T);
         if (b1 <= (size_t)m->smem_optin) {

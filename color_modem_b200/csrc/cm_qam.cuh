@@ -913,6 +913,82 @@ k_qam_bs_row(const __grid_constant__ DevParams<T> p, const __grid_constant__ IoA
     }
 }
 
+// Band-split decode, second generation (k_qam_bs_row2; NtscModem / PalSModem, BASELINE configs[0]): the chain of
+// k_qam_bs_row with the techniques of k_qam_rows2 — packed DF-I teams, band-pass || band-stop and u || v low-pass as task
+// pairs with one of each pair in place, the demodulating carrier from the row-independent table with the row's phase (and
+// the factor 2 of qam.py:50-51) applied as a rotation after the decimation.  One chunk length serves the three use-sites
+// (host: plan_row_kernel).  smem: scratch[128] | cb[N1] | a2[N2] (-> luma) | b2[N2] (-> u) | v2[N2]
+#define QF_BSROW_BP 6        // DevParams::filt slots (kind QAM_BANDSPLIT only; the comb kinds use them for k_qam_rows2)
+#define QF_BSROW_LP 7
+#define QF_BSROW_BS 8
+template <typename T, int GEO, int L>
+__device__ __forceinline__ void bs_row2_body(const DevParams<T> &p, const IoArgs<T> &io, T *scratch, T *sm) {
+    typedef RowL<GEO> RL;
+    constexpr int NW = RL::NW, TH = NW / 2, NT = 32 * NW;
+    const int W = p.W, W2 = 2 * W, N1 = p.n1p, hb = p.hb2, N2 = 2 * hb;
+    const int f = blockIdx.z, end = io.out_begin + io.out_count;
+    const int warp = threadIdx.x >> 5, task = warp / TH, wr = warp - task * TH;
+    T *cb = sm, *a2 = cb + N1, *b2 = a2 + N2, *v2 = b2 + N2;
+    const FirTaps<T> hup{p.firc[QR_UP2], p.fircp[QR_UP2]}, hdn{p.firc[QR_DOWN2], p.fircp[QR_DOWN2]};
+    const FiltHdr &fbp = p.filt[QF_BSROW_BP], &fbs = p.filt[QF_BSROW_BS], &fl = p.filt[QF_BSROW_LP];
+    const long long frame = io.first_frame + f;
+    const bool pre = io.in_u8 != nullptr && W <= 4 * RowPrefetch::kMaxQuads * NT;
+    RowPrefetch pf;
+    int row = io.out_begin + blockIdx.x;
+    if (pre && row < end) pf.fetch(io, f, row, W);
+    for (; row < end; row += gridDim.x) {
+        if (pre) pf.stage(cb, W);
+        else load_comp_row(cb, io, f, row, W);
+        __syncthreads();
+        if (pre && row + (int)gridDim.x < end) pf.fetch(io, f, row + gridDim.x, W);
+        fir_up2(a2, a2 + hb, cb, W, hup, threadIdx.x, NT);
+        __syncthreads();
+        warp_fill_tail<T, 2>(a2, hb, W2, max(iir_tail_end(fbp), iir_tail_end(fbs)));      // every warp writes the same values
+        if (task == 0)                                           // band-pass a2 -> b2 || band-stop a2 -> a2 (= luma at 2x)
+            team_iir_pk<T, 2, L, TH, true>(p.tab + fbp.off, fbp, LoadPoly2<T, L>{a2, a2 + hb}, Poly2Out<T>{b2, b2 + hb}, wr, 2, scratch);
+        else
+            team_iir_pk<T, 2, L, TH, true>(p.tab + fbs.off, fbs, LoadPoly2<T, L>{a2, a2 + hb}, Poly2Out<T>{a2, a2 + hb}, wr, 3,
+                                           scratch + 32);
+        __syncthreads();
+        {   // u' = LP(sin(theta) B) (team 0, over b2) || v' = LP(cos(theta) B) (team 1 -> v2)
+            warp_fill_tail<T, 2>(b2, hb, W2, iir_tail_end(fl));
+            T *de = task ? v2 : b2;
+            const T *ct = p.ctab + (size_t)task * fl.npad;
+            team_iir_pk<T, 2, L, TH, true>(p.tab + fl.off, fl, LoadPoly2Carrier<T, L>{b2, b2 + hb, ct, 32 * TH},
+                                           Poly2Out<T>{de, de + hb}, wr, 2 + task, scratch + 32 * task);
+        }
+        __syncthreads();
+        T sphi, cphi;
+        Real<T>::sincos_turns(start_phase(p, frame, io.y0 + row) + p.phases[QP_BP_SHIFT], sphi, cphi);
+        sphi *= (T)2;                                            // qam.py:50-51: 2 sin, 2 cos
+        cphi *= (T)2;
+        const bool alt = (p.flags & 1) && is_alternate(p, frame, io.y0 + row);
+        for (int j0 = 4 * threadIdx.x; j0 < W; j0 += 4 * NT) {
+            T y[4], a0[4], b0[4], u[4], v[4];
+            down2_quad(hdn, b2, b2 + hb, W, j0, a0);
+            down2_quad(hdn, v2, v2 + hb, W, j0, b0);
+            down2_quad(hdn, a2, a2 + hb, W, j0, y);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                u[i] = Real<T>::fma_(cphi, a0[i], sphi * b0[i]);
+                const T vv = Real<T>::fma_(cphi, b0[i], -(sphi * a0[i]));
+                v[i] = alt ? -vv : vv;
+            }
+            store_rgb4(p, io, f, row, j0, y, u, v);
+        }
+        __syncthreads();
+    }
+}
+
+template <typename T, int GEO>
+__global__ void __launch_bounds__(32 * RowL<GEO>::NW, sizeof(T) == 8 ? 1 : 16 / RowL<GEO>::NW)
+k_qam_bs_row2(const __grid_constant__ DevParams<T> p, const __grid_constant__ IoArgs<T> io) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T *scratch = reinterpret_cast<T *>(smem_raw), *sm = scratch + 128;
+    if (p.filt[QF_BSROW_LP].L == RowL<GEO>::LPA) bs_row2_body<T, GEO, RowL<GEO>::LPA>(p, io, scratch, sm);
+    else bs_row2_body<T, GEO, RowL<GEO>::LPB>(p, io, scratch, sm);
+}
+
 // QamColorModem.extract_chroma (qam.py:34-37) of one row per CTA: E = down2(BP(up2 c)), stored as the first output plane
 // (float output only; the L0 kit call of the drop-in boundary, not on the frame path).
 template <typename T>
