@@ -217,7 +217,7 @@ static int plan_secam_kernel(const cm_desc &d, FiltHdr *fh, std::vector<double> 
         }
         // the row encoder (k_secam_encode_row2): chroma low-pass and LF pre-emphasis sites, same team geometry
         const cm_filter &fp = d.filters[SF_PRE_LP], &fe = d.filters[SF_PRE_EMPH];
-        const int lf[2] = {12, 16}, le[2] = {13, 17}, lanes = 32 * 2 * th[k];      // (SecEncGeo: all warps as one team)
+        const int lf[2] = {13, 15}, le[2] = {13, 17}, lanes = 32 * 2 * th[k];      // (SecEncGeo: all warps as one team)
         if (fp.nsec && fp.n + fp.shift <= lanes * le[k] && (!fe.nsec || fe.n + fe.shift <= lanes * le[k]) &&
             d.width <= lanes * lf[k]) {
             build_filter_L(fp, fh[12], tab, le[k], 1, lanes);

@@ -179,6 +179,8 @@ k_niir_encode(const __grid_constant__ DevParams<T> p, const __grid_constant__ Io
                        [&](int j, T v) { buf[j] = v; });
     }
     __syncthreads();
+    T crs, crc;
+    Real<T>::sincos_turns(p.phases[NP_STEP1X], crs, crc);
     for (int k = 0; k < g.count; ++k) {
         const int row = g.r0 + 2 * k, line = io.y0 + row;
         const T *ys = sm + (size_t)k * 3 * N1, *bs = ys + N1, *rs_ = bs + N1;
@@ -186,16 +188,20 @@ k_niir_encode(const __grid_constant__ DevParams<T> p, const __grid_constant__ Io
         const bool alt = is_alternate(p, g.frame, line);
         for (int q = threadIdx.x; q < W4; q += blockDim.x) {
             const int x = 4 * q;
-            T y[4], db[4], dr[4], o[4];
+            T y[4], db[4], dr[4], o[4], s[4], c[4];
             ld4(ys + x, y);
             ld4(bs + x, db);
             ld4(rs_ + x, dr);
+            // u8 frames: hardware sin / cos seed + three rotations; float frames (parity path): exact per sample
+            if (io.in_u8) {
+                carrier4_fast(ph0 + (unsigned long long)x * p.phases[NP_STEP1X], crs, crc, s, c);
+            } else {
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                T s, c;
-                Real<T>::sincos_turns(ph0 + (unsigned long long)(x + i) * p.phases[NP_STEP1X], s, c);
-                o[i] = y[i] + (alt ? -Real<T>::sqrt_(db[i] * db[i] + dr[i] * dr[i]) * s : db[i] * s + dr[i] * c);
+                for (int i = 0; i < 4; ++i) Real<T>::sincos_turns(ph0 + (unsigned long long)(x + i) * p.phases[NP_STEP1X], s[i], c[i]);
             }
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                o[i] = y[i] + (alt ? -Real<T>::sqrt_(db[i] * db[i] + dr[i] * dr[i]) * s[i] : db[i] * s[i] + dr[i] * c[i]);
             store_comp4(io, ((size_t)g.fidx * io.nrows + row) * p.Wc + x, o);
         }
     }

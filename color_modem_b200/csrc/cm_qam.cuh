@@ -1098,11 +1098,14 @@ __device__ __forceinline__ void pair_uv(const PairCoef<T> &k, bool hp, bool hn, 
     }
 }
 // OUT: 0 = RGB; 1 = (y, u, v) to io.yuv (luma notch follows); 2 = (composite, u, v) to io.yuv with comb.minavg
-#ifndef CM_COMBINE_MINB
-#define CM_COMBINE_MINB 1      // CTAs per SM the compiler must leave room for (tools/variants.sh: register-budget A/B)
-#endif
+// (no minimum-blocks bound: with one the compiler spends registers freely and the 3-line modes lose an occupancy step —
+// 2.22 vs 1.90 us/frame; CM_COMBINE_MINB is the A/B hook of tools/variants.sh)
 template <typename T, int MODE, int OUT>
+#ifdef CM_COMBINE_MINB
 __global__ void __launch_bounds__(128, sizeof(T) == 4 ? CM_COMBINE_MINB : 1)
+#else
+__global__ void __launch_bounds__(128)
+#endif
 k_qam_combine(const __grid_constant__ DevParams<T> p, const __grid_constant__ IoArgs<T> io) {
     const int W = p.W, W4 = W >> 2;
     const int field = blockIdx.y, f = blockIdx.z;

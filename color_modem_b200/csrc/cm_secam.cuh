@@ -503,8 +503,10 @@ k_secam_decode2(const __grid_constant__ DevParams<T> p, const __grid_constant__ 
 #define SF_ENC_PRE 12        // DevParams::filt slots (cm_api.cu: plan_secam_kernel)
 #define SF_ENC_EMPH 13
 template <int GEO> struct SecEncGeo;
-template <> struct SecEncGeo<1> { static constexpr int NW = 2, KQ = 3, L1 = 13, LF = 12; };
-template <> struct SecEncGeo<3> { static constexpr int NW = 4, KQ = 4, L1 = 17, LF = 16; };
+// (LF odd: lane t of the FM synthesis starts at sample t * LF — an odd stride keeps the 32 lanes on 32 banks; 12 and 16
+// measured 4- and 16-way conflicts, 47 M per 16 frames of 1920x1080)
+template <> struct SecEncGeo<1> { static constexpr int NW = 2, KQ = 3, L1 = 13, LF = 13; };
+template <> struct SecEncGeo<3> { static constexpr int NW = 4, KQ = 4, L1 = 17, LF = 15; };
 
 
 template <typename T>
