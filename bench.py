@@ -280,6 +280,9 @@ class Dist(object):
             dist.init_process_group('nccl', device_id=torch.device('cuda', self.local))
         torch.cuda.set_device(self.local)
         self.dev = torch.device('cuda', self.local)
+        # host threads and pinned staging buffers of this rank on the NUMA node of its GPU (no-op where sysfs does not say)
+        from color_modem_b200.shard import bind_to_gpu_numa_node
+        self.numa_node = bind_to_gpu_numa_node(self.local)
 
     def barrier(self):
         if self.world > 1:
@@ -533,6 +536,7 @@ def run_pald(args, D, cpu_line):
                                   'api': 'ImageModem.transcode_batch (cm_transcode_frames_host): one call, composite handed '
                                          'over in device memory and copied out too',
                                   'h2d_bytes_per_step': Fe * 3 * W * H, 'd2h_bytes_per_step': d2h},
+                    'numa_node_of_rank0': D.numa_node,
                     'copy_peak': dict(link, min_over_ranks_both_each_way_gbs=-link_min,
                                       how='bare pinned cudaMemcpyAsync of 256 MiB, H2D alone / D2H alone / both at once'),
                     'achieved_each_way_gbs': e2e['pipelined']['frames_per_s'] / D.world * (h2d / Fe) / 1e9,

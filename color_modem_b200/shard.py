@@ -48,3 +48,42 @@ def process_sharded(total_frames, work, rank=None, world_size=None, gather=False
         b, e = frame_range(total_frames, r, world_size)
         keep.append(parts[r][:e - b])
     return torch.cat(keep, dim=0)
+
+
+def bind_to_gpu_numa_node(device_index):
+    """Restrict this process to the CPUs of the NUMA node its GPU hangs off (Linux sysfs; a no-op when that cannot be
+    determined).  Call it before allocating pinned staging buffers: first touch then places them on that node, so the
+    host<->device copies of the host entry points do not cross the inter-socket link.  Returns the node or None."""
+    import os
+    try:
+        import torch
+        bus = torch.cuda.get_device_properties(device_index).pci_bus_id      # torch >= 2.x: 'domain:bus:device.function'
+    except Exception:                                                       # noqa: BLE001
+        bus = None
+    try:
+        if not isinstance(bus, str):
+            import ctypes
+            rt = ctypes.CDLL('libcudart.so')
+            buf = ctypes.create_string_buffer(32)
+            if rt.cudaDeviceGetPCIBusId(buf, 32, int(device_index)) != 0:
+                return None
+            bus = buf.value.decode()
+        bus = bus.lower()
+        if len(bus.split(':')[0]) > 4:
+            bus = bus[-12:]                                                  # sysfs uses a 4-digit domain
+        with open('/sys/bus/pci/devices/%s/numa_node' % bus) as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return None
+        with open('/sys/devices/system/node/node%d/cpulist' % node) as f:
+            cpus = set()
+            for part in f.read().strip().split(','):
+                lo, _, hi = part.partition('-')
+                cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = cpus & set(os.sched_getaffinity(0))
+        if not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return node
+    except Exception:                                                       # noqa: BLE001
+        return None
