@@ -1,6 +1,6 @@
 """Dynamic SASS opcode mix of the kernel in an ncu report (--set full --import-source on).
 
-    python tools/ncu_opmix.py gpurun_out/prof.ncu-rep [rows]     # rows: units of work to normalise by
+    python tools/ncu_opmix.py gpurun_out/prof.ncu-rep [rows] [kernel-name-substring]     # rows: units of work to normalise by
 
 Reads `ncu --page source --print-source sass --csv` and sums "Instructions Executed" (warp level) and the stall samples per opcode."""
 import collections
@@ -17,6 +17,10 @@ def main():
     raw = subprocess.run(['ncu', '-i', rep, '--page', 'source', '--print-source', 'sass', '--csv'], capture_output=True,
                          text=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
+    pat = sys.argv[3] if len(sys.argv) > 3 else ''
+    starts = [i for i, r in enumerate(rows) if r and r[0] == 'Kernel Name']         # a report may hold several kernels
+    pick = next((i for i in starts if pat in rows[i][1]), starts[0])
+    rows = rows[pick:next((i for i in starts if i > pick), len(rows))]
     hdr = rows[1]
     ci, si, ni = hdr.index('Instructions Executed'), hdr.index('Source'), hdr.index('# Samples')
     ops, samp = collections.Counter(), collections.Counter()
