@@ -440,6 +440,7 @@ extern "C" int cm_create(const cm_desc *desc, int precision, cm_modem **out) {
         m->tune.rpc = env_int("CM_RPC", m->tune.rpc);
         m->tune.chunk = env_int("CM_CHUNK", m->tune.chunk);
         m->tune.host_chunk = env_int("CM_HOST_CHUNK", m->tune.host_chunk);
+        if (const char *e = getenv("CM_HOST_ROLES")) m->tune.host_roles = atoi(e);
         m->tune.rows_max = env_int("CM_ROWS_MAX", m->tune.rows_max);
         m->tune.min_warps = env_int("CM_MIN_WARPS", m->tune.min_warps);
         if (const char *e = getenv("CM_OVERLAP")) m->tune.overlap = atoi(e);
@@ -549,10 +550,16 @@ extern "C" void cm_destroy(cm_modem *m) {
         if (m->ev_p1[i]) cudaEventDestroy(m->ev_p1[i]);
         if (m->ev_p2[i]) cudaEventDestroy(m->ev_p2[i]);
     }
-    for (int i = 0; i < cm_modem::kHostStreams; ++i) {
+    for (int i = 0; i < cm_modem::kHostBufs; ++i) {
         cudaFree(m->d_in[i]);
         cudaFree(m->d_out[i]);
         cudaFree(m->d_mid[i]);
+        if (m->ev_in[i]) cudaEventDestroy(m->ev_in[i]);
+        if (m->ev_k[i]) cudaEventDestroy(m->ev_k[i]);
+        if (m->ev_mid[i]) cudaEventDestroy(m->ev_mid[i]);
+        if (m->ev_out[i]) cudaEventDestroy(m->ev_out[i]);
+    }
+    for (int i = 0; i < cm_modem::kHostStreams; ++i) {
         if (m->hs[i]) cudaStreamDestroy(m->hs[i]);
     }
     for (int i = 0; i < 12; ++i) cudaFree(m->d_aux[i]);
@@ -780,12 +787,70 @@ static int run_host(cm_modem *m, int what, const uint8_t *in, uint8_t *out, uint
     CUDA_TRY(cudaSetDevice(m->device));
     int chunk = m->tune.host_chunk;
     if (chunk > nframes) chunk = nframes;
-    for (int s = 0; s < cm_modem::kHostStreams; ++s) {
+    for (int s = 0; s < cm_modem::kHostStreams; ++s)
         if (!m->hs[s]) CUDA_TRY(cudaStreamCreateWithFlags(&m->hs[s], cudaStreamNonBlocking));
-        int rc = ensure(&m->d_in[s], &m->in_cap[s], (size_t)chunk * in_frame);
-        if (!rc) rc = ensure(&m->d_out[s], &m->out_cap[s], (size_t)chunk * out_frame);
-        if (!rc && what == 2) rc = ensure(&m->d_mid[s], &m->mid_cap[s], (size_t)chunk * mid_frame);
+    const bool roles = m->tune.host_roles < 0 ? what == 2 : m->tune.host_roles != 0;
+    const int nbuf = roles ? cm_modem::kHostBufs : cm_modem::kHostStreams;
+    for (int b = 0; b < nbuf; ++b) {
+        int rc = ensure(&m->d_in[b], &m->in_cap[b], (size_t)chunk * in_frame);
+        if (!rc) rc = ensure(&m->d_out[b], &m->out_cap[b], (size_t)chunk * out_frame);
+        if (!rc && what == 2) rc = ensure(&m->d_mid[b], &m->mid_cap[b], (size_t)chunk * mid_frame);
         if (rc) return rc;
+        if (!m->ev_in[b]) {
+            CUDA_TRY(cudaEventCreateWithFlags(&m->ev_in[b], cudaEventDisableTiming));
+            CUDA_TRY(cudaEventCreateWithFlags(&m->ev_k[b], cudaEventDisableTiming));
+            CUDA_TRY(cudaEventCreateWithFlags(&m->ev_mid[b], cudaEventDisableTiming));
+            CUDA_TRY(cudaEventCreateWithFlags(&m->ev_out[b], cudaEventDisableTiming));
+        }
+    }
+    if (roles) {
+        // One stream per role: every host->device copy on hs[0], every kernel on hs[1], every device->host copy on hs[2],
+        // chained per staging buffer by events.  (With one stream per chunk the copy-in of chunk i + 3 queued behind the
+        // copy-out of chunk i on the same stream, and the inbound engine idled whenever the outbound one was the busier.)
+        cudaStream_t s_in = m->hs[0], s_k = m->hs[1], s_out = m->hs[2];
+        int rc = CM_OK;
+        cudaError_t ce = cudaSuccess;
+        for (int f = 0, i = 0; f < nframes && rc == CM_OK && ce == cudaSuccess; f += chunk, ++i) {
+            const int b = i % nbuf;
+            const int n = nframes - f < chunk ? nframes - f : chunk;
+            const uint8_t *din = (const uint8_t *)m->d_in[b];
+            uint8_t *dout = (uint8_t *)m->d_out[b], *dmid = (uint8_t *)m->d_mid[b];
+            if (i >= nbuf) ce = cudaStreamWaitEvent(s_in, m->ev_k[b], 0);             // the kernels of chunk i - nbuf have read d_in[b]
+            if (ce == cudaSuccess)
+                ce = cudaMemcpyAsync(m->d_in[b], in + (size_t)f * in_frame, (size_t)n * in_frame, cudaMemcpyHostToDevice, s_in);
+            if (ce == cudaSuccess) ce = cudaEventRecord(m->ev_in[b], s_in);
+            if (ce == cudaSuccess) ce = cudaStreamWaitEvent(s_k, m->ev_in[b], 0);
+            if (ce == cudaSuccess && i >= nbuf) ce = cudaStreamWaitEvent(s_k, m->ev_out[b], 0);   // d_out[b] / d_mid[b] copied out
+            if (ce != cudaSuccess) break;
+            m->aux_slot = 1;                                                          // one kernel stream: one scratch
+            if (what == 0) rc = cm_encode_frames(m, din, dout, first_frame + f, n, s_k);
+            else if (what == 1) rc = cm_decode_frames(m, din, dout, first_frame + f, n, s_k);
+            else {
+                rc = cm_encode_frames(m, din, dmid, first_frame + f, n, s_k);
+                if (rc == CM_OK && mid) {
+                    ce = cudaEventRecord(m->ev_mid[b], s_k);
+                    if (ce == cudaSuccess) ce = cudaStreamWaitEvent(s_out, m->ev_mid[b], 0);
+                    if (ce == cudaSuccess)
+                        ce = cudaMemcpyAsync(mid + (size_t)f * mid_frame, dmid, (size_t)n * mid_frame, cudaMemcpyDeviceToHost, s_out);
+                }
+                if (rc == CM_OK && ce == cudaSuccess) rc = cm_decode_frames(m, dmid, dout, first_frame + f, n, s_k);
+            }
+            m->aux_slot = 0;
+            if (rc != CM_OK || ce != cudaSuccess) break;
+            ce = cudaEventRecord(m->ev_k[b], s_k);
+            if (ce == cudaSuccess) ce = cudaStreamWaitEvent(s_out, m->ev_k[b], 0);
+            if (ce == cudaSuccess)
+                ce = cudaMemcpyAsync(out + (size_t)f * out_frame, dout, (size_t)n * out_frame, cudaMemcpyDeviceToHost, s_out);
+            if (ce == cudaSuccess) ce = cudaEventRecord(m->ev_out[b], s_out);
+        }
+        // also on failure: no copy into the caller's memory may still be in flight when this returns
+        for (int s = 0; s < cm_modem::kHostStreams; ++s) {
+            const cudaError_t e2 = cudaStreamSynchronize(m->hs[s]);
+            if (ce == cudaSuccess) ce = e2;
+        }
+        if (rc != CM_OK) return rc;
+        if (ce != cudaSuccess) return fail(CM_ERR_CUDA, "host path: %s", cudaGetErrorString(ce));
+        return CM_OK;
     }
     int rc = CM_OK;
     cudaError_t ce = cudaSuccess;

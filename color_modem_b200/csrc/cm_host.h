@@ -27,6 +27,9 @@ struct cm_tune {
     int rpc = 0;               // rows a CTA of the row kernels walks through (the next one prefetched); 0 = cm_rows_per_cta decides
     int chunk = 0;             // frames per pass-1 / pass-2 launch pair (0: as many as a 2 GiB scratch holds)
     int host_chunk = 16;       // frames per host<->device chunk of the *_host entry points
+    int host_roles = -1;       // 1: one stream per role (copy in / kernels / copy out), 4 buffers; 0: three streams, one chunk each;
+                               // -1: by call — roles for encode->decode in one call (+8 %), streams for the single calls (two of which
+                               // usually run side by side from two host threads: 24.4 k vs 22.0 k frames/s)
     int rows_max = 0;          // upper bound of rows per CTA of the multi-row kernels (0: none)
     int min_warps = 2;         // fewest warps per CTA of the multi-row kernels
     int overlap = 0;           // pass 2 of chunk i on a second stream under pass 1 of chunk i + 1 (measured: no gain)
@@ -65,11 +68,13 @@ struct cm_modem {
     std::vector<Ev> events;
     // *_host entry points: the batch is cut into chunks that ping-pong over CM_HOST_STREAMS streams so that the
     // host->device copy of chunk i+1, the kernels of chunk i and the device->host copy of chunk i-1 overlap
-    static const int kHostStreams = 3;
+    static const int kHostStreams = 3;          // by role: 0 host->device copies, 1 kernels, 2 device->host copies
+    static const int kHostBufs = 4;             // staging buffers in flight
     cudaStream_t hs[kHostStreams] = {nullptr, nullptr, nullptr};
-    void *d_in[kHostStreams] = {nullptr, nullptr, nullptr}, *d_out[kHostStreams] = {nullptr, nullptr, nullptr};
-    void *d_mid[kHostStreams] = {nullptr, nullptr, nullptr};      // cm_transcode_frames_host: the composite between the two halves
-    size_t in_cap[kHostStreams] = {0, 0, 0}, out_cap[kHostStreams] = {0, 0, 0}, mid_cap[kHostStreams] = {0, 0, 0};
+    void *d_in[kHostBufs] = {}, *d_out[kHostBufs] = {};
+    void *d_mid[kHostBufs] = {};                // cm_transcode_frames_host: the composite between the two halves
+    size_t in_cap[kHostBufs] = {}, out_cap[kHostBufs] = {}, mid_cap[kHostBufs] = {};
+    cudaEvent_t ev_in[kHostBufs] = {}, ev_k[kHostBufs] = {}, ev_mid[kHostBufs] = {}, ev_out[kHostBufs] = {};
 };
 
 struct LaunchTimer {
