@@ -495,6 +495,48 @@ extern "C" int cm_create(const cm_desc *desc, int precision, cm_modem **out) {
     for (int i = 0; i < CM_NRES; ++i)
         if (poly[i].up) { poly[i].FP = mac_fp; poly[i].skew = mac_skew; }
     ptab.resize((ptab.size() + 3) & ~(size_t)3, 0.0);
+    memset(&m->mcf, 0, sizeof(m->mcf));
+    memset(&m->mcd, 0, sizeof(m->mcd));
+    if (desc->kind == CM_KIND_MAC && !getenv("CM_MAC_SMEM_TAPS")) {       // (the environment switch is the A/B hook)
+        // constant-bank copies of the tables whose shape matches a compiled one (MacConst, cm_common.cuh): row (a * up + r) of
+        // the polyphase table of a slot holds the taps of phase r for window alignment a (build_poly)
+        auto fill = [&](const PolyHdr &ph, int a, int r, auto *dstf, auto *dstd, int ku) {
+            for (int q = 0; q < ku; ++q) {
+                const double v = q < ph.KU ? ptab[(size_t)ph.off + (size_t)(a * ph.up + r) * ph.stride + q] : 0.0;
+                dstf[q] = (float)v;
+                dstd[q] = v;
+            }
+        };
+        const PolyHdr &pl = poly[MR_LUMA_IN], &pc = poly[MR_CHROMA_IN], &po = poly[MR_OUT], &pi = poly[MR_COMP_IN];
+        if (pl.up == 3 && pl.down % 4 == 0 && pl.KU <= MacShape::KL) {
+            const int a = (pl.lo0 + pl.FP) & 3;
+            for (int r = 0; r < 3; ++r) fill(pl, a, r, m->mcf.luma[r], m->mcd.luma[r], MacShape::KL);
+            m->mcf.ok_luma = m->mcd.ok_luma = 1;
+            if (mac_bp < MacShape::KL) mac_bp = MacShape::KL;       // the unrolled loop reads the whole compiled window
+        }
+        if (pc.up == 3 && pc.down % 4 == 0 && pc.KU <= MacShape::KC) {
+            const int a = (pc.lo0 + pc.FP) & 3;
+            for (int r = 0; r < 3; ++r) fill(pc, a, r, m->mcf.chroma[r], m->mcd.chroma[r], MacShape::KC);
+            m->mcf.ok_chroma = m->mcd.ok_chroma = 1;
+            if (mac_bp < MacShape::KC) mac_bp = MacShape::KC;
+        }
+        if (po.up == 2 && po.KU <= MacShape::KO) {
+            for (int j = 0; j < 4; ++j) {
+                const int a = (po.down * j + po.lo0 + po.FP) & 3;
+                for (int r = 0; r < 2; ++r) fill(po, a, r, m->mcf.out[j][r], m->mcd.out[j][r], MacShape::KO);
+            }
+            m->mcf.ok_out = m->mcd.ok_out = 1;
+            if (mac_bp < MacShape::KO) mac_bp = MacShape::KO;
+        }
+        if (pi.up == 3 && pi.KU <= MacShape::KI) {
+            for (int j = 0; j < 4; ++j) {
+                const int a = (pi.down * j + pi.lo0 + pi.FP) & 3;
+                for (int r = 0; r < 3; ++r) fill(pi, a, r, m->mcf.comp[j][r], m->mcd.comp[j][r], MacShape::KI);
+            }
+            m->mcf.ok_comp = m->mcd.ok_comp = 1;
+            if (mac_bp < MacShape::KI) mac_bp = MacShape::KI;
+        }
+    }
     const int row_geo = plan_row_kernel(*desc, fh, tab);
     const int enc_geo = plan_encode_kernel(*desc, fh, tab);
     std::vector<double> ctab;

@@ -43,6 +43,21 @@ struct PolyHdr {
     int lo0, skew;                            // skew: mask of poly_skew (cm_fir.cuh), the same for every resampler of a handle
 };
 
+// Taps of the MAC resamplers whose shape matches one of the compiled ones, as a kernel parameter: read with compile-time
+// indices they are constant-bank operands of the FMAs (cm_fir.cuh: fir_poly_ct_*), and the loop no longer competes with
+// itself for shared-memory bandwidth (taps and line both came from shared memory: 55 multiply-adds per clock and SM).
+//   luma / chroma: up = 3, `down` a multiple of 4 (every output group has the same window alignment): 3/8 and 3/16
+//   out / comp:    up = 2 / 3, any `down`: one table per alignment class m mod 4 of the output group
+struct MacShape { static constexpr int KL = 64, KC = 128, KO = 40, KI = 32; };
+template <typename T>
+struct MacConst {
+    T luma[3][MacShape::KL];
+    T chroma[3][MacShape::KC];
+    T out[4][2][MacShape::KO];
+    T comp[4][3][MacShape::KI];
+    int ok_luma, ok_chroma, ok_out, ok_comp;
+};
+
 template <typename T>
 struct DevParams {
     int kind, flags;

@@ -391,6 +391,37 @@ __device__ __forceinline__ void fir_poly_up(const T *__restrict__ xpad, int n_ou
     }
 }
 
+// The same with the taps in the constant bank (MacConst, cm_common.cuh), fully unrolled.  ALIGNED: `down` is a multiple of 4,
+// every group has the alignment the host built the table ct[0] for.  Otherwise the groups are walked in four passes by
+// alignment class j = m mod 4 (the alignment of group m depends on m mod 4 only), ct[j] the table of class j.
+template <typename T, int UP, int KU, bool SKEW, bool ALIGNED, int NCLS, class Post>
+__device__ __forceinline__ void fir_poly_ct(const T *__restrict__ xpad, int n_out, const PolyHdr &ph, const T (&ct)[NCLS][UP][KU],
+                                            int tid, int nthr, Post post) {
+    const int ngroups = (n_out + UP - 1) / UP;
+#pragma unroll
+    for (int j = 0; j < (ALIGNED ? 1 : 4); ++j) {
+        for (int m = ALIGNED ? tid : 4 * tid + j; m < ngroups; m += ALIGNED ? nthr : 4 * nthr) {
+            const int idx = m * ph.down + ph.lo0 + ph.FP;
+            const int s0 = idx & ~3;
+            T acc[UP];
+#pragma unroll
+            for (int r = 0; r < UP; ++r) acc[r] = (T)0;
+#pragma unroll
+            for (int q = 0; q < KU; q += 4) {
+                T xv[4];
+                ld4(xpad + (SKEW ? poly_skew(s0 + q, -1) : s0 + q), xv);
+#pragma unroll
+                for (int r = 0; r < UP; ++r)
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) acc[r] = Real<T>::fma_(ct[ALIGNED ? 0 : j][r][q + i], xv[i], acc[r]);
+            }
+#pragma unroll
+            for (int r = 0; r < UP; ++r)
+                if (UP * m + r < n_out) post(UP * m + r, acc[r]);
+        }
+    }
+}
+
 template <typename T, class Post>
 __device__ __forceinline__ void fir_poly(const T *__restrict__ xpad, int n_out, const PolyHdr &ph, const T *__restrict__ G,
                                          int tid, int nthr, Post post) {

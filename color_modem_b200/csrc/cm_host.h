@@ -44,6 +44,8 @@ struct cm_modem {
     int smem_optin;
     DevParams<float> pf;
     DevParams<double> pd;
+    MacConst<float> mcf;
+    MacConst<double> mcd;
     void *d_tab = nullptr;
     void *d_taps = nullptr;
     void *d_ctab = nullptr;

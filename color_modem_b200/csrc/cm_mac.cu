@@ -11,6 +11,10 @@ static int mac_taps_len(const DevParams<T> &p) {
     return (total + 3) & ~3;
 }
 
+template <typename T> static const MacConst<T> &mac_const(const cm_modem *m);
+template <> const MacConst<float> &mac_const<float>(const cm_modem *m) { return m->mcf; }
+template <> const MacConst<double> &mac_const<double>(const cm_modem *m) { return m->mcd; }
+
 template <typename T>
 int mac_encode(cm_modem *m, IoArgs<T> io, cudaStream_t st) {
     const DevParams<T> &p = params_of<T>(m);
@@ -22,13 +26,13 @@ int mac_encode(cm_modem *m, IoArgs<T> io, cudaStream_t st) {
     int R = pick_rows(m, 2, (size_t)m->smem_optin / 2, bytes);
     if (!R) return cm_fail(CM_ERR_UNSUPPORTED, "line too wide for the MAC encode kernel%s");
     set_groups(io, R);
-    void (*kern)(const DevParams<T>, const IoArgs<T>, int) = p.mac_skew ? k_mac_encode<T, -1> : k_mac_encode<T, 0>;
+    void (*kern)(const DevParams<T>, const IoArgs<T>, int, const MacConst<T>) = p.mac_skew ? k_mac_encode<T, -1> : k_mac_encode<T, 0>;
     int rc = set_smem(kern, bytes(R));
     if (rc) return rc;
     dim3 grid = cm_grid(io);
     {
         LaunchTimer lt(m, CM_K_ENCODE, st);
-        kern<<<grid, CM_NTHREADS, bytes(R), st>>>(p, io, tl);
+        kern<<<grid, CM_NTHREADS, bytes(R), st>>>(p, io, tl, mac_const<T>(m));
     }
     cm_count_launch();
     CUDA_TRY(cudaGetLastError());
@@ -47,13 +51,13 @@ int mac_decode(cm_modem *m, IoArgs<T> io, cudaStream_t st) {
     int R = pick_rows(m, 2, (size_t)m->smem_optin / 2, bytes);
     if (!R) return cm_fail(CM_ERR_UNSUPPORTED, "line too wide for the MAC decode kernel%s");
     set_groups(io, R);
-    void (*kern)(const DevParams<T>, const IoArgs<T>, int) = p.mac_skew ? k_mac_decode<T, -1> : k_mac_decode<T, 0>;
+    void (*kern)(const DevParams<T>, const IoArgs<T>, int, const MacConst<T>) = p.mac_skew ? k_mac_decode<T, -1> : k_mac_decode<T, 0>;
     int rc = set_smem(kern, bytes(R));
     if (rc) return rc;
     dim3 grid = cm_grid(io);
     {
         LaunchTimer lt(m, CM_K_DECODE_OTHER, st);
-        kern<<<grid, CM_NTHREADS, bytes(R), st>>>(p, io, tl);
+        kern<<<grid, CM_NTHREADS, bytes(R), st>>>(p, io, tl, mac_const<T>(m));
     }
     cm_count_launch();
     CUDA_TRY(cudaGetLastError());

@@ -42,7 +42,8 @@ __device__ __forceinline__ void mac_fit(const DevParams<T> &p, const T *tabs, in
 // Encode.  smem: tables + R * ( luma seg(W) | chroma seg(W) | luma720 | ch360 | line seg(1080) | out[1080] )
 template <typename T, int MSK>
 __global__ void __launch_bounds__(CM_NTHREADS)
-k_mac_encode(const __grid_constant__ DevParams<T> p, const __grid_constant__ IoArgs<T> io, int taps_len) {
+k_mac_encode(const __grid_constant__ DevParams<T> p, const __grid_constant__ IoArgs<T> io, int taps_len,
+             const __grid_constant__ MacConst<T> mc) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     T *sm = reinterpret_cast<T *>(smem_raw);
     RowGroup g;
@@ -84,8 +85,14 @@ k_mac_encode(const __grid_constant__ DevParams<T> p, const __grid_constant__ IoA
     __syncthreads();
     for (int k = 0; k < g.count; ++k) {
         T *yseg = rows + k * per_row, *cseg = yseg + segW, *l720 = cseg + segW, *c360 = l720 + 720;
-        mac_fit<T, MSK>(p, taps, MR_LUMA_IN, yseg, W, l720, 720, (T)0);
-        mac_fit<T, MSK>(p, taps, MR_CHROMA_IN, cseg, W, c360, 360, (T)0.5);         // mac.py:57 chroma += 0.5
+        if (mc.ok_luma)
+            fir_poly_ct<T, 3, MacShape::KL, MSK != 0, true>(yseg, 720, p.poly[MR_LUMA_IN], reinterpret_cast<const T (&)[1][3][MacShape::KL]>(mc.luma),
+                                                            threadIdx.x, blockDim.x, [&](int j, T v) { l720[j] = v; });
+        else mac_fit<T, MSK>(p, taps, MR_LUMA_IN, yseg, W, l720, 720, (T)0);
+        if (mc.ok_chroma)                                                       // mac.py:57 chroma += 0.5
+            fir_poly_ct<T, 3, MacShape::KC, MSK != 0, true>(cseg, 360, p.poly[MR_CHROMA_IN], reinterpret_cast<const T (&)[1][3][MacShape::KC]>(mc.chroma),
+                                                            threadIdx.x, blockDim.x, [&](int j, T v) { c360[j] = v + (T)0.5; });
+        else mac_fit<T, MSK>(p, taps, MR_CHROMA_IN, cseg, W, c360, 360, (T)0.5);
     }
     __syncthreads();
     for (int k = 0; k < g.count; ++k) {                                    // mac.py:58-69
@@ -111,7 +118,10 @@ k_mac_encode(const __grid_constant__ DevParams<T> p, const __grid_constant__ IoA
     for (int k = 0; k < g.count; ++k) {
         const T *oseg = rows + k * per_row + 2 * segW + 1080;
         T *outrow = rows + k * per_row + 2 * segW + 1080 + seg1080;
-        mac_fit<T, MSK>(p, taps, MR_OUT, oseg, 1080, outrow, Wc, (T)0);
+        if (mc.ok_out)
+            fir_poly_ct<T, 2, MacShape::KO, MSK != 0, false>(oseg, Wc, p.poly[MR_OUT], mc.out, threadIdx.x, blockDim.x,
+                                                             [&](int j, T v) { outrow[j] = v; });
+        else mac_fit<T, MSK>(p, taps, MR_OUT, oseg, 1080, outrow, Wc, (T)0);
     }
     __syncthreads();
     for (int k = 0; k < g.count; ++k) {
@@ -128,7 +138,8 @@ k_mac_encode(const __grid_constant__ DevParams<T> p, const __grid_constant__ IoA
 // Decode.  smem: tables + (R+1) rows x ( comp seg(Wc) | c1080 | luma720 | ch360 | XE[360] | XO[360] )
 template <typename T, int MSK>
 __global__ void __launch_bounds__(CM_NTHREADS)
-k_mac_decode(const __grid_constant__ DevParams<T> p, const __grid_constant__ IoArgs<T> io, int taps_len) {
+k_mac_decode(const __grid_constant__ DevParams<T> p, const __grid_constant__ IoArgs<T> io, int taps_len,
+             const __grid_constant__ MacConst<T> mc) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     T *sm = reinterpret_cast<T *>(smem_raw);
     RowGroup g;
@@ -159,7 +170,13 @@ k_mac_decode(const __grid_constant__ DevParams<T> p, const __grid_constant__ IoA
         }
     }
     __syncthreads();
-    for (int k = k_lo; k < g.count; ++k) mac_fit<T, MSK>(p, taps, MR_COMP_IN, rowp(k), Wc, rowp(k) + segC, 1080, (T)0);
+    for (int k = k_lo; k < g.count; ++k) {
+        T *c1080 = rowp(k) + segC;
+        if (mc.ok_comp)
+            fir_poly_ct<T, 3, MacShape::KI, MSK != 0, false>(rowp(k), 1080, p.poly[MR_COMP_IN], mc.comp, threadIdx.x, blockDim.x,
+                                                             [&](int j, T v) { c1080[j] = v; });
+        else mac_fit<T, MSK>(p, taps, MR_COMP_IN, rowp(k), Wc, c1080, 1080, (T)0);
+    }
     __syncthreads();
     for (int k = k_lo; k < g.count; ++k) {                                 // mac.py:86-109
         const T *c = rowp(k) + segC;
