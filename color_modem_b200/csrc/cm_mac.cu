@@ -20,7 +20,8 @@ int mac_encode(cm_modem *m, IoArgs<T> io, cudaStream_t st) {
     const DevParams<T> &p = params_of<T>(m);
     if (io.out_count <= 0) return CM_OK;
     if (p.Wc > 1080) return cm_fail(CM_ERR_UNSUPPORTED, "MAC widths above 1080 are not built%s");
-    const int tl = mac_taps_len(p);
+    const MacConst<T> &mc = mac_const<T>(m);
+    const int tl = (mc.ok_luma && mc.ok_chroma && mc.ok_out) ? 0 : mac_taps_len(p);     // nothing to stage: every ratio runs from the constant bank
     auto seg = [&](int n) { const int e = p.mac_fp + ((n + 3) & ~3) + p.mac_bp; return (size_t)(e + (((e >> 5) << 2) & p.mac_skew) + 4); };
     auto bytes = [&](int r) { return ((size_t)tl + (size_t)r * (2 * seg(p.W) + 720 + 360 + seg(1080) + 1080)) * sizeof(T); };
     int R = pick_rows(m, 2, (size_t)m->smem_optin / 2, bytes);
@@ -43,7 +44,7 @@ template <typename T>
 int mac_decode(cm_modem *m, IoArgs<T> io, cudaStream_t st) {
     const DevParams<T> &p = params_of<T>(m);
     if (io.out_count <= 0) return CM_OK;
-    const int tl = mac_taps_len(p);
+    const int tl = mac_const<T>(m).ok_comp ? 0 : mac_taps_len(p);
     auto bytes = [&](int r) {
         const int e = p.mac_fp + ((p.Wc + 3) & ~3) + p.mac_bp;
         return ((size_t)tl + (size_t)(r + 1) * ((size_t)(e + (((e >> 5) << 2) & p.mac_skew) + 4) + 1080 + 720 + 360 + 720)) * sizeof(T);
