@@ -50,7 +50,7 @@ struct PolyHdr {
 //   out / comp:    up = 2 / 3, any `down`: one table per alignment class m mod 4 of the output group
 struct MacShape { static constexpr int KL = 64, KC = 128, KO = 40, KI = 32; };
 template <typename T>
-struct MacConst {
+struct alignas(16) MacConst {      // 16-byte aligned in the parameter bank: tap pairs / quads are single uniform loads
     T luma[3][MacShape::KL];
     T chroma[3][MacShape::KC];
     T out[4][2][MacShape::KO];

@@ -404,16 +404,36 @@ __device__ __forceinline__ void fir_poly_ct(const T *__restrict__ xpad, int n_ou
             const int idx = m * ph.down + ph.lo0 + ph.FP;
             const int s0 = idx & ~3;
             T acc[UP];
+            if constexpr (IsF32<T>::value) {
+                // packed: the even and the odd taps of a phase accumulate side by side (FFMA2, taps as 64-bit uniform operands)
+                float2 a2[UP];
 #pragma unroll
-            for (int r = 0; r < UP; ++r) acc[r] = (T)0;
+                for (int r = 0; r < UP; ++r) a2[r] = make_float2(0.f, 0.f);
 #pragma unroll
-            for (int q = 0; q < KU; q += 4) {
-                T xv[4];
-                ld4(xpad + (SKEW ? poly_skew(s0 + q, -1) : s0 + q), xv);
+                for (int q = 0; q < KU; q += 4) {
+                    const float4 xv = *reinterpret_cast<const float4 *>(xpad + (SKEW ? poly_skew(s0 + q, -1) : s0 + q));
+                    const float2 x01 = make_float2(xv.x, xv.y), x23 = make_float2(xv.z, xv.w);
 #pragma unroll
-                for (int r = 0; r < UP; ++r)
+                    for (int r = 0; r < UP; ++r) {
+                        const float (&c)[KU] = ct[ALIGNED ? 0 : j][r];
+                        a2[r] = __ffma2_rn(make_float2(c[q], c[q + 1]), x01, a2[r]);
+                        a2[r] = __ffma2_rn(make_float2(c[q + 2], c[q + 3]), x23, a2[r]);
+                    }
+                }
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) acc[r] = Real<T>::fma_(ct[ALIGNED ? 0 : j][r][q + i], xv[i], acc[r]);
+                for (int r = 0; r < UP; ++r) acc[r] = a2[r].x + a2[r].y;
+            } else {
+#pragma unroll
+                for (int r = 0; r < UP; ++r) acc[r] = (T)0;
+#pragma unroll
+                for (int q = 0; q < KU; q += 4) {
+                    T xv[4];
+                    ld4(xpad + (SKEW ? poly_skew(s0 + q, -1) : s0 + q), xv);
+#pragma unroll
+                    for (int r = 0; r < UP; ++r)
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) acc[r] = Real<T>::fma_(ct[ALIGNED ? 0 : j][r][q + i], xv[i], acc[r]);
+                }
             }
 #pragma unroll
             for (int r = 0; r < UP; ++r)

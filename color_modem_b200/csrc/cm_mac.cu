@@ -11,9 +11,11 @@ static int mac_taps_len(const DevParams<T> &p) {
     return (total + 3) & ~3;
 }
 
-template <typename T> static const MacConst<T> &mac_const(const cm_modem *m);
-template <> const MacConst<float> &mac_const<float>(const cm_modem *m) { return m->mcf; }
-template <> const MacConst<double> &mac_const<double>(const cm_modem *m) { return m->mcd; }
+template <typename T>
+static const MacConst<T> &mac_const(const cm_modem *m) {
+    if constexpr (IsF32<T>::value) return m->mcf;
+    else return m->mcd;
+}
 
 template <typename T>
 int mac_encode(cm_modem *m, IoArgs<T> io, cudaStream_t st) {
@@ -23,7 +25,7 @@ int mac_encode(cm_modem *m, IoArgs<T> io, cudaStream_t st) {
     const MacConst<T> &mc = mac_const<T>(m);
     const int tl = (mc.ok_luma && mc.ok_chroma && mc.ok_out) ? 0 : mac_taps_len(p);     // nothing to stage: every ratio runs from the constant bank
     auto seg = [&](int n) { const int e = p.mac_fp + ((n + 3) & ~3) + p.mac_bp; return (size_t)(e + (((e >> 5) << 2) & p.mac_skew) + 4); };
-    auto bytes = [&](int r) { return ((size_t)tl + (size_t)r * (2 * seg(p.W) + 720 + 360 + seg(1080) + 1080)) * sizeof(T); };
+    auto bytes = [&](int r) { return ((size_t)tl + (size_t)r * mac_encode_row_elems((int)seg(p.W), (int)seg(1080))) * sizeof(T); };
     int R = pick_rows(m, 2, (size_t)m->smem_optin / 2, bytes);
     if (!R) return cm_fail(CM_ERR_UNSUPPORTED, "line too wide for the MAC encode kernel%s");
     set_groups(io, R);
@@ -47,9 +49,10 @@ int mac_decode(cm_modem *m, IoArgs<T> io, cudaStream_t st) {
     const int tl = mac_const<T>(m).ok_comp ? 0 : mac_taps_len(p);
     auto bytes = [&](int r) {
         const int e = p.mac_fp + ((p.Wc + 3) & ~3) + p.mac_bp;
-        return ((size_t)tl + (size_t)(r + 1) * ((size_t)(e + (((e >> 5) << 2) & p.mac_skew) + 4) + 1080 + 720 + 360 + 720)) * sizeof(T);
+        return ((size_t)tl + (size_t)(r + 1) * mac_decode_row_elems(e + (((e >> 5) << 2) & p.mac_skew) + 4)) * sizeof(T);
     };
-    int R = pick_rows(m, 2, (size_t)m->smem_optin / 2, bytes);
+    int R = pick_rows(m, 4, (size_t)m->smem_optin / 4, bytes);
+    if (!R) R = pick_rows(m, 2, (size_t)m->smem_optin / 2, bytes);
     if (!R) return cm_fail(CM_ERR_UNSUPPORTED, "line too wide for the MAC decode kernel%s");
     set_groups(io, R);
     void (*kern)(const DevParams<T>, const IoArgs<T>, int, const MacConst<T>) = p.mac_skew ? k_mac_decode<T, -1> : k_mac_decode<T, 0>;
