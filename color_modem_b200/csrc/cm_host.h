@@ -32,6 +32,7 @@ struct cm_tune {
                                // usually run side by side from two host threads: 24.4 k vs 22.0 k frames/s)
     int rows_max = 0;          // upper bound of rows per CTA of the multi-row kernels (0: none)
     int min_warps = 2;         // fewest warps per CTA of the multi-row kernels
+    int mac_threads = 128;     // threads per CTA of the MAC kernels (CM_MAC_THREADS)
     int overlap = 0;           // pass 2 of chunk i on a second stream under pass 1 of chunk i + 1 (measured: no gain)
 };
 

@@ -26,7 +26,8 @@ int mac_encode(cm_modem *m, IoArgs<T> io, cudaStream_t st) {
     const int tl = (mc.ok_luma && mc.ok_chroma && mc.ok_out) ? 0 : mac_taps_len(p);     // nothing to stage: every ratio runs from the constant bank
     auto seg = [&](int n) { const int e = p.mac_fp + ((n + 3) & ~3) + p.mac_bp; return (size_t)(e + (((e >> 5) << 2) & p.mac_skew) + 4); };
     auto bytes = [&](int r) { return ((size_t)tl + (size_t)r * mac_encode_row_elems((int)seg(p.W), (int)seg(1080))) * sizeof(T); };
-    int R = pick_rows(m, 2, (size_t)m->smem_optin / 2, bytes);
+    // measured (threads x rows per CTA, 720 and 1920 wide): four warps walking one row; eight CTAs per SM in different phases
+    int R = pick_rows(m, 1, (size_t)m->smem_optin / 2, bytes);
     if (!R) return cm_fail(CM_ERR_UNSUPPORTED, "line too wide for the MAC encode kernel%s");
     set_groups(io, R);
     void (*kern)(const DevParams<T>, const IoArgs<T>, int, const MacConst<T>) = p.mac_skew ? k_mac_encode<T, -1> : k_mac_encode<T, 0>;
@@ -35,7 +36,7 @@ int mac_encode(cm_modem *m, IoArgs<T> io, cudaStream_t st) {
     dim3 grid = cm_grid(io);
     {
         LaunchTimer lt(m, CM_K_ENCODE, st);
-        kern<<<grid, CM_NTHREADS, bytes(R), st>>>(p, io, tl, mac_const<T>(m));
+        kern<<<grid, m->tune.mac_threads, bytes(R), st>>>(p, io, tl, mac_const<T>(m));
     }
     cm_count_launch();
     CUDA_TRY(cudaGetLastError());
@@ -51,8 +52,7 @@ int mac_decode(cm_modem *m, IoArgs<T> io, cudaStream_t st) {
         const int e = p.mac_fp + ((p.Wc + 3) & ~3) + p.mac_bp;
         return ((size_t)tl + (size_t)(r + 1) * mac_decode_row_elems(e + (((e >> 5) << 2) & p.mac_skew) + 4)) * sizeof(T);
     };
-    int R = pick_rows(m, 4, (size_t)m->smem_optin / 4, bytes);
-    if (!R) R = pick_rows(m, 2, (size_t)m->smem_optin / 2, bytes);
+    int R = pick_rows(m, 2, (size_t)m->smem_optin / 2, bytes);           // measured: two rows + the chroma of the row ahead, four warps
     if (!R) return cm_fail(CM_ERR_UNSUPPORTED, "line too wide for the MAC decode kernel%s");
     set_groups(io, R);
     void (*kern)(const DevParams<T>, const IoArgs<T>, int, const MacConst<T>) = p.mac_skew ? k_mac_decode<T, -1> : k_mac_decode<T, 0>;
@@ -61,7 +61,7 @@ int mac_decode(cm_modem *m, IoArgs<T> io, cudaStream_t st) {
     dim3 grid = cm_grid(io);
     {
         LaunchTimer lt(m, CM_K_DECODE_OTHER, st);
-        kern<<<grid, CM_NTHREADS, bytes(R), st>>>(p, io, tl, mac_const<T>(m));
+        kern<<<grid, m->tune.mac_threads, bytes(R), st>>>(p, io, tl, mac_const<T>(m));
     }
     cm_count_launch();
     CUDA_TRY(cudaGetLastError());
