@@ -26,7 +26,7 @@ struct cm_tune {
     bool rows_v1 = false;      // first-generation pass-1 kernel (k_qam_rows)
     int rpc = 0;               // rows a CTA of the row kernels walks through (the next one prefetched); 0 = cm_rows_per_cta decides
     int chunk = 0;             // frames per pass-1 / pass-2 launch pair (0: as many as a 2 GiB scratch holds)
-    int host_chunk = 16;       // frames per host<->device chunk of the *_host entry points
+    int host_chunk = 32;       // frames per host<->device chunk of the *_host entry points
     int host_roles = -1;       // 1: one stream per role (copy in / kernels / copy out), 4 buffers; 0: three streams, one chunk each;
                                // -1: by call — roles for encode->decode in one call (+8 %), streams for the single calls (two of which
                                // usually run side by side from two host threads: 24.4 k vs 22.0 k frames/s)

@@ -73,7 +73,7 @@ def test_empty_batch(cuda_required):
 
 
 def test_batch_not_multiple_of_chunks(cuda_required):
-    """Ragged batches: 17 and 65 frames are one more than one / four 16-frame chunks of the host entry points; the
+    """Ragged batches: 17 frames are less than one 32-frame chunk of the host entry points, 33 and 129 one more than one / four; the
     pass-1 / pass-2 chunking of the comb decoders (frames per 2 GiB of scratch) is exercised with CM_CHUNK in
     tests/test_gpu_parity.py::test_comb_decoder_paths and below."""
     import torch
@@ -83,7 +83,7 @@ def test_batch_not_multiple_of_chunks(cuda_required):
     comp = m.encode_frames(x)
     out = m.decode_frames(comp).cpu().numpy()
     comp = comp.cpu().numpy()
-    for n in (17, 65):
+    for n in (17, 33, 129):
         c = m.encode_frames_host(rgb[:n], 0)
         assert np.array_equal(c, comp[:n])
         assert np.array_equal(m.decode_frames_host(c, 0), out[:n])

@@ -87,7 +87,7 @@ def test_1000_frames_batch_invariance(which, cuda_required):
     out = m.decode_frames(comp, first_frame=0)
     comp, out = comp.cpu().numpy(), out.cpu().numpy()
     del x
-    # host entry points (16-frame chunks over three streams) on a window that does not start at frame 0
+    # host entry points (32-frame chunks over three streams) on a window that does not start at frame 0
     lo, hi = 333, 333 + 100
     assert np.array_equal(m.encode_frames_host(rgb[lo:hi], lo), comp[lo:hi])
     assert np.array_equal(m.decode_frames_host(comp[lo:hi], lo), out[lo:hi])
