@@ -443,7 +443,9 @@ extern "C" int cm_create(const cm_desc *desc, int precision, cm_modem **out) {
         if (const char *e = getenv("CM_HOST_ROLES")) m->tune.host_roles = atoi(e);
         m->tune.rows_max = env_int("CM_ROWS_MAX", m->tune.rows_max);
         m->tune.min_warps = env_int("CM_MIN_WARPS", m->tune.min_warps);
-        m->tune.mac_threads = env_int("CM_MAC_THREADS", m->tune.mac_threads);
+        m->tune.mac_threads = env_int("CM_MAC_THREADS", m->tune.mac_threads) & ~31;
+        if (m->tune.mac_threads < 32) m->tune.mac_threads = 32;
+        if (m->tune.mac_threads > CM_NTHREADS) m->tune.mac_threads = CM_NTHREADS;       // the kernels' launch bound
         if (const char *e = getenv("CM_OVERLAP")) m->tune.overlap = atoi(e);
     }
     cudaError_t e = cudaGetDevice(&m->device);

@@ -24,7 +24,8 @@ for w in (720, 1920):
              ('secam', lambda: comb.ColorAveragingModem(secam.SecamModem(LineConfig((w, h), LS.GERBER_625), secam.SecamVariant.SECAM_III))),
              ('niir', lambda: niir.HueCorrectingNiirModem(LineConfig((w, h), LS.GERBER_625))),
              ('proto', lambda: comb.ColorAveragingModem(protosecam.ProtoSecamModem(LineConfig((w, h), LS.FRENCH_819)))),
-             ('mac7', lambda: mac.MacModem(LineConfig((w, h), LS.GERBER_625), mac.MacVariant.D2MAC_7MHZ))]
+             ('mac7', lambda: mac.MacModem(LineConfig((w, h), LS.GERBER_625), mac.MacVariant.D2MAC_7MHZ)),
+             ('mac12', lambda: comb.ColorAveragingModem(mac.MacModem(LineConfig((w, h), LS.GERBER_625))))]
     for name, make in cases:
         if only and only not in name:
             continue
