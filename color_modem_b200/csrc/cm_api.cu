@@ -142,9 +142,10 @@ static void build_filter_L(const cm_filter &f, FiltHdr &h, std::vector<double> &
 // Geometry of k_qam_encode_row2 (cm_qam.cuh) for this line length: 1 = 2 warps / 23 samples per lane, 2 = 4 warps / 23,
 // 3 = 4 warps / 31; fills the QF_ENC_PRE header.  0: none fits (the multi-row encoder serves the line).
 static int plan_encode_kernel(const cm_desc &d, FiltHdr *fh, std::vector<double> &tab) {
-    if (d.kind < CM_KIND_QAM_BANDSPLIT || d.kind > CM_KIND_PAL_3D) return 0;
-    const cm_filter &fpre = d.filters[QF_PRE_LP];
-    if (!fpre.nsec) return 0;
+    const bool qam = d.kind >= CM_KIND_QAM_BANDSPLIT && d.kind <= CM_KIND_PAL_3D;
+    if (!qam && d.kind != CM_KIND_NIIR) return 0;
+    const cm_filter &fpre = d.filters[qam ? QF_PRE_LP : NF_PRE_LP];       // slot 9 = QF_ENC_PRE = NF_ENC_PRE
+    if (!fpre.nsec || fpre.rate > 1) return 0;
     static const int th[3] = {1, 2, 2}, lpre[3] = {23, 23, 31}, wmax[3] = {768, 1536, 2048};
     for (int k = 0; k < 3; ++k) {
         if (d.width > wmax[k] || fpre.n + fpre.shift > 32 * th[k] * lpre[k]) continue;

@@ -85,7 +85,7 @@ struct DevParams {
     int mac_skew;         // mask of poly_skew: -1 when some resampler steps by a multiple of 8 samples, else 0
     int mac_fp, mac_bp;   // zero padding (elements, multiples of 4) in front of / behind every line a resampler reads
     const T *ctab;    // k_qam_rows2: row-independent carrier table [sin | cos][npad of the QF_ROW_LP site] (cm_api.cu)
-    int enc_geo;      // k_qam_encode_row2: geometry 1..3 (cm_api.cu: plan_encode_kernel); 0 = not served
+    int enc_geo;      // k_qam_encode_row2 / k_niir_encode2: geometry 1..3 (cm_api.cu: plan_encode_kernel); 0 = not served
     int row_geo;      // k_qam_rows2: geometry 1..3 (cm_qam.cuh: RowL) / k_secam_decode2: 1 or 3 (cm_secam.cuh: SecGeo);
                       // 0 = the row kernel does not serve this line length
     // dense taps of resampler slots 0 and 1 (the x2 / x3 half-band pair of every family except MAC), zero-filled:
@@ -201,6 +201,13 @@ template <> struct Real<double> {
 
 // 1 / x: float32 takes the hardware approximation (MUFU.RCP, ~1 ulp) instead of the IEEE division sequence; the float64
 // verification build divides.
+// Geometries of the u8 row encoders (k_qam_encode_row2, k_niir_encode2): warps per CTA, pixel quads per thread, chunk length
+// of the chroma low-pass site (cm_api.cu: plan_encode_kernel)
+template <int GEO> struct EncGeo;
+template <> struct EncGeo<1> { static constexpr int NW = 2, KQ = 3, PRE = 23; };
+template <> struct EncGeo<2> { static constexpr int NW = 4, KQ = 3, PRE = 23; };
+template <> struct EncGeo<3> { static constexpr int NW = 4, KQ = 4, PRE = 31; };
+
 template <typename T> struct FastRcp;
 template <> struct FastRcp<float> { static __device__ __forceinline__ float rcp(float x) { return __fdividef(1.0f, x); } };
 template <> struct FastRcp<double> { static __device__ __forceinline__ double rcp(double x) { return 1.0 / x; } };

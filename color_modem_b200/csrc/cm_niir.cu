@@ -27,6 +27,29 @@ static int launch_rows(cm_modem *m, IoArgs<T> io, cudaStream_t st, K kernel, F b
 template <typename T>
 int niir_encode(cm_modem *m, IoArgs<T> io, cudaStream_t st) {
     const DevParams<T> &p = params_of<T>(m);
+    if (io.in_u8 && p.enc_geo && !m->tune.rows_v1 && !m->tune.onepass) {           // strips of rows, one at a time (k_niir_encode2)
+        if (io.out_count <= 0) return CM_OK;
+        void (*kern)(const DevParams<T>, const IoArgs<T>) =
+            p.enc_geo == 1 ? k_niir_encode2<T, 1> : (p.enc_geo == 2 ? k_niir_encode2<T, 2> : k_niir_encode2<T, 3>);
+        const size_t b2 = (128 + 7 * (size_t)p.n1p) * sizeof(T);
+        int rc = set_smem(kern, b2);
+        if (rc) return rc;
+        // rows per strip: the averaging / hue-correcting front ends fetch one row more than the strip is long, so long strips
+        // are cheaper — as long as the grid still fills the chip (8 CTAs of 2 warps per SM, two waves)
+        const long long rows_total = (long long)io.out_count * io.nframes;
+        int R = (int)(rows_total / (16LL * m->sm_count));
+        R = R < 1 ? 1 : (R > 16 ? 16 : R);
+        if (m->tune.rows_max > 0) R = m->tune.rows_max;
+        set_groups(io, R);
+        const int nf = (io.out_count + 1) >> 1;
+        {
+            LaunchTimer lt(m, CM_K_ENCODE, st);
+            kern<<<dim3((unsigned)((nf + R - 1) / R), 2u, (unsigned)io.nframes), p.enc_geo == 1 ? 64 : 128, b2, st>>>(p, io);
+        }
+        cm_count_launch();
+        CUDA_TRY(cudaGetLastError());
+        return CM_OK;
+    }
     auto bytes = [&](int r) { return (size_t)r * 3 * p.n1p * sizeof(T); };
     return launch_rows<T>(m, io, st, k_niir_encode<T>, bytes, 1, 2, 0, CM_K_ENCODE, "NIIR encode");
 }

@@ -55,6 +55,50 @@ __device__ __forceinline__ void niir_chroma_f64(const double *e, double r, doubl
     dr = __dadd_rn(__dadd_rn(__dmul_rn(e[6], r), __dmul_rn(e[7], g)), __dmul_rn(e[8], b));
 }
 
+// One pixel of the NIIR encoder front end in float64 with the reference's operation order (niir.py:40-48, 186-197;
+// comb.py:149-150): (r, g, b) of the row and (r2, g2, b2) of its field neighbour -> (db, dr) with the saturation offset.
+template <typename T>
+__device__ __forceinline__ void niir_exact_pixel(const DevParams<T> &p, bool hue, bool avg, double r, double g, double b,
+                                                 double r2, double g2, double b2, T &db, T &dr) {
+    double vb, vr, nb = 0.0, nr = 0.0, mag_out;
+    niir_chroma_f64(p.encd, r, g, b, vb, vr);
+    if (avg || hue) niir_chroma_f64(p.encd, r2, g2, b2, nb, nr);
+    if (p.ident_enc) {
+        vb = g;
+        vr = b;
+        if (avg || hue) { nb = g2; nr = b2; }
+    }
+    if (hue) {
+        const double ls = sqrt(__dadd_rn(__dmul_rn(vb, vb), __dmul_rn(vr, vr)));
+        const double sn = sqrt(__dadd_rn(__dmul_rn(nb, nb), __dmul_rn(nr, nr)));
+        double div = __dadd_rn(ls, sn);
+        if (div == 0.0) div = 1.0;
+        const double ab = __ddiv_rn(__dadd_rn(__dmul_rn(vb, ls), __dmul_rn(nb, sn)), div);
+        const double ar = __ddiv_rn(__dadd_rn(__dmul_rn(vr, ls), __dmul_rn(nr, sn)), div);
+        mag_out = ls + 0.1;
+        vb = ab;
+        vr = ar;
+    } else {
+        if (avg) {                                                    // comb.py:149-150
+            vb = __dmul_rn(0.5, __dadd_rn(nb, vb));
+            vr = __dmul_rn(0.5, __dadd_rn(nr, vr));
+        }
+        mag_out = sqrt(__dadd_rn(__dmul_rn(vb, vb), __dmul_rn(vr, vr))) + 0.1;
+    }
+    const double m2 = vb * vb + vr * vr;
+    if (m2 > 0.0) {
+        const double sc = mag_out / sqrt(m2);
+        db = (T)(vb * sc);
+        dr = (T)(vr * sc);
+    } else if (!signbit(vr)) {        // atan2(+-0, +0) = +-0 -> (sin, cos) = (+-0, 1)
+        db = (T)(mag_out * copysign(0.0, vb));
+        dr = (T)mag_out;
+    } else {                          // atan2(+-0, -0) = +-pi -> (sin, cos) = (+-1.2e-16, -1), as numpy has it
+        db = (T)(mag_out * copysign(1.2246467991473532e-16, vb));
+        dr = (T)(-mag_out);
+    }
+}
+
 // ------------------------------------------------------------------------------------------------------------
 // Encode.  2 warps per row.  smem: R * 3 * N1   (luma | db | dr)
 // ------------------------------------------------------------------------------------------------------------
@@ -125,43 +169,7 @@ k_niir_encode(const __grid_constant__ DevParams<T> p, const __grid_constant__ Io
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     if (!exact[i]) continue;
-                    double vb, vr, nb = 0.0, nr = 0.0, mag_out;
-                    niir_chroma_f64(p.encd, rd[i], gd[i], bd[i], vb, vr);
-                    if (avg || hue) niir_chroma_f64(p.encd, r2d[i], g2d[i], b2d[i], nb, nr);
-                    if (p.ident_enc) {
-                        vb = gd[i];
-                        vr = bd[i];
-                        if (avg || hue) { nb = g2d[i]; nr = b2d[i]; }
-                    }
-                    if (hue) {
-                        const double ls = sqrt(__dadd_rn(__dmul_rn(vb, vb), __dmul_rn(vr, vr)));
-                        const double sn = sqrt(__dadd_rn(__dmul_rn(nb, nb), __dmul_rn(nr, nr)));
-                        double div = __dadd_rn(ls, sn);
-                        if (div == 0.0) div = 1.0;
-                        const double ab = __ddiv_rn(__dadd_rn(__dmul_rn(vb, ls), __dmul_rn(nb, sn)), div);
-                        const double ar = __ddiv_rn(__dadd_rn(__dmul_rn(vr, ls), __dmul_rn(nr, sn)), div);
-                        mag_out = ls + 0.1;
-                        vb = ab;
-                        vr = ar;
-                    } else {
-                        if (avg) {                                                    // comb.py:149-150
-                            vb = __dmul_rn(0.5, __dadd_rn(nb, vb));
-                            vr = __dmul_rn(0.5, __dadd_rn(nr, vr));
-                        }
-                        mag_out = sqrt(__dadd_rn(__dmul_rn(vb, vb), __dmul_rn(vr, vr))) + 0.1;
-                    }
-                    const double m2 = vb * vb + vr * vr;
-                    if (m2 > 0.0) {
-                        const double sc = mag_out / sqrt(m2);
-                        db[i] = (T)(vb * sc);
-                        dr[i] = (T)(vr * sc);
-                    } else if (!signbit(vr)) {        // atan2(+-0, +0) = +-0 -> (sin, cos) = (+-0, 1)
-                        db[i] = (T)(mag_out * copysign(0.0, vb));
-                        dr[i] = (T)mag_out;
-                    } else {                          // atan2(+-0, -0) = +-pi -> (sin, cos) = (+-1.2e-16, -1), as numpy has it
-                        db[i] = (T)(mag_out * copysign(1.2246467991473532e-16, vb));
-                        dr[i] = (T)(-mag_out);
-                    }
+                    niir_exact_pixel<T>(p, hue, avg, rd[i], gd[i], bd[i], r2d[i], g2d[i], b2d[i], db[i], dr[i]);
                 }
             }
             st4(ys + x, y);
@@ -204,6 +212,195 @@ k_niir_encode(const __grid_constant__ DevParams<T> p, const __grid_constant__ Io
                 o[i] = y[i] + (alt ? -Real<T>::sqrt_(db[i] * db[i] + dr[i] * dr[i]) * s[i] : db[i] * s[i] + dr[i] * c[i]);
             store_comp4(io, ((size_t)g.fidx * io.nrows + row) * p.Wc + x, o);
         }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Encoder for u8 frames, second generation (k_niir_encode2): a CTA of 2 or 4 warps (EncGeo, cm_qam.cuh) walks a STRIP of
+// consecutive rows of one field, one row at a time.  The hue-correcting and the averaging front ends read the row and its field
+// neighbour (niir.py:186-197, comb.py:149-150): the neighbour's planes before the polar step are kept in shared memory (each thread
+// its own pixels) and are the row's own planes one iteration later, so every row is fetched, unpacked and matrixed once per
+// strip; the words of the row after are in flight during the filtering.  The two chroma
+// low-passes are packed DF-I team recursions (team_iir_pk).  fp32: |v| = m rsqrt(m) and one hardware reciprocal per pixel
+// instead of two square roots and two divisions (the parity bound is 1e-4; the float64 build keeps the exact forms).
+// smem: scratch[128] | y[N1] | db[N1] | dr[N1] | stash: y, db, dr, |c| of the row [4 N1]
+// ------------------------------------------------------------------------------------------------------------
+#define NF_ENC_PRE 9     // DevParams::filt slot of this kernel's low-pass site (cm_api.cu: plan_encode_kernel)
+template <typename T> struct NiirFast {
+    static __device__ __forceinline__ T norm(T m2) { return Real<T>::sqrt_(m2); }
+};
+template <> struct NiirFast<float> {
+    static __device__ __forceinline__ float norm(float m2) { return m2 > 0.f ? m2 * rsqrtf(m2) : 0.f; }
+};
+
+template <typename T, int GEO>
+__global__ void __launch_bounds__(32 * EncGeo<GEO>::NW, sizeof(T) == 8 ? 1 : 16 / EncGeo<GEO>::NW)
+k_niir_encode2(const __grid_constant__ DevParams<T> p, const __grid_constant__ IoArgs<T> io) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T *scratch = reinterpret_cast<T *>(smem_raw), *sm = scratch + 128;
+    typedef EncGeo<GEO> EG;
+    constexpr int kQ = EG::KQ, NT = 32 * EG::NW, TH = EG::NW / 2;
+    const int W = p.W, N1 = p.n1p, W4 = W >> 2;
+    const int warp = threadIdx.x >> 5, task = warp / TH, wr = warp - task * TH;
+    const bool avg = (p.flags & 2) != 0, hue = (p.flags & 4) != 0, two = avg || hue;
+    const int field = blockIdx.y, f = blockIdx.z;
+    const long long frame = io.first_frame + f;
+    const int first = io.out_begin + field, nout = (io.out_count - field + 1) >> 1;
+    const int R = io.rows_per_cta;
+    const int k0 = blockIdx.x * R, k1 = min(k0 + R, nout);
+    if (k0 >= nout) return;
+    const FiltHdr &fpre = p.filt[NF_ENC_PRE];
+    T *ys = sm, *bs = ys + N1, *rs_ = bs + N1;
+    T *st_y = rs_ + N1, *st_b = st_y + N1, *st_r = st_b + N1, *st_s = st_r + N1;      // the row's own planes, kept from the iteration before
+    uint32_t wn[kQ][3], wt[kQ][3];
+    auto next_of = [&](int row) { return (row + 2 < io.nrows) ? row + 2 : row; };
+    auto fetch = [&](int row, uint32_t (*w)[3]) {
+        const uint32_t *a = reinterpret_cast<const uint32_t *>(io.in_u8 + ((size_t)f * io.nrows + row) * W * 3);
+#pragma unroll
+        for (int j = 0; j < kQ; ++j) {
+            const int q = threadIdx.x + j * NT;
+            if (q < W4) {
+#pragma unroll
+                for (int i = 0; i < 3; ++i) w[j][i] = __ldg(a + 3 * q + i);
+            }
+        }
+    };
+    // (y, db, dr) of four pixels before the polar step, and |(db, dr)| for the hue-correcting front end
+    auto planes4 = [&](const uint32_t *w, T *y, T *vb, T *vr, T *mag) {
+        unsigned char bytes[12];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            bytes[i] = (w[0] >> (8 * i)) & 0xff;
+            bytes[4 + i] = (w[1] >> (8 * i)) & 0xff;
+            bytes[8 + i] = (w[2] >> (8 * i)) & 0xff;
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const T r = Real<T>::from_u8(bytes[3 * i]), g = Real<T>::from_u8(bytes[3 * i + 1]), b = Real<T>::from_u8(bytes[3 * i + 2]);
+            y[i] = p.enc[0] * r + p.enc[1] * g + p.enc[2] * b;
+            vb[i] = p.enc[3] * r + p.enc[4] * g + p.enc[5] * b;
+            vr[i] = p.enc[6] * r + p.enc[7] * g + p.enc[8] * b;
+            if (p.ident_enc) { y[i] = r; vb[i] = g; vr[i] = b; }                    // modulate_components: planes as given
+            mag[i] = hue ? NiirFast<T>::norm(vb[i] * vb[i] + vr[i] * vr[i]) : (T)0;
+        }
+    };
+    T crs, crc;
+    Real<T>::sincos_turns(p.phases[NP_STEP1X], crs, crc);
+    fetch(first + 2 * k0, wn);
+    if (two) {                  // the strip's first row: its planes into the stash, then the words of its field neighbour
+#pragma unroll
+        for (int j = 0; j < kQ; ++j) {
+            const int q = threadIdx.x + j * NT;
+            if (q < W4) {
+                T y[4], vb[4], vr[4], mg[4];
+                planes4(wn[j], y, vb, vr, mg);
+                st4(st_y + 4 * q, y);
+                st4(st_b + 4 * q, vb);
+                st4(st_r + 4 * q, vr);
+                st4(st_s + 4 * q, mg);
+            }
+        }
+        fetch(next_of(first + 2 * k0), wn);
+    }
+    for (int k = k0; k < k1; ++k) {
+        const int row = first + 2 * k, nrow = next_of(row), line = io.y0 + row;
+#pragma unroll
+        for (int j = 0; j < kQ; ++j) {
+            const int q = threadIdx.x + j * NT;
+            if (q < W4) {
+                const int x = 4 * q;
+                T y[4], vb4[4], vr4[4], ls4[4], yn[4], nb4[4], nr4[4], sn4[4], db[4], dr[4];
+                planes4(wn[j], yn, nb4, nr4, sn4);                                  // wn: the neighbour row (or, without one, the row)
+                if (two) {
+                    ld4(st_y + x, y);
+                    ld4(st_b + x, vb4);
+                    ld4(st_r + x, vr4);
+                    ld4(st_s + x, ls4);
+                    st4(st_y + x, yn);                                              // the neighbour is the next row of the strip
+                    st4(st_b + x, nb4);
+                    st4(st_r + x, nr4);
+                    st4(st_s + x, sn4);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) { y[i] = yn[i]; vb4[i] = nb4[i]; vr4[i] = nr4[i]; ls4[i] = sn4[i]; }
+                }
+                bool exact[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    T vb = vb4[i], vr = vr4[i];
+                    const T nb = nb4[i], nr = nr4[i];
+                    T mag_out, m2;
+                    if (hue) {                                                      // niir.py:186-197
+                        const T ls = ls4[i], sn = sn4[i];
+                        T div = ls + sn;
+                        if (div == (T)0) div = (T)1;
+                        const T inv = FastRcp<T>::rcp(div);
+                        const T ab = (vb * ls + nb * sn) * inv, ar = (vr * ls + nr * sn) * inv;
+                        mag_out = ls + (T)0.1;
+                        vb = ab;
+                        vr = ar;
+                        m2 = vb * vb + vr * vr;
+                    } else {
+                        if (avg) {                                                  // comb.py:149-150
+                            vb = (T)0.5 * (nb + vb);
+                            vr = (T)0.5 * (nr + vr);
+                        }
+                        m2 = vb * vb + vr * vr;
+                        mag_out = NiirFast<T>::norm(m2) + (T)0.1;                   // niir.py:43
+                    }
+                    // direction of a vector shorter than 1e-4: float64, the reference's way (see k_niir_encode)
+                    exact[i] = sizeof(T) == 8 || !(m2 >= (T)1e-8);
+                    const T sc = mag_out * Real<T>::rsqrt_(m2);
+                    db[i] = vb * sc;
+                    dr[i] = vr * sc;
+                }
+                if (exact[0] || exact[1] || exact[2] || exact[3]) {
+                    const size_t px = ((size_t)f * io.nrows + row) * W + x, pxn = ((size_t)f * io.nrows + nrow) * W + x;
+                    double rd[4], gd[4], bd[4], r2d[4], g2d[4], b2d[4];
+                    niir_load_rgb4_f64(io, px, rd, gd, bd);
+                    if (two) niir_load_rgb4_f64(io, pxn, r2d, g2d, b2d);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        if (!exact[i]) continue;
+                        T ob, orr;
+                        niir_exact_pixel<T>(p, hue, avg, rd[i], gd[i], bd[i], r2d[i], g2d[i], b2d[i], ob, orr);
+                        db[i] = ob;
+                        dr[i] = orr;
+                    }
+                }
+                st4(ys + x, y);
+                st4(bs + x, db);
+                st4(rs_ + x, dr);
+            }
+        }
+        __syncthreads();
+        if (k + 1 < k1) fetch(two ? next_of(row + 2) : row + 2, wt);               // in flight during the filtering
+        {
+            T *buf = task ? rs_ : bs;
+            warp_fill_tail<T, 1>(buf, N1, W, iir_tail_end(fpre));                  // every warp of the team writes the same values
+            team_iir_pk<T, 1, EG::PRE, TH>(p.tab + fpre.off, fpre, LoadLinear<T, EG::PRE>{buf}, [&](int j, T x) { buf[j] = x; },
+                                           wr, 2 + task, scratch + 32 * task);
+        }
+        __syncthreads();
+        const unsigned long long ph0 = start_phase(p, frame, line);
+        const bool alt = is_alternate(p, frame, line);
+        for (int q = threadIdx.x; q < W4; q += NT) {
+            const int x = 4 * q;
+            T y[4], db[4], dr[4], o[4], s[4], c[4];
+            ld4(ys + x, y);
+            ld4(bs + x, db);
+            ld4(rs_ + x, dr);
+            carrier4_fast(ph0 + (unsigned long long)x * p.phases[NP_STEP1X], crs, crc, s, c);
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                o[i] = y[i] + (alt ? -NiirFast<T>::norm(db[i] * db[i] + dr[i] * dr[i]) * s[i] : db[i] * s[i] + dr[i] * c[i]);
+            store_comp4(io, ((size_t)f * io.nrows + row) * p.Wc + x, o);
+        }
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < kQ; ++j)
+#pragma unroll
+            for (int i = 0; i < 3; ++i) wn[j][i] = wt[j][i];
     }
 }
 

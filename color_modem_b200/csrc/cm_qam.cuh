@@ -205,10 +205,7 @@ k_qam_encode_row(const __grid_constant__ DevParams<T> p, const __grid_constant__
 // thread (RGB words of the next row, and of its field neighbour for the ColorAveraging front end, prefetched in registers).
 //   GEO 1: 2 warps, 3 quads (<= 768 samples);  2: 4 warps, 3 quads (<= 1536);  3: 4 warps, 4 quads, longer chunks (<= 2048)
 #define QF_ENC_PRE 9     // DevParams::filt slot of this kernel's low-pass site (cm_api.cu: plan_encode_kernel)
-template <int GEO> struct EncGeo;
-template <> struct EncGeo<1> { static constexpr int NW = 2, KQ = 3, PRE = 23; };
-template <> struct EncGeo<2> { static constexpr int NW = 4, KQ = 3, PRE = 23; };
-template <> struct EncGeo<3> { static constexpr int NW = 4, KQ = 4, PRE = 31; };
+// (EncGeo: cm_common.cuh — the NIIR row encoder shares the geometries)
 
 template <typename T, int GEO>
 __global__ void __launch_bounds__(32 * EncGeo<GEO>::NW, sizeof(T) == 8 ? 1 : 16 / EncGeo<GEO>::NW)
