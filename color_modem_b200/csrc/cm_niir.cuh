@@ -57,8 +57,10 @@ __device__ __forceinline__ void niir_chroma_f64(const double *e, double r, doubl
 
 // One pixel of the NIIR encoder front end in float64 with the reference's operation order (niir.py:40-48, 186-197;
 // comb.py:149-150): (r, g, b) of the row and (r2, g2, b2) of its field neighbour -> (db, dr) with the saturation offset.
+// (not inlined: grey pixels are the exception, and twelve to sixteen inlined copies of the float64 square roots and divisions
+// made the row encoder 138 KB of code)
 template <typename T>
-__device__ __forceinline__ void niir_exact_pixel(const DevParams<T> &p, bool hue, bool avg, double r, double g, double b,
+__device__ __noinline__ void niir_exact_pixel(const DevParams<T> &p, bool hue, bool avg, double r, double g, double b,
                                                  double r2, double g2, double b2, T &db, T &dr) {
     double vb, vr, nb = 0.0, nr = 0.0, mag_out;
     niir_chroma_f64(p.encd, r, g, b, vb, vr);
@@ -97,6 +99,18 @@ __device__ __forceinline__ void niir_exact_pixel(const DevParams<T> &p, bool hue
         db = (T)(mag_out * copysign(1.2246467991473532e-16, vb));
         dr = (T)(-mag_out);
     }
+}
+
+// The pixels of a quad whose chroma vector is too short for fp32 (mask bit i), redone in float64 from the frame itself.
+template <typename T>
+__device__ __noinline__ void niir_exact_quad(const DevParams<T> &p, const IoArgs<T> &io, size_t px, size_t pxn, bool hue, bool avg,
+                                             unsigned mask, T *db, T *dr) {
+    double rd[4], gd[4], bd[4], r2d[4] = {0, 0, 0, 0}, g2d[4] = {0, 0, 0, 0}, b2d[4] = {0, 0, 0, 0};
+    niir_load_rgb4_f64(io, px, rd, gd, bd);
+    if (avg || hue) niir_load_rgb4_f64(io, pxn, r2d, g2d, b2d);
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+        if (mask & (1u << i)) niir_exact_pixel<T>(p, hue, avg, rd[i], gd[i], bd[i], r2d[i], g2d[i], b2d[i], db[i], dr[i]);
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -354,20 +368,9 @@ k_niir_encode2(const __grid_constant__ DevParams<T> p, const __grid_constant__ I
                     db[i] = vb * sc;
                     dr[i] = vr * sc;
                 }
-                if (exact[0] || exact[1] || exact[2] || exact[3]) {
-                    const size_t px = ((size_t)f * io.nrows + row) * W + x, pxn = ((size_t)f * io.nrows + nrow) * W + x;
-                    double rd[4], gd[4], bd[4], r2d[4], g2d[4], b2d[4];
-                    niir_load_rgb4_f64(io, px, rd, gd, bd);
-                    if (two) niir_load_rgb4_f64(io, pxn, r2d, g2d, b2d);
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        if (!exact[i]) continue;
-                        T ob, orr;
-                        niir_exact_pixel<T>(p, hue, avg, rd[i], gd[i], bd[i], r2d[i], g2d[i], b2d[i], ob, orr);
-                        db[i] = ob;
-                        dr[i] = orr;
-                    }
-                }
+                if (exact[0] || exact[1] || exact[2] || exact[3])
+                    niir_exact_quad<T>(p, io, ((size_t)f * io.nrows + row) * W + x, ((size_t)f * io.nrows + nrow) * W + x, hue, avg,
+                                       (exact[0] ? 1u : 0u) | (exact[1] ? 2u : 0u) | (exact[2] ? 4u : 0u) | (exact[3] ? 8u : 0u), db, dr);
                 st4(ys + x, y);
                 st4(bs + x, db);
                 st4(rs_ + x, dr);
