@@ -113,6 +113,28 @@ def test_decode_chunking_is_invisible(cuda_required, monkeypatch):
     assert np.array_equal(s1.decode_frames(c24).cpu().numpy(), want)
 
 
+@pytest.mark.parametrize('kind', ['niir', 'niir_hue'])
+def test_niir_encoder_strip_length_is_invisible(kind, cuda_required, monkeypatch):
+    """k_niir_encode2 walks strips of consecutive field rows and keeps the field neighbour's planes for the next iteration:
+    the composite must not depend on where the strips are cut (1, 3 or 16 rows, against the launcher's own choice), and
+    must stay within 1 LSB of the oracle; the averaging front end (ColorAveragingModem) takes the same path."""
+    import torch
+    h, w = 70, 720
+    lc = LineConfig((w, h), LS.GERBER_625)
+    make = {'niir': lambda: comb.ColorAveragingModem(niir.NiirModem(lc)), 'niir_hue': lambda: niir.HueCorrectingNiirModem(lc)}[kind]
+    rgb = synth_frames_u8(3, h, w, first_frame=6, seed=13)
+    x = torch.from_numpy(rgb).cuda()
+    ref = make().encode_frames(x, first_frame=6).cpu().numpy()
+    for r in ('1', '3', '16'):
+        monkeypatch.setenv('CM_ROWS_MAX', r)          # read once per handle
+        assert np.array_equal(make().encode_frames(x, first_frame=6).cpu().numpy(), ref), r
+    monkeypatch.delenv('CM_ROWS_MAX')
+    if kind == 'niir_hue':
+        om = oracle.build(oracle.ModemSpec('niir_hue', 'PAL', w, h, 'GERBER_625'))
+        for i in range(3):
+            assert _lsb(ref[i], oframe.encode_frame_u8(om, 6 + i, rgb[i])) <= 1
+
+
 def test_unsupported_width_is_a_clean_error(cuda_required):
     """Line widths must be multiples of 4 samples (the reference accepts any): refused when the modem is constructed,
     and by cm_create for callers of the C ABI."""
