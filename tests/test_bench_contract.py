@@ -43,3 +43,29 @@ def test_workload_names_and_defaults():
         sys.argv = old
     assert (a.gpus, a.impl, a.workload) == (1, 'ours', 'pald576') and a.steps >= 1 and a.warmup >= 3
     assert bench.BYTES_PER_FRAME == 3317760 and bench.DECODE_BYTES_PER_FRAME == 1658880
+
+
+def test_committed_bench_lines_carry_the_contract():
+    """The lines bench.py printed on the B200 boxes (profiles/r2_bench*.json) have every key of the measurement contract: the base
+    keys, `clocks`, `parity` within 1 LSB, `e2e` with its byte counts and the two beside-forms, `gpu_launches` > 0,
+    `roofline` (HBM, live achieved / measured peak), `roofline_fma` and `cpu_baseline`."""
+    for name, n in (('r2_bench.json', 1), ('r2_bench_n2.json', 2), ('r2_bench_n8.json', 8)):
+        with open(os.path.join(ROOT, 'profiles', name)) as f:
+            d = _last_json(f.read())
+        for k in ('metric', 'value', 'unit', 'n_gpus', 'steps', 'warmup', 'ms_per_step', 'higher_is_better', 'scaling',
+                  'vs_baseline', 'dtype', 'data', 'config', 'clocks', 'e2e', 'gpu_launches', 'roofline', 'cpu_baseline'):
+            assert k in d, (name, k)
+        assert d['n_gpus'] == n and d['unit'] == 'frames/s' and d['scaling'] == 'weak' and d['vs_baseline'] is None
+        assert d['warmup'] >= 3 and d['config']['timed_region_s'] >= 1.5 and 'workload' in d['config']
+        assert not set(d['clocks']['reasons']) & {'hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown'}
+        assert max(d['parity'][k] for k in ('max_lsb_comp', 'max_lsb_rgb', 'e2e_max_lsb_comp', 'e2e_max_lsb_rgb')) <= 1
+        e = d['e2e']
+        assert e['value'] > 0 and e['h2d_bytes_per_step'] > 0 and e['d2h_bytes_per_step'] > 0
+        assert e['with_composite_out']['value'] > 0 and e['two_calls']['value'] > 0 and 0 < e['frac_of_copy_peak'] < 1.2
+        assert d['gpu_launches'] > 0
+        r = d['roofline']
+        assert r['bound'] == 'hbm' and r['unit'] == 'GB/s' and abs(r['frac'] - r['achieved'] / r['peak']) < 1e-9
+        assert 0 < d['roofline_fma']['frac'] < 1
+        c = d['cpu_baseline']
+        assert c['kind'] == 'port' and c['cores'] >= 1 and c['value'] > 0 and c['sample']
+        assert d['value'] / c['value'] > 100          # the GPU arm against the CPU port on the same box
